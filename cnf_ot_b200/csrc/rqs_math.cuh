@@ -1,0 +1,423 @@
+// Per-element rational-quadratic-spline math, shared by every kernel.
+//
+// Mirrors the spline the reference instantiates at
+// /root/reference/cnf_ot/models/flows.py:124-132 (distrax
+// RationalQuadraticSpline, 'unconstrained' boundary slopes, linear tails) and
+// evaluates at /root/reference/cnf_ot/models/autoregressive.py:100,130.
+// distrax is not vendored in the reference; the algorithm is the published one
+// (SURVEY.md Appendix B).  Everything here is register-resident: knot
+// normalisation (two softmaxes, cumulative sums, softplus slopes), the bin
+// search, the forward / inverse map, the log-det and their reverse-mode
+// adjoints.  Functions are templated on the scalar type so the same source is
+// compiled for float on the device and for float/double in the host-side
+// test harness (tests/hostsim), which checks the adjoints against autograd.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CNFOT_HD __host__ __device__ __forceinline__
+#else
+#define CNFOT_HD inline
+#endif
+
+namespace cnfot {
+
+template <typename T>
+struct SplineConsts {
+  T lo, hi;        // range_min, range_max
+  T min_bin;       // min_bin_size
+  T bin_scale;     // (hi - lo) - K * min_bin
+  T min_slope;     // min_knot_slope
+  T slope_offset;  // log(exp(1 - min_slope) - 1)
+};
+
+template <typename T>
+inline SplineConsts<T> make_spline_consts(int K, double lo, double hi, double min_bin,
+                                          double min_slope) {
+  SplineConsts<T> c;
+  c.lo = (T)lo;
+  c.hi = (T)hi;
+  c.min_bin = (T)min_bin;
+  c.bin_scale = (T)((hi - lo) - K * min_bin);
+  c.min_slope = (T)min_slope;
+  c.slope_offset = (T)log(exp(1.0 - min_slope) - 1.0);
+  return c;
+}
+
+// ---- scalar helpers (overloaded so float uses the f-suffixed device paths) --
+CNFOT_HD float m_exp(float v) { return expf(v); }
+CNFOT_HD double m_exp(double v) { return exp(v); }
+CNFOT_HD float m_log(float v) { return logf(v); }
+CNFOT_HD double m_log(double v) { return log(v); }
+CNFOT_HD float m_log1p(float v) { return log1pf(v); }
+CNFOT_HD double m_log1p(double v) { return log1p(v); }
+CNFOT_HD float m_sqrt(float v) { return sqrtf(v); }
+CNFOT_HD double m_sqrt(double v) { return sqrt(v); }
+CNFOT_HD float m_abs(float v) { return fabsf(v); }
+CNFOT_HD double m_abs(double v) { return fabs(v); }
+CNFOT_HD float m_max(float a, float b) { return fmaxf(a, b); }
+CNFOT_HD double m_max(double a, double b) { return fmax(a, b); }
+CNFOT_HD float m_min(float a, float b) { return fminf(a, b); }
+CNFOT_HD double m_min(double a, double b) { return fmin(a, b); }
+CNFOT_HD float m_tiny(float) { return 1.17549435e-38f; }
+CNFOT_HD double m_tiny(double) { return 2.2250738585072014e-308; }
+
+// softplus(v) = log(1 + e^v), overflow-safe; sigmoid is its derivative.
+template <typename T>
+CNFOT_HD T softplus(T v) {
+  return m_max(v, (T)0) + m_log1p(m_exp(-m_abs(v)));
+}
+template <typename T>
+CNFOT_HD T sigmoid(T v) {
+  T e = m_exp(-m_abs(v));
+  T r = (T)1 / ((T)1 + e);
+  return v >= (T)0 ? r : e * r;
+}
+
+// Everything one spline evaluation needs again in its backward pass.
+template <typename T, int K>
+struct SplineState {
+  T pw[K];    // softmax probabilities of the width logits
+  T ph[K];    // softmax probabilities of the height logits
+  int idx;    // selected bin (0 in either tail)
+  int tail;   // 0 inside, 1 below the range, 2 above it
+  T x0, x1, y0, y1, d0, d1;  // gathered knot data of the selected bin
+  T u0, u1;   // raw slope logits (+offset) of the two gathered knots
+  T s_tail;   // boundary slope used by the active tail (if any)
+  T u_tail;   // its logit (+offset)
+};
+
+template <typename T, int K>
+CNFOT_HD void softmax_bins(const T* u, const SplineConsts<T>& c, T* prob, T* size) {
+  T m = u[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m = m_max(m, u[k]);
+  T sum = (T)0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    prob[k] = m_exp(u[k] - m);
+    sum += prob[k];
+  }
+  T inv = (T)1 / sum;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    prob[k] *= inv;
+    size[k] = prob[k] * c.bin_scale + c.min_bin;
+  }
+}
+
+// Knot positions from bin sizes: pos[0] = lo, pos[K] = hi exactly (the last
+// knot is the constant range end, not a cumulative sum).
+template <typename T, int K>
+CNFOT_HD void knot_positions(const T* size, const SplineConsts<T>& c, T* pos) {
+  pos[0] = c.lo;
+  T acc = (T)0;
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    acc += size[k - 1];
+    pos[k] = c.lo + acc;
+  }
+  pos[K] = c.hi;
+}
+
+// Bin search + gather.  `search` are the knot positions on the axis the input
+// lives on, `other` the positions on the opposite axis.  Half-open bins
+// [pos[k], pos[k+1]); outside the range the reference falls back to bin 0.
+template <typename T, int K>
+CNFOT_HD void locate(T v, const T* search, const T* other, const T* us,
+                     const SplineConsts<T>& c, SplineState<T, K>& st, T& s0, T& s1,
+                     T& o0, T& o1) {
+  int tail = 0;
+  if (v <= search[0]) tail = 1;
+  if (v >= search[K]) tail = 2;
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k) idx += (v >= search[k]) ? 1 : 0;
+  if (v < search[0] || v >= search[K]) idx = 0;
+  s0 = search[0]; s1 = search[1];
+  o0 = other[0]; o1 = other[1];
+  T u0 = us[0], u1 = us[1];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    bool hit = (idx == k);
+    s0 = hit ? search[k] : s0;
+    s1 = hit ? search[k + 1] : s1;
+    o0 = hit ? other[k] : o0;
+    o1 = hit ? other[k + 1] : o1;
+    u0 = hit ? us[k] : u0;
+    u1 = hit ? us[k + 1] : u1;
+  }
+  st.idx = idx;
+  st.tail = tail;
+  st.u0 = u0 + c.slope_offset;
+  st.u1 = u1 + c.slope_offset;
+  st.d0 = softplus(st.u0) + c.min_slope;
+  st.d1 = softplus(st.u1) + c.min_slope;
+  st.s_tail = st.d0;
+  st.u_tail = st.u0;
+  if (tail == 2) {  // rare: needs the last knot's slope
+    st.u_tail = us[K] + c.slope_offset;
+    st.s_tail = softplus(st.u_tail) + c.min_slope;
+  }
+}
+
+// y = S(x), log|S'(x)|.  theta: raw params [K widths | K heights | K+1 slopes].
+template <typename T, int K>
+CNFOT_HD void rqs_forward(T x, const T* theta, const SplineConsts<T>& c,
+                          SplineState<T, K>& st, T& y, T& logdet) {
+  T w[K], h[K], xp[K + 1], yp[K + 1];
+  softmax_bins<T, K>(theta, c, st.pw, w);
+  softmax_bins<T, K>(theta + K, c, st.ph, h);
+  knot_positions<T, K>(w, c, xp);
+  knot_positions<T, K>(h, c, yp);
+  locate<T, K>(x, xp, yp, theta + 2 * K, c, st, st.x0, st.x1, st.y0, st.y1);
+  if (st.tail == 0) {
+    T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
+    T sl = bh / bw;
+    T z = (x - st.x0) / bw;
+    z = m_min(m_max(z, (T)0), (T)1);
+    T z2 = z * z, z1 = z - z2, omz = (T)1 - z;
+    T stt = st.d1 + st.d0 - (T)2 * sl;
+    T den = sl + stt * z1;
+    y = st.y0 + bh * (sl * z2 + st.d0 * z1) / den;
+    T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * omz * omz;
+    logdet = (T)2 * m_log(sl) + m_log(A) - (T)2 * m_log(den);
+  } else {
+    T px = st.tail == 1 ? c.lo : c.hi;
+    y = (x - px) * st.s_tail + px;  // range ends coincide on both axes
+    logdet = m_log(st.s_tail);
+  }
+}
+
+// x = S^{-1}(y), log|dS^{-1}/dy|.
+template <typename T, int K>
+CNFOT_HD void rqs_inverse(T y, const T* theta, const SplineConsts<T>& c,
+                          SplineState<T, K>& st, T& x, T& logdet) {
+  T w[K], h[K], xp[K + 1], yp[K + 1];
+  softmax_bins<T, K>(theta, c, st.pw, w);
+  softmax_bins<T, K>(theta + K, c, st.ph, h);
+  knot_positions<T, K>(w, c, xp);
+  knot_positions<T, K>(h, c, yp);
+  locate<T, K>(y, yp, xp, theta + 2 * K, c, st, st.y0, st.y1, st.x0, st.x1);
+  if (st.tail == 0) {
+    T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
+    T sl = bh / bw;
+    T w_ = (y - st.y0) / bh;
+    w_ = m_min(m_max(w_, (T)0), (T)1);
+    T stt = st.d1 + st.d0 - (T)2 * sl;
+    T qc = -sl * w_;
+    T qb = st.d0 - stt * w_;
+    T qa = sl - qb;
+    T disc = qb * qb - (T)4 * qa * qc;
+    T root = disc > (T)0 ? m_sqrt(m_max(disc, m_tiny((T)0))) : (T)0;
+    T z = qb >= (T)0 ? ((T)2 * qc) / (-qb - root) : (-qb + root) / ((T)2 * qa);
+    z = m_min(m_max(z, (T)0), (T)1);
+    x = bw * z + st.x0;
+    T z2 = z * z, z1 = z - z2, omz = (T)1 - z;
+    T den = sl + stt * z1;
+    T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * omz * omz;
+    logdet = -(T)2 * m_log(sl) - m_log(A) + (T)2 * m_log(den);
+  } else {
+    T px = st.tail == 1 ? c.lo : c.hi;
+    x = (y - px) / st.s_tail + px;
+    logdet = -m_log(st.s_tail);
+  }
+}
+
+// Adjoints of the six gathered knot scalars -> adjoints of the raw params.
+// Knot positions: pos[j] = lo + sum_{i<j} size[i] for 1 <= j <= K-1; pos[0]
+// and pos[K] are constants, so the last bin's size only gets gradient through
+// earlier cumulative sums.  Slopes: softplus'(u) = sigmoid(u).
+template <typename T, int K>
+CNFOT_HD void scatter_to_raw(const SplineState<T, K>& st, const SplineConsts<T>& c,
+                             T gx0, T gx1, T gy0, T gy1, T gd0, T gd1, T gs_tail,
+                             T* gtheta) {
+  T gsx[K], gsy[K];  // adjoints of the bin sizes
+  {
+    // adjoint of pos[j] for interior knots j = idx (left) and idx+1 (right)
+    T accx = (T)0, accy = (T)0;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+      // size[i] feeds pos[j] for all interior j >= i+1
+      int j = i + 1;
+      if (j <= K - 1) {
+        accx += (j == st.idx ? gx0 : (T)0) + (j == st.idx + 1 ? gx1 : (T)0);
+        accy += (j == st.idx ? gy0 : (T)0) + (j == st.idx + 1 ? gy1 : (T)0);
+      }
+      gsx[i] = accx;
+      gsy[i] = accy;
+    }
+  }
+  T dotx = (T)0, doty = (T)0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    dotx += st.pw[k] * gsx[k];
+    doty += st.ph[k] * gsy[k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    gtheta[k] = c.bin_scale * st.pw[k] * (gsx[k] - dotx);
+    gtheta[K + k] = c.bin_scale * st.ph[k] * (gsy[k] - doty);
+  }
+  T gu0 = gd0 * sigmoid(st.u0);
+  T gu1 = gd1 * sigmoid(st.u1);
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+    gtheta[2 * K + k] = (k == st.idx ? gu0 : (T)0) + (k == st.idx + 1 ? gu1 : (T)0);
+  }
+  if (st.tail == 1) gtheta[2 * K] += gs_tail * sigmoid(st.u_tail);
+  if (st.tail == 2) gtheta[3 * K] += gs_tail * sigmoid(st.u_tail);
+}
+
+// Reverse mode of rqs_forward: given (gy, gl) = adjoints of (y, logdet),
+// returns gx and writes gtheta[3K+1] (overwrites).
+template <typename T, int K>
+CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<T>& c,
+                           T gy, T gl, T* gtheta) {
+  T gx;
+  T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
+  if (st.tail == 0) {
+    T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
+    T ibw = (T)1 / bw;
+    T sl = bh * ibw;
+    T zr = (x - st.x0) * ibw;
+    T z = m_min(m_max(zr, (T)0), (T)1);
+    T z2 = z * z, z1 = z - z2, omz = (T)1 - z, o2 = omz * omz;
+    T stt = st.d1 + st.d0 - (T)2 * sl;
+    T q = sl * z2 + st.d0 * z1;
+    T nu = bh * q;
+    T den = sl + stt * z1;
+    T iden = (T)1 / den;
+    T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * o2;
+    T g_nu = gy * iden;
+    T g_den = -gy * nu * iden * iden - (T)2 * gl * iden;
+    T g_A = gl / A;
+    T g_sl = (T)2 * gl / sl + (T)2 * g_A * z1 + g_den;
+    gd1 = g_A * z2;
+    gd0 = g_A * o2;
+    T g_z2 = g_A * st.d1;
+    T g_z1 = (T)2 * g_A * sl + g_den * stt;
+    T g_o2 = g_A * st.d0;
+    T g_stt = g_den * z1;
+    T g_bh = g_nu * q;
+    T g_q = g_nu * bh;
+    g_sl += g_q * z2;
+    g_z2 += g_q * sl;
+    gd0 += g_q * z1;
+    g_z1 += g_q * st.d0;
+    gd1 += g_stt;
+    gd0 += g_stt;
+    g_sl -= (T)2 * g_stt;
+    T g_z = g_z1 + (T)2 * z * (g_z2 - g_z1) - (T)2 * omz * g_o2;
+    T g_zr = (zr > (T)0 && zr < (T)1) ? g_z : (T)0;
+    gx = g_zr * ibw;
+    gx0 = -gx;
+    T g_bw = -g_zr * zr * ibw - g_sl * sl * ibw;
+    g_bh += g_sl * ibw;
+    gx1 = g_bw;
+    gx0 -= g_bw;
+    gy1 = g_bh;
+    gy0 = gy - g_bh;
+  } else {
+    T px = st.tail == 1 ? c.lo : c.hi;
+    gx = gy * st.s_tail;
+    gst = gy * (x - px) + gl / st.s_tail;
+  }
+  scatter_to_raw<T, K>(st, c, gx0, gx1, gy0, gy1, gd0, gd1, gst, gtheta);
+  return gx;
+}
+
+// Reverse mode of rqs_inverse: (gx_out, gl) = adjoints of (x, logdet);
+// returns the adjoint of the input y and writes gtheta.
+template <typename T, int K>
+CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<T>& c,
+                           T gxo, T gl, T* gtheta) {
+  T gyin;
+  T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
+  if (st.tail == 0) {
+    T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
+    T ibw = (T)1 / bw, ibh = (T)1 / bh;
+    T sl = bh * ibw;
+    T wr = (y - st.y0) * ibh;
+    T w_ = m_min(m_max(wr, (T)0), (T)1);
+    T stt = st.d1 + st.d0 - (T)2 * sl;
+    T qc = -sl * w_;
+    T qb = st.d0 - stt * w_;
+    T qa = sl - qb;
+    T disc = qb * qb - (T)4 * qa * qc;
+    bool pos = disc > (T)0;
+    T root = pos ? m_sqrt(m_max(disc, m_tiny((T)0))) : (T)0;
+    bool bpos = qb >= (T)0;
+    T dn = bpos ? (-qb - root) : ((T)2 * qa);
+    T idn = (T)1 / dn;
+    T zr = (bpos ? ((T)2 * qc) : (-qb + root)) * idn;
+    T z = m_min(m_max(zr, (T)0), (T)1);
+    T z2 = z * z, z1 = z - z2, omz = (T)1 - z, o2 = omz * omz;
+    T den = sl + stt * z1;
+    T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * o2;
+    // x = bw * z + x0
+    T g_bw = gxo * z;
+    T g_z = gxo * bw;
+    gx0 = gxo;
+    // logdet = -(2 log sl + log A - 2 log den)
+    T gF = -gl;
+    T g_A = gF / A;
+    T g_den = -(T)2 * gF / den;
+    T g_sl = (T)2 * gF / sl + (T)2 * g_A * z1 + g_den;
+    gd1 = g_A * z2;
+    gd0 = g_A * o2;
+    T g_z2 = g_A * st.d1;
+    T g_z1 = (T)2 * g_A * sl + g_den * stt;
+    T g_o2 = g_A * st.d0;
+    T g_stt = g_den * z1;
+    g_z += g_z1 + (T)2 * z * (g_z2 - g_z1) - (T)2 * omz * g_o2;
+    T g_zr = (zr > (T)0 && zr < (T)1) ? g_z : (T)0;
+    // z = num / dn
+    T g_num = g_zr * idn;
+    T g_dn = -g_zr * zr * idn;
+    T g_qa = 0, g_qb = 0, g_qc = 0, g_root = 0;
+    if (bpos) {
+      g_qc += (T)2 * g_num;
+      g_qb -= g_dn;
+      g_root -= g_dn;
+    } else {
+      g_qb -= g_num;
+      g_root += g_num;
+      g_qa += (T)2 * g_dn;
+    }
+    T g_disc = (pos && disc >= m_tiny((T)0)) ? g_root / ((T)2 * root) : (T)0;
+    g_qb += (T)2 * qb * g_disc;
+    g_qa -= (T)4 * qc * g_disc;
+    g_qc -= (T)4 * qa * g_disc;
+    // qa = sl - qb
+    g_sl += g_qa;
+    g_qb -= g_qa;
+    // qb = d0 - stt * w ; qc = -sl * w
+    gd0 += g_qb;
+    g_stt -= g_qb * w_;
+    T g_w = -g_qb * stt - g_qc * sl;
+    g_sl -= g_qc * w_;
+    // stt = d1 + d0 - 2 sl
+    gd1 += g_stt;
+    gd0 += g_stt;
+    g_sl -= (T)2 * g_stt;
+    T g_wr = (wr > (T)0 && wr < (T)1) ? g_w : (T)0;
+    gyin = g_wr * ibh;
+    T g_bh = -g_wr * wr * ibh + g_sl * ibw;
+    g_bw -= g_sl * sl * ibw;
+    gx1 = g_bw;
+    gx0 -= g_bw;
+    gy1 = g_bh;
+    gy0 = -gyin - g_bh;
+  } else {
+    T px = st.tail == 1 ? c.lo : c.hi;
+    T is = (T)1 / st.s_tail;
+    gyin = gxo * is;
+    gst = -gxo * (y - px) * is * is - gl * is;
+  }
+  scatter_to_raw<T, K>(st, c, gx0, gx1, gy0, gy1, gd0, gd1, gst, gtheta);
+  return gyin;
+}
+
+}  // namespace cnfot

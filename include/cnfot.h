@@ -1,0 +1,190 @@
+/* cnfot.h -- C ABI of libcnfot.so: B200 (sm_100a) kernels for the cnf_ot flow
+ * train step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (pure Python/JAX) has no FFI of its own; the seams this library plugs into
+ * are the ones SURVEY.md section 8(b) lists:
+ *   seam 2  Autoregressive(bijector=...)          cnf_ot/models/flows.py:124-132
+ *           -> cnfot_rqs_*                         (one scalar spline per row)
+ *   seam 1  Flow namedtuple of RQSFlow(...)        cnf_ot/models/flows.py:213-226
+ *           -> cnfot_flow_*                        (whole conditional flow)
+ *   seam 3  loss_fn consumed by value_and_grad     cnf_ot/mfc/solvers.py:90-97
+ *           -> cnfot_mfc_step*                     (loss + parameter gradient)
+ * Every entry point is shaped so an XLA FFI handler can forward to it 1:1
+ * (stream + device buffers + scalar attributes); INTEGRATION.md shows the
+ * binding.
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers to dense row-major float32 unless
+ *     the name ends in _host.  Sizes are int64_t, the stream is a cudaStream_t
+ *     passed as void*.
+ *   - Calls are stream-ordered and never synchronise the stream (the _host
+ *     variants synchronise once, to hand results back).
+ *   - No persistent allocation behind the caller's back: scratch memory is a
+ *     caller-owned workspace sized by the matching *_workspace_bytes().
+ *   - Return value 0 = ok; non-zero = error, message via cnfot_last_error()
+ *     (thread-local).  Nothing throws.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with CNFOT_ERR_CUDA.
+ */
+#ifndef CNFOT_H_
+#define CNFOT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNFOT_ABI_VERSION 1
+
+enum {
+  CNFOT_OK = 0,
+  CNFOT_ERR_ARG = 1,         /* bad argument / unsupported shape */
+  CNFOT_ERR_CUDA = 2,        /* CUDA runtime error (incl. no device) */
+  CNFOT_ERR_WORKSPACE = 3    /* workspace too small */
+};
+
+/* general.type of config/mfc.yaml (cnf_ot/mfc/solvers.py:58-88) */
+enum { CNFOT_OT = 0, CNFOT_RWPO = 1, CNFOT_FP = 2 };
+/* ot.subtype, rwpo.pot_type, fp.velocity_field_type */
+enum { CNFOT_OT_FREE = 0, CNFOT_OT_OBSTACLE = 1 };
+enum { CNFOT_POT_QUADRATIC = 0, CNFOT_POT_DOUBLE_WELL = 1 };
+enum { CNFOT_FP_GRADIENT = 0, CNFOT_FP_NONGRADIENT = 1, CNFOT_FP_LORENZ = 2 };
+
+/* Static shape of RQSFlow(event_shape=(dim,), num_layers, hidden_sizes=[hidden]*mlp_layers,
+ * num_bins) -- cnf_ot/models/flows.py:178-199 -- plus the spline constants the
+ * reference hard-codes at flows.py:124-132 (-10, 10, min_knot_slope 1e-4; min_bin_size
+ * 1e-4 is the distrax default). */
+typedef struct cnfot_flow_desc {
+  int32_t dim;          /* general.dim            */
+  int32_t num_layers;   /* cnf.flow_num_layers    */
+  int32_t mlp_layers;   /* cnf.mlp_num_layers     */
+  int32_t hidden;       /* cnf.hidden_size        */
+  int32_t num_bins;     /* cnf.num_bins           */
+  float range_min, range_max, min_bin_size, min_knot_slope;
+} cnfot_flow_desc;
+
+/* The loss selected by general.type and its hyper-parameters (config/mfc.yaml:6-27). */
+typedef struct cnfot_problem_desc {
+  int32_t type;     /* CNFOT_OT / CNFOT_RWPO / CNFOT_FP */
+  int32_t subtype;  /* see enums above */
+  float T;          /* rwpo.T / fp.T (ot uses 1) */
+  float beta;       /* rwpo.beta (fp hard-codes 4, applications.py:432) */
+  float a;          /* rwpo.a / fp.a */
+  float sigma;      /* fp.sigma */
+  float dt, dx;     /* general.dt, general.dx (fp hard-codes 0.01, applications.py:286,301) */
+} cnfot_problem_desc;
+
+int cnfot_abi_version(void);
+const char* cnfot_last_error(void);
+
+/* ---- parameter blob ---------------------------------------------------------------
+ * The haiku pytree of SURVEY.md A.3 flattened into one fp32 buffer (layout documented in
+ * DESIGN.md and cnf_ot_b200/csrc/flow_math.cuh).  Offsets are in floats. */
+int64_t cnfot_param_count(const cnfot_flow_desc* flow);               /* blob length */
+int64_t cnfot_spline_param_stride(const cnfot_flow_desc* flow);       /* Pp = roundup(3K+1, 4) */
+int64_t cnfot_offset_first(const cnfot_flow_desc* flow);              /* "~/first" */
+/* linear m of "mlp_layer{l}_d{d}/~/linear_{m}" (0 <= m < mlp_layers) or, with
+ * m == mlp_layers, "linear_out_layer{l}_d{d}"; bias != 0 selects "b" instead of "w". */
+int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t d, int32_t m,
+                            int32_t bias);
+/* 0 if the fused kernels support this shape, else CNFOT_ERR_ARG (message says why). */
+int cnfot_flow_supported(const cnfot_flow_desc* flow);
+
+/* ---- seam 2: one scalar spline per row (distrax.RationalQuadraticSpline) ------------
+ * params: (rows, 3K+1) raw [K widths | K heights | K+1 slopes], replaces
+ * bijector_fn(params).forward_and_log_det / inverse_and_log_det
+ * (cnf_ot/models/flows.py:124-132, cnf_ot/models/autoregressive.py:100,130).
+ * bin_idx (int32, may be NULL) receives the selected bin (0 in either tail). */
+int cnfot_rqs_forward(void* stream, const float* x, const float* params, int64_t rows,
+                      int32_t num_bins, float range_min, float range_max, float min_bin_size,
+                      float min_knot_slope, float* y, float* logdet, int32_t* bin_idx);
+int cnfot_rqs_inverse(void* stream, const float* y, const float* params, int64_t rows,
+                      int32_t num_bins, float range_min, float range_max, float min_bin_size,
+                      float min_knot_slope, float* x, float* logdet, int32_t* bin_idx);
+/* Vector-Jacobian products of the two calls above: given the adjoints of (out, logdet)
+ * returns the adjoint of the input (rows) and of params (rows, 3K+1). */
+int cnfot_rqs_forward_vjp(void* stream, const float* x, const float* params, const float* g_y,
+                          const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
+                          float range_max, float min_bin_size, float min_knot_slope, float* g_x,
+                          float* g_params);
+int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, const float* g_x,
+                          const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
+                          float range_max, float min_bin_size, float min_knot_slope, float* g_y,
+                          float* g_params);
+
+/* ---- seam 1: the conditional flow (Flow namedtuple, cnf_ot/models/flows.py:213-226) --
+ * cond is one time per row (cond_stride = 1, like the (N,1) `cond` of sample()) or a single
+ * broadcast time (cond_stride = 0, like the (1,) `cond` of log_prob()).
+ *   forward : flow.bijector.forward(_and_log_det)   latent -> physical  ("sample direction")
+ *   inverse : flow.bijector.inverse(_and_log_det)   physical -> latent  ("log-prob direction")
+ * logdet may be NULL.  With add_base != 0, `logdet` instead receives the log-density the
+ * reference's ConditionalTransformed returns (cnf_ot/models/conditional.py:316-321,382-402):
+ *   forward: log N(in) - fldj  (sample_and_log_prob)   inverse: log N(out) + ildj  (log_prob) */
+int cnfot_flow_forward(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                       const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                       float* out, float* logdet, int32_t add_base);
+int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                       const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                       float* out, float* logdet, int32_t add_base);
+/* VJPs of the two calls above (what a jax.custom_vjp backward rule calls): given g_out (rows,D)
+ * and g_logdet (rows, may be NULL = zeros; it is the adjoint of the `logdet` OUTPUT, so it
+ * honours add_base) writes g_in (rows,D, may be NULL) and writes the parameter gradient,
+ * summed over rows, to g_weights (blob layout, overwritten). */
+int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows);
+int cnfot_flow_forward_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                           const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                           const float* g_out, const float* g_logdet, int32_t add_base,
+                           float* g_in, float* g_weights, void* workspace,
+                           int64_t workspace_bytes);
+int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                           const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                           const float* g_out, const float* g_logdet, int32_t add_base,
+                           float* g_in, float* g_weights, void* workspace,
+                           int64_t workspace_bytes);
+
+/* ---- seam 3: the train step's value_and_grad (cnf_ot/mfc/solvers.py:94) --------------
+ * Evaluates loss_fn = ot_loss_fn / rwpo_loss_fn / fp_loss_fn
+ * (cnf_ot/mfc/applications.py:377-441) and its gradient w.r.t. the parameter blob on this
+ * GPU's shard of the batch.  Inputs replace the reference's PRNG draws:
+ *   latent  (rows_B, D)  N(0,I) draws; the B//32 sub-batch terms use `latent_sub`
+ *   latent_sub (rows_b, D)  this shard's rows of the b = B//32 sub-batch
+ *   src, tgt (rows_B, D) data batches of kl_loss_fn (ot only; NULL otherwise)
+ *   t_batch (n_t) on the HOST: the uniform times of applications.py:392,416,435
+ * rows_B / rows_b are LOCAL row counts, global_B / global_b the whole-job counts used for
+ * the means, so out buffers from different GPUs sum to the reference's result.
+ * out: [ gradient (param_count) | loss slots (8) ] fp32, overwritten:
+ *   slot 0 total loss, 1 fit term at t=0 (lambda-weighted), 2 fit term at t=T, 3 potential,
+ *   4 kinetic; 5-7 reserved (zero). */
+#define CNFOT_NUM_LOSS_SLOTS 8
+int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
+                                       int64_t rows_b, int32_t n_t);
+int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                   const float* weights, const float* latent, const float* latent_sub,
+                   const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
+                   int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
+                   float lambda, float* out, void* workspace, int64_t workspace_bytes);
+/* Same step with HOST buffers in and out (weights, latent, latent_sub, src, tgt, out are host
+ * pointers): copies inputs to the device workspace, runs the step, copies `out` back and
+ * synchronises the stream.  The workspace must be
+ * cnfot_mfc_step_host_workspace_bytes() of DEVICE memory. */
+int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
+                                            int64_t rows_b, int32_t n_t);
+int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow,
+                        const cnfot_problem_desc* problem, const float* weights_host,
+                        const float* latent_host, const float* latent_sub_host,
+                        const float* src_host, const float* tgt_host, const float* t_batch_host,
+                        int32_t n_t, int64_t rows_B, int64_t rows_b, int64_t global_B,
+                        int64_t global_b, float lambda, float* out_host, void* workspace,
+                        int64_t workspace_bytes);
+
+/* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
+ * element-wise update; step is the 1-based update count. */
+int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v,
+                      int64_t count, float lr, float b1, float b2, float eps, int64_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNFOT_H_ */

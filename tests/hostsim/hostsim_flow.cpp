@@ -1,0 +1,183 @@
+// Host-side harness (TEST ONLY, see hostsim_rqs.cpp): runs the per-row flow and
+// loss-term functions the kernels inline, with a plain accumulating gradient
+// sink, so values and adjoints can be checked against the autograd oracle
+// without a GPU.  Never loaded by the cnf_ot_b200 package.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../cnf_ot_b200/csrc/step_host.h"
+
+using namespace cnfot;
+
+template <typename T>
+struct HostSink {
+  double* G;  // gradient blob (double accumulation)
+  template <int NAMAX, int NG>
+  void outer(int w_off, int Na, const T* a, const T* g) {
+    for (int i = 0; i < Na; ++i)
+      for (int j = 0; j < NG; ++j) G[w_off + i * NG + j] += (double)a[i] * (double)g[j];
+    for (int j = 0; j < NG; ++j) G[w_off + Na * NG + j] += (double)g[j];
+  }
+};
+
+template <typename T, class Net>
+static int flow_eval(int D, int L, int dir, int64_t rows, const T* W, const T* in, const T* cond,
+                     int64_t cs, T* out, T* ld, int add_base) {
+  if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
+  Dims<0, 0> dm{D, L};
+  SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
+  for (int64_t r = 0; r < rows; ++r) {
+    T st[kMaxStateFloats];
+    for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
+    T l = flow_pass<T, Net, Dims<0, 0>>(dir, dm, W, sc, cond[r * cs], st);
+    for (int i = 0; i < D; ++i) out[r * D + i] = st[L * D + i];
+    if (ld) {
+      if (add_base) l = dir == 0 ? base_log_prob<T>(st, D) - l : base_log_prob<T>(st + L * D, D) + l;
+      ld[r] = l;
+    }
+  }
+  return 0;
+}
+
+template <typename T, class Net>
+static int flow_vjp(int D, int L, int dir, int64_t rows, const T* W, const T* in, const T* cond,
+                    int64_t cs, const T* gout, const T* gld, int add_base, T* gin, double* G) {
+  if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
+  Dims<0, 0> dm{D, L};
+  SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
+  HostSink<T> sink{G};
+  std::vector<T> gfirst(Net::kPp, (T)0);
+  for (int64_t r = 0; r < rows; ++r) {
+    T st[kMaxStateFloats], g[kMaxDim];
+    for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
+    flow_pass<T, Net, Dims<0, 0>>(dir, dm, W, sc, cond[r * cs], st);
+    T gl = gld ? gld[r] : (T)0;
+    for (int i = 0; i < D; ++i) g[i] = gout[r * D + i];
+    T gl_pass = gl;
+    if (add_base) {
+      if (dir == 0) gl_pass = -gl;                                         // lp = logN(in) - fldj
+      else for (int i = 0; i < D; ++i) g[i] += gl * (-st[L * D + i]);     // lp = logN(out) + ildj
+    }
+    flow_pass_bwd<T, Net, Dims<0, 0>, HostSink<T>>(dir, dm, W, sc, cond[r * cs], st, g, gl_pass,
+                                                    gfirst.data(), sink);
+    if (add_base && dir == 0) for (int i = 0; i < D; ++i) g[i] += gl * (-st[i]);
+    if (gin) for (int i = 0; i < D; ++i) gin[r * D + i] = g[i];
+  }
+  for (int j = 0; j < Net::kPp; ++j) G[j] += (double)gfirst[j];
+  return 0;
+}
+
+template <typename T, class Net>
+static int step(int D, int L, const cnfot_problem_desc* pd, const T* W, const T* latent,
+                const T* latent_sub, const T* src, const T* tgt, const double* t_batch, int n_t,
+                int64_t rows_B, int64_t rows_b, int64_t gB, int64_t gb, double lambda, double* G,
+                double* slots) {
+  if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
+  Dims<0, 0> dm{D, L};
+  SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
+  StepConsts<T> pc;
+  const char* err = nullptr;
+  if (make_step_consts<T>(*pd, D, lambda, gB, gb, n_t, &pc, &err)) return 2;
+  HostSink<T> sink{G};
+  std::vector<T> gfirst(Net::kPp, (T)0);
+  for (int s = 0; s < kNumSlots; ++s) slots[s] = 0.0;
+  if (pd->type == CNFOT_OT) {
+    for (int64_t r = 0; r < rows_B; ++r) {
+      slots[kSlotFit0] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T>>(
+          dm, W, sc, (T)0, src + r * D, pc.w_fit, gfirst.data(), sink);
+      slots[kSlotFitT] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T>>(
+          dm, W, sc, pc.horizon, tgt + r * D, pc.w_fit, gfirst.data(), sink);
+    }
+  } else {
+    for (int64_t r = 0; r < rows_B; ++r) {
+      T lf = 0, lp = 0;
+      row_sample_terms<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, (T)0, latent + r * D, true,
+                                                        false, pc, &lf, &lp, gfirst.data(), sink);
+      if (pd->type == CNFOT_RWPO)
+        row_sample_terms<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, pc.horizon, latent + r * D,
+                                                          false, true, pc, &lf, &lp,
+                                                          gfirst.data(), sink);
+      slots[kSlotFit0] += (double)lf;
+      slots[kSlotPotential] += (double)lp;
+    }
+  }
+  for (int it = 0; it < n_t; ++it)
+    for (int64_t r = 0; r < rows_b; ++r) {
+      T lk = 0, lp = 0;
+      row_kinetic<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, (T)t_batch[it], latent_sub + r * D,
+                                                   pc, &lk, &lp, gfirst.data(), sink);
+      slots[kSlotKinetic] += (double)lk;
+      slots[kSlotPotential] += (double)lp;
+    }
+  for (int j = 0; j < Net::kPp; ++j) G[j] += (double)gfirst[j];
+  return 0;
+}
+
+#define NET_CASE(H_, K_, M_) \
+  if (H == H_ && K == K_ && M == M_) { using Net = NetCfg<H_, K_, M_>; return CALL; }
+
+extern "C" int hs_layout(int D, int L, int M, int H, int K, int64_t* total, int64_t* Pp) {
+  FlowLayout f = make_layout(D, L, M, H, K);
+  *total = f.total;
+  *Pp = f.Pp;
+  return 0;
+}
+extern "C" int64_t hs_mlp_offset(int D, int H, int K, int M, int layer, int d) {
+  FlowLayout f = make_layout(D, 1, M, H, K);
+  return f.Pp + (int64_t)layer * f.layer_stride + (d - 1) * f.mlp_const + H * ((d - 1) * (d + 2) / 2);
+}
+
+extern "C" int hs_flow_eval_f64(int D, int L, int M, int H, int K, int dir, int64_t rows,
+                                const double* W, const double* in, const double* cond, int64_t cs,
+                                double* out, double* ld, int add_base) {
+#define CALL flow_eval<double, Net>(D, L, dir, rows, W, in, cond, cs, out, ld, add_base)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
+extern "C" int hs_flow_eval_f32(int D, int L, int M, int H, int K, int dir, int64_t rows,
+                                const float* W, const float* in, const float* cond, int64_t cs,
+                                float* out, float* ld, int add_base) {
+#define CALL flow_eval<float, Net>(D, L, dir, rows, W, in, cond, cs, out, ld, add_base)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
+extern "C" int hs_flow_vjp_f64(int D, int L, int M, int H, int K, int dir, int64_t rows,
+                               const double* W, const double* in, const double* cond, int64_t cs,
+                               const double* gout, const double* gld, int add_base, double* gin,
+                               double* G) {
+#define CALL flow_vjp<double, Net>(D, L, dir, rows, W, in, cond, cs, gout, gld, add_base, gin, G)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
+extern "C" int hs_flow_vjp_f32(int D, int L, int M, int H, int K, int dir, int64_t rows,
+                               const float* W, const float* in, const float* cond, int64_t cs,
+                               const float* gout, const float* gld, int add_base, float* gin,
+                               double* G) {
+#define CALL flow_vjp<float, Net>(D, L, dir, rows, W, in, cond, cs, gout, gld, add_base, gin, G)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
+extern "C" int hs_step_f64(int D, int L, int M, int H, int K, const cnfot_problem_desc* pd,
+                           const double* W, const double* latent, const double* latent_sub,
+                           const double* src, const double* tgt, const double* t_batch, int n_t,
+                           int64_t rows_B, int64_t rows_b, int64_t gB, int64_t gb, double lambda,
+                           double* G, double* slots) {
+#define CALL step<double, Net>(D, L, pd, W, latent, latent_sub, src, tgt, t_batch, n_t, rows_B, rows_b, gB, gb, lambda, G, slots)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
+extern "C" int hs_step_f32(int D, int L, int M, int H, int K, const cnfot_problem_desc* pd,
+                           const float* W, const float* latent, const float* latent_sub,
+                           const float* src, const float* tgt, const double* t_batch, int n_t,
+                           int64_t rows_B, int64_t rows_b, int64_t gB, int64_t gb, double lambda,
+                           double* G, double* slots) {
+#define CALL step<float, Net>(D, L, pd, W, latent, latent_sub, src, tgt, t_batch, n_t, rows_B, rows_b, gB, gb, lambda, G, slots)
+  CNFOT_NET_LIST(NET_CASE)
+#undef CALL
+  return 3;
+}
