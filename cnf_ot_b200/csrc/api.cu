@@ -1,0 +1,565 @@
+// C ABI of libcnfot.so (declared in include/cnfot.h): argument checking, kernel
+// selection, launch configuration, workspace carving.  No torch types, no
+// allocation, no stream synchronisation (except the *_host convenience entry).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cnfot.h"
+#include "device_common.cuh"
+#include "dispatch.h"
+#include "flow_kernels.cuh"
+#include "step_host.h"
+
+namespace cnfot {
+
+// rqs_kernels.cu
+cudaError_t rqs_eval_dispatch(int K, bool inverse, cudaStream_t s, const float* v,
+                              const float* params, int64_t rows, const SplineConsts<float>& sc,
+                              float* out, float* ld, int32_t* bin, int num_sms, bool* known);
+cudaError_t rqs_vjp_dispatch(int K, bool inverse, cudaStream_t s, const float* v,
+                             const float* params, const float* go, const float* gl, int64_t rows,
+                             const SplineConsts<float>& sc, float* gi, float* gp, int num_sms,
+                             bool* known);
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(CNFOT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+};
+
+// Properties of the current device (cached per device id).
+static int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (no CUDA device? libcnfot has no CPU path)");
+  if (dev < 0 || dev >= 64) return fail(CNFOT_ERR_CUDA, "device id %d out of range", dev);
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    e = cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    e = cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    cache[dev] = d;
+  }
+  *out = cache[dev];
+  return 0;
+}
+
+constexpr int kMaxGrid = 148 * 8;   // upper bound on persistent CTAs (workspace sizing)
+constexpr int64_t kCounterBytes = 256;
+
+static int check_flow(const cnfot_flow_desc* f, FlowLayout* lay) {
+  if (!f) return fail(CNFOT_ERR_ARG, "flow descriptor is NULL");
+  if (f->dim < 1 || f->num_layers < 1 || f->mlp_layers < 1 || f->hidden < 1 || f->num_bins < 1)
+    return fail(CNFOT_ERR_ARG, "flow descriptor has non-positive sizes");
+  if (f->hidden % 4 != 0) return fail(CNFOT_ERR_ARG, "hidden size %d must be a multiple of 4", f->hidden);
+  if (!(f->range_max > f->range_min) || f->num_bins * f->min_bin_size > f->range_max - f->range_min)
+    return fail(CNFOT_ERR_ARG, "min_bin_size too large for the spline range");
+  if (!(f->min_knot_slope < 1.f)) return fail(CNFOT_ERR_ARG, "min_knot_slope must be < 1");
+  *lay = make_layout(f->dim, f->num_layers, f->mlp_layers, f->hidden, f->num_bins);
+  return 0;
+}
+
+static int check_fused(const cnfot_flow_desc* f, const FlowLayout& lay) {
+  if (f->dim > kMaxDim) return fail(CNFOT_ERR_ARG, "fused kernels support dim <= %d (got %d)", kMaxDim, f->dim);
+  if ((f->num_layers + 1) * f->dim > kMaxStateFloats)
+    return fail(CNFOT_ERR_ARG, "fused kernels need (num_layers+1)*dim <= %d (got %d)", kMaxStateFloats,
+                (f->num_layers + 1) * f->dim);
+  if (!find_flow_eval_kernel(lay))
+    return fail(CNFOT_ERR_ARG,
+                "no fused kernel instantiated for hidden=%d num_bins=%d mlp_layers=%d "
+                "(see CNFOT_NET_LIST in cnf_ot_b200/csrc/dispatch.h)",
+                f->hidden, f->num_bins, f->mlp_layers);
+  return 0;
+}
+
+static SplineConsts<float> spline_consts(const cnfot_flow_desc* f) {
+  return make_spline_consts<float>(f->num_bins, f->range_min, f->range_max, f->min_bin_size,
+                                   f->min_knot_slope);
+}
+
+struct LaunchCfg {
+  int grid;
+  size_t smem;
+};
+
+// Persistent launch: as many CTAs as fit on the chip, capped by the tile count.
+static int configure(const void* kernel, const SmemPlan& sp, int64_t tiles, LaunchCfg* cfg) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  size_t smem = (size_t)sp.floats * sizeof(float);
+  if ((int64_t)smem > di.max_smem_optin)
+    return fail(CNFOT_ERR_ARG, "network too large for the fused kernels: needs %zu B of shared memory, device allows %d",
+                smem, di.max_smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTile, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (occ < 1) return fail(CNFOT_ERR_CUDA, "kernel does not fit on an SM");
+  int64_t cap = (int64_t)di.num_sms * occ;
+  if (cap > kMaxGrid) cap = kMaxGrid;
+  int64_t g = tiles < cap ? tiles : cap;
+  cfg->grid = (int)(g > 0 ? g : 1);
+  cfg->smem = smem;
+  return 0;
+}
+
+static int64_t partial_bytes(const FlowLayout& lay) {
+  int64_t loss = (int64_t)kMaxGrid * kNumSlots * sizeof(double);
+  int64_t grad = (int64_t)kMaxGrid * lay.total * sizeof(float);
+  return kCounterBytes + loss + grad;
+}
+
+static PartialBuf carve_partials(void* ws, unsigned long long** counter) {
+  char* p = (char*)ws;
+  *counter = (unsigned long long*)p;
+  PartialBuf pb;
+  pb.loss = (double*)(p + kCounterBytes);
+  pb.grad = (float*)(p + kCounterBytes + (int64_t)kMaxGrid * kNumSlots * sizeof(double));
+  return pb;
+}
+
+// ---- finalize: sum per-CTA partials (double) into the output buffer ------------------
+// out = [ grad (total) | loss slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic ]
+__global__ void finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss,
+                                int n_cta, int total, float* __restrict__ out_grad,
+                                float* __restrict__ out_slots,
+                                unsigned long long* tile_counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    double acc = 0.0;
+    for (int c = 0; c < n_cta; ++c) acc += (double)pgrad[(int64_t)c * total + i];
+    out_grad[i] = (float)acc;
+  }
+  if (out_slots && blockIdx.x == 0 && threadIdx.x < kNumSlots) {
+    double acc = 0.0;
+    for (int c = 0; c < n_cta; ++c) acc += ploss[(int64_t)c * kNumSlots + threadIdx.x];
+    __shared__ double s[kNumSlots];
+    s[threadIdx.x] = acc;
+    __syncwarp(0xffu);
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < 4; ++k) tot += s[k];
+      out_slots[0] = (float)tot;
+      for (int k = 0; k < 4; ++k) out_slots[1 + k] = (float)s[k];
+      for (int k = 5; k < kNumSlots; ++k) out_slots[k] = 0.f;
+    }
+  }
+  if (tile_counter && i == 0) *tile_counter = 0ULL;  // re-arm for the next step
+}
+
+static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int total, float* out_grad,
+                           float* out_slots) {
+  int threads = 256;
+  int blocks = (total + threads - 1) / threads;
+  finalize_kernel<<<blocks, threads, 0, s>>>(pb.grad, pb.loss, n_cta, total, out_grad, out_slots, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "finalize_kernel launch");
+  return 0;
+}
+
+// ---- Adam ----------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float c1, float c2) {
+  // optax.scale_by_adam + scale(-lr): m_hat = m / (1 - b1^t), v_hat = v / (1 - b2^t),
+  // update = -lr * m_hat / (sqrt(v_hat) + eps)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  }
+}
+
+}  // namespace cnfot
+
+using namespace cnfot;
+
+extern "C" {
+
+int cnfot_abi_version(void) { return CNFOT_ABI_VERSION; }
+const char* cnfot_last_error(void) { return g_err; }
+
+int64_t cnfot_param_count(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return lay.total;
+}
+
+int64_t cnfot_spline_param_stride(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return lay.Pp;
+}
+
+int64_t cnfot_offset_first(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return 0;
+}
+
+int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t d, int32_t m, int32_t bias) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  if (layer < 0 || layer >= lay.L || d < 1 || d >= lay.D || m < 0 || m > lay.M) {
+    fail(CNFOT_ERR_ARG, "offset_linear: index out of range");
+    return -1;
+  }
+  const int H = lay.H;
+  int64_t off = lay.Pp + (int64_t)layer * lay.layer_stride + (int64_t)(d - 1) * lay.mlp_const +
+                (int64_t)H * ((d - 1) * (d + 2) / 2);
+  const int n_in = d + 1;
+  if (m == 0) return off + (bias ? n_in * H : 0);
+  off += n_in * H + H + (int64_t)(m - 1) * (H * H + H);
+  if (m < lay.M) return off + (bias ? H * H : 0);
+  return off + (bias ? H * lay.Pp : 0);
+}
+
+int cnfot_flow_supported(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  return check_fused(flow, lay);
+}
+
+// ---- seam 2 ---------------------------------------------------------------------------
+static int rqs_call(bool inverse, void* stream, const float* v, const float* params, int64_t rows,
+                    int32_t K, float lo, float hi, float min_bin, float min_slope, float* out,
+                    float* ld, int32_t* bin) {
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (rows == 0) return 0;
+  if (!v || !params || !out || !ld) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (K < 1 || !(hi > lo) || K * min_bin > hi - lo || !(min_slope < 1.f))
+    return fail(CNFOT_ERR_ARG, "bad spline constants");
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  bool known = false;
+  cudaError_t e = rqs_eval_dispatch(K, inverse, (cudaStream_t)stream, v, params, rows,
+                                    make_spline_consts<float>(K, lo, hi, min_bin, min_slope), out, ld,
+                                    bin, di.num_sms, &known);
+  if (!known) return fail(CNFOT_ERR_ARG, "num_bins=%d not instantiated (see CNFOT_BINS_LIST)", K);
+  if (e != cudaSuccess) return cuda_fail(e, "rqs kernel launch");
+  return 0;
+}
+
+static int rqs_vjp_call(bool inverse, void* stream, const float* v, const float* params,
+                        const float* go, const float* gl, int64_t rows, int32_t K, float lo, float hi,
+                        float min_bin, float min_slope, float* gi, float* gp) {
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (rows == 0) return 0;
+  if (!v || !params || !go || !gl || !gi || !gp) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (K < 1 || !(hi > lo) || K * min_bin > hi - lo || !(min_slope < 1.f))
+    return fail(CNFOT_ERR_ARG, "bad spline constants");
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  bool known = false;
+  cudaError_t e = rqs_vjp_dispatch(K, inverse, (cudaStream_t)stream, v, params, go, gl, rows,
+                                   make_spline_consts<float>(K, lo, hi, min_bin, min_slope), gi, gp,
+                                   di.num_sms, &known);
+  if (!known) return fail(CNFOT_ERR_ARG, "num_bins=%d not instantiated (see CNFOT_BINS_LIST)", K);
+  if (e != cudaSuccess) return cuda_fail(e, "rqs vjp kernel launch");
+  return 0;
+}
+
+int cnfot_rqs_forward(void* stream, const float* x, const float* params, int64_t rows, int32_t num_bins,
+                      float range_min, float range_max, float min_bin_size, float min_knot_slope,
+                      float* y, float* logdet, int32_t* bin_idx) {
+  return rqs_call(false, stream, x, params, rows, num_bins, range_min, range_max, min_bin_size,
+                  min_knot_slope, y, logdet, bin_idx);
+}
+int cnfot_rqs_inverse(void* stream, const float* y, const float* params, int64_t rows, int32_t num_bins,
+                      float range_min, float range_max, float min_bin_size, float min_knot_slope,
+                      float* x, float* logdet, int32_t* bin_idx) {
+  return rqs_call(true, stream, y, params, rows, num_bins, range_min, range_max, min_bin_size,
+                  min_knot_slope, x, logdet, bin_idx);
+}
+int cnfot_rqs_forward_vjp(void* stream, const float* x, const float* params, const float* g_y,
+                          const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
+                          float range_max, float min_bin_size, float min_knot_slope, float* g_x,
+                          float* g_params) {
+  return rqs_vjp_call(false, stream, x, params, g_y, g_logdet, rows, num_bins, range_min, range_max,
+                      min_bin_size, min_knot_slope, g_x, g_params);
+}
+int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, const float* g_x,
+                          const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
+                          float range_max, float min_bin_size, float min_knot_slope, float* g_y,
+                          float* g_params) {
+  return rqs_vjp_call(true, stream, y, params, g_x, g_logdet, rows, num_bins, range_min, range_max,
+                      min_bin_size, min_knot_slope, g_y, g_params);
+}
+
+// ---- seam 1 ---------------------------------------------------------------------------
+static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, const float* weights,
+                          const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                          float* out, float* logdet, int32_t add_base) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (int rc = check_fused(flow, lay)) return rc;
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
+  if (rows == 0) return 0;
+  if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  const void* kernel = find_flow_eval_kernel(lay);
+  SmemPlan sp = plan_smem(lay, false);
+  LaunchCfg cfg;
+  if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
+  EvalArgs a;
+  a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
+  a.out = out; a.logdet = logdet; a.dir = dir; a.add_base = add_base;
+  a.D = lay.D; a.L = lay.L; a.total = lay.total;
+  a.sc = spline_consts(flow);
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "flow_eval_kernel launch");
+  return 0;
+}
+
+int cnfot_flow_forward(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* in,
+                       const float* cond, int64_t cond_stride, int64_t rows, float* out, float* logdet,
+                       int32_t add_base) {
+  return flow_eval_call(0, stream, flow, weights, in, cond, cond_stride, rows, out, logdet, add_base);
+}
+int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* in,
+                       const float* cond, int64_t cond_stride, int64_t rows, float* out, float* logdet,
+                       int32_t add_base) {
+  return flow_eval_call(1, stream, flow, weights, in, cond, cond_stride, rows, out, logdet, add_base);
+}
+
+int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows) {
+  (void)rows;
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return partial_bytes(lay);
+}
+
+static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, const float* weights,
+                         const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                         const float* g_out, const float* g_logdet, int32_t add_base, float* g_in,
+                         float* g_weights, void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (int rc = check_fused(flow, lay)) return rc;
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
+  if (!weights || !g_weights || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (workspace_bytes < partial_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                                        (long long)workspace_bytes, (long long)partial_bytes(lay));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows == 0) {
+    cudaError_t e = cudaMemsetAsync(g_weights, 0, (size_t)lay.total * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return 0;
+  }
+  if (!in || !cond || !g_out) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  const void* kernel = find_flow_vjp_kernel(lay);
+  SmemPlan sp = plan_smem(lay, true);
+  LaunchCfg cfg;
+  if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
+  unsigned long long* counter;
+  VjpArgs a;
+  a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
+  a.g_out = g_out; a.g_logdet = g_logdet; a.g_in = g_in; a.dir = dir; a.add_base = add_base;
+  a.D = lay.D; a.L = lay.L; a.total = lay.total;
+  a.lda = sp.lda; a.ldg = sp.ldg; a.off_acc = sp.off_acc; a.off_sta = sp.off_sta; a.off_stg = sp.off_stg;
+  a.sc = spline_consts(flow);
+  a.pb = carve_partials(workspace, &counter);
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  if (e != cudaSuccess) return cuda_fail(e, "flow_vjp_kernel launch");
+  return launch_finalize(s, a.pb, cfg.grid, lay.total, g_weights, nullptr);
+}
+
+int cnfot_flow_forward_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                           const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                           const float* g_out, const float* g_logdet, int32_t add_base, float* g_in,
+                           float* g_weights, void* workspace, int64_t workspace_bytes) {
+  return flow_vjp_call(0, stream, flow, weights, in, cond, cond_stride, rows, g_out, g_logdet, add_base,
+                       g_in, g_weights, workspace, workspace_bytes);
+}
+int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                           const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                           const float* g_out, const float* g_logdet, int32_t add_base, float* g_in,
+                           float* g_weights, void* workspace, int64_t workspace_bytes) {
+  return flow_vjp_call(1, stream, flow, weights, in, cond, cond_stride, rows, g_out, g_logdet, add_base,
+                       g_in, g_weights, workspace, workspace_bytes);
+}
+
+// ---- seam 3 ---------------------------------------------------------------------------
+int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B, int64_t rows_b,
+                                       int32_t n_t) {
+  (void)rows_B; (void)rows_b; (void)n_t;
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return partial_bytes(lay);
+}
+
+int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                   const float* weights, const float* latent, const float* latent_sub, const float* src,
+                   const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
+                   int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
+                   void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (int rc = check_fused(flow, lay)) return rc;
+  if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");
+  if (rows_B < 0 || rows_b < 0 || global_B < 1 || global_b < 1 || rows_B > global_B || rows_b > global_b)
+    return fail(CNFOT_ERR_ARG, "bad row counts");
+  if (n_t < 1 || n_t > kMaxSegments - 4) return fail(CNFOT_ERR_ARG, "t_batch_size must be in [1, %d]", kMaxSegments - 4);
+  if (!weights || !out || !workspace || !t_batch_host) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (workspace_bytes < partial_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                                        (long long)workspace_bytes, (long long)partial_bytes(lay));
+  StepArgs a;
+  const char* err = nullptr;
+  if (make_step_consts<float>(*problem, lay.D, (double)lambda, global_B, global_b, n_t, &a.pc, &err))
+    return fail(CNFOT_ERR_ARG, "%s", err);
+  if (problem->type == CNFOT_OT) {
+    if (rows_B > 0 && (!src || !tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
+  } else {
+    if (rows_B > 0 && !latent) return fail(CNFOT_ERR_ARG, "latent is NULL");
+  }
+  if (rows_b > 0 && !latent_sub) return fail(CNFOT_ERR_ARG, "latent_sub is NULL");
+
+  // segments, most expensive first (kinetic rows run 3..3+4D passes each)
+  int ns = 0;
+  int64_t tiles = 0;
+  auto add = [&](int kind, int slot, int do_fit, int do_pot, float t, const float* rows, int64_t n) {
+    if (n <= 0) return;
+    Segment& sg = a.seg[ns++];
+    sg.kind = kind; sg.slot = slot; sg.do_fit = do_fit; sg.do_pot = do_pot; sg.t = t; sg.rows = rows;
+    sg.n = n; sg.first_tile = tiles;
+    tiles += (n + kTile - 1) / kTile;
+  };
+  for (int i = 0; i < n_t; ++i) add(kSegKinetic, kSlotKinetic, 0, 0, t_batch_host[i], latent_sub, rows_b);
+  if (problem->type == CNFOT_OT) {
+    add(kSegNll, kSlotFit0, 1, 0, 0.f, src, rows_B);
+    add(kSegNll, kSlotFitT, 1, 0, (float)a.pc.horizon, tgt, rows_B);
+  } else {
+    add(kSegSample, kSlotFit0, 1, 0, 0.f, latent, rows_B);
+    if (problem->type == CNFOT_RWPO) add(kSegSample, kSlotFit0, 0, 1, (float)a.pc.horizon, latent, rows_B);
+  }
+  a.n_seg = ns;
+  a.n_tiles = tiles;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tiles == 0) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return 0;
+  }
+  const void* kernel = find_mfc_step_kernel(lay);
+  SmemPlan sp = plan_smem(lay, true);
+  LaunchCfg cfg;
+  if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
+  a.W = weights;
+  a.D = lay.D; a.L = lay.L; a.total = lay.total;
+  a.lda = sp.lda; a.ldg = sp.ldg; a.off_acc = sp.off_acc; a.off_sta = sp.off_sta; a.off_stg = sp.off_stg;
+  a.sc = spline_consts(flow);
+  a.pb = carve_partials(workspace, &a.tile_counter);
+  cudaError_t e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  void* args[] = {&a};
+  e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
+  return launch_finalize(s, a.pb, cfg.grid, lay.total, out, out + lay.total);
+}
+
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B, int64_t rows_b,
+                                            int32_t n_t) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  (void)n_t;
+  int64_t rowsB = align256(rows_B * lay.D * (int64_t)sizeof(float));
+  int64_t rowsb = align256(rows_b * lay.D * (int64_t)sizeof(float));
+  int64_t w = align256((int64_t)lay.total * sizeof(float));
+  int64_t o = align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
+  return align256(partial_bytes(lay)) + w + o + 3 * rowsB + rowsb;
+}
+
+int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                        const float* weights_host, const float* latent_host,
+                        const float* latent_sub_host, const float* src_host, const float* tgt_host,
+                        const float* t_batch_host, int32_t n_t, int64_t rows_B, int64_t rows_b,
+                        int64_t global_B, int64_t global_b, float lambda, float* out_host,
+                        void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (!weights_host || !out_host || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (rows_B < 0 || rows_b < 0) return fail(CNFOT_ERR_ARG, "bad row counts");
+  int64_t need = cnfot_mfc_step_host_workspace_bytes(flow, rows_B, rows_b, n_t);
+  if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                          (long long)workspace_bytes, (long long)need);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* p = (char*)workspace;
+  void* ws = p; p += align256(partial_bytes(lay));
+  float* dW = (float*)p; p += align256((int64_t)lay.total * sizeof(float));
+  float* dOut = (float*)p; p += align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
+  const int64_t bytesB = rows_B * lay.D * (int64_t)sizeof(float);
+  const int64_t bytesb = rows_b * lay.D * (int64_t)sizeof(float);
+  float* dLat = (float*)p; p += align256(bytesB);
+  float* dSrc = (float*)p; p += align256(bytesB);
+  float* dTgt = (float*)p; p += align256(bytesB);
+  float* dSub = (float*)p;
+  auto h2d = [&](float* dst, const float* src, int64_t bytes) -> cudaError_t {
+    if (!src || bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, s);
+  };
+  cudaError_t e;
+  if ((e = h2d(dW, weights_host, (int64_t)lay.total * sizeof(float))) != cudaSuccess) return cuda_fail(e, "H2D weights");
+  if ((e = h2d(dLat, latent_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D latent");
+  if ((e = h2d(dSrc, src_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D src");
+  if ((e = h2d(dTgt, tgt_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D tgt");
+  if ((e = h2d(dSub, latent_sub_host, bytesb)) != cudaSuccess) return cuda_fail(e, "H2D latent_sub");
+  int rc = cnfot_mfc_step(stream, flow, problem, dW, latent_host ? dLat : nullptr,
+                          latent_sub_host ? dSub : nullptr, src_host ? dSrc : nullptr,
+                          tgt_host ? dTgt : nullptr, t_batch_host, n_t, rows_B, rows_b, global_B,
+                          global_b, lambda, dOut, ws, align256(partial_bytes(lay)));
+  if (rc) return rc;
+  e = cudaMemcpyAsync(out_host, dOut, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float),
+                      cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_fail(e, "D2H out");
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v, int64_t count,
+                      float lr, float b1, float b2, float eps, int64_t step) {
+  if (count < 0 || step < 1) return fail(CNFOT_ERR_ARG, "bad count/step");
+  if (count == 0) return 0;
+  if (!params || !grads || !m || !v) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  float c1 = (float)(1.0 - pow((double)b1, (double)step)), c2 = (float)(1.0 - pow((double)b2, (double)step));
+  int threads = 256;
+  int64_t blocks = (count + threads - 1) / threads;
+  if (blocks > (int64_t)di.num_sms * 8) blocks = (int64_t)di.num_sms * 8;
+  adam_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, m, v, count, lr, b1, b2, eps, c1, c2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adam_kernel launch");
+  return 0;
+}
+
+}  // extern "C"

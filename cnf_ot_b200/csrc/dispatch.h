@@ -1,0 +1,24 @@
+// Kernel lookup: (hidden, bins, mlp layers, dim, layers) -> compiled kernel.
+#pragma once
+
+#include "flow_math.cuh"
+
+namespace cnfot {
+
+// Each returns the __global__ function to pass to cudaLaunchKernel, or nullptr
+// when no instantiation exists for the network shape.  Shapes with a
+// compile-time (dim, layers) specialisation keep the per-row state in registers;
+// all others use the runtime-shape kernel (state in local memory).
+const void* find_flow_eval_kernel(const FlowLayout& f);
+const void* find_flow_vjp_kernel(const FlowLayout& f);
+const void* find_mfc_step_kernel(const FlowLayout& f);
+
+// (hidden, bins, mlp layers) combinations compiled into the fused kernels.
+#define CNFOT_NET_LIST(X) \
+  X(16, 5, 2)             \
+  X(16, 5, 1)             \
+  X(16, 5, 3)             \
+  X(32, 8, 2)             \
+  X(8, 3, 1)
+
+}  // namespace cnfot

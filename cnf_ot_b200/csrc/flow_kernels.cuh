@@ -1,0 +1,219 @@
+// Fused whole-flow kernels (one thread = one sample row, weights in shared
+// memory) behind cnfot_flow_* and cnfot_mfc_step.  Templated on the network
+// shape (hidden, bins, mlp layers) and on a runtime / compile-time flow shape.
+#pragma once
+
+#include "device_common.cuh"
+#include "step_math.cuh"
+
+namespace cnfot {
+
+// ---- forward-only evaluation (model API: sample / forward / inverse / log_prob) ----
+struct EvalArgs {
+  const float* W;
+  const float* in;
+  const float* cond;
+  int64_t cond_stride;
+  int64_t rows;
+  float* out;
+  float* logdet;
+  int dir;
+  int add_base;
+  int D, L, total;
+  SplineConsts<float> sc;
+};
+
+template <class Net, class DimsT>
+__global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  load_weights(smem, a.W, a.total);
+  __syncthreads();
+  const DimsT dm{a.D, a.L};
+  const int D = dm.D(), L = dm.L();
+  for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
+    const int64_t r = tile * kTile + threadIdx.x;
+    if (r >= a.rows) continue;
+    float st[kMaxStateFloats];
+    for (int i = 0; i < D; ++i) st[i] = a.in[r * D + i];
+    const float t = a.cond[r * a.cond_stride];
+    float ld = flow_pass<float, Net, DimsT>(a.dir, dm, smem, a.sc, t, st);
+    for (int i = 0; i < D; ++i) a.out[r * D + i] = st[L * D + i];
+    if (a.logdet) {
+      if (a.add_base)
+        ld = a.dir == 0 ? base_log_prob<float>(st, D) - ld
+                        : base_log_prob<float>(st + L * D, D) + ld;
+      a.logdet[r] = ld;
+    }
+  }
+}
+
+// ---- per-CTA partial results -------------------------------------------------------
+struct PartialBuf {
+  float* grad;     // [n_cta][total]
+  double* loss;    // [n_cta][kNumSlots]
+};
+
+__device__ inline void flush_partials(const PartialBuf& pb, const float* sAcc, int total,
+                                      const double* loss /* kNumSlots, thread-local */,
+                                      double* scratch) {
+  __syncthreads();
+  float* dst = pb.grad + (int64_t)blockIdx.x * total;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = sAcc[i];
+  for (int s = 0; s < kNumSlots; ++s) {
+    double v = block_sum(loss[s], scratch);
+    if (threadIdx.x == 0) pb.loss[(int64_t)blockIdx.x * kNumSlots + s] = v;
+  }
+}
+
+// ---- generic VJP of one flow pass (what a custom_vjp backward rule calls) ----------
+struct VjpArgs {
+  const float* W;
+  const float* in;
+  const float* cond;
+  int64_t cond_stride;
+  int64_t rows;
+  const float* g_out;
+  const float* g_logdet;
+  float* g_in;
+  int dir;
+  int add_base;
+  int D, L, total;
+  int lda, ldg, off_acc, off_sta, off_stg;
+  SplineConsts<float> sc;
+  PartialBuf pb;
+};
+
+template <class Net, class DimsT>
+__global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double scratch[kWarps];
+  float* sW = smem;
+  float* sAcc = smem + a.off_acc;
+  load_weights(sW, a.W, a.total);
+  for (int i = threadIdx.x; i < a.total; i += blockDim.x) sAcc[i] = 0.f;
+  __syncthreads();
+  DeviceSink sink{sAcc, smem + a.off_sta, smem + a.off_stg, a.lda, a.ldg};
+  const DimsT dm{a.D, a.L};
+  const int D = dm.D(), L = dm.L();
+  float gfirst[Net::kPp];
+#pragma unroll
+  for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
+  for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
+    const int64_t r = tile * kTile + threadIdx.x;
+    const bool live = r < a.rows;
+    float st[kMaxStateFloats], g[kMaxDim];
+    for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
+    const float t = live ? a.cond[r * a.cond_stride] : 0.f;
+    flow_pass<float, Net, DimsT>(a.dir, dm, sW, a.sc, t, st);
+    const float gl = (live && a.g_logdet) ? a.g_logdet[r] : 0.f;
+    for (int i = 0; i < D; ++i) g[i] = live ? a.g_out[r * D + i] : 0.f;
+    float gl_pass = gl;
+    if (a.add_base) {
+      if (a.dir == 0) gl_pass = -gl;
+      else
+        for (int i = 0; i < D; ++i) g[i] -= gl * st[L * D + i];
+    }
+    flow_pass_bwd<float, Net, DimsT, DeviceSink>(a.dir, dm, sW, a.sc, t, st, g, gl_pass, gfirst,
+                                                 sink);
+    if (a.add_base && a.dir == 0)
+      for (int i = 0; i < D; ++i) g[i] -= gl * st[i];
+    if (live && a.g_in)
+      for (int i = 0; i < D; ++i) a.g_in[r * D + i] = g[i];
+  }
+  sink.template outer<kMaxDim, Net::kPp>(0, 0, nullptr, gfirst);
+  double zero[kNumSlots];
+  for (int s = 0; s < kNumSlots; ++s) zero[s] = 0.0;
+  flush_partials(a.pb, sAcc, a.total, zero, scratch);
+}
+
+// ---- the fused train step ---------------------------------------------------------------
+// One persistent kernel evaluates every term of the configured loss: the work is a list
+// of segments (one per loss term and time), cut into 128-row tiles handed out by an
+// atomic counter, most expensive segments first.
+enum SegmentKind { kSegNll = 0, kSegSample = 1, kSegKinetic = 2 };
+
+struct Segment {
+  int kind;
+  int slot;          // loss slot of the fit term (kSegNll / kSegSample)
+  int do_fit, do_pot;
+  float t;
+  const float* rows; // (n, D) data or latent rows
+  int64_t n;
+  int64_t first_tile;
+};
+
+constexpr int kMaxSegments = 40;
+
+struct StepArgs {
+  const float* W;
+  int D, L, total;
+  int lda, ldg, off_acc, off_sta, off_stg;
+  SplineConsts<float> sc;
+  StepConsts<float> pc;
+  int n_seg;
+  int64_t n_tiles;
+  Segment seg[kMaxSegments];
+  unsigned long long* tile_counter;
+  PartialBuf pb;
+};
+
+template <class Net, class DimsT>
+__global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double scratch[kWarps];
+  __shared__ long long s_tile;
+  float* sW = smem;
+  float* sAcc = smem + a.off_acc;
+  load_weights(sW, a.W, a.total);
+  for (int i = threadIdx.x; i < a.total; i += blockDim.x) sAcc[i] = 0.f;
+  __syncthreads();
+  DeviceSink sink{sAcc, smem + a.off_sta, smem + a.off_stg, a.lda, a.ldg};
+  const DimsT dm{a.D, a.L};
+  const int D = dm.D();
+  float gfirst[Net::kPp];
+#pragma unroll
+  for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
+  double loss[kNumSlots];
+#pragma unroll
+  for (int s = 0; s < kNumSlots; ++s) loss[s] = 0.0;
+
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(a.tile_counter, 1ULL);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= a.n_tiles) break;
+    int si = 0;
+    while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
+    const Segment& sg = a.seg[si];
+    const int64_t r = (tile - sg.first_tile) * kTile + threadIdx.x;
+    const bool live = r < sg.n;
+    float row[kMaxDim];
+    for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;
+    if (sg.kind == kSegNll) {
+      float v = row_nll<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row,
+                                                       live ? a.pc.w_fit : 0.f, gfirst, sink);
+      loss[sg.slot] += (double)v;
+    } else if (sg.kind == kSegSample) {
+      StepConsts<float> pc = a.pc;
+      if (!live) { pc.w_fit = 0.f; pc.w_pot = 0.f; }
+      float lf = 0.f, lp = 0.f;
+      row_sample_terms<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row, sg.do_fit != 0,
+                                                      sg.do_pot != 0, pc, &lf, &lp, gfirst, sink);
+      loss[sg.slot] += (double)lf;
+      loss[kSlotPotential] += (double)lp;
+    } else {
+      StepConsts<float> pc = a.pc;
+      if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
+      float lk = 0.f, lp = 0.f;
+      row_kinetic<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
+                                                 sink);
+      loss[kSlotKinetic] += (double)lk;
+      loss[kSlotPotential] += (double)lp;
+    }
+  }
+  sink.template outer<kMaxDim, Net::kPp>(0, 0, nullptr, gfirst);
+  flush_partials(a.pb, sAcc, a.total, loss, scratch);
+}
+
+}  // namespace cnfot

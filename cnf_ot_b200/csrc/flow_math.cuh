@@ -196,7 +196,7 @@ CNFOT_HD void mlp_backward(const T* W, int w_off, int n_in, const T* in, const T
 // states[0..D) is the input; states[(s+1)*D ..] the result of step s.
 // Returns the summed log-det of the pass.
 template <typename T, class Net, class DimsT>
-CNFOT_HD T flow_pass(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t,
+CNFOT_CALL T flow_pass(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t,
                      T* states) {
   constexpr int H = Net::kH, K = Net::kK, M = Net::kM, Pp = Net::kPp;
   const int D = dm.D(), L = dm.L();
@@ -235,7 +235,7 @@ CNFOT_HD T flow_pass(int dir, const DimsT& dm, const T* W, const SplineConsts<T>
 // the adjoint of the pass input.  gfirst[Pp] accumulates the adjoint of the
 // shared `first` parameter (flushed to the sink once per kernel).
 template <typename T, class Net, class DimsT, class Sink>
-CNFOT_HD void flow_pass_bwd(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc,
+CNFOT_CALL void flow_pass_bwd(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc,
                             T t, const T* states, T* g, T gld, T* gfirst, Sink& sink) {
   constexpr int H = Net::kH, K = Net::kK, M = Net::kM, Pp = Net::kPp;
   const int D = dm.D(), L = dm.L();

@@ -17,8 +17,12 @@
 
 #if defined(__CUDACC__)
 #define CNFOT_HD __host__ __device__ __forceinline__
+// real function calls on the device: used for the big per-pass routines that are
+// invoked from several places, to bound code size and compile time
+#define CNFOT_CALL __host__ __device__ __noinline__
 #else
 #define CNFOT_HD inline
+#define CNFOT_CALL inline
 #endif
 
 namespace cnfot {

@@ -3,17 +3,10 @@
 #pragma once
 
 #include "../../include/cnfot.h"
+#include "dispatch.h"
 #include "step_math.cuh"
 
 namespace cnfot {
-
-// Instantiated (hidden, bins, mlp_layers) combinations of the fused kernels.
-#define CNFOT_NET_LIST(X) \
-  X(16, 5, 2)             \
-  X(16, 5, 1)             \
-  X(16, 5, 3)             \
-  X(32, 8, 2)             \
-  X(8, 3, 1)
 
 // Scalings of applications.py folded into per-row weights:
 //   ot    (:377-402)  lambda * [KL(0) + KL(T)] + sum_t kinetic / Tn (+ sum_t obstacle, not / Tn)

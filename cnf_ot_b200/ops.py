@@ -1,0 +1,241 @@
+"""Tensor-level entry points over the C ABI.
+
+torch is used for device memory and the current CUDA stream only; every
+computation happens inside libcnfot.so.  All functions require CUDA float32
+tensors (they raise otherwise -- there is no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .layout import FlowShape
+
+
+def _stream() -> int:
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: Optional[torch.Tensor], name: str, dtype=torch.float32) -> Optional[torch.Tensor]:
+  if t is None:
+    return None
+  if not t.is_cuda:
+    raise _lib.CnfotError(f"{name}: expected a CUDA tensor (cnf_ot_b200 has no CPU path)")
+  if t.dtype != dtype:
+    raise _lib.CnfotError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+  return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+  return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------- seam 2: splines
+def _rqs(inverse: bool, v, params, num_bins, range_min, range_max, min_bin_size, min_knot_slope,
+         want_bins):
+  lib = _lib.load()
+  v = _dev(v, "input").reshape(-1)
+  P = 3 * num_bins + 1
+  params = _dev(params, "params").reshape(-1, P)
+  rows = v.numel()
+  if params.shape[0] != rows:
+    raise _lib.CnfotError(f"params has {params.shape[0]} rows, input has {rows}")
+  out = torch.empty_like(v)
+  ld = torch.empty_like(v)
+  bins = torch.empty(rows, dtype=torch.int32, device=v.device) if want_bins else None
+  fn = lib.cnfot_rqs_inverse if inverse else lib.cnfot_rqs_forward
+  with torch.cuda.device(v.device):
+    _lib.check(fn(_stream(), _ptr(v), _ptr(params), rows, num_bins, range_min, range_max,
+                  min_bin_size, min_knot_slope, _ptr(out), _ptr(ld), _ptr(bins)))
+  return out, ld, bins
+
+
+def rqs_forward(x, params, num_bins, range_min=-10.0, range_max=10.0, min_bin_size=1e-4,
+                min_knot_slope=1e-4, want_bins=False):
+  """RationalQuadraticSpline(params).forward_and_log_det(x) for one scalar per row."""
+  return _rqs(False, x, params, num_bins, range_min, range_max, min_bin_size, min_knot_slope,
+              want_bins)
+
+
+def rqs_inverse(y, params, num_bins, range_min=-10.0, range_max=10.0, min_bin_size=1e-4,
+                min_knot_slope=1e-4, want_bins=False):
+  """RationalQuadraticSpline(params).inverse_and_log_det(y)."""
+  return _rqs(True, y, params, num_bins, range_min, range_max, min_bin_size, min_knot_slope,
+              want_bins)
+
+
+def rqs_vjp(inverse: bool, v, params, g_out, g_logdet, num_bins, range_min=-10.0, range_max=10.0,
+            min_bin_size=1e-4, min_knot_slope=1e-4):
+  """Adjoints of (input, params) given adjoints of (output, logdet)."""
+  lib = _lib.load()
+  v = _dev(v, "input").reshape(-1)
+  P = 3 * num_bins + 1
+  params = _dev(params, "params").reshape(-1, P)
+  g_out = _dev(g_out, "g_out").reshape(-1)
+  g_logdet = _dev(g_logdet, "g_logdet").reshape(-1)
+  rows = v.numel()
+  g_in = torch.empty_like(v)
+  g_params = torch.empty_like(params)
+  fn = lib.cnfot_rqs_inverse_vjp if inverse else lib.cnfot_rqs_forward_vjp
+  with torch.cuda.device(v.device):
+    _lib.check(fn(_stream(), _ptr(v), _ptr(params), _ptr(g_out), _ptr(g_logdet), rows, num_bins,
+                  range_min, range_max, min_bin_size, min_knot_slope, _ptr(g_in), _ptr(g_params)))
+  return g_in, g_params
+
+
+# ---------------------------------------------------------------- seam 1: the flow
+def _cond(cond, rows, device) -> Tuple[torch.Tensor, int]:
+  cond = torch.as_tensor(cond, dtype=torch.float32, device=device).reshape(-1).contiguous()
+  if cond.numel() == 1:
+    return cond, 0
+  if cond.numel() != rows:
+    raise _lib.CnfotError(f"cond has {cond.numel()} entries, expected 1 or {rows}")
+  return cond, 1
+
+
+def flow_eval(shape: FlowShape, weights, x, cond, inverse: bool, want_logdet=True, add_base=False):
+  """flow.bijector.forward/inverse(_and_log_det); with add_base the second output is the
+  log-density ConditionalTransformed returns."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  x = _dev(x, "x").reshape(-1, shape.dim)
+  rows = x.shape[0]
+  c, cs = _cond(cond, rows, x.device)
+  out = torch.empty_like(x)
+  ld = torch.empty(rows, dtype=torch.float32, device=x.device) if want_logdet else None
+  fn = lib.cnfot_flow_inverse if inverse else lib.cnfot_flow_forward
+  desc = _lib.flow_desc(shape)
+  with torch.cuda.device(x.device):
+    _lib.check(fn(_stream(), desc, _ptr(weights), _ptr(x), _ptr(c), cs, rows, _ptr(out), _ptr(ld),
+                  1 if add_base else 0))
+  return out, ld
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+  key = (device.index if device.index is not None else torch.cuda.current_device())
+  ws = _workspaces.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _workspaces[key] = ws
+  return ws
+
+
+def flow_vjp(shape: FlowShape, weights, x, cond, g_out, g_logdet, inverse: bool, add_base=False,
+             want_g_in=True):
+  """(g_in, g_weights) of flow_eval; g_weights is summed over rows (blob layout)."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  x = _dev(x, "x").reshape(-1, shape.dim)
+  rows = x.shape[0]
+  c, cs = _cond(cond, rows, x.device)
+  g_out = _dev(g_out, "g_out").reshape(-1, shape.dim)
+  g_logdet = _dev(g_logdet, "g_logdet")
+  g_in = torch.empty_like(x) if want_g_in else None
+  g_w = torch.empty(shape.blob_size, dtype=torch.float32, device=x.device)
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_flow_vjp_workspace_bytes(desc, rows)
+  ws = _workspace(nbytes, x.device)
+  fn = lib.cnfot_flow_inverse_vjp if inverse else lib.cnfot_flow_forward_vjp
+  with torch.cuda.device(x.device):
+    _lib.check(fn(_stream(), desc, _ptr(weights), _ptr(x), _ptr(c), cs, rows, _ptr(g_out),
+                  _ptr(g_logdet), 1 if add_base else 0, _ptr(g_in), _ptr(g_w), ws.data_ptr(),
+                  ws.numel()))
+  return g_in, g_w
+
+
+# ---------------------------------------------------------------- seam 3: the train step
+def problem_desc(cfg: dict) -> _lib.ProblemDesc:
+  """mfc.yaml dict -> cnfot_problem_desc (solvers.py:58-88)."""
+  g = cfg["general"]
+  typ = g["type"]
+  if typ not in _lib.TYPES:
+    raise Exception(f"Unknown problem type: {typ}...")
+  if typ == "ot":
+    sub, T, beta, a, sigma = cfg["ot"]["subtype"], 1.0, 1.0, 0.0, 0.0
+  elif typ == "rwpo":
+    r = cfg["rwpo"]
+    sub, T, beta, a, sigma = r["pot_type"], r["T"], r["beta"], r["a"], 0.0
+  else:
+    f = cfg["fp"]
+    sub, T, beta, a, sigma = f["velocity_field_type"], f["T"], 4.0, f["a"], f["sigma"]
+  if sub not in _lib.SUBTYPES[typ]:
+    raise Exception(f"Unknown {typ} subtype: {sub}")
+  return _lib.ProblemDesc(_lib.TYPES[typ], _lib.SUBTYPES[typ][sub], float(T), float(beta), float(a),
+                          float(sigma), float(g["dt"]), float(g["dx"]))
+
+
+def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, latent_sub, src, tgt,
+             t_batch: Sequence[float], lam: float, global_B: int, global_b: int,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """value_and_grad of the configured loss on this GPU's shard.
+
+  Returns the fp32 buffer [gradient (blob_size) | 8 loss slots] (see include/cnfot.h);
+  buffers of different ranks sum to the whole-batch result."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  device = weights.device
+  latent = _dev(latent, "latent")
+  latent_sub = _dev(latent_sub, "latent_sub")
+  src = _dev(src, "src")
+  tgt = _dev(tgt, "tgt")
+  rows_B = 0
+  for t in (src, latent):
+    if t is not None:
+      rows_B = t.reshape(-1, shape.dim).shape[0]
+      break
+  rows_b = 0 if latent_sub is None else latent_sub.reshape(-1, shape.dim).shape[0]
+  tb = torch.as_tensor(list(t_batch), dtype=torch.float32)  # host
+  n_t = tb.numel()
+  if out is None:
+    out = torch.empty(shape.blob_size + _lib.NUM_LOSS_SLOTS, dtype=torch.float32, device=device)
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_mfc_step_workspace_bytes(desc, rows_B, rows_b, n_t)
+  ws = _workspace(nbytes, device)
+  with torch.cuda.device(device):
+    _lib.check(lib.cnfot_mfc_step(_stream(), desc, problem, _ptr(weights), _ptr(latent),
+                                  _ptr(latent_sub), _ptr(src), _ptr(tgt), tb.data_ptr(), n_t, rows_B,
+                                  rows_b, global_B, global_b, float(lam), _ptr(out), ws.data_ptr(),
+                                  ws.numel()))
+  return out
+
+
+def mfc_step_host(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, latent_sub, src,
+                  tgt, t_batch: Sequence[float], lam: float, global_B: int, global_b: int,
+                  out: torch.Tensor, device=None) -> torch.Tensor:
+  """Same step with HOST (ideally pinned) tensors in and out; copies are inside the call."""
+  lib = _lib.load()
+  device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+  for name, t in (("weights", weights), ("latent", latent), ("latent_sub", latent_sub),
+                  ("src", src), ("tgt", tgt), ("out", out)):
+    if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+      raise _lib.CnfotError(f"{name}: expected a contiguous float32 host tensor")
+  rows_B = 0
+  for t in (src, latent):
+    if t is not None:
+      rows_B = t.reshape(-1, shape.dim).shape[0]
+      break
+  rows_b = 0 if latent_sub is None else latent_sub.reshape(-1, shape.dim).shape[0]
+  tb = torch.as_tensor(list(t_batch), dtype=torch.float32)
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_mfc_step_host_workspace_bytes(desc, rows_B, rows_b, tb.numel())
+  ws = _workspace(nbytes, device)
+  with torch.cuda.device(device):
+    _lib.check(lib.cnfot_mfc_step_host(_stream(), desc, problem, _ptr(weights), _ptr(latent),
+                                       _ptr(latent_sub), _ptr(src), _ptr(tgt), tb.data_ptr(),
+                                       tb.numel(), rows_B, rows_b, global_B, global_b, float(lam),
+                                       _ptr(out), ws.data_ptr(), ws.numel()))
+  return out
+
+
+def adam_update(params, grads, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8) -> None:
+  """In-place optax.adam(lr) update of the parameter blob."""
+  lib = _lib.load()
+  params, grads, m, v = (_dev(t, n) for t, n in ((params, "params"), (grads, "grads"), (m, "m"), (v, "v")))
+  with torch.cuda.device(params.device):
+    _lib.check(lib.cnfot_adam_update(_stream(), _ptr(params), _ptr(grads), _ptr(m), _ptr(v),
+                                     params.numel(), lr, b1, b2, eps, step))

@@ -36,6 +36,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CNFOT_API __attribute__((visibility("default")))
+#else
+#define CNFOT_API
+#endif
+
 #define CNFOT_ABI_VERSION 1
 
 enum {
@@ -76,40 +82,40 @@ typedef struct cnfot_problem_desc {
   float dt, dx;     /* general.dt, general.dx (fp hard-codes 0.01, applications.py:286,301) */
 } cnfot_problem_desc;
 
-int cnfot_abi_version(void);
-const char* cnfot_last_error(void);
+CNFOT_API int cnfot_abi_version(void);
+CNFOT_API const char* cnfot_last_error(void);
 
 /* ---- parameter blob ---------------------------------------------------------------
  * The haiku pytree of SURVEY.md A.3 flattened into one fp32 buffer (layout documented in
  * DESIGN.md and cnf_ot_b200/csrc/flow_math.cuh).  Offsets are in floats. */
-int64_t cnfot_param_count(const cnfot_flow_desc* flow);               /* blob length */
-int64_t cnfot_spline_param_stride(const cnfot_flow_desc* flow);       /* Pp = roundup(3K+1, 4) */
-int64_t cnfot_offset_first(const cnfot_flow_desc* flow);              /* "~/first" */
+CNFOT_API int64_t cnfot_param_count(const cnfot_flow_desc* flow);               /* blob length */
+CNFOT_API int64_t cnfot_spline_param_stride(const cnfot_flow_desc* flow);       /* Pp = roundup(3K+1, 4) */
+CNFOT_API int64_t cnfot_offset_first(const cnfot_flow_desc* flow);              /* "~/first" */
 /* linear m of "mlp_layer{l}_d{d}/~/linear_{m}" (0 <= m < mlp_layers) or, with
  * m == mlp_layers, "linear_out_layer{l}_d{d}"; bias != 0 selects "b" instead of "w". */
-int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t d, int32_t m,
+CNFOT_API int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t d, int32_t m,
                             int32_t bias);
 /* 0 if the fused kernels support this shape, else CNFOT_ERR_ARG (message says why). */
-int cnfot_flow_supported(const cnfot_flow_desc* flow);
+CNFOT_API int cnfot_flow_supported(const cnfot_flow_desc* flow);
 
 /* ---- seam 2: one scalar spline per row (distrax.RationalQuadraticSpline) ------------
  * params: (rows, 3K+1) raw [K widths | K heights | K+1 slopes], replaces
  * bijector_fn(params).forward_and_log_det / inverse_and_log_det
  * (cnf_ot/models/flows.py:124-132, cnf_ot/models/autoregressive.py:100,130).
  * bin_idx (int32, may be NULL) receives the selected bin (0 in either tail). */
-int cnfot_rqs_forward(void* stream, const float* x, const float* params, int64_t rows,
+CNFOT_API int cnfot_rqs_forward(void* stream, const float* x, const float* params, int64_t rows,
                       int32_t num_bins, float range_min, float range_max, float min_bin_size,
                       float min_knot_slope, float* y, float* logdet, int32_t* bin_idx);
-int cnfot_rqs_inverse(void* stream, const float* y, const float* params, int64_t rows,
+CNFOT_API int cnfot_rqs_inverse(void* stream, const float* y, const float* params, int64_t rows,
                       int32_t num_bins, float range_min, float range_max, float min_bin_size,
                       float min_knot_slope, float* x, float* logdet, int32_t* bin_idx);
 /* Vector-Jacobian products of the two calls above: given the adjoints of (out, logdet)
  * returns the adjoint of the input (rows) and of params (rows, 3K+1). */
-int cnfot_rqs_forward_vjp(void* stream, const float* x, const float* params, const float* g_y,
+CNFOT_API int cnfot_rqs_forward_vjp(void* stream, const float* x, const float* params, const float* g_y,
                           const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
                           float range_max, float min_bin_size, float min_knot_slope, float* g_x,
                           float* g_params);
-int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, const float* g_x,
+CNFOT_API int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, const float* g_x,
                           const float* g_logdet, int64_t rows, int32_t num_bins, float range_min,
                           float range_max, float min_bin_size, float min_knot_slope, float* g_y,
                           float* g_params);
@@ -122,23 +128,23 @@ int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, con
  * logdet may be NULL.  With add_base != 0, `logdet` instead receives the log-density the
  * reference's ConditionalTransformed returns (cnf_ot/models/conditional.py:316-321,382-402):
  *   forward: log N(in) - fldj  (sample_and_log_prob)   inverse: log N(out) + ildj  (log_prob) */
-int cnfot_flow_forward(void* stream, const cnfot_flow_desc* flow, const float* weights,
+CNFOT_API int cnfot_flow_forward(void* stream, const cnfot_flow_desc* flow, const float* weights,
                        const float* in, const float* cond, int64_t cond_stride, int64_t rows,
                        float* out, float* logdet, int32_t add_base);
-int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* weights,
+CNFOT_API int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* weights,
                        const float* in, const float* cond, int64_t cond_stride, int64_t rows,
                        float* out, float* logdet, int32_t add_base);
 /* VJPs of the two calls above (what a jax.custom_vjp backward rule calls): given g_out (rows,D)
  * and g_logdet (rows, may be NULL = zeros; it is the adjoint of the `logdet` OUTPUT, so it
  * honours add_base) writes g_in (rows,D, may be NULL) and writes the parameter gradient,
  * summed over rows, to g_weights (blob layout, overwritten). */
-int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows);
-int cnfot_flow_forward_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+CNFOT_API int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows);
+CNFOT_API int cnfot_flow_forward_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
                            const float* in, const float* cond, int64_t cond_stride, int64_t rows,
                            const float* g_out, const float* g_logdet, int32_t add_base,
                            float* g_in, float* g_weights, void* workspace,
                            int64_t workspace_bytes);
-int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
+CNFOT_API int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const float* weights,
                            const float* in, const float* cond, int64_t cond_stride, int64_t rows,
                            const float* g_out, const float* g_logdet, int32_t add_base,
                            float* g_in, float* g_weights, void* workspace,
@@ -158,9 +164,9 @@ int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const floa
  *   slot 0 total loss, 1 fit term at t=0 (lambda-weighted), 2 fit term at t=T, 3 potential,
  *   4 kinetic; 5-7 reserved (zero). */
 #define CNFOT_NUM_LOSS_SLOTS 8
-int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
+CNFOT_API int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
                                        int64_t rows_b, int32_t n_t);
-int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+CNFOT_API int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
                    const float* weights, const float* latent, const float* latent_sub,
                    const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
                    int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
@@ -169,9 +175,9 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
  * pointers): copies inputs to the device workspace, runs the step, copies `out` back and
  * synchronises the stream.  The workspace must be
  * cnfot_mfc_step_host_workspace_bytes() of DEVICE memory. */
-int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
+CNFOT_API int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B,
                                             int64_t rows_b, int32_t n_t);
-int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow,
+CNFOT_API int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow,
                         const cnfot_problem_desc* problem, const float* weights_host,
                         const float* latent_host, const float* latent_sub_host,
                         const float* src_host, const float* tgt_host, const float* t_batch_host,
@@ -181,7 +187,7 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow,
 
 /* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
  * element-wise update; step is the 1-based update count. */
-int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v,
+CNFOT_API int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v,
                       int64_t count, float lr, float b1, float b2, float eps, int64_t step);
 
 #ifdef __cplusplus
