@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the cnf_ot flow train step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one evaluation of the configured MFC loss and its parameter gradient
+(all flow passes forward + inverse + log-det + loss terms + backward; optimiser
+excluded) over one synthetic batch.  Workload = BASELINE.json
+configs[1]: mfc.yaml type=ot subtype=obstacle, 2-D, RQS flow (2 layers, 2x16
+conditioner, 5 bins), batch 2^18 per GPU (weak scaling), lambda=5000, dt=0.01.
+
+  value  samples/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e    the same through the C-ABI call with HOST (pinned) buffers: H2D of the batch
+         and the weights, the step, D2H of [gradient | loss] inside the timed region
+  --impl reference : the CPU restatement of the reference step (oracle/, torch f64,
+         all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "flow train-step samples/s (fwd+inv+logdet+loss+grad)"
+UNIT = "samples/s"
+B_PER_GPU = 1 << 18
+SIGMA = 0.3  # parameter perturbation
+
+
+def workload_cfg(batch):
+  return {
+    "general": {"type": "ot", "dim": 2, "dx": 0.01, "dt": 0.01, "t_batch_size": 1, "seed": 42},
+    "ot": {"subtype": "obstacle"},
+    "rwpo": {"T": 1, "beta": 1, "a": 1, "pot_type": "double_well"},
+    "fp": {"T": 1, "a": 1, "sigma": 0.5, "velocity_field_type": "nongradient"},
+    "cnf": {"flow_num_layers": 2, "mlp_num_layers": 2, "hidden_size": 16, "num_bins": 5},
+    "train": {"epochs": 1, "lr": 1e-3, "_lambda": 5000.0, "batch_size": batch, "eval_frequency": 100},
+  }
+
+
+def config_block(n_gpus, extra=None):
+  c = {
+    "workload": "mfc.yaml type=ot subtype=obstacle (BASELINE configs[1])",
+    "dim": 2, "flow_num_layers": 2, "mlp": "2x16", "num_bins": 5, "params": 1200,
+    "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "sub_batch": "batch//32",
+    "t_batch_size": 1, "lambda": 5000.0, "param_sigma": SIGMA,
+    "rows_through_flow_per_step": "2B log-prob dir + 3(B/32) sample dir",
+    "parallelism": f"dp{n_gpus} (rows sharded, one all-reduce of [grad|loss])",
+  }
+  if extra:
+    c.update(extra)
+  return c
+
+
+# ---------------------------------------------------------------- clocks (NVML, in-process)
+class ClockSampler:
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz = [], set(), None
+    self._stop = threading.Event()
+    self._t = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:  # no NVML: report nulls
+      self.nv = None
+
+  def _loop(self):
+    nv = self.nv
+    names = {
+      getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+    }
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      time.sleep(0.002)
+
+  def __enter__(self):
+    if self.nv:
+      self._t = threading.Thread(target=self._loop, daemon=True)
+      self._t.start()
+    return self
+
+  def __exit__(self, *a):
+    self._stop.set()
+    if self._t:
+      self._t.join()
+
+  def summary(self):
+    s = sorted(self.samples)
+    return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------- CPU reference arm
+def oracle_step_timer(rows):
+  """One reference train step on the host: value_and_grad of the CPU restatement."""
+  from oracle import losses as olosses
+  from util import make_inputs, make_params
+  cfg = workload_cfg(rows)
+  spec, params = make_params(cfg, SIGMA)
+  inputs = make_inputs(cfg)
+
+  def step():
+    t0 = time.perf_counter()
+    loss, _ = olosses.value_and_grad(cfg, spec, params, inputs)
+    return time.perf_counter() - t0, float(loss)
+
+  return step
+
+
+def cpu_baseline(budget_s=15.0):
+  torch.set_num_threads(os.cpu_count() or 1)
+  probe = oracle_step_timer(1 << 13)
+  probe()
+  dt, _ = probe()
+  rate = (1 << 13) / dt
+  rows = 1 << 13
+  while rows < B_PER_GPU and (rows * 2) / rate * 3 < budget_s:
+    rows *= 2
+  step = oracle_step_timer(rows)
+  step()
+  ts = [step()[0] for _ in range(2)]
+  best = min(ts)
+  return {"value": rows / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"oracle (torch f64 restatement of the reference step) on {rows} rows of the "
+                    f"same workload, best of 2 after 1 warm-up"}
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  torch.set_num_threads(os.cpu_count() or 1)
+  # bounded sample per step so K + W steps end within minutes
+  probe = oracle_step_timer(1 << 12)
+  probe()
+  dt, _ = probe()
+  rate = (1 << 12) / dt
+  total = args.steps + args.warmup
+  rows = 1 << 12
+  while rows < B_PER_GPU and (rows * 2) / rate * total < 120.0:
+    rows *= 2
+  step = oracle_step_timer(rows)
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    step()
+  el = time.perf_counter() - t0
+  value = rows * args.steps / el
+  sample = (f"reference step restated on CPU (oracle/, torch f64, autograd), {rows} rows per step "
+            f"(bounded sample of the 2^18-row workload), {torch.get_num_threads()} threads")
+  line = {
+    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+    "data": "synthetic", "config": config_block(args.gpus, {"rows_per_step_cpu": rows}),
+    "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                     "sample": sample},
+    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- our arm
+def make_blob(shape, device):
+  """Reference init + N(0, sigma^2) on biases, output layers and `first` (seed 43)."""
+  from cnf_ot_b200 import random as crandom
+  from cnf_ot_b200.flows import FlowModel
+  model = FlowModel(shape, device)
+  params = model.init(crandom.PRNGKey(3))
+  g = torch.Generator(device="cpu").manual_seed(43)
+  for mod, leaves in params.items():
+    for name, v in leaves.items():
+      if name == "w" and mod.startswith("mlp_"):
+        continue
+      v.add_((torch.randn(v.shape, generator=g) * SIGMA).to(device))
+  return params.blob
+
+
+def peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      return json.load(f), "measured (MEASURED_PEAKS.json)"
+  return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def time_region(fn, n, stream_sync):
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  stream_sync()
+  e0.record()
+  for i in range(n):
+    fn(i)
+  e1.record()
+  stream_sync()
+  return e0.elapsed_time(e1) / 1e3  # seconds
+
+
+def spline_rooflines(peak_gbs):
+  """Stand-alone spline kernels (seam 2), HBM-bound: algorithmic bytes 4P+12 / 8P+16 per row."""
+  from cnf_ot_b200 import _lib, ops
+  lib = _lib.load()
+  n, K, P = 1 << 24, 5, 16
+  theta = torch.randn(n, P, device="cuda") * SIGMA
+  v = torch.randn(n, device="cuda") * 3
+  y, ld = torch.empty_like(v), torch.empty_like(v)
+  go, gl = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+  gi, gp = torch.empty_like(v), torch.empty_like(theta)
+  s = torch.cuda.current_stream().cuda_stream
+  calls = {
+    "rqs_forward": (lambda i: lib.cnfot_rqs_forward(s, v.data_ptr(), theta.data_ptr(), n, K, -10., 10., 1e-4, 1e-4, y.data_ptr(), ld.data_ptr(), 0), 4 * P + 12),
+    "rqs_inverse": (lambda i: lib.cnfot_rqs_inverse(s, v.data_ptr(), theta.data_ptr(), n, K, -10., 10., 1e-4, 1e-4, y.data_ptr(), ld.data_ptr(), 0), 4 * P + 12),
+    "rqs_forward_vjp": (lambda i: lib.cnfot_rqs_forward_vjp(s, v.data_ptr(), theta.data_ptr(), go.data_ptr(), gl.data_ptr(), n, K, -10., 10., 1e-4, 1e-4, gi.data_ptr(), gp.data_ptr()), 8 * P + 16),
+    "rqs_inverse_vjp": (lambda i: lib.cnfot_rqs_inverse_vjp(s, v.data_ptr(), theta.data_ptr(), go.data_ptr(), gl.data_ptr(), n, K, -10., 10., 1e-4, 1e-4, gi.data_ptr(), gp.data_ptr()), 8 * P + 16),
+  }
+  out = {}
+  for name, (fn, bpr) in calls.items():
+    for i in range(3):
+      fn(i)
+    el = time_region(fn, 10, torch.cuda.synchronize) / 10
+    gbs = n * bpr / el / 1e9
+    out[name] = {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s",
+                 "frac": gbs / peak_gbs, "rows": n, "bytes_per_row": bpr, "us": el * 1e6}
+  return out
+
+
+def run_ours(args):
+  import torch.distributed as td
+  from cnf_ot_b200 import _lib, ops
+  from cnf_ot_b200.layout import FlowShape
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device: cnf_ot_b200 has no CPU path")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    td.init_process_group("nccl", device_id=dev)
+  _lib.load()
+
+  n_gpus = world
+  B, b = B_PER_GPU, B_PER_GPU // 32
+  gB, gb = B * n_gpus, b * n_gpus
+  cfg = workload_cfg(gB)
+  shape = FlowShape(2, 2, 2, 16, 5)
+  problem = ops.problem_desc(cfg)
+  lam = 5000.0
+  W = make_blob(shape, dev)
+  if world > 1:
+    td.broadcast(W, 0)
+
+  # rotating input sets, > 2x L2 in aggregate, so every step streams its batch from HBM
+  bytes_per_set = (2 * B + b) * 2 * 4
+  n_sets = max(4, (2 * 126 * 2**20) // bytes_per_set + 1)
+  g = torch.Generator(device=dev).manual_seed(42 + rank)
+  centres = torch.tensor([[0., 5.], [5., 0.], [0., -5.], [-5., 0.], [3., 4.], [3., -4.], [-3., -4.], [-3., 4.]], device=dev)
+  sets = []
+  for _ in range(n_sets):
+    z = torch.randn(B, 2, device=dev, generator=g)
+    src = z + centres[torch.randint(0, 8, (B, ), device=dev, generator=g)]
+    sets.append((src, z, torch.randn(b, 2, device=dev, generator=g)))
+  tgen = torch.Generator().manual_seed(42)
+  t_vals = torch.rand(4096, generator=tgen).tolist()
+  out = torch.empty(shape.blob_size + 8, dtype=torch.float32, device=dev)
+
+  def step(i):
+    src, tgt, sub = sets[i % n_sets]
+    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
+    if world > 1:
+      td.all_reduce(out)
+
+  def sync():
+    if world > 1:
+      td.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(max(args.warmup, 3)):
+    step(i)
+  with ClockSampler(local) as clk:
+    el = time_region(step, args.steps, sync)
+  t = torch.tensor([el], dtype=torch.float64, device=dev)
+  if world > 1:
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+  el = float(t)
+  value = gB * args.steps / el
+  loss_dev = float(out[shape.blob_size])
+
+  # ---- e2e: host buffers through the C ABI (N=1) / pinned copies + all-reduce (N>1)
+  n_host = 3
+  pin = lambda x: x.cpu().contiguous().pin_memory()
+  hsets = [(pin(s[0]), pin(s[1]), pin(s[2])) for s in sets[:n_host]]
+  hW = pin(W)
+  hout = torch.empty(shape.blob_size + 8, dtype=torch.float32).pin_memory()
+  dsrc, dtgt, dsub = torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1]), torch.empty_like(sets[0][2])
+  dW2 = torch.empty_like(W)
+
+  def step_e2e(i):
+    src, tgt, sub = hsets[i % n_host]
+    if world == 1:
+      ops.mfc_step_host(shape, problem, hW, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, hout, device=dev)
+    else:
+      dW2.copy_(hW, non_blocking=True); dsrc.copy_(src, non_blocking=True)
+      dtgt.copy_(tgt, non_blocking=True); dsub.copy_(sub, non_blocking=True)
+      ops.mfc_step(shape, problem, dW2, None, dsub, dsrc, dtgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
+      td.all_reduce(out)
+      hout.copy_(out, non_blocking=True)
+      torch.cuda.synchronize()
+
+  for i in range(3):
+    step_e2e(i)
+  el_e = time_region(step_e2e, args.steps, sync)
+  t = torch.tensor([el_e], dtype=torch.float64, device=dev)
+  if world > 1:
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+  el_e = float(t)
+  h2d = (2 * B + b) * 2 * 4 + shape.blob_size * 4
+  d2h = (shape.blob_size + 8) * 4
+
+  if rank == 0:
+    pk, pk_src = peaks()
+    hbm = float(pk["hbm_gbs"])
+    # dominant kernel: mfc_step_kernel (one launch per step; finalize + an 8-byte memset ride along)
+    alg_bytes = (2 * B + b) * 2 * 4 + shape.blob_size * 4 + (shape.blob_size + 8) * 4
+    t_launch = el / args.steps
+    ach = alg_bytes / t_launch / 1e9
+    # fp32 view of the same kernel: algorithmic FLOPs = conditioner fwd+dgrad+wgrad (3 x 2176/row/pass)
+    rows_evals = 2 * B + 3 * b
+    flops = rows_evals * 3 * 2176.0
+    fp32_peak = 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+      with open(tpath) as f:
+        traffic = json.load(f).get("mfc_step_kernel_dram_bytes_per_launch")
+    line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+      "warmup": max(args.warmup, 3), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": config_block(n_gpus, {"l2_policy": f"{n_sets} rotating input sets ({n_sets * bytes_per_set >> 20} MiB > 2x L2)",
+                                      "loss_last_step": loss_dev}),
+      "e2e": {"value": gB * args.steps / el_e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+              "d2h_bytes_per_step": d2h, "ms_per_step": el_e / args.steps * 1e3,
+              "api": "cnfot_mfc_step_host (C ABI, pinned host buffers)" if world == 1 else
+                     "pinned H2D + cnfot_mfc_step + NCCL all-reduce + D2H"},
+      "gpu_launches": 2 * args.steps,
+      "clocks": clk.summary(),
+      "roofline": {"bound": "hbm", "kernel": "mfc_step_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                   "frac": ach / hbm, "traffic": traffic, "peak_source": pk_src,
+                   "note": "fused step kernel is fp32-issue bound, not HBM bound (SURVEY.md §8d): see roofline_fp32; "
+                           "the HBM-bound kernels of the path are the stand-alone spline kernels in roofline_spline"},
+      "roofline_fp32": {"bound": "fp32", "kernel": "mfc_step_kernel", "achieved": flops / t_launch / 1e12,
+                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / fp32_peak,
+                        "flops_per_launch": flops,
+                        "note": "algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only; peak = 148 SM x 128 FMA x 2 x max clock"},
+    }
+    if world == 1:
+      line["roofline_spline"] = spline_rooflines(hbm)
+      line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    td.barrier()
+    td.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=50)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -179,11 +179,19 @@ def flow_matching_loss(spec, params, latent, t, a, sigma, subtype):
 
 
 # ---------------------------------------------------------------- full losses
+def _sub_batch(inputs):
+  """Latent rows of the B//32 sub-batch terms: an explicit `latent_sub` draw (the
+  reference draws a fresh (b, D) normal from the same key) or the first b rows."""
+  if inputs.get("latent_sub") is not None:
+    return inputs["latent_sub"]
+  lat = inputs["latent"]
+  return lat[:lat.shape[0] // 32]
+
+
 def ot_loss(spec, params, inputs, lam, *, T, dt, subtype):
   """ot_loss_fn (applications.py:377-402)."""
   tb = inputs["t_batch"]
-  b = inputs["latent"].shape[0] // 32
-  sub = inputs["latent"][:b]
+  sub = _sub_batch(inputs)
   loss = lam * density_fit_kl_loss(spec, params, inputs["src"], inputs["tgt"], T)
   for t in tb.tolist():
     loss = loss + kinetic_loss(spec, params, sub, t, dt) / len(tb)
@@ -196,7 +204,7 @@ def rwpo_loss(spec, params, inputs, lam, *, T, beta, dt, dx, subtype, a):
   """rwpo_loss_fn (applications.py:405-421)."""
   tb = inputs["t_batch"]
   lat = inputs["latent"]
-  sub = lat[:lat.shape[0] // 32]
+  sub = _sub_batch(inputs)
   loss = lam * reverse_kl_loss(spec, params, lat, 0.0, T, beta)
   loss = loss + potential_loss(spec, params, lat, T, subtype, a)
   for t in tb.tolist():
@@ -210,7 +218,7 @@ def fp_loss(spec, params, inputs, lam, *, T, a, sigma, subtype):
   """fp_loss_fn (applications.py:424-441); beta = 4 is hard-coded (:432)."""
   tb = inputs["t_batch"]
   lat = inputs["latent"]
-  sub = lat[:lat.shape[0] // 32]
+  sub = _sub_batch(inputs)
   loss = lam * reverse_kl_loss(spec, params, lat, 0.0, T, 4.0)
   for t in tb.tolist():
     loss = loss + flow_matching_loss(
