@@ -102,6 +102,18 @@ struct LaunchCfg {
   size_t smem;
 };
 
+// Shared-memory plan: weights live in shared memory when weights + accumulators + row
+// tiles leave room for at least two CTAs per SM; otherwise they are read from global
+// memory (L1-cached broadcast loads).
+static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  SmemPlan p = plan_smem(lay, with_grad, true);
+  if ((int64_t)p.floats * 4 * 2 > di.max_smem_optin) p = plan_smem(lay, with_grad, false);
+  *sp = p;
+  return 0;
+}
+
 // Persistent launch: as many CTAs as fit on the chip, capped by the tile count.
 static int configure(const void* kernel, const SmemPlan& sp, int64_t tiles, LaunchCfg* cfg) {
   DeviceInfo di;
@@ -141,38 +153,45 @@ static PartialBuf carve_partials(void* ws, unsigned long long** counter) {
 
 // ---- finalize: sum per-CTA partials (double) into the output buffer ------------------
 // out = [ grad (total) | loss slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic ]
-__global__ void finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss,
-                                int n_cta, int total, float* __restrict__ out_grad,
-                                float* __restrict__ out_slots,
-                                unsigned long long* tile_counter) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) {
-    double acc = 0.0;
-    for (int c = 0; c < n_cta; ++c) acc += (double)pgrad[(int64_t)c * total + i];
-    out_grad[i] = (float)acc;
+// One block reduces 32 consecutive parameters: warp w sums partials w, w+8, ... (coalesced
+// 128-byte reads), the 8 warps are folded through shared memory.  Fixed order => the
+// result is bit-reproducible for a given grid size.
+constexpr int kFinWarps = 8;
+__global__ void __launch_bounds__(32 * kFinWarps)
+finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss, int n_cta,
+                int total, float* __restrict__ out_grad, float* __restrict__ out_slots) {
+  __shared__ double part[kFinWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (i < total)
+    for (int c = warp; c < n_cta; c += kFinWarps) acc += (double)pgrad[(int64_t)c * total + i];
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < total) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
+    out_grad[i] = (float)t;
   }
-  if (out_slots && blockIdx.x == 0 && threadIdx.x < kNumSlots) {
-    double acc = 0.0;
-    for (int c = 0; c < n_cta; ++c) acc += ploss[(int64_t)c * kNumSlots + threadIdx.x];
-    __shared__ double s[kNumSlots];
-    s[threadIdx.x] = acc;
-    __syncwarp(0xffu);
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int k = 0; k < 4; ++k) tot += s[k];
-      out_slots[0] = (float)tot;
-      for (int k = 0; k < 4; ++k) out_slots[1 + k] = (float)s[k];
-      for (int k = 5; k < kNumSlots; ++k) out_slots[k] = 0.f;
-    }
+  if (out_slots && blockIdx.x == 0 && warp == 1) {
+    // lanes 0..7 <-> internal slots (fit0, fitT, potential, kinetic, unused...)
+    double v = 0.0;
+    if (lane < kNumSlots)
+      for (int c = 0; c < n_cta; ++c) v += ploss[(int64_t)c * kNumSlots + lane];
+    double tot = v;
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);  // lanes 0..3 now hold the sum of slots 0..3
+    if (lane == 0) out_slots[0] = (float)tot;
+    if (lane < 4) out_slots[1 + lane] = (float)v;
+    if (lane >= 5 && lane < kNumSlots) out_slots[lane] = 0.f;
   }
-  if (tile_counter && i == 0) *tile_counter = 0ULL;  // re-arm for the next step
 }
 
 static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int total, float* out_grad,
                            float* out_slots) {
-  int threads = 256;
-  int blocks = (total + threads - 1) / threads;
-  finalize_kernel<<<blocks, threads, 0, s>>>(pb.grad, pb.loss, n_cta, total, out_grad, out_slots, nullptr);
+  int blocks = (total + 31) / 32;
+  finalize_kernel<<<blocks, 32 * kFinWarps, 0, s>>>(pb.grad, pb.loss, n_cta, total, out_grad, out_slots);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "finalize_kernel launch");
   return 0;
@@ -322,13 +341,14 @@ static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, co
   if (rows == 0) return 0;
   if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
   const void* kernel = find_flow_eval_kernel(lay);
-  SmemPlan sp = plan_smem(lay, false);
+  SmemPlan sp;
+  if (int rc = make_plan(lay, false, &sp)) return rc;
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   EvalArgs a;
   a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
   a.out = out; a.logdet = logdet; a.dir = dir; a.add_base = add_base;
-  a.D = lay.D; a.L = lay.L; a.total = lay.total;
+  a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
   void* args[] = {&a};
   cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, (cudaStream_t)stream);
@@ -374,15 +394,15 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
   }
   if (!in || !cond || !g_out) return fail(CNFOT_ERR_ARG, "NULL buffer");
   const void* kernel = find_flow_vjp_kernel(lay);
-  SmemPlan sp = plan_smem(lay, true);
+  SmemPlan sp;
+  if (int rc = make_plan(lay, true, &sp)) return rc;
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   unsigned long long* counter;
   VjpArgs a;
   a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
   a.g_out = g_out; a.g_logdet = g_logdet; a.g_in = g_in; a.dir = dir; a.add_base = add_base;
-  a.D = lay.D; a.L = lay.L; a.total = lay.total;
-  a.lda = sp.lda; a.ldg = sp.ldg; a.off_acc = sp.off_acc; a.off_sta = sp.off_sta; a.off_stg = sp.off_stg;
+  a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
   a.pb = carve_partials(workspace, &counter);
   void* args[] = {&a};
@@ -468,12 +488,12 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
     return 0;
   }
   const void* kernel = find_mfc_step_kernel(lay);
-  SmemPlan sp = plan_smem(lay, true);
+  SmemPlan sp;
+  if (int rc = make_plan(lay, true, &sp)) return rc;
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
   a.W = weights;
-  a.D = lay.D; a.L = lay.L; a.total = lay.total;
-  a.lda = sp.lda; a.ldg = sp.ldg; a.off_acc = sp.off_acc; a.off_sta = sp.off_sta; a.off_stg = sp.off_stg;
+  a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
   a.pb = carve_partials(workspace, &a.tile_counter);
   cudaError_t e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s);

@@ -1,5 +1,6 @@
 // Device-side plumbing shared by the fused flow / train-step kernels:
-// shared-memory carving, the CTA-wide weight-gradient sink, loss reductions.
+// shared-memory carving, the per-row activation tiles, the CTA-wide
+// weight-gradient sink, loss reductions.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -14,32 +15,49 @@ constexpr int kWarps = kTile / 32;
 
 // Row stride (floats) for a staged [kTile][n] tile, n a multiple of 4: an odd
 // number of 16-byte units, so 8 consecutive rows hit 8 distinct bank groups and
-// both the per-row float4 stores and the strided float4 reads are conflict-free.
+// both the per-row float4 accesses and the strided float4 reads of the
+// reduction are conflict-free.
 __host__ __device__ inline int staged_stride(int n) {
   int q = (n + 3) / 4;
   if ((q & 1) == 0) q += 1;
   return q * 4;
 }
 
+// Shared-memory layout of one CTA (offsets in floats).
 struct SmemPlan {
-  int total;   // blob floats
-  int lda;     // staging stride of the activation tile
-  int ldg;     // staging stride of the adjoint tile
-  int off_acc, off_sta, off_stg, floats;
+  int total;            // blob floats
+  int w_in_smem;        // 1: whole blob resident in shared memory; 0: `first` resident and one
+                        //    conditioner at a time staged at off_w (weights stream from L2)
+  int off_w;            // resident blob, or [first (Pp) | staging buffer] when not resident
+  int w_stage;          // floats of the staging buffer (largest conditioner), 0 if resident
+  int off_acc;          // gradient accumulators (same layout as the blob); -1 if none
+  int off_in, ld_in;    // [kTile][ld_in]  conditioner inputs
+  int off_hid, ld_h;    // M tiles [kTile][ld_h] hidden activations
+  int off_gh;           // M tiles [kTile][ld_h] hidden adjoints; -1 if none
+  int off_gth, ld_p;    // [kTile][ld_p] spline-parameter adjoints; -1 if none
+  int floats;
 };
 
-inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad) {
+inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = true) {
   SmemPlan p;
   p.total = f.total;
-  int wa = f.H > ((f.D + 3) / 4 * 4) ? f.H : (f.D + 3) / 4 * 4;
-  int wg = f.H > f.Pp ? f.H : f.Pp;
-  p.lda = staged_stride(wa);
-  p.ldg = staged_stride(wg);
-  int tot4 = (f.total + 3) / 4 * 4;
-  p.off_acc = tot4;
-  p.off_sta = with_grad ? 2 * tot4 : tot4;
-  p.off_stg = p.off_sta + (with_grad ? kTile * p.lda : 0);
-  p.floats = p.off_stg + (with_grad ? kTile * p.ldg : 0);
+  p.w_in_smem = w_in_smem ? 1 : 0;
+  const int tot4 = (f.total + 3) / 4 * 4;
+  p.ld_in = staged_stride((f.D + 3) / 4 * 4);
+  p.ld_h = staged_stride(f.H);
+  p.ld_p = staged_stride(f.Pp);
+  p.off_w = 0;
+  p.w_stage = w_in_smem ? 0 : (f.D * f.H + f.mlp_const + 3) / 4 * 4;
+  int o = w_in_smem ? tot4 : f.Pp + p.w_stage;
+  p.off_acc = with_grad ? o : -1;
+  if (with_grad) o += tot4;
+  p.off_in = o; o += kTile * p.ld_in;
+  p.off_hid = o; o += f.M * kTile * p.ld_h;
+  p.off_gh = with_grad ? o : -1;
+  if (with_grad) o += f.M * kTile * p.ld_h;
+  p.off_gth = with_grad ? o : -1;
+  if (with_grad) o += kTile * p.ld_p;
+  p.floats = o;
   return p;
 }
 
@@ -52,105 +70,227 @@ __device__ inline void load_weights(float* sW, const float* __restrict__ gW, int
   for (int i = (n4 << 2) + threadIdx.x; i < total; i += blockDim.x) sW[i] = __ldg(gW + i);
 }
 
-// CTA-wide weight-gradient reduction.
-//
-// outer<NAMAX, NG>(w_off, Na, a, g): every thread (= row) contributes the rank-1
-// update a (x) g to the (Na x NG) matrix at blob offset w_off and g to the bias
-// row that directly follows it.  All threads of the CTA must call it together.
-//
-// Mechanics: each thread stores its a / g row into padded shared-memory tiles;
-// after a barrier the CTA re-partitions the work GEMM-style: a lane owns one
-// 4x4 block of the matrix for one eighth of the tile's rows (8 row groups x 4
-// blocks per warp), accumulates 16 FMAs per float4 pair, the 8 row groups are
-// folded with a reduce-scatter butterfly (14 shuffles) and each lane adds its 2
-// results to the CTA's shared-memory accumulator.  Every accumulator element
-// has exactly one owner lane per call, so no atomics are needed.
-struct DeviceSink {
-  float* acc;
-  float* stA;
-  float* stG;
-  int lda, ldg;
+template <class Net>
+__device__ inline RowTiles<float, Net> make_row_tiles(float* smem, const SmemPlan& p) {
+  RowTiles<float, Net> tl;
+  const int r = threadIdx.x;
+  tl.in = smem + p.off_in + r * p.ld_in;
+#pragma unroll
+  for (int m = 0; m < Net::kM; ++m) {
+    tl.hid[m] = smem + p.off_hid + (m * kTile + r) * p.ld_h;
+    tl.gh[m] = p.off_gh >= 0 ? smem + p.off_gh + (m * kTile + r) * p.ld_h : nullptr;
+  }
+  tl.gth = p.off_gth >= 0 ? smem + p.off_gth + r * p.ld_p : nullptr;
+  return tl;
+}
 
-  template <int NG>
-  __device__ __noinline__ void reduce_tile(int Na, float* dst) {
-    constexpr int NCB = NG / 4;
-    const int nrb = (Na + 3) >> 2;
-    const int nblk = (nrb + 1) * NCB;  // + one row of bias blocks
+// The CTA-wide context of the fused kernels (the `Ctx` policy of flow_math.cuh):
+// weights in shared memory and the weight-gradient reduction over the staged row tiles.
+//
+// commit(): after every thread (= row) has written its conditioner input, hidden
+// activations and adjoints into the tiles, the CTA re-partitions GEMM-style: the
+// gradient of each layer, dW = A^T G over the tile's 128 rows, is cut into 4x4
+// blocks; a lane owns one block for one eighth of the rows (8 row groups x 4 blocks
+// per warp, 16 FMAs per pair of float4 loads), the 8 row groups are folded with a
+// reduce-scatter butterfly (14 shuffles) and each lane adds its 2 results to the
+// CTA's shared-memory accumulator.  Bias gradients (column sums of G) take a second,
+// cheap phase.  Every accumulator element has exactly one owner lane per call, so no
+// atomics are needed; the accumulators are flushed once per CTA at kernel end.
+template <class Net>
+struct DeviceCtx {
+  static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
+  float* smem;
+  const float* gW;   // the blob in global memory
+  SmemPlan p;
+
+  // once per kernel: bring the blob (or just `first`) into shared memory
+  __device__ __forceinline__ void load() {
+    if (p.w_in_smem) load_weights(smem + p.off_w, gW, p.total);
+    else load_weights(smem + p.off_w, gW, Pp);
+    if (p.off_acc >= 0)
+      for (int i = threadIdx.x; i < p.total; i += blockDim.x) smem[p.off_acc + i] = 0.f;
+    __syncthreads();
+  }
+
+  __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
+
+  __device__ __forceinline__ const float* weights(int w_off, int count) {
+    if (p.w_in_smem) return smem + p.off_w + w_off;
+    __syncthreads();  // previous conditioner's readers are done with the staging buffer
+    float* dst = smem + p.off_w + Pp;
+    const float4* src = reinterpret_cast<const float4*>(gW + w_off);
+    for (int i = threadIdx.x; i < (count >> 2); i += blockDim.x)
+      reinterpret_cast<float4*>(dst)[i] = __ldg(src + i);
+    __syncthreads();
+    return dst;
+  }
+
+  __device__ __forceinline__ void begin() { __syncthreads(); }
+
+  // one 4x4 block: rows rb*4.. of A (tile pa, stride lda) x cols cb*4.. of G
+  __device__ __forceinline__ void block_accumulate(const float* pa, int lda, const float* pg,
+                                                   int ldg, float* c) {
+#pragma unroll 4
+    for (int k = 0; k < kTile / 8; ++k) {
+      const float4 g4 = *reinterpret_cast<const float4*>(pg + k * 8 * ldg);
+      const float4 a4 = *reinterpret_cast<const float4*>(pa + k * 8 * lda);
+      c[0] += a4.x * g4.x; c[1] += a4.x * g4.y; c[2] += a4.x * g4.z; c[3] += a4.x * g4.w;
+      c[4] += a4.y * g4.x; c[5] += a4.y * g4.y; c[6] += a4.y * g4.z; c[7] += a4.y * g4.w;
+      c[8] += a4.z * g4.x; c[9] += a4.z * g4.y; c[10] += a4.z * g4.z; c[11] += a4.z * g4.w;
+      c[12] += a4.w * g4.x; c[13] += a4.w * g4.y; c[14] += a4.w * g4.z; c[15] += a4.w * g4.w;
+    }
+  }
+
+  __device__ __noinline__ void reduce(int w_off, int n_in) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rg = lane & 7, slot = lane >> 3;
-    for (int base = warp * 4; base < nblk; base += 4 * kWarps) {
+    constexpr int CH = H / 4, CP = Pp / 4;
+    const int nb0 = ((n_in + 3) >> 2) * CH;          // input layer blocks
+    constexpr int nbm = CH * CH;                       // each hidden layer
+    constexpr int nbo = CH * CP;                       // output layer
+    const int total = nb0 + (M - 1) * nbm + nbo;
+    float* acc = smem + p.off_acc + w_off;
+    CNFOT_ASSUME_SHARED(acc);
+    const float* t_in = smem + p.off_in;
+    const float* t_hid = smem + p.off_hid;
+    const float* t_gh = smem + p.off_gh;
+    const float* t_gth = smem + p.off_gth;
+    CNFOT_ASSUME_SHARED(t_in);
+    CNFOT_ASSUME_SHARED(t_hid);
+    CNFOT_ASSUME_SHARED(t_gh);
+    CNFOT_ASSUME_SHARED(t_gth);
+    const int off_hidden0 = n_in * H + H;             // first hidden (H x H) matrix
+    for (int base = warp * 4; base < total; base += 4 * kWarps) {
       const int b = base + slot;
-      const bool valid = b < nblk;
-      const int rb = valid ? b / NCB : 0, cb = valid ? b - rb * NCB : 0;
-      const bool bias = rb == nrb;
+      const bool valid = b < total;
+      const float *pa = t_in, *pg = t_gh;
+      int lda = p.ld_in, ldg = p.ld_h, Na = n_in, ncol = H, rb = 0, cb = 0;
+      float* dst = acc;
+      if (valid) {
+        if (b < nb0) {
+          rb = b / CH; cb = b - rb * CH;
+        } else if (b < nb0 + (M - 1) * nbm) {
+          const int q = b - nb0;
+          const int m = 1 + q / nbm;                  // hidden layer m: A = hid[m-1], G = gh[m]
+          const int r = q - (m - 1) * nbm;
+          rb = r / CH; cb = r - rb * CH;
+          pa = t_hid + (m - 1) * kTile * p.ld_h; lda = p.ld_h; Na = H;
+          pg = t_gh + m * kTile * p.ld_h;
+          dst = acc + off_hidden0 + (m - 1) * (H * H + H);
+        } else {
+          const int r = b - nb0 - (M - 1) * nbm;     // output layer: A = hid[M-1], G = gth
+          rb = r / CP; cb = r - rb * CP;
+          pa = t_hid + (M - 1) * kTile * p.ld_h; lda = p.ld_h; Na = H;
+          pg = t_gth; ldg = p.ld_p; ncol = Pp;
+          dst = acc + off_hidden0 + (M - 1) * (H * H + H);
+        }
+      }
       float c[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) c[e] = 0.f;
-      if (valid) {
-        const float* pg = stG + rg * ldg + cb * 4;
-        const float* pa = stA + rg * lda + (bias ? 0 : rb * 4);
-#pragma unroll 4
-        for (int k = 0; k < kTile / 8; ++k) {
-          float4 g4 = *reinterpret_cast<const float4*>(pg + k * 8 * ldg);
-          float4 a4 = *reinterpret_cast<const float4*>(pa + k * 8 * lda);
-          if (bias) a4 = make_float4(1.f, 0.f, 0.f, 0.f);
-          c[0] += a4.x * g4.x; c[1] += a4.x * g4.y; c[2] += a4.x * g4.z; c[3] += a4.x * g4.w;
-          c[4] += a4.y * g4.x; c[5] += a4.y * g4.y; c[6] += a4.y * g4.z; c[7] += a4.y * g4.w;
-          c[8] += a4.z * g4.x; c[9] += a4.z * g4.y; c[10] += a4.z * g4.z; c[11] += a4.z * g4.w;
-          c[12] += a4.w * g4.x; c[13] += a4.w * g4.y; c[14] += a4.w * g4.z; c[15] += a4.w * g4.w;
-        }
-      }
+      if (valid) block_accumulate(pa + rg * lda + rb * 4, lda, pg + rg * ldg + cb * 4, ldg, c);
       // reduce-scatter over the 8 row groups (lane bits 0..2)
       const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
       float v8[8], v4[4], v2[2];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float keep = b2 ? c[8 + q] : c[q], send = b2 ? c[q] : c[8 + q];
+        const float keep = b2 ? c[8 + q] : c[q], send = b2 ? c[q] : c[8 + q];
         v8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float keep = b1 ? v8[4 + q] : v8[q], send = b1 ? v8[q] : v8[4 + q];
+        const float keep = b1 ? v8[4 + q] : v8[q], send = b1 ? v8[q] : v8[4 + q];
         v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        float keep = b0 ? v4[2 + q] : v4[q], send = b0 ? v4[q] : v4[2 + q];
+        const float keep = b0 ? v4[2 + q] : v4[q], send = b0 ? v4[q] : v4[2 + q];
         v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
-      if (valid) {
-        const int i = (b2 ? 2 : 0) + (b1 ? 1 : 0);
-        const int j = b0 ? 2 : 0;
-        const int row = bias ? Na : rb * 4 + i;
-        if (bias ? (i == 0) : (row < Na)) {
-          float2* p = reinterpret_cast<float2*>(dst + row * NG + cb * 4 + j);
-          float2 cur = *p;
-          cur.x += v2[0];
-          cur.y += v2[1];
-          *p = cur;
-        }
+      const int row = rb * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+      if (valid && row < Na) {
+        float2* q = reinterpret_cast<float2*>(dst + row * ncol + cb * 4 + (b0 ? 2 : 0));
+        float2 cur = *q;
+        cur.x += v2[0];
+        cur.y += v2[1];
+        *q = cur;
+      }
+    }
+    // bias gradients: column sums of every G tile; one (tile, 4-column block) task per
+    // warp iteration, the 32 lanes split the 128 rows
+    constexpr int tasks = M * CH + CP;
+    for (int task = warp; task < tasks; task += kWarps) {
+      const float* pg;
+      int ldg, cb;
+      float* dst;
+      if (task < M * CH) {
+        const int m = task / CH;
+        cb = task - m * CH;
+        pg = t_gh + m * kTile * p.ld_h; ldg = p.ld_h;
+        dst = m == 0 ? acc + n_in * H : acc + off_hidden0 + (m - 1) * (H * H + H) + H * H;
+      } else {
+        cb = task - M * CH;
+        pg = t_gth; ldg = p.ld_p;
+        dst = acc + off_hidden0 + (M - 1) * (H * H + H) + H * Pp;
+      }
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kTile / 32; ++k) {
+        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * ldg + cb * 4);
+        s.x += g4.x; s.y += g4.y; s.z += g4.z; s.w += g4.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+        s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+      }
+      if (lane == 0) {
+        float4* q = reinterpret_cast<float4*>(dst + cb * 4);
+        float4 cur = *q;
+        cur.x += s.x; cur.y += s.y; cur.z += s.z; cur.w += s.w;
+        *q = cur;
       }
     }
   }
 
-  template <int NAMAX, int NG>
-  __device__ __forceinline__ void outer(int w_off, int Na, const float* a, const float* g) {
-    __syncthreads();  // previous call's readers are done with the staging tiles
-    float* ra = stA + threadIdx.x * lda;
-    float* rgp = stG + threadIdx.x * ldg;
-    if (NAMAX == kMaxDim) {
-      const int na4 = (Na + 3) & ~3;
-      for (int i = 0; i < na4; ++i) ra[i] = i < Na ? a[i] : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < NAMAX; i += 4)
-        *reinterpret_cast<float4*>(ra + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
-    }
-#pragma unroll
-    for (int j = 0; j < NG; j += 4)
-      *reinterpret_cast<float4*>(rgp + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+  __device__ __forceinline__ void commit(int w_off, int n_in, const RowTiles<float, Net>&) {
+    __syncthreads();  // every row's tiles are written
+    reduce(w_off, n_in);
+  }
+
+  // flush the per-thread adjoint of the shared `first` parameter (blob offset 0)
+  __device__ __forceinline__ void flush_first(const float* gfirst, const RowTiles<float, Net>& tl) {
     __syncthreads();
-    reduce_tile<NG>(Na, acc + w_off);
+#pragma unroll
+    for (int j = 0; j < Pp; j += 4)
+      *reinterpret_cast<float4*>(tl.gth + j) = make_float4(gfirst[j], gfirst[j + 1], gfirst[j + 2], gfirst[j + 3]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* pg = smem + p.off_gth;
+    for (int cb = warp; cb < Pp / 4; cb += kWarps) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kTile / 32; ++k) {
+        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * p.ld_p + cb * 4);
+        s.x += g4.x; s.y += g4.y; s.z += g4.z; s.w += g4.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+        s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+      }
+      if (lane == 0) {
+        float4* q = reinterpret_cast<float4*>(smem + p.off_acc + cb * 4);
+        float4 cur = *q;
+        cur.x += s.x; cur.y += s.y; cur.z += s.z; cur.w += s.w;
+        *q = cur;
+      }
+    }
+    __syncthreads();
   }
 };
 

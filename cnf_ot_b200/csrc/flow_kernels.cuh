@@ -19,24 +19,28 @@ struct EvalArgs {
   float* logdet;
   int dir;
   int add_base;
-  int D, L, total;
+  int D, L;
+  SmemPlan plan;
   SplineConsts<float> sc;
 };
 
 template <class Net, class DimsT>
 __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
   extern __shared__ __align__(16) float smem[];
-  load_weights(smem, a.W, a.total);
-  __syncthreads();
+  DeviceCtx<Net> ctx{smem, a.W, a.plan};
+  ctx.load();
+  const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
   for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
     const int64_t r = tile * kTile + threadIdx.x;
-    if (r >= a.rows) continue;
+    const bool live = r < a.rows;  // every thread runs the pass: the context has CTA barriers
     float st[kMaxStateFloats];
-    for (int i = 0; i < D; ++i) st[i] = a.in[r * D + i];
-    const float t = a.cond[r * a.cond_stride];
-    float ld = flow_pass<float, Net, DimsT>(a.dir, dm, smem, a.sc, t, st);
+    for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
+    const float t = live ? a.cond[r * a.cond_stride] : 0.f;
+    float ld = a.dir == 0 ? flow_pass<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx)
+                          : flow_pass<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
+    if (!live) continue;
     for (int i = 0; i < D; ++i) a.out[r * D + i] = st[L * D + i];
     if (a.logdet) {
       if (a.add_base)
@@ -77,8 +81,8 @@ struct VjpArgs {
   float* g_in;
   int dir;
   int add_base;
-  int D, L, total;
-  int lda, ldg, off_acc, off_sta, off_stg;
+  int D, L;
+  SmemPlan plan;
   SplineConsts<float> sc;
   PartialBuf pb;
 };
@@ -87,12 +91,10 @@ template <class Net, class DimsT>
 __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double scratch[kWarps];
-  float* sW = smem;
-  float* sAcc = smem + a.off_acc;
-  load_weights(sW, a.W, a.total);
-  for (int i = threadIdx.x; i < a.total; i += blockDim.x) sAcc[i] = 0.f;
-  __syncthreads();
-  DeviceSink sink{sAcc, smem + a.off_sta, smem + a.off_stg, a.lda, a.ldg};
+  float* sAcc = smem + a.plan.off_acc;
+  DeviceCtx<Net> ctx{smem, a.W, a.plan};
+  ctx.load();
+  const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
   float gfirst[Net::kPp];
@@ -104,7 +106,8 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
     float st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    flow_pass<float, Net, DimsT>(a.dir, dm, sW, a.sc, t, st);
+    if (a.dir == 0) flow_pass<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
+    else flow_pass<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
     const float gl = (live && a.g_logdet) ? a.g_logdet[r] : 0.f;
     for (int i = 0; i < D; ++i) g[i] = live ? a.g_out[r * D + i] : 0.f;
     float gl_pass = gl;
@@ -113,17 +116,19 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
       else
         for (int i = 0; i < D; ++i) g[i] -= gl * st[L * D + i];
     }
-    flow_pass_bwd<float, Net, DimsT, DeviceSink>(a.dir, dm, sW, a.sc, t, st, g, gl_pass, gfirst,
-                                                 sink);
+    if (a.dir == 0)
+      flow_pass_bwd<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
+    else
+      flow_pass_bwd<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
     if (a.add_base && a.dir == 0)
       for (int i = 0; i < D; ++i) g[i] -= gl * st[i];
     if (live && a.g_in)
       for (int i = 0; i < D; ++i) a.g_in[r * D + i] = g[i];
   }
-  sink.template outer<kMaxDim, Net::kPp>(0, 0, nullptr, gfirst);
+  ctx.flush_first(gfirst, tl);
   double zero[kNumSlots];
   for (int s = 0; s < kNumSlots; ++s) zero[s] = 0.0;
-  flush_partials(a.pb, sAcc, a.total, zero, scratch);
+  flush_partials(a.pb, sAcc, a.plan.total, zero, scratch);
 }
 
 // ---- the fused train step ---------------------------------------------------------------
@@ -146,8 +151,8 @@ constexpr int kMaxSegments = 40;
 
 struct StepArgs {
   const float* W;
-  int D, L, total;
-  int lda, ldg, off_acc, off_sta, off_stg;
+  int D, L;
+  SmemPlan plan;
   SplineConsts<float> sc;
   StepConsts<float> pc;
   int n_seg;
@@ -162,12 +167,10 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
   extern __shared__ __align__(16) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ long long s_tile;
-  float* sW = smem;
-  float* sAcc = smem + a.off_acc;
-  load_weights(sW, a.W, a.total);
-  for (int i = threadIdx.x; i < a.total; i += blockDim.x) sAcc[i] = 0.f;
-  __syncthreads();
-  DeviceSink sink{sAcc, smem + a.off_sta, smem + a.off_stg, a.lda, a.ldg};
+  float* sAcc = smem + a.plan.off_acc;
+  DeviceCtx<Net> ctx{smem, a.W, a.plan};
+  ctx.load();
+  const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D();
   float gfirst[Net::kPp];
@@ -191,29 +194,29 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
     float row[kMaxDim];
     for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;
     if (sg.kind == kSegNll) {
-      float v = row_nll<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row,
-                                                       live ? a.pc.w_fit : 0.f, gfirst, sink);
+      float v = row_nll<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row,
+                                                           live ? a.pc.w_fit : 0.f, gfirst, tl, ctx);
       loss[sg.slot] += (double)v;
     } else if (sg.kind == kSegSample) {
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_fit = 0.f; pc.w_pot = 0.f; }
       float lf = 0.f, lp = 0.f;
-      row_sample_terms<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row, sg.do_fit != 0,
-                                                      sg.do_pot != 0, pc, &lf, &lp, gfirst, sink);
+      row_sample_terms<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row, sg.do_fit != 0,
+                                                          sg.do_pot != 0, pc, &lf, &lp, gfirst, tl, ctx);
       loss[sg.slot] += (double)lf;
       loss[kSlotPotential] += (double)lp;
     } else {
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
       float lk = 0.f, lp = 0.f;
-      row_kinetic<float, Net, DimsT, DeviceSink>(dm, sW, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
-                                                 sink);
+      row_kinetic<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
+                                                     tl, ctx);
       loss[kSlotKinetic] += (double)lk;
       loss[kSlotPotential] += (double)lp;
     }
   }
-  sink.template outer<kMaxDim, Net::kPp>(0, 0, nullptr, gfirst);
-  flush_partials(a.pb, sAcc, a.total, loss, scratch);
+  ctx.flush_first(gfirst, tl);
+  flush_partials(a.pb, sAcc, a.plan.total, loss, scratch);
 }
 
 }  // namespace cnfot

@@ -11,11 +11,16 @@
 //   stacking, direction  /root/reference/cnf_ot/models/flows.py:138-175,
 //                        /root/reference/cnf_ot/models/conditional.py:147-177,217-243
 //
-// The weight-gradient reduction over rows is delegated to a `Sink` policy:
-// the device sink stages (activation, adjoint) pairs in shared memory and
-// reduces them CTA-wide (flow_kernels.cuh); the host test harness uses a
-// plain accumulating sink.  Control flow is uniform across rows, which the
-// device sink relies on (it contains CTA-wide barriers).
+// Everything that is CTA-wide on the device is delegated to a context policy `Ctx`:
+//   first_params()               the shared `first` spline parameters (Pp floats)
+//   weights(w_off, count)        the weights of the conditioner at blob offset w_off
+//                                (device: resident in, or staged into, shared memory)
+//   begin()                      the row tiles may be overwritten (device: barrier)
+//   commit(w_off, n_in, tiles)   add this row's rank-1 updates of every layer of that
+//                                conditioner to the gradient (device: barrier + CTA-wide
+//                                reduction of the staged tiles)
+// The host test harness uses a plain context.  Control flow is uniform across rows,
+// which the device context relies on (it contains CTA-wide barriers).
 #pragma once
 
 #include "rqs_math.cuh"
@@ -80,16 +85,24 @@ CNFOT_HD int mlp_offset(int D, int layer, int d) {
 // permutations: flows.py:141-143 with minimum_perm=True)
 CNFOT_HD int perm_at(int layer, int d, int D) { return (layer & 1) ? (D - 1 - d) : d; }
 
-// ---- 4-wide weight loads -------------------------------------------------------
+// ---- 4-wide loads / stores ------------------------------------------------------
 template <typename T>
 CNFOT_HD void load4(const T* p, T (&v)[4]) {
   v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+}
+template <typename T>
+CNFOT_HD void store4(T* p, T a, T b, T c, T d) {
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
 }
 #if defined(__CUDA_ARCH__)
 template <>
 __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
   float4 q = *reinterpret_cast<const float4*>(p);
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 #endif
 
@@ -121,107 +134,186 @@ CNFOT_HD T dot_row(const T* g, const T* row) {
   return acc0 + acc1;
 }
 
-// Conditioner forward.  `in` holds n_in = d+1 values [t, conditioning coords].
-// hid[m*H + j] receives the post-ReLU activations of hidden layer m.
+// ---- per-row tiles ------------------------------------------------------------------
+// The activations of one conditioner evaluation live in per-row tiles rather than in
+// registers.  On the device every pointer addresses the calling thread's row of a
+// CTA-wide shared-memory tile ([128 rows][padded width]): that is exactly the staging
+// the CTA-wide weight-gradient reduction (DeviceSink) reads, so nothing is copied
+// twice, and the layer loops below can stay rolled (small code: the fully unrolled
+// register version overflowed the instruction cache).  On the host they are plain arrays.
 template <typename T, class Net>
-CNFOT_HD void mlp_forward(const T* W, int n_in, const T* in, T* hid, T* theta) {
+struct RowTiles {
+  T* in;                 // [roundup4(n_in)]  MLP input [t, conditioning coords...], zero padded
+  T* hid[Net::kM];       // [H]   post-ReLU activations of hidden layer m
+  T* gh[Net::kM];        // [H]   adjoint of the pre-activations of hidden layer m
+  T* gth;                // [Pp]  adjoint of the raw spline params (the MLP output)
+};
+
+// Conditioner forward: tiles.in -> tiles.hid[*] -> theta (registers).
+template <typename T, class Net>
+CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* theta) {
   constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   const T* b0 = W + n_in * H;
   T acc[H];
 #pragma unroll
   for (int j = 0; j < H; ++j) acc[j] = b0[j];
-  for (int i = 0; i < n_in; ++i) axpy_row<T, H>(in[i], W + i * H, acc);
+#pragma unroll 1
+  for (int i = 0; i < n_in; ++i) axpy_row<T, H>(tl.in[i], W + i * H, acc);
 #pragma unroll
-  for (int j = 0; j < H; ++j) hid[j] = m_max(acc[j], (T)0);
+  for (int j = 0; j < H; j += 4)
+    store4<T>(tl.hid[0] + j, m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0), m_max(acc[j + 2], (T)0),
+              m_max(acc[j + 3], (T)0));
   const T* Wm = b0 + H;
 #pragma unroll
   for (int m = 1; m < M; ++m) {
     const T* bm = Wm + H * H;
 #pragma unroll
     for (int j = 0; j < H; ++j) acc[j] = bm[j];
+#pragma unroll 1
+    for (int i = 0; i < H; i += 4) {
+      T a[4];
+      load4<T>(tl.hid[m - 1] + i, a);
 #pragma unroll
-    for (int i = 0; i < H; ++i) axpy_row<T, H>(hid[(m - 1) * H + i], Wm + i * H, acc);
+      for (int q = 0; q < 4; ++q) axpy_row<T, H>(a[q], Wm + (i + q) * H, acc);
+    }
 #pragma unroll
-    for (int j = 0; j < H; ++j) hid[m * H + j] = m_max(acc[j], (T)0);
+    for (int j = 0; j < H; j += 4)
+      store4<T>(tl.hid[m] + j, m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0),
+                m_max(acc[j + 2], (T)0), m_max(acc[j + 3], (T)0));
     Wm = bm + H;
   }
   const T* bo = Wm + H * Pp;
 #pragma unroll
   for (int j = 0; j < Pp; ++j) theta[j] = bo[j];
+#pragma unroll 1
+  for (int i = 0; i < H; i += 4) {
+    T a[4];
+    load4<T>(tl.hid[M - 1] + i, a);
 #pragma unroll
-  for (int i = 0; i < H; ++i) axpy_row<T, Pp>(hid[(M - 1) * H + i], Wm + i * Pp, theta);
+    for (int q = 0; q < 4; ++q) axpy_row<T, Pp>(a[q], Wm + (i + q) * Pp, theta);
+  }
 }
 
-// Conditioner backward: pushes (activation, adjoint) pairs of every layer into
-// the sink (weight + bias gradients) and returns the adjoint of the inputs
-// in gin[1..n_in) (gin[0], the adjoint of t, is not needed by the train step).
-template <typename T, class Net, class Sink>
-CNFOT_HD void mlp_backward(const T* W, int w_off, int n_in, const T* in, const T* hid,
-                           const T* gtheta, T* gin, Sink& sink) {
+// Conditioner backward (data gradients): given gtheta (registers) fills tiles.gth and
+// tiles.gh[*] and returns the adjoint of the inputs in gin[1..n_in) (gin[0], the adjoint
+// of t, is not needed).  The weight gradients are taken from the tiles by Sink::commit.
+template <typename T, class Net>
+CNFOT_HD void mlp_backward(const T* W, int n_in, const RowTiles<T, Net>& tl, const T* gtheta,
+                           T* gin) {
   constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
-  int off_out = w_off + n_in * H + H + (M - 1) * (H * H + H);
-  const T* Wout = W + (off_out - w_off);
-  sink.template outer<H, Pp>(off_out, H, hid + (M - 1) * H, gtheta);
+#pragma unroll
+  for (int j = 0; j < Pp; j += 4)
+    store4<T>(tl.gth + j, gtheta[j], gtheta[j + 1], gtheta[j + 2], gtheta[j + 3]);
+  const T* Wout = W + n_in * H + H + (M - 1) * (H * H + H);
+#pragma unroll 1
+  for (int i = 0; i < H; i += 4) {
+    T a[4], r[4];
+    load4<T>(tl.hid[M - 1] + i, a);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      T v = dot_row<T, Pp>(gtheta, Wout + (i + q) * Pp);
+      r[q] = a[q] > (T)0 ? v : (T)0;
+    }
+    store4<T>(tl.gh[M - 1] + i, r[0], r[1], r[2], r[3]);
+  }
   T g[H];
 #pragma unroll
-  for (int i = 0; i < H; ++i) {
-    T v = dot_row<T, Pp>(gtheta, Wout + i * Pp);
-    g[i] = hid[(M - 1) * H + i] > (T)0 ? v : (T)0;
-  }
-#pragma unroll
   for (int m = M - 1; m >= 1; --m) {
-    int off_m = w_off + n_in * H + H + (m - 1) * (H * H + H);
-    const T* Wm = W + (off_m - w_off);
-    sink.template outer<H, H>(off_m, H, hid + (m - 1) * H, g);
-    T gp[H];
+    const T* Wm = W + n_in * H + H + (m - 1) * (H * H + H);
 #pragma unroll
-    for (int i = 0; i < H; ++i) {
-      T v = dot_row<T, H>(g, Wm + i * H);
-      gp[i] = hid[(m - 1) * H + i] > (T)0 ? v : (T)0;
+    for (int j = 0; j < H; j += 4) {
+      T v[4];
+      load4<T>(tl.gh[m] + j, v);
+      g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
     }
+#pragma unroll 1
+    for (int i = 0; i < H; i += 4) {
+      T a[4], r[4];
+      load4<T>(tl.hid[m - 1] + i, a);
 #pragma unroll
-    for (int i = 0; i < H; ++i) g[i] = gp[i];
+      for (int q = 0; q < 4; ++q) {
+        T v = dot_row<T, H>(g, Wm + (i + q) * H);
+        r[q] = a[q] > (T)0 ? v : (T)0;
+      }
+      store4<T>(tl.gh[m - 1] + i, r[0], r[1], r[2], r[3]);
+    }
   }
-  sink.template outer<kMaxDim, H>(w_off, n_in, in, g);
+#pragma unroll
+  for (int j = 0; j < H; j += 4) {
+    T v[4];
+    load4<T>(tl.gh[0] + j, v);
+    g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
+  }
+#pragma unroll 1
   for (int i = 1; i < n_in; ++i) gin[i] = dot_row<T, H>(g, W + i * H);
 }
 
+template <typename T, class Net>
+CNFOT_HD void assume_tiles_shared(const RowTiles<T, Net>& tl, bool with_grad) {
+  CNFOT_ASSUME_SHARED(tl.in);
+#pragma unroll
+  for (int m = 0; m < Net::kM; ++m) CNFOT_ASSUME_SHARED(tl.hid[m]);
+  if (with_grad) {
+#pragma unroll
+    for (int m = 0; m < Net::kM; ++m) CNFOT_ASSUME_SHARED(tl.gh[m]);
+    CNFOT_ASSUME_SHARED(tl.gth);
+  }
+}
+
+// Fill tiles.in with [t, cvec[perm(0)], ..., cvec[perm(d-1)]], zero padded to a multiple of 4.
+template <typename T, class Net>
+CNFOT_HD void fill_mlp_input(const RowTiles<T, Net>& tl, T t, const T* cvec, int layer, int d,
+                             int D) {
+  tl.in[0] = t;
+  for (int j = 0; j < d; ++j) tl.in[1 + j] = cvec[perm_at(layer, j, D)];
+  for (int j = d + 1; j < ((d + 4) & ~3); ++j) tl.in[j] = (T)0;
+}
+
 // ---- one pass through the flow -----------------------------------------------
-// dir 0: "sample direction", latent -> physical: layers 0..L-1, each applying
+// DIR 0: "sample direction", latent -> physical: layers 0..L-1, each applying
 //        Autoregressive.inverse_and_log_det (conditioners read the layer INPUT,
 //        spline inverse formula).
-// dir 1: "log-prob direction", physical -> latent: layers L-1..0, each applying
+// DIR 1: "log-prob direction", physical -> latent: layers L-1..0, each applying
 //        Autoregressive.forward_and_log_det (conditioners read the OUTPUT being
 //        built, sequential in d, spline forward formula).
 // states[0..D) is the input; states[(s+1)*D ..] the result of step s.
 // Returns the summed log-det of the pass.
-template <typename T, class Net, class DimsT>
-CNFOT_CALL T flow_pass(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t,
-                     T* states) {
-  constexpr int H = Net::kH, K = Net::kK, M = Net::kM, Pp = Net::kPp;
+template <int DIR, typename T, class Net, class DimsT, class Ctx>
+CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* states,
+                       const RowTiles<T, Net>& tl, Ctx& ctx) {
+  constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
+  assume_tiles_shared<T, Net>(tl, false);
+  CNFOT_ASSUME_LOCAL(states);
   T ld_total = (T)0;
+#pragma unroll 1
   for (int s = 0; s < L; ++s) {
-    const int layer = dir == 0 ? s : L - 1 - s;
+    const int layer = DIR == 0 ? s : L - 1 - s;
     const T* v = states + s * D;
     T* u = states + (s + 1) * D;
-    const T* cvec = dir == 0 ? v : u;
+    const T* cvec = DIR == 0 ? v : u;
+#pragma unroll 1
     for (int d = 0; d < D; ++d) {
       const int i = perm_at(layer, d, D);
       T theta[Pp];
       if (d == 0) {
+        const T* F = ctx.first_params();
+        CNFOT_ASSUME_SHARED(F);
 #pragma unroll
-        for (int j = 0; j < Pp; ++j) theta[j] = W[j];
+        for (int j = 0; j < Pp; j += 4) {
+          T w[4];
+          load4<T>(F + j, w);
+          theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
+        }
       } else {
-        T in[kMaxDim + 1];
-        in[0] = t;
-        for (int j = 0; j < d; ++j) in[1 + j] = cvec[perm_at(layer, j, D)];
-        T hid[M * H];
-        mlp_forward<T, Net>(W + mlp_offset<Net>(D, layer, d), d + 1, in, hid, theta);
+        const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
+        CNFOT_ASSUME_SHARED(W);
+        fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
+        mlp_forward<T, Net>(W, d + 1, tl, theta);
       }
       SplineState<T, K> st;
       T out, ld;
-      if (dir == 0) rqs_inverse<T, K>(v[i], theta, sc, st, out, ld);
+      if (DIR == 0) rqs_inverse<T, K>(v[i], theta, sc, st, out, ld);
       else rqs_forward<T, K>(v[i], theta, sc, st, out, ld);
       u[i] = out;
       ld_total += ld;
@@ -233,40 +325,54 @@ CNFOT_CALL T flow_pass(int dir, const DimsT& dm, const T* W, const SplineConsts<
 // Reverse mode of flow_pass.  On entry g[0..D) is the adjoint of the pass
 // output (states[L*D..]), gld the adjoint of the summed log-det; on exit g is
 // the adjoint of the pass input.  gfirst[Pp] accumulates the adjoint of the
-// shared `first` parameter (flushed to the sink once per kernel).
-template <typename T, class Net, class DimsT, class Sink>
-CNFOT_CALL void flow_pass_bwd(int dir, const DimsT& dm, const T* W, const SplineConsts<T>& sc,
-                            T t, const T* states, T* g, T gld, T* gfirst, Sink& sink) {
-  constexpr int H = Net::kH, K = Net::kK, M = Net::kM, Pp = Net::kPp;
+// shared `first` parameter (flushed to the sink once per kernel).  Conditioner
+// activations are re-computed, not stored.
+template <int DIR, typename T, class Net, class DimsT, class Ctx>
+CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* states,
+                              T* g, T gld, T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
+  constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
+  assume_tiles_shared<T, Net>(tl, true);
+  CNFOT_ASSUME_LOCAL(states);
+  CNFOT_ASSUME_LOCAL(g);
+  CNFOT_ASSUME_LOCAL(gfirst);
+#pragma unroll 1
   for (int s = L - 1; s >= 0; --s) {
-    const int layer = dir == 0 ? s : L - 1 - s;
+    const int layer = DIR == 0 ? s : L - 1 - s;
     const T* v = states + s * D;
     const T* u = states + (s + 1) * D;
-    const T* cvec = dir == 0 ? v : u;
-    // dir 0: any order works, ascending keeps the in-place update valid;
-    // dir 1: descending, so g[coordinate] is complete before it is consumed.
+    const T* cvec = DIR == 0 ? v : u;
+    // DIR 0: any order works, ascending keeps the in-place update valid;
+    // DIR 1: descending, so g[coordinate] is complete before it is consumed.
+#pragma unroll 1
     for (int dd = 0; dd < D; ++dd) {
-      const int d = dir == 0 ? dd : D - 1 - dd;
+      const int d = DIR == 0 ? dd : D - 1 - dd;
       const int i = perm_at(layer, d, D);
       T theta[Pp], gtheta[Pp];
-      T in[kMaxDim + 1];
-      T hid[M * H];
       int w_off = 0;
+      const T* W = nullptr;
       if (d == 0) {
+        const T* F = ctx.first_params();
+        CNFOT_ASSUME_SHARED(F);
 #pragma unroll
-        for (int j = 0; j < Pp; ++j) theta[j] = W[j];
+        for (int j = 0; j < Pp; j += 4) {
+          T w[4];
+          load4<T>(F + j, w);
+          theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
+        }
       } else {
-        in[0] = t;
-        for (int j = 0; j < d; ++j) in[1 + j] = cvec[perm_at(layer, j, D)];
         w_off = mlp_offset<Net>(D, layer, d);
-        mlp_forward<T, Net>(W + w_off, d + 1, in, hid, theta);
+        ctx.begin();  // the tiles of the previous conditioner are free again
+        W = ctx.weights(w_off, (d + 1) * H + Net::kMlpConst);
+        CNFOT_ASSUME_SHARED(W);
+        fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
+        mlp_forward<T, Net>(W, d + 1, tl, theta);
       }
       SplineState<T, K> st;
       T out, ld;
 #pragma unroll
       for (int j = 0; j < Pp; ++j) gtheta[j] = (T)0;
-      if (dir == 0) {
+      if (DIR == 0) {
         rqs_inverse<T, K>(v[i], theta, sc, st, out, ld);
         g[i] = rqs_inverse_bwd<T, K>(v[i], st, sc, g[i], gld, gtheta);
       } else {
@@ -278,8 +384,9 @@ CNFOT_CALL void flow_pass_bwd(int dir, const DimsT& dm, const T* W, const Spline
         for (int j = 0; j < Pp; ++j) gfirst[j] += gtheta[j];
       } else {
         T gin[kMaxDim + 1];
-        mlp_backward<T, Net, Sink>(W + w_off, w_off, d + 1, in, hid, gtheta, gin, sink);
+        mlp_backward<T, Net>(W, d + 1, tl, gtheta, gin);
         for (int j = 0; j < d; ++j) g[perm_at(layer, j, D)] += gin[1 + j];
+        ctx.commit(w_off, d + 1, tl);
       }
     }
   }

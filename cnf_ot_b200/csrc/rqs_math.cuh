@@ -25,6 +25,16 @@
 #define CNFOT_CALL inline
 #endif
 
+// Address-space hint: inside device code the pointer is known to address shared memory,
+// so loads/stores through it compile to LDS/STS instead of generic LD/ST.
+#if defined(__CUDA_ARCH__)
+#define CNFOT_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define CNFOT_ASSUME_LOCAL(p) __builtin_assume(__isLocal(p))
+#else
+#define CNFOT_ASSUME_SHARED(p) ((void)0)
+#define CNFOT_ASSUME_LOCAL(p) ((void)0)
+#endif
+
 namespace cnfot {
 
 template <typename T>

@@ -4,7 +4,7 @@
 // /root/reference/cnf_ot/mfc/applications.py needs, adds the row's weighted
 // contribution to the loss slots, and immediately back-propagates through the
 // passes (re-computing conditioner activations), pushing weight gradients to
-// the sink.  Nothing per-row is ever written to HBM.
+// the CTA context.  Nothing per-row is ever written to HBM.
 //
 //   row_nll            kl_loss_fn                    applications.py:11-86
 //   row_sample_terms   reverse_kl_loss_fn            applications.py:129-163
@@ -116,32 +116,32 @@ CNFOT_HD void drift_pullback(int kind, T a, const T* r, int D, const T* gres, T*
 }
 
 // ---- KL row: -w log p(data | t) --------------------------------------------------
-template <typename T, class Net, class DimsT, class Sink>
-CNFOT_HD T row_nll(const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t, const T* data,
-                   T weight, T* gfirst, Sink& sink) {
+template <typename T, class Net, class DimsT, class Ctx>
+CNFOT_HD T row_nll(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* data, T weight,
+                   T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
   for (int i = 0; i < D; ++i) st[i] = data[i];
-  T ld = flow_pass<T, Net, DimsT>(1, dm, W, sc, t, st);
+  T ld = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
   const T* x = st + L * D;
   T lp = base_log_prob<T>(x, D) + ld;
   T g[kMaxDim];
   for (int i = 0; i < D; ++i) g[i] = weight * x[i];  // d(-w lp)/dx = w x
-  flow_pass_bwd<T, Net, DimsT, Sink>(1, dm, W, sc, t, st, g, -weight, gfirst, sink);
+  flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, st, g, -weight, gfirst, tl, ctx);
   return -weight * lp;
 }
 
 // ---- rows pushed through the sample direction at one time t ----------------------
 // do_fit: reverse-KL term  w_fit (log p(y) - log q_t(y));  do_pot: w_pot V(y).
-template <typename T, class Net, class DimsT, class Sink>
-CNFOT_HD void row_sample_terms(const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t,
+template <typename T, class Net, class DimsT, class Ctx>
+CNFOT_HD void row_sample_terms(const DimsT& dm, const SplineConsts<T>& sc, T t,
                                const T* latent, bool do_fit, bool do_pot,
                                const StepConsts<T>& pc, T* loss_fit, T* loss_pot, T* gfirst,
-                               Sink& sink) {
+                               const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
   for (int i = 0; i < D; ++i) st[i] = latent[i];
-  T fldj = flow_pass<T, Net, DimsT>(0, dm, W, sc, t, st);
+  T fldj = flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
   const T* y = st + L * D;
   T g[kMaxDim];
   for (int i = 0; i < D; ++i) g[i] = (T)0;
@@ -179,7 +179,7 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const T* W, const SplineConsts<T
     *loss_pot += pc.w_pot * v;
     for (int i = 0; i < D; ++i) g[i] += pc.w_pot * gp[i];
   }
-  flow_pass_bwd<T, Net, DimsT, Sink>(0, dm, W, sc, t, st, g, gld, gfirst, sink);
+  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, st, g, gld, gfirst, tl, ctx);
 }
 
 // ---- kinetic-energy rows ----------------------------------------------------------
@@ -187,19 +187,19 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const T* W, const SplineConsts<T
 // rwpo/fp:  v += kappa * score,  score_i = (log p(r3 + e_i dx/2) - log p(r3 - e_i dx/2)) / dx
 //           fp additionally subtracts the drift target.
 // Every pass starts from the SAME latent row (the reference reuses one PRNG key).
-template <typename T, class Net, class DimsT, class Sink>
-CNFOT_HD void row_kinetic(const DimsT& dm, const T* W, const SplineConsts<T>& sc, T t,
-                          const T* latent, const StepConsts<T>& pc, T* loss_kin, T* loss_pot,
-                          T* gfirst, Sink& sink) {
+template <typename T, class Net, class DimsT, class Ctx>
+CNFOT_HD void row_kinetic(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* latent,
+                          const StepConsts<T>& pc, T* loss_kin, T* loss_pot, T* gfirst,
+                          const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   const bool with_score = pc.type != kOT;
   const bool need_r3 = with_score || pc.potential == kPotObstacle;
   const T t1 = t - pc.dt / (T)2, t2 = t + pc.dt / (T)2;
   T s1[kMaxStateFloats], s2[kMaxStateFloats], s3[kMaxStateFloats];
   for (int i = 0; i < D; ++i) { s1[i] = latent[i]; s2[i] = latent[i]; s3[i] = latent[i]; }
-  flow_pass<T, Net, DimsT>(0, dm, W, sc, t1, s1);
-  flow_pass<T, Net, DimsT>(0, dm, W, sc, t2, s2);
-  if (need_r3) flow_pass<T, Net, DimsT>(0, dm, W, sc, t, s3);
+  flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t1, s1, tl, ctx);
+  flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t2, s2, tl, ctx);
+  if (need_r3) flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t, s3, tl, ctx);
   const T* r1 = s1 + L * D;
   const T* r2 = s2 + L * D;
   const T* r3 = s3 + L * D;
@@ -231,8 +231,8 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const T* W, const SplineConsts<T>& sc
       for (int j = 0; j < D; ++j) { sp[j] = r3[j]; sm[j] = r3[j]; }
       sp[i] = r3[i] + pc.dx / (T)2;
       sm[i] = r3[i] - pc.dx / (T)2;
-      T ldp = flow_pass<T, Net, DimsT>(1, dm, W, sc, t, sp);
-      T ldm = flow_pass<T, Net, DimsT>(1, dm, W, sc, t, sm);
+      T ldp = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, sp, tl, ctx);
+      T ldm = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, sm, tl, ctx);
       T lpp = base_log_prob<T>(sp + L * D, D) + ldp;
       T lpm = base_log_prob<T>(sm + L * D, D) + ldm;
       T score = (lpp - lpm) / pc.dx;
@@ -243,10 +243,10 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const T* W, const SplineConsts<T>& sc
       T glp = gres[i] * pc.kappa / pc.dx;
       T g[kMaxDim];
       for (int j = 0; j < D; ++j) g[j] = -glp * sp[L * D + j];  // d lp / d latent = -x
-      flow_pass_bwd<T, Net, DimsT, Sink>(1, dm, W, sc, t, sp, g, glp, gfirst, sink);
+      flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, sp, g, glp, gfirst, tl, ctx);
       for (int j = 0; j < D; ++j) g3[j] += g[j];
       for (int j = 0; j < D; ++j) g[j] = glp * sm[L * D + j];
-      flow_pass_bwd<T, Net, DimsT, Sink>(1, dm, W, sc, t, sm, g, -glp, gfirst, sink);
+      flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, sm, g, -glp, gfirst, tl, ctx);
       for (int j = 0; j < D; ++j) g3[j] += g[j];
     }
     *loss_kin += pc.w_kin * acc;
@@ -254,9 +254,9 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const T* W, const SplineConsts<T>& sc
   }
   T g1[kMaxDim];
   for (int i = 0; i < D; ++i) g1[i] = -g2[i];
-  flow_pass_bwd<T, Net, DimsT, Sink>(0, dm, W, sc, t2, s2, g2, (T)0, gfirst, sink);
-  flow_pass_bwd<T, Net, DimsT, Sink>(0, dm, W, sc, t1, s1, g1, (T)0, gfirst, sink);
-  if (need_r3) flow_pass_bwd<T, Net, DimsT, Sink>(0, dm, W, sc, t, s3, g3, (T)0, gfirst, sink);
+  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t2, s2, g2, (T)0, gfirst, tl, ctx);
+  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t1, s1, g1, (T)0, gfirst, tl, ctx);
+  if (need_r3) flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, s3, g3, (T)0, gfirst, tl, ctx);
 }
 
 }  // namespace cnfot

@@ -9,14 +9,43 @@
 
 using namespace cnfot;
 
-template <typename T>
+// plain arrays standing in for the CTA's shared-memory row tiles
+template <typename T, class Net>
+struct HostTiles {
+  T in[kMaxDim + 4];
+  T hid[Net::kM][Net::kH];
+  T gh[Net::kM][Net::kH];
+  T gth[Net::kPp];
+  RowTiles<T, Net> view() {
+    RowTiles<T, Net> tl;
+    tl.in = in;
+    for (int m = 0; m < Net::kM; ++m) { tl.hid[m] = hid[m]; tl.gh[m] = gh[m]; }
+    tl.gth = gth;
+    return tl;
+  }
+};
+
+template <typename T, class Net>
 struct HostSink {
-  double* G;  // gradient blob (double accumulation)
-  template <int NAMAX, int NG>
-  void outer(int w_off, int Na, const T* a, const T* g) {
+  double* G;     // gradient blob (double accumulation)
+  const T* Wb;   // weight blob
+  const T* first_params() const { return Wb; }
+  const T* weights(int w_off, int) const { return Wb + w_off; }
+  void begin() {}
+  static void outer(double* dst, int Na, const T* a, int Ng, const T* g) {
     for (int i = 0; i < Na; ++i)
-      for (int j = 0; j < NG; ++j) G[w_off + i * NG + j] += (double)a[i] * (double)g[j];
-    for (int j = 0; j < NG; ++j) G[w_off + Na * NG + j] += (double)g[j];
+      for (int j = 0; j < Ng; ++j) dst[i * Ng + j] += (double)a[i] * (double)g[j];
+    for (int j = 0; j < Ng; ++j) dst[Na * Ng + j] += (double)g[j];
+  }
+  void commit(int w_off, int n_in, const RowTiles<T, Net>& tl) {
+    constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
+    outer(G + w_off, n_in, tl.in, H, tl.gh[0]);
+    int off = w_off + n_in * H + H;
+    for (int m = 1; m < M; ++m) {
+      outer(G + off, H, tl.hid[m - 1], H, tl.gh[m]);
+      off += H * H + H;
+    }
+    outer(G + off, H, tl.hid[M - 1], Pp, tl.gth);
   }
 };
 
@@ -26,10 +55,14 @@ static int flow_eval(int D, int L, int dir, int64_t rows, const T* W, const T* i
   if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
   Dims<0, 0> dm{D, L};
   SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
+  HostTiles<T, Net> ht;
+  RowTiles<T, Net> tl = ht.view();
+  HostSink<T, Net> sink{nullptr, W};
   for (int64_t r = 0; r < rows; ++r) {
     T st[kMaxStateFloats];
     for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
-    T l = flow_pass<T, Net, Dims<0, 0>>(dir, dm, W, sc, cond[r * cs], st);
+    T l = dir == 0 ? flow_pass<0, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, tl, sink)
+                   : flow_pass<1, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, tl, sink);
     for (int i = 0; i < D; ++i) out[r * D + i] = st[L * D + i];
     if (ld) {
       if (add_base) l = dir == 0 ? base_log_prob<T>(st, D) - l : base_log_prob<T>(st + L * D, D) + l;
@@ -45,12 +78,15 @@ static int flow_vjp(int D, int L, int dir, int64_t rows, const T* W, const T* in
   if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
   Dims<0, 0> dm{D, L};
   SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
-  HostSink<T> sink{G};
+  HostSink<T, Net> sink{G, W};
+  HostTiles<T, Net> ht;
+  RowTiles<T, Net> tl = ht.view();
   std::vector<T> gfirst(Net::kPp, (T)0);
   for (int64_t r = 0; r < rows; ++r) {
     T st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
-    flow_pass<T, Net, Dims<0, 0>>(dir, dm, W, sc, cond[r * cs], st);
+    if (dir == 0) flow_pass<0, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, tl, sink);
+    else flow_pass<1, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, tl, sink);
     T gl = gld ? gld[r] : (T)0;
     for (int i = 0; i < D; ++i) g[i] = gout[r * D + i];
     T gl_pass = gl;
@@ -58,8 +94,12 @@ static int flow_vjp(int D, int L, int dir, int64_t rows, const T* W, const T* in
       if (dir == 0) gl_pass = -gl;                                         // lp = logN(in) - fldj
       else for (int i = 0; i < D; ++i) g[i] += gl * (-st[L * D + i]);     // lp = logN(out) + ildj
     }
-    flow_pass_bwd<T, Net, Dims<0, 0>, HostSink<T>>(dir, dm, W, sc, cond[r * cs], st, g, gl_pass,
-                                                    gfirst.data(), sink);
+    if (dir == 0)
+      flow_pass_bwd<0, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, g, gl_pass,
+                                                             gfirst.data(), tl, sink);
+    else
+      flow_pass_bwd<1, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, g, gl_pass,
+                                                             gfirst.data(), tl, sink);
     if (add_base && dir == 0) for (int i = 0; i < D; ++i) g[i] += gl * (-st[i]);
     if (gin) for (int i = 0; i < D; ++i) gin[r * D + i] = g[i];
   }
@@ -78,25 +118,27 @@ static int step(int D, int L, const cnfot_problem_desc* pd, const T* W, const T*
   StepConsts<T> pc;
   const char* err = nullptr;
   if (make_step_consts<T>(*pd, D, lambda, gB, gb, n_t, &pc, &err)) return 2;
-  HostSink<T> sink{G};
+  HostSink<T, Net> sink{G, W};
+  HostTiles<T, Net> ht;
+  RowTiles<T, Net> tl = ht.view();
   std::vector<T> gfirst(Net::kPp, (T)0);
   for (int s = 0; s < kNumSlots; ++s) slots[s] = 0.0;
   if (pd->type == CNFOT_OT) {
     for (int64_t r = 0; r < rows_B; ++r) {
-      slots[kSlotFit0] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T>>(
-          dm, W, sc, (T)0, src + r * D, pc.w_fit, gfirst.data(), sink);
-      slots[kSlotFitT] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T>>(
-          dm, W, sc, pc.horizon, tgt + r * D, pc.w_fit, gfirst.data(), sink);
+      slots[kSlotFit0] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T, Net>>(
+          dm, sc, (T)0, src + r * D, pc.w_fit, gfirst.data(), tl, sink);
+      slots[kSlotFitT] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T, Net>>(
+          dm, sc, pc.horizon, tgt + r * D, pc.w_fit, gfirst.data(), tl, sink);
     }
   } else {
     for (int64_t r = 0; r < rows_B; ++r) {
       T lf = 0, lp = 0;
-      row_sample_terms<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, (T)0, latent + r * D, true,
-                                                        false, pc, &lf, &lp, gfirst.data(), sink);
+      row_sample_terms<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, (T)0, latent + r * D, true,
+                                                             false, pc, &lf, &lp, gfirst.data(), tl, sink);
       if (pd->type == CNFOT_RWPO)
-        row_sample_terms<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, pc.horizon, latent + r * D,
-                                                          false, true, pc, &lf, &lp,
-                                                          gfirst.data(), sink);
+        row_sample_terms<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, pc.horizon, latent + r * D,
+                                                               false, true, pc, &lf, &lp,
+                                                               gfirst.data(), tl, sink);
       slots[kSlotFit0] += (double)lf;
       slots[kSlotPotential] += (double)lp;
     }
@@ -104,8 +146,8 @@ static int step(int D, int L, const cnfot_problem_desc* pd, const T* W, const T*
   for (int it = 0; it < n_t; ++it)
     for (int64_t r = 0; r < rows_b; ++r) {
       T lk = 0, lp = 0;
-      row_kinetic<T, Net, Dims<0, 0>, HostSink<T>>(dm, W, sc, (T)t_batch[it], latent_sub + r * D,
-                                                   pc, &lk, &lp, gfirst.data(), sink);
+      row_kinetic<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, (T)t_batch[it], latent_sub + r * D,
+                                                        pc, &lk, &lp, gfirst.data(), tl, sink);
       slots[kSlotKinetic] += (double)lk;
       slots[kSlotPotential] += (double)lp;
     }
