@@ -13,14 +13,27 @@ namespace cnfot {
 constexpr int kTile = 128;       // rows per CTA tile == threads per CTA (one row per thread)
 constexpr int kWarps = kTile / 32;
 
-// Row stride (floats) for a staged [kTile][n] tile, n a multiple of 4: an odd
-// number of 16-byte units, so 8 consecutive rows hit 8 distinct bank groups and
-// both the per-row float4 accesses and the strided float4 reads of the
-// reduction are conflict-free.
+// Staged [kTile][n] tiles (n a multiple of 4) are read 128 bits at a time by 8
+// consecutive rows at once; those 8 accesses must fall into 8 distinct 16-byte bank
+// groups.  With C = n/4 chunks per row:
+//   C odd            dense rows already do (row stride is an odd number of groups)
+//   C = 2, 4, 8k     dense rows + XOR swizzle of the chunk index with tile_swizzle(row)
+//   other even C     pad the row to an odd number of groups (no swizzle)
+__host__ __device__ inline bool tile_uses_swizzle(int n) {
+  const int c = (n + 3) / 4;
+  return c == 2 || c == 4 || (c >= 8 && c % 8 == 0);
+}
 __host__ __device__ inline int staged_stride(int n) {
   int q = (n + 3) / 4;
-  if ((q & 1) == 0) q += 1;
+  if ((q & 1) == 0 && !tile_uses_swizzle(n)) q += 1;
   return q * 4;
+}
+__host__ __device__ inline int tile_swizzle(int n, int row) {
+  if (!tile_uses_swizzle(n)) return 0;
+  const int c = (n + 3) / 4;
+  if (c == 2) return (row >> 2) & 1;
+  if (c == 4) return (row >> 1) & 3;
+  return row & 7;
 }
 
 // Shared-memory layout of one CTA (offsets in floats).
@@ -81,6 +94,8 @@ __device__ inline RowTiles<float, Net> make_row_tiles(float* smem, const SmemPla
     tl.gh[m] = p.off_gh >= 0 ? smem + p.off_gh + (m * kTile + r) * p.ld_h : nullptr;
   }
   tl.gth = p.off_gth >= 0 ? smem + p.off_gth + r * p.ld_p : nullptr;
+  tl.sw_h = tile_swizzle(Net::kH, r);
+  tl.sw_p = tile_swizzle(Net::kPp, r);
   return tl;
 }
 
@@ -150,15 +165,10 @@ struct DeviceCtx {
     constexpr int nbo = CH * CP;                       // output layer
     const int total = nb0 + (M - 1) * nbm + nbo;
     float* acc = smem + p.off_acc + w_off;
-    CNFOT_ASSUME_SHARED(acc);
     const float* t_in = smem + p.off_in;
     const float* t_hid = smem + p.off_hid;
     const float* t_gh = smem + p.off_gh;
     const float* t_gth = smem + p.off_gth;
-    CNFOT_ASSUME_SHARED(t_in);
-    CNFOT_ASSUME_SHARED(t_hid);
-    CNFOT_ASSUME_SHARED(t_gh);
-    CNFOT_ASSUME_SHARED(t_gth);
     const int off_hidden0 = n_in * H + H;             // first hidden (H x H) matrix
     for (int base = warp * 4; base < total; base += 4 * kWarps) {
       const int b = base + slot;
@@ -188,7 +198,12 @@ struct DeviceCtx {
       float c[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) c[e] = 0.f;
-      if (valid) block_accumulate(pa + rg * lda + rb * 4, lda, pg + rg * ldg + cb * 4, ldg, c);
+      if (valid) {
+        // rows rg, rg+8, ...: their swizzle depends on rg only (the +8k does not reach it)
+        const int sa = pa == t_in ? 0 : tile_swizzle(H, rg);
+        const int sg = ncol == H ? tile_swizzle(H, rg) : tile_swizzle(Pp, rg);
+        block_accumulate(pa + rg * lda + ((rb ^ sa) << 2), lda, pg + rg * ldg + ((cb ^ sg) << 2), ldg, c);
+      }
       // reduce-scatter over the 8 row groups (lane bits 0..2)
       const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
       float v8[8], v4[4], v2[2];
@@ -234,9 +249,10 @@ struct DeviceCtx {
         dst = acc + off_hidden0 + (M - 1) * (H * H + H) + H * Pp;
       }
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int sg = task < M * CH ? tile_swizzle(H, lane) : tile_swizzle(Pp, lane);
 #pragma unroll
       for (int k = 0; k < kTile / 32; ++k) {
-        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * ldg + cb * 4);
+        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * ldg + ((cb ^ sg) << 2));
         s.x += g4.x; s.y += g4.y; s.z += g4.z; s.w += g4.w;
       }
 #pragma unroll
@@ -265,15 +281,17 @@ struct DeviceCtx {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < Pp; j += 4)
-      *reinterpret_cast<float4*>(tl.gth + j) = make_float4(gfirst[j], gfirst[j + 1], gfirst[j + 2], gfirst[j + 3]);
+      *reinterpret_cast<float4*>(tl.gth + chunk_at(j, tl.sw_p)) =
+          make_float4(gfirst[j], gfirst[j + 1], gfirst[j + 2], gfirst[j + 3]);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* pg = smem + p.off_gth;
     for (int cb = warp; cb < Pp / 4; cb += kWarps) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int sg = tile_swizzle(Pp, lane);
 #pragma unroll
       for (int k = 0; k < kTile / 32; ++k) {
-        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * p.ld_p + cb * 4);
+        const float4 g4 = *reinterpret_cast<const float4*>(pg + (k * 32 + lane) * p.ld_p + ((cb ^ sg) << 2));
         s.x += g4.x; s.y += g4.y; s.z += g4.z; s.w += g4.w;
       }
 #pragma unroll

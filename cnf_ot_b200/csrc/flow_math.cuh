@@ -141,13 +141,21 @@ CNFOT_HD T dot_row(const T* g, const T* row) {
 // the CTA-wide weight-gradient reduction (DeviceSink) reads, so nothing is copied
 // twice, and the layer loops below can stay rolled (small code: the fully unrolled
 // register version overflowed the instruction cache).  On the host they are plain arrays.
+// A row is stored as 16-byte chunks; chunk c lives at chunk position c ^ sw (sw_h for the
+// H-wide tiles, sw_p for the Pp-wide one).  On the device sw is a per-row XOR swizzle that
+// makes the strided 128-bit accesses of the reduction bank-conflict-free without padding
+// (see tile_swizzle in device_common.cuh); on the host it is 0.
 template <typename T, class Net>
 struct RowTiles {
   T* in;                 // [roundup4(n_in)]  MLP input [t, conditioning coords...], zero padded
   T* hid[Net::kM];       // [H]   post-ReLU activations of hidden layer m
   T* gh[Net::kM];        // [H]   adjoint of the pre-activations of hidden layer m
   T* gth;                // [Pp]  adjoint of the raw spline params (the MLP output)
+  int sw_h, sw_p;
 };
+
+// element offset of the 4-float chunk that starts at logical element j (j % 4 == 0)
+CNFOT_HD int chunk_at(int j, int sw) { return ((j >> 2) ^ sw) << 2; }
 
 // Conditioner forward: tiles.in -> tiles.hid[*] -> theta (registers).
 template <typename T, class Net>
@@ -161,7 +169,7 @@ CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* t
   for (int i = 0; i < n_in; ++i) axpy_row<T, H>(tl.in[i], W + i * H, acc);
 #pragma unroll
   for (int j = 0; j < H; j += 4)
-    store4<T>(tl.hid[0] + j, m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0), m_max(acc[j + 2], (T)0),
+    store4<T>(tl.hid[0] + chunk_at(j, tl.sw_h), m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0), m_max(acc[j + 2], (T)0),
               m_max(acc[j + 3], (T)0));
   const T* Wm = b0 + H;
 #pragma unroll
@@ -172,13 +180,13 @@ CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* t
 #pragma unroll 1
     for (int i = 0; i < H; i += 4) {
       T a[4];
-      load4<T>(tl.hid[m - 1] + i, a);
+      load4<T>(tl.hid[m - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
       for (int q = 0; q < 4; ++q) axpy_row<T, H>(a[q], Wm + (i + q) * H, acc);
     }
 #pragma unroll
     for (int j = 0; j < H; j += 4)
-      store4<T>(tl.hid[m] + j, m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0),
+      store4<T>(tl.hid[m] + chunk_at(j, tl.sw_h), m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0),
                 m_max(acc[j + 2], (T)0), m_max(acc[j + 3], (T)0));
     Wm = bm + H;
   }
@@ -188,7 +196,7 @@ CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* t
 #pragma unroll 1
   for (int i = 0; i < H; i += 4) {
     T a[4];
-    load4<T>(tl.hid[M - 1] + i, a);
+    load4<T>(tl.hid[M - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
     for (int q = 0; q < 4; ++q) axpy_row<T, Pp>(a[q], Wm + (i + q) * Pp, theta);
   }
@@ -203,18 +211,18 @@ CNFOT_HD void mlp_backward(const T* W, int n_in, const RowTiles<T, Net>& tl, con
   constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
 #pragma unroll
   for (int j = 0; j < Pp; j += 4)
-    store4<T>(tl.gth + j, gtheta[j], gtheta[j + 1], gtheta[j + 2], gtheta[j + 3]);
+    store4<T>(tl.gth + chunk_at(j, tl.sw_p), gtheta[j], gtheta[j + 1], gtheta[j + 2], gtheta[j + 3]);
   const T* Wout = W + n_in * H + H + (M - 1) * (H * H + H);
 #pragma unroll 1
   for (int i = 0; i < H; i += 4) {
     T a[4], r[4];
-    load4<T>(tl.hid[M - 1] + i, a);
+    load4<T>(tl.hid[M - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       T v = dot_row<T, Pp>(gtheta, Wout + (i + q) * Pp);
       r[q] = a[q] > (T)0 ? v : (T)0;
     }
-    store4<T>(tl.gh[M - 1] + i, r[0], r[1], r[2], r[3]);
+    store4<T>(tl.gh[M - 1] + chunk_at(i, tl.sw_h), r[0], r[1], r[2], r[3]);
   }
   T g[H];
 #pragma unroll
@@ -223,25 +231,25 @@ CNFOT_HD void mlp_backward(const T* W, int n_in, const RowTiles<T, Net>& tl, con
 #pragma unroll
     for (int j = 0; j < H; j += 4) {
       T v[4];
-      load4<T>(tl.gh[m] + j, v);
+      load4<T>(tl.gh[m] + chunk_at(j, tl.sw_h), v);
       g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
     }
 #pragma unroll 1
     for (int i = 0; i < H; i += 4) {
       T a[4], r[4];
-      load4<T>(tl.hid[m - 1] + i, a);
+      load4<T>(tl.hid[m - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         T v = dot_row<T, H>(g, Wm + (i + q) * H);
         r[q] = a[q] > (T)0 ? v : (T)0;
       }
-      store4<T>(tl.gh[m - 1] + i, r[0], r[1], r[2], r[3]);
+      store4<T>(tl.gh[m - 1] + chunk_at(i, tl.sw_h), r[0], r[1], r[2], r[3]);
     }
   }
 #pragma unroll
   for (int j = 0; j < H; j += 4) {
     T v[4];
-    load4<T>(tl.gh[0] + j, v);
+    load4<T>(tl.gh[0] + chunk_at(j, tl.sw_h), v);
     g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
   }
 #pragma unroll 1

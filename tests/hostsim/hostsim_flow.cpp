@@ -21,6 +21,8 @@ struct HostTiles {
     tl.in = in;
     for (int m = 0; m < Net::kM; ++m) { tl.hid[m] = hid[m]; tl.gh[m] = gh[m]; }
     tl.gth = gth;
+    tl.sw_h = 0;
+    tl.sw_p = 0;
     return tl;
   }
 };
