@@ -259,6 +259,8 @@ def run_ours(args):
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
+    # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     td.init_process_group("nccl", device_id=dev)
   _lib.load()
 
