@@ -60,6 +60,7 @@ _STEP = [c_void_p, _F, _P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_v
 SIGNATURES = {
   "cnfot_abi_version": (c_int32, []),
   "cnfot_last_error": (c_char_p, []),
+  "cnfot_last_launch_info": (None, [POINTER(c_int32)] * 4),
   "cnfot_param_count": (c_int64, [_F]),
   "cnfot_spline_param_stride": (c_int64, [_F]),
   "cnfot_offset_first": (c_int64, [_F]),
@@ -104,6 +105,13 @@ def load() -> ctypes.CDLL:
     raise CnfotError("libcnfot.so ABI version mismatch; rebuild")
   _lib = lib
   return lib
+
+
+def last_launch_info() -> dict:
+  vals = [c_int32(0) for _ in range(4)]
+  load().cnfot_last_launch_info(*[ctypes.byref(v) for v in vals])
+  return {"grid": vals[0].value, "smem_bytes": vals[1].value, "ctas_per_sm": vals[2].value,
+          "tensor_cores": bool(vals[3].value)}
 
 
 def check(rc: int) -> None:

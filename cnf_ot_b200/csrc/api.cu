@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cnfot.h"
@@ -101,13 +102,32 @@ struct LaunchCfg {
   int grid;
   size_t smem;
 };
+static thread_local int g_last_launch[4] = {0, 0, 0, 0};
 
 // Shared-memory plan: weights live in shared memory when weights + accumulators + row
 // tiles leave room for at least two CTAs per SM; otherwise they are read from global
 // memory (L1-cached broadcast loads).
-static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp) {
+// The tcgen05 engine variant (tc_engine.cuh) exists for 16-wide layers with resident weights.
+// Round-1 measurements: numerically equivalent, but its per-layer
+// issue / commit / wait round trips make it slower than the CUDA-core layers at hidden = 16,
+// so it is opt-in: CNFOT_TC=1 in the environment (read on every call).
+static bool tc_enabled() {
+  const char* e = getenv("CNFOT_TC");
+  return e && e[0] == '1';
+}
+
+static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, bool* use_tc) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
+  *use_tc = false;
+  if (tc_enabled() && tc_available(lay)) {
+    SmemPlan t = plan_smem(lay, with_grad, true, true);
+    if ((int64_t)t.floats * 4 * 2 <= di.max_smem_optin) {
+      *sp = t;
+      *use_tc = true;
+      return 0;
+    }
+  }
   SmemPlan p = plan_smem(lay, with_grad, true);
   if ((int64_t)p.floats * 4 * 2 > di.max_smem_optin) p = plan_smem(lay, with_grad, false);
   *sp = p;
@@ -127,12 +147,42 @@ static int configure(const void* kernel, const SmemPlan& sp, int64_t tiles, Laun
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTile, smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (sp.off_wmma >= 0) {
+    // The occupancy query answers 1 for any kernel that contains tcgen05.alloc (it cannot know how
+    // many of the 512 TMEM columns a CTA takes; ours takes 32).  Size the persistent grid from the
+    // real limits instead: shared memory and registers.
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes");
+    int smem_sm = 0, regs_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, di.device);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, di.device);
+    int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
+    int by_regs = regs_sm / (fa.numRegs * kTile > 0 ? fa.numRegs * kTile : 1);
+    int by_tmem = 512 / 32;
+    occ = by_smem < by_regs ? by_smem : by_regs;
+    if (occ > by_tmem) occ = by_tmem;
+  }
+  if (getenv("CNFOT_DEBUG")) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kernel);
+    int o0 = 0, o1 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, kernel, kTile, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, kernel, kTile, 60000);
+    fprintf(stderr, "[cnfot] occ=%d (smem %zu) occ@0=%d occ@60000=%d regs=%d static_smem=%zu local=%zu maxdyn=%d carveout=%d\n",
+            occ, smem, o0, o1, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes,
+            fa.preferredShmemCarveout);
+  }
   if (occ < 1) return fail(CNFOT_ERR_CUDA, "kernel does not fit on an SM");
   int64_t cap = (int64_t)di.num_sms * occ;
   if (cap > kMaxGrid) cap = kMaxGrid;
   int64_t g = tiles < cap ? tiles : cap;
   cfg->grid = (int)(g > 0 ? g : 1);
   cfg->smem = smem;
+  g_last_launch[0] = cfg->grid;
+  g_last_launch[1] = (int)smem;
+  g_last_launch[2] = occ;
+  g_last_launch[3] = sp.off_wmma >= 0 ? 1 : 0;
   return 0;
 }
 
@@ -220,6 +270,12 @@ using namespace cnfot;
 extern "C" {
 
 int cnfot_abi_version(void) { return CNFOT_ABI_VERSION; }
+void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* tensor_cores) {
+  if (grid) *grid = g_last_launch[0];
+  if (smem_bytes) *smem_bytes = g_last_launch[1];
+  if (ctas_per_sm) *ctas_per_sm = g_last_launch[2];
+  if (tensor_cores) *tensor_cores = g_last_launch[3];
+}
 const char* cnfot_last_error(void) { return g_err; }
 
 int64_t cnfot_param_count(const cnfot_flow_desc* flow) {
@@ -340,9 +396,10 @@ static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, co
   if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
   if (rows == 0) return 0;
   if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
-  const void* kernel = find_flow_eval_kernel(lay);
   SmemPlan sp;
-  if (int rc = make_plan(lay, false, &sp)) return rc;
+  bool use_tc;
+  if (int rc = make_plan(lay, false, &sp, &use_tc)) return rc;
+  const void* kernel = find_flow_eval_kernel(lay, use_tc);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   EvalArgs a;
@@ -393,9 +450,10 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
     return 0;
   }
   if (!in || !cond || !g_out) return fail(CNFOT_ERR_ARG, "NULL buffer");
-  const void* kernel = find_flow_vjp_kernel(lay);
   SmemPlan sp;
-  if (int rc = make_plan(lay, true, &sp)) return rc;
+  bool use_tc;
+  if (int rc = make_plan(lay, true, &sp, &use_tc)) return rc;
+  const void* kernel = find_flow_vjp_kernel(lay, use_tc);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   unsigned long long* counter;
@@ -487,9 +545,10 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     return 0;
   }
-  const void* kernel = find_mfc_step_kernel(lay);
   SmemPlan sp;
-  if (int rc = make_plan(lay, true, &sp)) return rc;
+  bool use_tc;
+  if (int rc = make_plan(lay, true, &sp, &use_tc)) return rc;
+  const void* kernel = find_mfc_step_kernel(lay, use_tc);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
   a.W = weights;

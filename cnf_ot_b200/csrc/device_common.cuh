@@ -48,10 +48,16 @@ struct SmemPlan {
   int off_hid, ld_h;    // M tiles [kTile][ld_h] hidden activations
   int off_gh;           // M tiles [kTile][ld_h] hidden adjoints; -1 if none
   int off_gth, ld_p;    // [kTile][ld_p] spline-parameter adjoints; -1 if none
+  int off_lo;           // tcgen05 engine: [kTile][16] scratch tile for the low tf32 halves; -1 if unused
+  int off_wmma;         // tcgen05 engine: weights in MMA layout (4 tiles of 16x16 per dense layer)
   int floats;
 };
 
-inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = true) {
+constexpr int kTileAlign = 128;  // tiles start on 512-byte boundaries (hardware swizzle = address bits)
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = true,
+                          bool tensor_cores = false) {
   SmemPlan p;
   p.total = f.total;
   p.w_in_smem = w_in_smem ? 1 : 0;
@@ -64,12 +70,21 @@ inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = 
   int o = w_in_smem ? tot4 : f.Pp + p.w_stage;
   p.off_acc = with_grad ? o : -1;
   if (with_grad) o += tot4;
+  o = align_up(o, kTileAlign);
   p.off_in = o; o += kTile * p.ld_in;
+  o = align_up(o, kTileAlign);
   p.off_hid = o; o += f.M * kTile * p.ld_h;
   p.off_gh = with_grad ? o : -1;
   if (with_grad) o += f.M * kTile * p.ld_h;
   p.off_gth = with_grad ? o : -1;
   if (with_grad) o += kTile * p.ld_p;
+  p.off_lo = -1;
+  p.off_wmma = -1;
+  if (tensor_cores) {
+    o = align_up(o, kTileAlign);
+    p.off_lo = o; o += kTile * 16;
+    p.off_wmma = o; o += f.L * (f.D - 1) * f.M * 4 * 256;
+  }
   p.floats = o;
   return p;
 }
@@ -113,6 +128,7 @@ __device__ inline RowTiles<float, Net> make_row_tiles(float* smem, const SmemPla
 // atomics are needed; the accumulators are flushed once per CTA at kernel end.
 template <class Net>
 struct DeviceCtx {
+  using NetT = Net;
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   float* smem;
   const float* gW;   // the blob in global memory
@@ -141,6 +157,16 @@ struct DeviceCtx {
   }
 
   __device__ __forceinline__ void begin() { __syncthreads(); }
+
+  // dense contractions of the hidden / output layers on the CUDA cores (see flow_math.cuh)
+  template <int K, int N>
+  __device__ __forceinline__ void dense_fwd(const float* xt, int sw, const float*, const float* Wm, int, float* y) {
+    dense_fwd_from_tile<float, K, N>(xt, sw, Wm, y);
+  }
+  template <int K, int N>
+  __device__ __forceinline__ void dense_bwd(const float*, int, const float* g, const float* Wm, int, float* y) {
+    dense_bwd_from_regs<float, K, N>(g, Wm, y);
+  }
 
   // one 4x4 block: rows rb*4.. of A (tile pa, stride lda) x cols cb*4.. of G
   __device__ __forceinline__ void block_accumulate(const float* pa, int lda, const float* pg,

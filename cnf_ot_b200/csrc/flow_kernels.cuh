@@ -3,10 +3,29 @@
 // shape (hidden, bins, mlp layers) and on a runtime / compile-time flow shape.
 #pragma once
 
+#include <type_traits>
+
 #include "device_common.cuh"
 #include "step_math.cuh"
+#include "tc_engine.cuh"
 
 namespace cnfot {
+
+// CTA context: CUDA-core dense layers, or the tcgen05 engine (TC) for 16-wide networks
+template <class Net, bool TC>
+struct CtxSelect { using type = DeviceCtx<Net>; };
+template <class Net>
+struct CtxSelect<Net, true> { using type = DeviceCtxTC<Net>; };
+
+template <class Ctx>
+__device__ __forceinline__ void ctx_setup(Ctx& ctx, int D, int L, uint64_t* mbar, uint32_t* slot) {
+  ctx.load();
+  if constexpr (!std::is_same<Ctx, DeviceCtx<typename Ctx::NetT>>::value) ctx.tc_setup(D, L, mbar, slot);
+}
+template <class Ctx>
+__device__ __forceinline__ void ctx_teardown(Ctx& ctx) {
+  if constexpr (!std::is_same<Ctx, DeviceCtx<typename Ctx::NetT>>::value) ctx.tc_teardown();
+}
 
 // ---- forward-only evaluation (model API: sample / forward / inverse / log_prob) ----
 struct EvalArgs {
@@ -24,11 +43,15 @@ struct EvalArgs {
   SplineConsts<float> sc;
 };
 
-template <class Net, class DimsT>
+template <class Net, class DimsT, bool TC>
 __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  DeviceCtx<Net> ctx{smem, a.W, a.plan};
-  ctx.load();
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ __align__(8) uint64_t tc_mbar;
+  __shared__ uint32_t tc_slot;
+  using Ctx = typename CtxSelect<Net, TC>::type;
+  Ctx ctx;
+  ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
@@ -38,8 +61,8 @@ __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
     float st[kMaxStateFloats];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    float ld = a.dir == 0 ? flow_pass<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx)
-                          : flow_pass<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
+    float ld = a.dir == 0 ? flow_pass<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx)
+                          : flow_pass<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
     if (!live) continue;
     for (int i = 0; i < D; ++i) a.out[r * D + i] = st[L * D + i];
     if (a.logdet) {
@@ -49,6 +72,7 @@ __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
       a.logdet[r] = ld;
     }
   }
+  ctx_teardown(ctx);
 }
 
 // ---- per-CTA partial results -------------------------------------------------------
@@ -87,13 +111,17 @@ struct VjpArgs {
   PartialBuf pb;
 };
 
-template <class Net, class DimsT>
+template <class Net, class DimsT, bool TC>
 __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
+  __shared__ __align__(8) uint64_t tc_mbar;
+  __shared__ uint32_t tc_slot;
   float* sAcc = smem + a.plan.off_acc;
-  DeviceCtx<Net> ctx{smem, a.W, a.plan};
-  ctx.load();
+  using Ctx = typename CtxSelect<Net, TC>::type;
+  Ctx ctx;
+  ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
@@ -106,8 +134,8 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
     float st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    if (a.dir == 0) flow_pass<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
-    else flow_pass<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, tl, ctx);
+    if (a.dir == 0) flow_pass<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
+    else flow_pass<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
     const float gl = (live && a.g_logdet) ? a.g_logdet[r] : 0.f;
     for (int i = 0; i < D; ++i) g[i] = live ? a.g_out[r * D + i] : 0.f;
     float gl_pass = gl;
@@ -117,9 +145,9 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
         for (int i = 0; i < D; ++i) g[i] -= gl * st[L * D + i];
     }
     if (a.dir == 0)
-      flow_pass_bwd<0, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
     else
-      flow_pass_bwd<1, float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
     if (a.add_base && a.dir == 0)
       for (int i = 0; i < D; ++i) g[i] -= gl * st[i];
     if (live && a.g_in)
@@ -129,6 +157,7 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
   double zero[kNumSlots];
   for (int s = 0; s < kNumSlots; ++s) zero[s] = 0.0;
   flush_partials(a.pb, sAcc, a.plan.total, zero, scratch);
+  ctx_teardown(ctx);
 }
 
 // ---- the fused train step ---------------------------------------------------------------
@@ -162,14 +191,18 @@ struct StepArgs {
   PartialBuf pb;
 };
 
-template <class Net, class DimsT>
+template <class Net, class DimsT, bool TC>
 __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__ StepArgs a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ long long s_tile;
+  __shared__ __align__(8) uint64_t tc_mbar;
+  __shared__ uint32_t tc_slot;
   float* sAcc = smem + a.plan.off_acc;
-  DeviceCtx<Net> ctx{smem, a.W, a.plan};
-  ctx.load();
+  using Ctx = typename CtxSelect<Net, TC>::type;
+  Ctx ctx;
+  ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D();
@@ -194,14 +227,14 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
     float row[kMaxDim];
     for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;
     if (sg.kind == kSegNll) {
-      float v = row_nll<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row,
+      float v = row_nll<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row,
                                                            live ? a.pc.w_fit : 0.f, gfirst, tl, ctx);
       loss[sg.slot] += (double)v;
     } else if (sg.kind == kSegSample) {
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_fit = 0.f; pc.w_pot = 0.f; }
       float lf = 0.f, lp = 0.f;
-      row_sample_terms<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row, sg.do_fit != 0,
+      row_sample_terms<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row, sg.do_fit != 0,
                                                           sg.do_pot != 0, pc, &lf, &lp, gfirst, tl, ctx);
       loss[sg.slot] += (double)lf;
       loss[kSlotPotential] += (double)lp;
@@ -209,7 +242,7 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
       float lk = 0.f, lp = 0.f;
-      row_kinetic<float, Net, DimsT, DeviceCtx<Net>>(dm, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
+      row_kinetic<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
                                                      tl, ctx);
       loss[kSlotKinetic] += (double)lk;
       loss[kSlotPotential] += (double)lp;
@@ -217,6 +250,7 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
   }
   ctx.flush_first(gfirst, tl);
   flush_partials(a.pb, sAcc, a.plan.total, loss, scratch);
+  ctx_teardown(ctx);
 }
 
 }  // namespace cnfot

@@ -157,9 +157,35 @@ struct RowTiles {
 // element offset of the 4-float chunk that starts at logical element j (j % 4 == 0)
 CNFOT_HD int chunk_at(int j, int sw) { return ((j >> 2) ^ sw) << 2; }
 
+// The two dense contractions of a hidden / output layer, CUDA-core flavour: the input
+// vector is read back from its row tile four entries at a time (rolled loop, small code).
+// A context may override them (DeviceCtx with tensor cores: tcgen05 over the same tiles).
+//   forward   y[j] = sum_i x[i] W[i][j]          W: (K x N) row-major
+//   backward  y[i] = sum_j g[j] W[i][j]          W: (N x K) row-major, g given in registers
+template <typename T, int K, int N>
+CNFOT_HD void dense_fwd_from_tile(const T* xt, int sw, const T* W, T* y) {
+#pragma unroll 1
+  for (int i = 0; i < K; i += 4) {
+    T a[4];
+    load4<T>(xt + chunk_at(i, sw), a);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) axpy_row<T, N>(a[q], W + (i + q) * N, y);
+  }
+}
+template <typename T, int K, int N>
+CNFOT_HD void dense_bwd_from_regs(const T* g, const T* W, T* y) {
+#pragma unroll 1
+  for (int i = 0; i < N; i += 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[i + q] = dot_row<T, K>(g, W + (i + q) * K);
+  }
+}
+
 // Conditioner forward: tiles.in -> tiles.hid[*] -> theta (registers).
-template <typename T, class Net>
-CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* theta) {
+// `mlp` is the running index of the conditioner, layer * (D-1) + (d-1).
+template <typename T, class Net, class Ctx>
+CNFOT_HD void mlp_forward(const T* W, int mlp, int n_in, const RowTiles<T, Net>& tl, T* theta,
+                          Ctx& ctx) {
   constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   const T* b0 = W + n_in * H;
   T acc[H];
@@ -168,89 +194,66 @@ CNFOT_HD void mlp_forward(const T* W, int n_in, const RowTiles<T, Net>& tl, T* t
 #pragma unroll 1
   for (int i = 0; i < n_in; ++i) axpy_row<T, H>(tl.in[i], W + i * H, acc);
 #pragma unroll
+  for (int j = 0; j < H; ++j) acc[j] = m_max(acc[j], (T)0);
+#pragma unroll
   for (int j = 0; j < H; j += 4)
-    store4<T>(tl.hid[0] + chunk_at(j, tl.sw_h), m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0), m_max(acc[j + 2], (T)0),
-              m_max(acc[j + 3], (T)0));
+    store4<T>(tl.hid[0] + chunk_at(j, tl.sw_h), acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
   const T* Wm = b0 + H;
 #pragma unroll
   for (int m = 1; m < M; ++m) {
     const T* bm = Wm + H * H;
+    T y[H];
 #pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = bm[j];
-#pragma unroll 1
-    for (int i = 0; i < H; i += 4) {
-      T a[4];
-      load4<T>(tl.hid[m - 1] + chunk_at(i, tl.sw_h), a);
+    for (int j = 0; j < H; ++j) y[j] = (T)0;
+    ctx.template dense_fwd<H, H>(tl.hid[m - 1], tl.sw_h, acc, Wm, mlp * M + m - 1, y);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) axpy_row<T, H>(a[q], Wm + (i + q) * H, acc);
-    }
+    for (int j = 0; j < H; ++j) acc[j] = m_max(y[j] + bm[j], (T)0);
 #pragma unroll
     for (int j = 0; j < H; j += 4)
-      store4<T>(tl.hid[m] + chunk_at(j, tl.sw_h), m_max(acc[j], (T)0), m_max(acc[j + 1], (T)0),
-                m_max(acc[j + 2], (T)0), m_max(acc[j + 3], (T)0));
+      store4<T>(tl.hid[m] + chunk_at(j, tl.sw_h), acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     Wm = bm + H;
   }
   const T* bo = Wm + H * Pp;
 #pragma unroll
-  for (int j = 0; j < Pp; ++j) theta[j] = bo[j];
-#pragma unroll 1
-  for (int i = 0; i < H; i += 4) {
-    T a[4];
-    load4<T>(tl.hid[M - 1] + chunk_at(i, tl.sw_h), a);
+  for (int j = 0; j < Pp; ++j) theta[j] = (T)0;
+  ctx.template dense_fwd<H, Pp>(tl.hid[M - 1], tl.sw_h, acc, Wm, mlp * M + M - 1, theta);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) axpy_row<T, Pp>(a[q], Wm + (i + q) * Pp, theta);
-  }
+  for (int j = 0; j < Pp; ++j) theta[j] += bo[j];
 }
 
 // Conditioner backward (data gradients): given gtheta (registers) fills tiles.gth and
 // tiles.gh[*] and returns the adjoint of the inputs in gin[1..n_in) (gin[0], the adjoint
-// of t, is not needed).  The weight gradients are taken from the tiles by Sink::commit.
-template <typename T, class Net>
-CNFOT_HD void mlp_backward(const T* W, int n_in, const RowTiles<T, Net>& tl, const T* gtheta,
-                           T* gin) {
+// of t, is not needed).  The weight gradients are taken from the tiles by Ctx::commit.
+template <typename T, class Net, class Ctx>
+CNFOT_HD void mlp_backward(const T* W, int mlp, int n_in, const RowTiles<T, Net>& tl,
+                           const T* gtheta, T* gin, Ctx& ctx) {
   constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
 #pragma unroll
   for (int j = 0; j < Pp; j += 4)
     store4<T>(tl.gth + chunk_at(j, tl.sw_p), gtheta[j], gtheta[j + 1], gtheta[j + 2], gtheta[j + 3]);
   const T* Wout = W + n_in * H + H + (M - 1) * (H * H + H);
-#pragma unroll 1
+  T g[H], y[H];
+  ctx.template dense_bwd<Pp, H>(tl.gth, tl.sw_p, gtheta, Wout, mlp * M + M - 1, y);
+#pragma unroll
   for (int i = 0; i < H; i += 4) {
-    T a[4], r[4];
+    T a[4];
     load4<T>(tl.hid[M - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      T v = dot_row<T, Pp>(gtheta, Wout + (i + q) * Pp);
-      r[q] = a[q] > (T)0 ? v : (T)0;
-    }
-    store4<T>(tl.gh[M - 1] + chunk_at(i, tl.sw_h), r[0], r[1], r[2], r[3]);
+    for (int q = 0; q < 4; ++q) g[i + q] = a[q] > (T)0 ? y[i + q] : (T)0;
+    store4<T>(tl.gh[M - 1] + chunk_at(i, tl.sw_h), g[i], g[i + 1], g[i + 2], g[i + 3]);
   }
-  T g[H];
 #pragma unroll
   for (int m = M - 1; m >= 1; --m) {
     const T* Wm = W + n_in * H + H + (m - 1) * (H * H + H);
+    ctx.template dense_bwd<H, H>(tl.gh[m], tl.sw_h, g, Wm, mlp * M + m - 1, y);
 #pragma unroll
-    for (int j = 0; j < H; j += 4) {
-      T v[4];
-      load4<T>(tl.gh[m] + chunk_at(j, tl.sw_h), v);
-      g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
-    }
-#pragma unroll 1
     for (int i = 0; i < H; i += 4) {
-      T a[4], r[4];
+      T a[4];
       load4<T>(tl.hid[m - 1] + chunk_at(i, tl.sw_h), a);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        T v = dot_row<T, H>(g, Wm + (i + q) * H);
-        r[q] = a[q] > (T)0 ? v : (T)0;
-      }
-      store4<T>(tl.gh[m - 1] + chunk_at(i, tl.sw_h), r[0], r[1], r[2], r[3]);
+      for (int q = 0; q < 4; ++q) g[i + q] = a[q] > (T)0 ? y[i + q] : (T)0;
+      store4<T>(tl.gh[m - 1] + chunk_at(i, tl.sw_h), g[i], g[i + 1], g[i + 2], g[i + 3]);
     }
-  }
-#pragma unroll
-  for (int j = 0; j < H; j += 4) {
-    T v[4];
-    load4<T>(tl.gh[0] + chunk_at(j, tl.sw_h), v);
-    g[j] = v[0]; g[j + 1] = v[1]; g[j + 2] = v[2]; g[j + 3] = v[3];
   }
 #pragma unroll 1
   for (int i = 1; i < n_in; ++i) gin[i] = dot_row<T, H>(g, W + i * H);
@@ -317,7 +320,7 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* state
         const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
         CNFOT_ASSUME_SHARED(W);
         fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
-        mlp_forward<T, Net>(W, d + 1, tl, theta);
+        mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
       }
       SplineState<T, K> st;
       T out, ld;
@@ -374,7 +377,7 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
         W = ctx.weights(w_off, (d + 1) * H + Net::kMlpConst);
         CNFOT_ASSUME_SHARED(W);
         fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
-        mlp_forward<T, Net>(W, d + 1, tl, theta);
+        mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
       }
       SplineState<T, K> st;
       T out, ld;
@@ -392,7 +395,7 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
         for (int j = 0; j < Pp; ++j) gfirst[j] += gtheta[j];
       } else {
         T gin[kMaxDim + 1];
-        mlp_backward<T, Net>(W, d + 1, tl, gtheta, gin);
+        mlp_backward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, gtheta, gin, ctx);
         for (int j = 0; j < d; ++j) g[perm_at(layer, j, D)] += gin[1 + j];
         ctx.commit(w_off, d + 1, tl);
       }

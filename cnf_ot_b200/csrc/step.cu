@@ -6,11 +6,19 @@ namespace cnfot {
 
 #define STEP_CASE(H_, K_, M_)                                                            \
   if (f.H == H_ && f.K == K_ && f.M == M_)                                               \
-    return (const void*)&mfc_step_kernel<NetCfg<H_, K_, M_>, Dims<0, 0>>;
+    return (const void*)&mfc_step_kernel<NetCfg<H_, K_, M_>, Dims<0, 0>, false>;
+#define STEP_TC_CASE(M_)                                                                 \
+  if (f.M == M_) return (const void*)&mfc_step_kernel<NetCfg<16, 5, M_>, Dims<0, 0>, true>;
 
-const void* find_mfc_step_kernel(const FlowLayout& f) {
+const void* find_mfc_step_kernel(const FlowLayout& f, bool tc) {
+  if (tc && tc_available(f)) {
+    if (f.M == 2 && f.D == 2 && f.L == 2)
+      return (const void*)&mfc_step_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, true>;
+    STEP_TC_CASE(1) STEP_TC_CASE(2) STEP_TC_CASE(3)
+    return nullptr;
+  }
   if (f.H == 16 && f.K == 5 && f.M == 2 && f.D == 2 && f.L == 2)
-    return (const void*)&mfc_step_kernel<NetCfg<16, 5, 2>, Dims<2, 2>>;
+    return (const void*)&mfc_step_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, false>;
   CNFOT_NET_LIST(STEP_CASE)
   return nullptr;
 }

@@ -84,6 +84,11 @@ typedef struct cnfot_problem_desc {
 
 CNFOT_API int cnfot_abi_version(void);
 CNFOT_API const char* cnfot_last_error(void);
+/* Launch configuration of the calling thread's most recent fused-kernel launch (diagnostics for
+ * bench.py / profiles): persistent grid size, dynamic shared memory per CTA in bytes, resident
+ * CTAs per SM the grid was sized for, and whether the tcgen05 engine variant was selected. */
+CNFOT_API void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm,
+                                      int32_t* tensor_cores);
 
 /* ---- parameter blob ---------------------------------------------------------------
  * The haiku pytree of SURVEY.md A.3 flattened into one fp32 buffer (layout documented in

@@ -34,6 +34,10 @@ struct HostSink {
   const T* first_params() const { return Wb; }
   const T* weights(int w_off, int) const { return Wb + w_off; }
   void begin() {}
+  template <int K, int N>
+  void dense_fwd(const T* xt, int sw, const T*, const T* Wm, int, T* y) { dense_fwd_from_tile<T, K, N>(xt, sw, Wm, y); }
+  template <int K, int N>
+  void dense_bwd(const T*, int, const T* g, const T* Wm, int, T* y) { dense_bwd_from_regs<T, K, N>(g, Wm, y); }
   static void outer(double* dst, int Na, const T* a, int Ng, const T* g) {
     for (int i = 0; i < Na; ++i)
       for (int j = 0; j < Ng; ++j) dst[i * Ng + j] += (double)a[i] * (double)g[j];

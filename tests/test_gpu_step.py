@@ -116,3 +116,26 @@ def test_adam_matches_optax_formula():
     v64 = b2 * v64 + (1 - b2) * g64 * g64
     p64 = p64 - lr * (m64 / (1 - b1**step)) / (torch.sqrt(v64 / (1 - b2**step)) + eps)
   assert float((pd.cpu().double() - p64).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("typ,sub,kw", [("ot", "obstacle", {}), ("rwpo", "double_well", {}),
+                                        ("fp", "nongradient", {}), ("fp", "gradient", {}),
+                                        ("ot", "free", dict(M=3)), ("ot", "obstacle", dict(M=1))])
+def test_tcgen05_engine_variant(typ, sub, kw, monkeypatch):
+  """The opt-in variant whose hidden/output linears run on tcgen05 (3xTF32, TMEM accumulators)
+  meets the same tolerances as the CUDA-core layers."""
+  from cnf_ot_b200 import _lib
+  monkeypatch.setenv("CNFOT_TC", "1")
+  kw = dict(kw)
+  sigma = kw.pop("sigma", 0.3)
+  cfg = make_cfg(typ, sub, Tn=2, lam=500.0, **({"B": 1024 + 64} | kw))
+  shape = shape_of(cfg)
+  spec, params = make_params(cfg, sigma)
+  inputs = make_inputs(cfg)
+  loss, grads = olosses.value_and_grad(cfg, spec, params, inputs)
+  Gor = pack(shape, grads, torch.float64)
+  out = run_gpu(cfg, shape, params, inputs, 500.0)
+  assert _lib.last_launch_info()["tensor_cores"]
+  G, slots = out[:shape.blob_size], out[shape.blob_size:]
+  assert abs(float(slots[0]) - float(loss)) <= TOL_LOSS * abs(float(loss))
+  assert float((G - Gor).abs().max() / Gor.abs().max()) <= TOL_GRAD

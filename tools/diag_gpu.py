@@ -66,7 +66,8 @@ for typ, sub, B, D, sigma in [("ot","obstacle",1<<18,2,0.3), ("rwpo","double_wel
     for _ in range(10): ops.mfc_step(*args, out=out)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)/10
-    print(f"{typ}/{sub} D{D} B={B}: {ms*1000:.1f} us/step -> {B/ms*1000/1e6:.1f} M samples/s; loss {float(out[shape.blob_size]):.4e}")
+    from cnf_ot_b200 import _lib
+    print(f"{typ}/{sub} D{D} B={B}: {ms*1000:.1f} us/step -> {B/ms*1000/1e6:.1f} M samples/s; loss {float(out[shape.blob_size]):.4e} {_lib.last_launch_info()}")
 
 print("== rqs kernel bandwidth (K=5)")
 n = 1 << 24
