@@ -209,7 +209,8 @@ static PartialBuf carve_partials(void* ws, unsigned long long** counter) {
 constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(32 * kFinWarps)
 finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss, int n_cta,
-                int total, float* __restrict__ out_grad, float* __restrict__ out_slots) {
+                int total, float* __restrict__ out_grad, float* __restrict__ out_slots,
+                int accumulate) {
   __shared__ double part[kFinWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -222,7 +223,7 @@ finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ plos
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
-    out_grad[i] = (float)t;
+    out_grad[i] = accumulate ? out_grad[i] + (float)t : (float)t;
   }
   if (out_slots && blockIdx.x == 0 && warp == 1) {
     // lanes 0..7 <-> internal slots (fit0, fitT, potential, kinetic, unused...)
@@ -232,16 +233,17 @@ finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ plos
     double tot = v;
     tot += __shfl_xor_sync(0xffffffffu, tot, 1);
     tot += __shfl_xor_sync(0xffffffffu, tot, 2);  // lanes 0..3 now hold the sum of slots 0..3
-    if (lane == 0) out_slots[0] = (float)tot;
-    if (lane < 4) out_slots[1 + lane] = (float)v;
+    if (lane == 0) out_slots[0] = accumulate ? out_slots[0] + (float)tot : (float)tot;
+    if (lane < 4) out_slots[1 + lane] = accumulate ? out_slots[1 + lane] + (float)v : (float)v;
     if (lane >= 5 && lane < kNumSlots) out_slots[lane] = 0.f;
   }
 }
 
 static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int total, float* out_grad,
-                           float* out_slots) {
+                           float* out_slots, bool accumulate = false) {
   int blocks = (total + 31) / 32;
-  finalize_kernel<<<blocks, 32 * kFinWarps, 0, s>>>(pb.grad, pb.loss, n_cta, total, out_grad, out_slots);
+  finalize_kernel<<<blocks, 32 * kFinWarps, 0, s>>>(pb.grad, pb.loss, n_cta, total, out_grad, out_slots,
+                                                   accumulate ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "finalize_kernel launch");
   return 0;
@@ -493,11 +495,11 @@ int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows
   return partial_bytes(lay);
 }
 
-int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
-                   const float* weights, const float* latent, const float* latent_sub, const float* src,
-                   const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
-                   int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
-                   void* workspace, int64_t workspace_bytes) {
+static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                         const float* weights, const float* latent, const float* latent_sub,
+                         const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
+                         int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b, float lambda,
+                         float* out, void* workspace, int64_t workspace_bytes, bool accumulate) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
   if (int rc = check_fused(flow, lay)) return rc;
@@ -541,6 +543,7 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
   a.n_tiles = tiles;
   cudaStream_t s = (cudaStream_t)stream;
   if (tiles == 0) {
+    if (accumulate) return 0;
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     return 0;
@@ -560,10 +563,43 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
   void* args[] = {&a};
   e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
   if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
-  return launch_finalize(s, a.pb, cfg.grid, lay.total, out, out + lay.total);
+  return launch_finalize(s, a.pb, cfg.grid, lay.total, out, out + lay.total, accumulate);
+}
+
+int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                   const float* weights, const float* latent, const float* latent_sub, const float* src,
+                   const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
+                   int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
+                   void* workspace, int64_t workspace_bytes) {
+  return mfc_step_impl(stream, flow, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t,
+                       rows_B, rows_b, global_B, global_b, lambda, out, workspace, workspace_bytes, false);
 }
 
 static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+// Copy stream + events of the *_host entry (one set per device, created on first use).
+struct HostPipe {
+  bool ready_ = false;
+  cudaStream_t copy;
+  cudaEvent_t start;
+  cudaEvent_t ready[4];
+};
+static int host_pipe(HostPipe** out) {
+  static HostPipe pipes[64];
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  HostPipe& p = pipes[di.device];
+  if (!p.ready_) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithFlags");
+    if ((e = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    for (int k = 0; k < 4; ++k)
+      if ((e = cudaEventCreateWithFlags(&p.ready[k], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    p.ready_ = true;
+  }
+  *out = &p;
+  return 0;
+}
 
 int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B, int64_t rows_b,
                                             int32_t n_t) {
@@ -601,21 +637,44 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
   float* dSrc = (float*)p; p += align256(bytesB);
   float* dTgt = (float*)p; p += align256(bytesB);
   float* dSub = (float*)p;
-  auto h2d = [&](float* dst, const float* src, int64_t bytes) -> cudaError_t {
-    if (!src || bytes == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, s);
-  };
+  // Row chunks: the H2D copy of chunk k+1 (internal copy stream) overlaps the kernels of chunk k
+  // (caller's stream); every chunk adds into dOut.  The b-row sub-batch terms ride with chunk 0.
+  HostPipe* hp = nullptr;
+  if (int rc = host_pipe(&hp)) return rc;
+  // measured on B200 (tools/host_chunks.py, cfg 2): 1 chunk 540-580 us, 2: 575, 4: 675 -> no split by default
+  int nchunk = 1;
+  if (const char* ev = getenv("CNFOT_HOST_CHUNKS")) {  // tuning knob (1..4)
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 4) nchunk = v;
+  }
   cudaError_t e;
-  if ((e = h2d(dW, weights_host, (int64_t)lay.total * sizeof(float))) != cudaSuccess) return cuda_fail(e, "H2D weights");
-  if ((e = h2d(dLat, latent_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D latent");
-  if ((e = h2d(dSrc, src_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D src");
-  if ((e = h2d(dTgt, tgt_host, bytesB)) != cudaSuccess) return cuda_fail(e, "H2D tgt");
-  if ((e = h2d(dSub, latent_sub_host, bytesb)) != cudaSuccess) return cuda_fail(e, "H2D latent_sub");
-  int rc = cnfot_mfc_step(stream, flow, problem, dW, latent_host ? dLat : nullptr,
-                          latent_sub_host ? dSub : nullptr, src_host ? dSrc : nullptr,
-                          tgt_host ? dTgt : nullptr, t_batch_host, n_t, rows_B, rows_b, global_B,
-                          global_b, lambda, dOut, ws, align256(partial_bytes(lay)));
-  if (rc) return rc;
+  if ((e = cudaEventRecord(hp->start, s)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+  if ((e = cudaStreamWaitEvent(hp->copy, hp->start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+  auto h2d = [&](cudaStream_t st, float* dst, const float* src, int64_t off_rows, int64_t n_rows) -> cudaError_t {
+    if (!src || n_rows == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst + off_rows * lay.D, src + off_rows * lay.D, (size_t)(n_rows * lay.D) * sizeof(float),
+                           cudaMemcpyHostToDevice, st);
+  };
+  if ((e = cudaMemcpyAsync(dW, weights_host, (size_t)lay.total * sizeof(float), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    return cuda_fail(e, "H2D weights");
+  if ((e = h2d(s, dSub, latent_sub_host, 0, rows_b)) != cudaSuccess) return cuda_fail(e, "H2D latent_sub");
+  for (int k = 0; k < nchunk; ++k) {
+    const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
+    if ((e = h2d(hp->copy, dLat, latent_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D latent");
+    if ((e = h2d(hp->copy, dSrc, src_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D src");
+    if ((e = h2d(hp->copy, dTgt, tgt_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D tgt");
+    if ((e = cudaEventRecord(hp->ready[k], hp->copy)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+  }
+  for (int k = 0; k < nchunk; ++k) {
+    const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
+    if ((e = cudaStreamWaitEvent(s, hp->ready[k], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    int rc = mfc_step_impl(stream, flow, problem, dW, latent_host ? dLat + lo * lay.D : nullptr,
+                           latent_sub_host ? dSub : nullptr, src_host ? dSrc + lo * lay.D : nullptr,
+                           tgt_host ? dTgt + lo * lay.D : nullptr, t_batch_host, n_t, hi - lo,
+                           k == 0 ? rows_b : 0, global_B, global_b, lambda, dOut, ws,
+                           align256(partial_bytes(lay)), k > 0);
+    if (rc) return rc;
+  }
   e = cudaMemcpyAsync(out_host, dOut, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float),
                       cudaMemcpyDeviceToHost, s);
   if (e != cudaSuccess) return cuda_fail(e, "D2H out");

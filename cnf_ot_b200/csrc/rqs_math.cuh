@@ -60,10 +60,25 @@ inline SplineConsts<T> make_spline_consts(int K, double lo, double hi, double mi
 }
 
 // ---- scalar helpers (overloaded so float uses the f-suffixed device paths) --
+// On the device the float versions of exp / log / divide / reciprocal map to the SFU
+// approximations (ex2.approx, lg2.approx, rcp.approx: <= 2-3 ulp), which cuts the spline from
+// ~250 to ~120 instructions; the parity tests bound the effect (it is below the float32
+// rounding already present in the knot positions).  -DCNFOT_PRECISE_MATH restores libm paths.
+#if defined(__CUDA_ARCH__) && !defined(CNFOT_PRECISE_MATH)
+CNFOT_HD float m_exp(float v) { return __expf(v); }
+CNFOT_HD float m_log(float v) { return __logf(v); }
+CNFOT_HD float m_div(float a, float b) { return __fdividef(a, b); }
+CNFOT_HD float m_rcp(float a) { return __fdividef(1.f, a); }
+#else
 CNFOT_HD float m_exp(float v) { return expf(v); }
-CNFOT_HD double m_exp(double v) { return exp(v); }
 CNFOT_HD float m_log(float v) { return logf(v); }
+CNFOT_HD float m_div(float a, float b) { return a / b; }
+CNFOT_HD float m_rcp(float a) { return 1.f / a; }
+#endif
+CNFOT_HD double m_exp(double v) { return exp(v); }
 CNFOT_HD double m_log(double v) { return log(v); }
+CNFOT_HD double m_div(double a, double b) { return a / b; }
+CNFOT_HD double m_rcp(double a) { return 1.0 / a; }
 CNFOT_HD float m_log1p(float v) { return log1pf(v); }
 CNFOT_HD double m_log1p(double v) { return log1p(v); }
 CNFOT_HD float m_sqrt(float v) { return sqrtf(v); }
@@ -85,7 +100,7 @@ CNFOT_HD T softplus(T v) {
 template <typename T>
 CNFOT_HD T sigmoid(T v) {
   T e = m_exp(-m_abs(v));
-  T r = (T)1 / ((T)1 + e);
+  T r = m_rcp((T)1 + e);
   return v >= (T)0 ? r : e * r;
 }
 
@@ -113,7 +128,7 @@ CNFOT_HD void softmax_bins(const T* u, const SplineConsts<T>& c, T* prob, T* siz
     prob[k] = m_exp(u[k] - m);
     sum += prob[k];
   }
-  T inv = (T)1 / sum;
+  T inv = m_rcp(sum);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     prob[k] *= inv;
@@ -188,15 +203,19 @@ CNFOT_HD void rqs_forward(T x, const T* theta, const SplineConsts<T>& c,
   locate<T, K>(x, xp, yp, theta + 2 * K, c, st, st.x0, st.x1, st.y0, st.y1);
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
-    T sl = bh / bw;
-    T z = (x - st.x0) / bw;
+    T ibw = m_rcp(bw);
+    T sl = bh * ibw;
+    T z = (x - st.x0) * ibw;
     z = m_min(m_max(z, (T)0), (T)1);
     T z2 = z * z, z1 = z - z2, omz = (T)1 - z;
     T stt = st.d1 + st.d0 - (T)2 * sl;
     T den = sl + stt * z1;
-    y = st.y0 + bh * (sl * z2 + st.d0 * z1) / den;
+    T iden = m_rcp(den);
+    y = st.y0 + bh * (sl * z2 + st.d0 * z1) * iden;
     T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * omz * omz;
-    logdet = (T)2 * m_log(sl) + m_log(A) - (T)2 * m_log(den);
+    // 2 log(sl) + log(A) - 2 log(den) as one logarithm
+    T r = sl * iden;
+    logdet = m_log(r * r * A);
   } else {
     T px = st.tail == 1 ? c.lo : c.hi;
     y = (x - px) * st.s_tail + px;  // range ends coincide on both axes
@@ -216,8 +235,8 @@ CNFOT_HD void rqs_inverse(T y, const T* theta, const SplineConsts<T>& c,
   locate<T, K>(y, yp, xp, theta + 2 * K, c, st, st.y0, st.y1, st.x0, st.x1);
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
-    T sl = bh / bw;
-    T w_ = (y - st.y0) / bh;
+    T sl = m_div(bh, bw);
+    T w_ = m_div(y - st.y0, bh);
     w_ = m_min(m_max(w_, (T)0), (T)1);
     T stt = st.d1 + st.d0 - (T)2 * sl;
     T qc = -sl * w_;
@@ -225,16 +244,18 @@ CNFOT_HD void rqs_inverse(T y, const T* theta, const SplineConsts<T>& c,
     T qa = sl - qb;
     T disc = qb * qb - (T)4 * qa * qc;
     T root = disc > (T)0 ? m_sqrt(m_max(disc, m_tiny((T)0))) : (T)0;
-    T z = qb >= (T)0 ? ((T)2 * qc) / (-qb - root) : (-qb + root) / ((T)2 * qa);
+    T z = qb >= (T)0 ? m_div((T)2 * qc, -qb - root) : m_div(-qb + root, (T)2 * qa);
     z = m_min(m_max(z, (T)0), (T)1);
     x = bw * z + st.x0;
     T z2 = z * z, z1 = z - z2, omz = (T)1 - z;
     T den = sl + stt * z1;
     T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * omz * omz;
-    logdet = -(T)2 * m_log(sl) - m_log(A) + (T)2 * m_log(den);
+    // -(2 log(sl) + log(A) - 2 log(den)) as one logarithm
+    T r = m_div(den, sl);
+    logdet = m_log(m_div(r * r, A));
   } else {
     T px = st.tail == 1 ? c.lo : c.hi;
-    x = (y - px) / st.s_tail + px;
+    x = m_div(y - px, st.s_tail) + px;
     logdet = -m_log(st.s_tail);
   }
 }
@@ -293,7 +314,7 @@ CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
-    T ibw = (T)1 / bw;
+    T ibw = m_rcp(bw);
     T sl = bh * ibw;
     T zr = (x - st.x0) * ibw;
     T z = m_min(m_max(zr, (T)0), (T)1);
@@ -302,12 +323,12 @@ CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<
     T q = sl * z2 + st.d0 * z1;
     T nu = bh * q;
     T den = sl + stt * z1;
-    T iden = (T)1 / den;
+    T iden = m_rcp(den);
     T A = st.d1 * z2 + (T)2 * sl * z1 + st.d0 * o2;
     T g_nu = gy * iden;
     T g_den = -gy * nu * iden * iden - (T)2 * gl * iden;
-    T g_A = gl / A;
-    T g_sl = (T)2 * gl / sl + (T)2 * g_A * z1 + g_den;
+    T g_A = m_div(gl, A);
+    T g_sl = m_div((T)2 * gl, sl) + (T)2 * g_A * z1 + g_den;
     gd1 = g_A * z2;
     gd0 = g_A * o2;
     T g_z2 = g_A * st.d1;
@@ -336,7 +357,7 @@ CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<
   } else {
     T px = st.tail == 1 ? c.lo : c.hi;
     gx = gy * st.s_tail;
-    gst = gy * (x - px) + gl / st.s_tail;
+    gst = gy * (x - px) + m_div(gl, st.s_tail);
   }
   scatter_to_raw<T, K>(st, c, gx0, gx1, gy0, gy1, gd0, gd1, gst, gtheta);
   return gx;
@@ -351,7 +372,7 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
-    T ibw = (T)1 / bw, ibh = (T)1 / bh;
+    T ibw = m_rcp(bw), ibh = m_rcp(bh);
     T sl = bh * ibw;
     T wr = (y - st.y0) * ibh;
     T w_ = m_min(m_max(wr, (T)0), (T)1);
@@ -364,7 +385,7 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<
     T root = pos ? m_sqrt(m_max(disc, m_tiny((T)0))) : (T)0;
     bool bpos = qb >= (T)0;
     T dn = bpos ? (-qb - root) : ((T)2 * qa);
-    T idn = (T)1 / dn;
+    T idn = m_rcp(dn);
     T zr = (bpos ? ((T)2 * qc) : (-qb + root)) * idn;
     T z = m_min(m_max(zr, (T)0), (T)1);
     T z2 = z * z, z1 = z - z2, omz = (T)1 - z, o2 = omz * omz;
@@ -376,9 +397,9 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<
     gx0 = gxo;
     // logdet = -(2 log sl + log A - 2 log den)
     T gF = -gl;
-    T g_A = gF / A;
-    T g_den = -(T)2 * gF / den;
-    T g_sl = (T)2 * gF / sl + (T)2 * g_A * z1 + g_den;
+    T g_A = m_div(gF, A);
+    T g_den = m_div(-(T)2 * gF, den);
+    T g_sl = m_div((T)2 * gF, sl) + (T)2 * g_A * z1 + g_den;
     gd1 = g_A * z2;
     gd0 = g_A * o2;
     T g_z2 = g_A * st.d1;
@@ -400,7 +421,7 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<
       g_root += g_num;
       g_qa += (T)2 * g_dn;
     }
-    T g_disc = (pos && disc >= m_tiny((T)0)) ? g_root / ((T)2 * root) : (T)0;
+    T g_disc = (pos && disc >= m_tiny((T)0)) ? m_div(g_root, (T)2 * root) : (T)0;
     g_qb += (T)2 * qb * g_disc;
     g_qa -= (T)4 * qc * g_disc;
     g_qc -= (T)4 * qa * g_disc;
@@ -426,7 +447,7 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<
     gy0 = -gyin - g_bh;
   } else {
     T px = st.tail == 1 ? c.lo : c.hi;
-    T is = (T)1 / st.s_tail;
+    T is = m_rcp(st.s_tail);
     gyin = gxo * is;
     gst = -gxo * (y - px) * is * is - gl * is;
   }
