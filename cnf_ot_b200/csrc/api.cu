@@ -104,27 +104,45 @@ struct LaunchCfg {
 };
 static thread_local int g_last_launch[4] = {0, 0, 0, 0};
 
-// Shared-memory plan: weights live in shared memory when weights + accumulators + row
-// tiles leave room for at least two CTAs per SM; otherwise they are read from global
-// memory (L1-cached broadcast loads).
-// The tcgen05 engine variant (tc_engine.cuh) exists for 16-wide layers with resident weights.
-// Round-1 measurements: numerically equivalent, but its per-layer
-// issue / commit / wait round trips make it slower than the CUDA-core layers at hidden = 16,
-// so it is opt-in: CNFOT_TC=1 in the environment (read on every call).
-static bool tc_enabled() {
-  const char* e = getenv("CNFOT_TC");
-  return e && e[0] == '1';
+// Shared-memory plan and engine choice.
+//   warp-MMA engine (warp_mlp.cuh)  16-wide networks whose weights + hi/lo fragments + per-warp
+//                                   tiles leave room for >= 2 CTAs per SM: the default there
+//   CUDA-core engine                everything else; weights live in shared memory when weights +
+//                                   accumulators + row tiles leave room for two CTAs per SM, otherwise
+//                                   one conditioner at a time is staged from L2
+//   tcgen05 engine (tc_engine.cuh)  16-wide networks, opt-in: its per-layer issue / commit / wait round
+//                                   trips make it slower than both at hidden = 16
+// CNFOT_ENGINE=cuda|tc|mma in the environment overrides the choice (read on every call).
+static int engine_override() {
+  const char* e = getenv("CNFOT_ENGINE");
+  if (!e) {
+    const char* t = getenv("CNFOT_TC");
+    return (t && t[0] == '1') ? kEngTc : -1;
+  }
+  if (!strcmp(e, "cuda")) return kEngCuda;
+  if (!strcmp(e, "tc")) return kEngTc;
+  if (!strcmp(e, "mma")) return kEngMma;
+  return -1;
 }
 
-static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, bool* use_tc) {
+static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, int* engine) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  *use_tc = false;
-  if (tc_enabled() && tc_available(lay)) {
+  const int want = engine_override();
+  *engine = kEngCuda;
+  if (want == kEngTc && tc_available(lay)) {
     SmemPlan t = plan_smem(lay, with_grad, true, true);
     if ((int64_t)t.floats * 4 * 2 <= di.max_smem_optin) {
       *sp = t;
-      *use_tc = true;
+      *engine = kEngTc;
+      return 0;
+    }
+  }
+  if ((want == kEngMma || want < 0) && tc_available(lay)) {
+    SmemPlan m = plan_smem_mma(lay, with_grad);
+    if ((int64_t)m.floats * 4 * 2 <= di.max_smem_optin) {
+      *sp = m;
+      *engine = kEngMma;
       return 0;
     }
   }
@@ -182,7 +200,7 @@ static int configure(const void* kernel, const SmemPlan& sp, int64_t tiles, Laun
   g_last_launch[0] = cfg->grid;
   g_last_launch[1] = (int)smem;
   g_last_launch[2] = occ;
-  g_last_launch[3] = sp.off_wmma >= 0 ? 1 : 0;
+  g_last_launch[3] = sp.off_wmma >= 0 ? kEngTc : (sp.off_frag >= 0 ? kEngMma : kEngCuda);
   return 0;
 }
 
@@ -399,9 +417,9 @@ static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, co
   if (rows == 0) return 0;
   if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
   SmemPlan sp;
-  bool use_tc;
-  if (int rc = make_plan(lay, false, &sp, &use_tc)) return rc;
-  const void* kernel = find_flow_eval_kernel(lay, use_tc);
+  int engine;
+  if (int rc = make_plan(lay, false, &sp, &engine)) return rc;
+  const void* kernel = find_flow_eval_kernel(lay, engine);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   EvalArgs a;
@@ -453,9 +471,9 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
   }
   if (!in || !cond || !g_out) return fail(CNFOT_ERR_ARG, "NULL buffer");
   SmemPlan sp;
-  bool use_tc;
-  if (int rc = make_plan(lay, true, &sp, &use_tc)) return rc;
-  const void* kernel = find_flow_vjp_kernel(lay, use_tc);
+  int engine;
+  if (int rc = make_plan(lay, true, &sp, &engine)) return rc;
+  const void* kernel = find_flow_vjp_kernel(lay, engine);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   unsigned long long* counter;
@@ -549,9 +567,9 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     return 0;
   }
   SmemPlan sp;
-  bool use_tc;
-  if (int rc = make_plan(lay, true, &sp, &use_tc)) return rc;
-  const void* kernel = find_mfc_step_kernel(lay, use_tc);
+  int engine;
+  if (int rc = make_plan(lay, true, &sp, &engine)) return rc;
+  const void* kernel = find_mfc_step_kernel(lay, engine);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
   a.W = weights;

@@ -50,6 +50,8 @@ struct SmemPlan {
   int off_gth, ld_p;    // [kTile][ld_p] spline-parameter adjoints; -1 if none
   int off_lo;           // tcgen05 engine: [kTile][16] scratch tile for the low tf32 halves; -1 if unused
   int off_wmma;         // tcgen05 engine: weights in MMA layout (4 tiles of 16x16 per dense layer)
+  int off_frag;         // warp-MMA engine: hi/lo weight fragments (warp_mlp.cuh); -1 if unused
+  int off_wt, wt_stride;  // warp-MMA engine: per-warp [32 x 16] tiles, floats per warp
   int floats;
 };
 
@@ -80,6 +82,9 @@ inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = 
   if (with_grad) o += kTile * p.ld_p;
   p.off_lo = -1;
   p.off_wmma = -1;
+  p.off_frag = -1;
+  p.off_wt = -1;
+  p.wt_stride = 0;
   if (tensor_cores) {
     o = align_up(o, kTileAlign);
     p.off_lo = o; o += kTile * 16;
@@ -129,10 +134,15 @@ __device__ inline RowTiles<float, Net> make_row_tiles(float* smem, const SmemPla
 template <class Net>
 struct DeviceCtx {
   using NetT = Net;
+  static constexpr bool kWarpMlp = false;
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   float* smem;
   const float* gW;   // the blob in global memory
   SmemPlan p;
+
+  __device__ __forceinline__ int row_in_tile() const { return threadIdx.x; }
+  __device__ __forceinline__ void setup(int, int, uint64_t*, uint32_t*) { load(); }
+  __device__ __forceinline__ void teardown() {}
 
   // once per kernel: bring the blob (or just `first`) into shared memory
   __device__ __forceinline__ void load() {

@@ -9,12 +9,12 @@ namespace cnfot {
 // when no instantiation exists for the network shape.  Shapes with a
 // compile-time (dim, layers) specialisation keep the per-row state in registers;
 // all others use the runtime-shape kernel (state in local memory).
-// tc = true selects the variant whose hidden / output linears run on tcgen05 (tc_engine.cuh);
-// it exists for hidden == 16 and num_bins == 5 only (tc_available()).
-const void* find_flow_eval_kernel(const FlowLayout& f, bool tc = false);
-const void* find_flow_vjp_kernel(const FlowLayout& f, bool tc = false);
-const void* find_mfc_step_kernel(const FlowLayout& f, bool tc = false);
-inline bool tc_available(const FlowLayout& f) { return f.H == 16 && f.K == 5 && f.D >= 2; }
+// engine: 0 CUDA cores, 1 tcgen05 (tc_engine.cuh), 2 warp-level MMA (warp_mlp.cuh); engines 1 and 2
+// exist for hidden == 16 and num_bins == 5 only (tc_available()).
+const void* find_flow_eval_kernel(const FlowLayout& f, int engine = 0);
+const void* find_flow_vjp_kernel(const FlowLayout& f, int engine = 0);
+const void* find_mfc_step_kernel(const FlowLayout& f, int engine = 0);
+inline bool tc_available(const FlowLayout& f) { return f.H == 16 && f.K == 5 && f.D >= 2 && f.M <= 3; }
 
 // (hidden, bins, mlp layers) combinations compiled into the fused kernels.
 #define CNFOT_NET_LIST(X) \

@@ -8,24 +8,26 @@
 #include "device_common.cuh"
 #include "step_math.cuh"
 #include "tc_engine.cuh"
+#include "warp_mlp.cuh"
 
 namespace cnfot {
 
-// CTA context: CUDA-core dense layers, or the tcgen05 engine (TC) for 16-wide networks
-template <class Net, bool TC>
+// CTA context by engine: 0 CUDA-core dense layers, 1 the tcgen05 engine (tc_engine.cuh),
+// 2 the warp-level tensor-core engine (warp_mlp.cuh); 1 and 2 exist for 16-wide networks
+enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2 };
+template <class Net, int ENG>
 struct CtxSelect { using type = DeviceCtx<Net>; };
 template <class Net>
-struct CtxSelect<Net, true> { using type = DeviceCtxTC<Net>; };
+struct CtxSelect<Net, kEngTc> { using type = DeviceCtxTC<Net>; };
+template <class Net>
+struct CtxSelect<Net, kEngMma> { using type = DeviceCtxMma<Net>; };
 
 template <class Ctx>
 __device__ __forceinline__ void ctx_setup(Ctx& ctx, int D, int L, uint64_t* mbar, uint32_t* slot) {
-  ctx.load();
-  if constexpr (!std::is_same<Ctx, DeviceCtx<typename Ctx::NetT>>::value) ctx.tc_setup(D, L, mbar, slot);
+  ctx.setup(D, L, mbar, slot);
 }
 template <class Ctx>
-__device__ __forceinline__ void ctx_teardown(Ctx& ctx) {
-  if constexpr (!std::is_same<Ctx, DeviceCtx<typename Ctx::NetT>>::value) ctx.tc_teardown();
-}
+__device__ __forceinline__ void ctx_teardown(Ctx& ctx) { ctx.teardown(); }
 
 // ---- forward-only evaluation (model API: sample / forward / inverse / log_prob) ----
 struct EvalArgs {
@@ -43,12 +45,12 @@ struct EvalArgs {
   SplineConsts<float> sc;
 };
 
-template <class Net, class DimsT, bool TC>
+template <class Net, class DimsT, int ENG>
 __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
-  using Ctx = typename CtxSelect<Net, TC>::type;
+  using Ctx = typename CtxSelect<Net, ENG>::type;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
   for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
-    const int64_t r = tile * kTile + threadIdx.x;
+    const int64_t r = tile * kTile + ctx.row_in_tile();
     const bool live = r < a.rows;  // every thread runs the pass: the context has CTA barriers
     float st[kMaxStateFloats];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
@@ -111,14 +113,14 @@ struct VjpArgs {
   PartialBuf pb;
 };
 
-template <class Net, class DimsT, bool TC>
+template <class Net, class DimsT, int ENG>
 __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
   float* sAcc = smem + a.plan.off_acc;
-  using Ctx = typename CtxSelect<Net, TC>::type;
+  using Ctx = typename CtxSelect<Net, ENG>::type;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
 #pragma unroll
   for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
   for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
-    const int64_t r = tile * kTile + threadIdx.x;
+    const int64_t r = tile * kTile + ctx.row_in_tile();
     const bool live = r < a.rows;
     float st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
@@ -191,7 +193,7 @@ struct StepArgs {
   PartialBuf pb;
 };
 
-template <class Net, class DimsT, bool TC>
+template <class Net, class DimsT, int ENG>
 __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
   float* sAcc = smem + a.plan.off_acc;
-  using Ctx = typename CtxSelect<Net, TC>::type;
+  using Ctx = typename CtxSelect<Net, ENG>::type;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__
     int si = 0;
     while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
     const Segment& sg = a.seg[si];
-    const int64_t r = (tile - sg.first_tile) * kTile + threadIdx.x;
+    const int64_t r = (tile - sg.first_tile) * kTile + ctx.row_in_tile();
     const bool live = r < sg.n;
     float row[kMaxDim];
     for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;

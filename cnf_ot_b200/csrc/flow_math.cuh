@@ -294,7 +294,7 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* state
                        const RowTiles<T, Net>& tl, Ctx& ctx) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
-  assume_tiles_shared<T, Net>(tl, false);
+  if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, false);
   CNFOT_ASSUME_LOCAL(states);
   T ld_total = (T)0;
 #pragma unroll 1
@@ -316,6 +316,8 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* state
           load4<T>(F + j, w);
           theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
         }
+      } else if constexpr (Ctx::kWarpMlp) {
+        ctx.cond_forward(D, layer, d, t, cvec, theta, false);
       } else {
         const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
         CNFOT_ASSUME_SHARED(W);
@@ -343,7 +345,7 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
                               T* g, T gld, T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
-  assume_tiles_shared<T, Net>(tl, true);
+  if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, true);
   CNFOT_ASSUME_LOCAL(states);
   CNFOT_ASSUME_LOCAL(g);
   CNFOT_ASSUME_LOCAL(gfirst);
@@ -371,6 +373,8 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
           load4<T>(F + j, w);
           theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
         }
+      } else if constexpr (Ctx::kWarpMlp) {
+        ctx.cond_forward(D, layer, d, t, cvec, theta, true);
       } else {
         w_off = mlp_offset<Net>(D, layer, d);
         ctx.begin();  // the tiles of the previous conditioner are free again
@@ -393,6 +397,8 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
       if (d == 0) {
 #pragma unroll
         for (int j = 0; j < Pp; ++j) gfirst[j] += gtheta[j];
+      } else if constexpr (Ctx::kWarpMlp) {
+        ctx.cond_backward(D, layer, d, t, cvec, gtheta, g);
       } else {
         T gin[kMaxDim + 1];
         mlp_backward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, gtheta, gin, ctx);

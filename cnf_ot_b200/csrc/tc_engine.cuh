@@ -79,6 +79,12 @@ struct DeviceCtxTC : DeviceCtx<Net> {
   uint32_t mbar;    // shared address of the MMA-completion mbarrier
   uint32_t phase;   // parity of the next completion
 
+  __device__ __forceinline__ void setup(int D, int L, uint64_t* mbar_ptr, uint32_t* tmem_slot) {
+    this->load();
+    tc_setup(D, L, mbar_ptr, tmem_slot);
+  }
+  __device__ __forceinline__ void teardown() { tc_teardown(); }
+
   // swizzled position of element (row n, col k) inside a [16][16] MMA tile
   __device__ __forceinline__ static int tile_pos(int n, int k) {
     return n * 16 + ((((k >> 2) ^ ((n >> 1) & 3)) << 2) | (k & 3));

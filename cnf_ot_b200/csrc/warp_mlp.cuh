@@ -1,0 +1,497 @@
+// Warp-level tensor-core engine for the conditioner MLP of 16-wide networks
+// (hidden == 16, padded spline-parameter count == 16: the mfc.yaml defaults).
+//
+// A warp owns 32 sample rows.  The per-row code (splines, loss terms, flow state) keeps its
+// "one thread = one row" form; every conditioner evaluation inside it is done by the warp as
+// a whole with mma.sync.m16n8k8 (tf32 inputs, fp32 accumulate), chained in registers:
+//
+//   * "C layout": thread (g = lane/4, t = lane%4) holds rows 8q+g (q = 0..3) x columns
+//     {2t, 2t+1, 8+2t, 9+2t} of a [32 x 16] activation matrix -- the accumulator fragments of
+//     2 m-tiles x 2 n-tiles.  An accumulator fragment is fed straight back as the A fragment
+//     of the next layer by re-labelling the contraction index (logical k = t <-> feature 2t,
+//     k = t+4 <-> feature 2t+1 inside each 8-wide k-step); the weight fragments are built with
+//     the same re-labelling, so chaining layers costs no shuffles and no shared memory.
+//   * fp32 fidelity: every product is split  x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo  with
+//     x_hi = x truncated to tf32 and x_lo = x - x_hi (exact); the weights' hi/lo fragments are
+//     built once per CTA.  24 MMAs replace the 256 FMAs per row of a 16x16 layer.
+//   * row <-> C-layout changes (the spline needs all 16 parameters of its row in one thread) and
+//     the transposed operands of the weight gradient  dW = A^T G  go through per-warp
+//     [32 x 16] shared-memory tiles with an XOR swizzle that makes all four access patterns
+//     (C-layout float2, row float4, transposed scalar A^T / G reads) bank-conflict-free.
+//   * the thread <-> row map inside a warp is  row = 8t + g, so the quad (same g) that holds a
+//     row's C-layout pieces also contains its owner: layer-0 inputs and the input gradients
+//     move with quad-local shuffles only.
+//   * weight gradients: per-warp MMA over its 32 rows, then added to the CTA's shared-memory
+//     accumulator (atomicAdd; warps are otherwise independent -- no CTA barrier in the loop).
+//
+// Reference semantics: the conditioner of /root/reference/cnf_ot/models/flows.py:46-86
+// (hk.nets.MLP([H]*M, activate_final=True) -> hk.Linear(P)), evaluated on [t, y[perm[:d]]]
+// (/root/reference/cnf_ot/models/autoregressive.py:94-98,124-128).
+#pragma once
+
+#include "device_common.cuh"
+
+namespace cnfot {
+
+constexpr int kWtFloats = 32 * 16;   // one per-warp tile
+constexpr int kFragFloats = 1024;    // per dense matrix: forward (512) + transposed (512) fragments
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+// Shared-memory plan of the warp-MMA kernels (same struct as the CUDA-core plan; the row tiles
+// of the latter are not used).
+inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad) {
+  SmemPlan p;
+  p.total = f.total;
+  p.w_in_smem = 1;
+  const int tot4 = (f.total + 3) / 4 * 4;
+  p.ld_in = p.ld_h = p.ld_p = 0;
+  p.off_w = 0;
+  p.w_stage = 0;
+  int o = tot4;
+  p.off_acc = with_grad ? o : -1;
+  if (with_grad) o += tot4;
+  p.off_in = p.off_hid = p.off_gh = p.off_gth = p.off_lo = p.off_wmma = -1;
+  o = align_up(o, 32);
+  p.off_frag = o;
+  o += f.L * (f.D - 1) * f.M * kFragFloats;
+  p.off_wt = o;
+  p.wt_stride = (with_grad ? f.M + 1 : 1) * kWtFloats;
+  o += kWarps * p.wt_stride;
+  p.floats = o;
+  return p;
+}
+
+// ---- shared-memory accessors on 32-bit shared-window addresses ------------------------------
+// (the contexts are passed by reference through non-inlined per-row functions, so generic
+// pointers kept in them would turn every access into a generic LD/ST with 64-bit address math)
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// read-only data (weights, fragments): not volatile, the compiler may schedule / merge them
+__device__ __forceinline__ float2 ldw64(uint32_t a) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 ldw128(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void red_shared(uint32_t a, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
+// per-thread constants of the engine (recomputed from threadIdx.x where needed: cheaper than
+// re-loading them from a context that lives in local memory)
+struct MmaLane {
+  uint32_t lane, g, t;
+  uint32_t cbase;   // C-layout byte offset inside a tile, before the chunk term: (g*16 + 2*(t&1))*4
+  uint32_t cu;      // C-layout chunk selector: chunk(q, nt) = cu ^ (2nt ^ q)
+  uint32_t rbase;   // row-layout byte offset: (8t+g)*64
+  uint32_t ru;      // row-layout chunk selector: chunk(c) = ru ^ c
+  uint32_t tbase;   // transposed reads: (t*16 + (g&3))*4
+  uint32_t tu;      // transposed reads: chunk selector (g>>2) ^ (t&2); chunk = tu ^ ks ^ {0,2} (^1 for rows +4)
+  __device__ __forceinline__ MmaLane() {
+    lane = threadIdx.x & 31;
+    g = lane >> 2;
+    t = lane & 3;
+    const uint32_t fg = ((g >> 1) & 1) * 2 + ((g >> 2) & 1);
+    cbase = (g * 16 + 2 * (t & 1)) * 4;
+    cu = (t >> 1) ^ fg;
+    rbase = (8 * t + g) * 64;
+    ru = t ^ fg;
+    tbase = (t * 16 + (g & 3)) * 4;
+    tu = (g >> 2) ^ (t & 2);
+  }
+};
+
+template <class Net>
+struct DeviceCtxMma {
+  using NetT = Net;
+  static constexpr bool kWarpMlp = true;
+  static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
+  static_assert(H == 16 && Pp == 16, "the warp-MMA engine is written for 16-wide layers");
+  float* smem;
+  const float* gW;
+  SmemPlan p;
+  // shared-window byte addresses, filled by setup()
+  uint32_t s_w, s_acc, s_frag, s_wt;   // blob, accumulators, fragments, this warp's tiles
+
+  // row of the CTA tile owned by the calling thread
+  __device__ __forceinline__ int row_in_tile() const {
+    const int lane = threadIdx.x & 31;
+    return (threadIdx.x & ~31) + 8 * (lane & 3) + (lane >> 2);
+  }
+
+  __device__ __forceinline__ void setup(int D, int L, uint64_t*, uint32_t*) {
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+    s_w = s0 + p.off_w * 4;
+    s_acc = s0 + (p.off_acc >= 0 ? p.off_acc : 0) * 4;
+    s_frag = s0 + p.off_frag * 4;
+    s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
+    load_weights(smem + p.off_w, gW, p.total);
+    if (p.off_acc >= 0)
+      for (int i = threadIdx.x; i < p.total; i += blockDim.x) smem[p.off_acc + i] = 0.f;
+    __syncthreads();
+    // weight fragments, hi/lo split: element e = ((mat * 2 + dir) * 4 + ks * 2 + nt) * 32 + lane
+    //   dir 0 (y = x W):    b0 = W[8ks+2t][8nt+g]   b1 = W[8ks+2t+1][8nt+g]
+    //   dir 1 (y = g W^T):  b0 = W[8nt+g][8ks+2t]   b1 = W[8nt+g][8ks+2t+1]
+    const int n_mat = L * (D - 1) * M;
+    for (int e = threadIdx.x; e < n_mat * 256; e += blockDim.x) {
+      const int ln = e & 31, ksnt = (e >> 5) & 3, dir = (e >> 7) & 1, mat = e >> 8;
+      const int mlp = mat / M, slot = mat - mlp * M;
+      const int layer = mlp / (D - 1), d = mlp - layer * (D - 1) + 1;
+      const float* Ws = smem + p.off_w + mlp_offset<Net>(D, layer, d) + (d + 1) * H + H + slot * (H * H + H);
+      const int ks = ksnt >> 1, nt = ksnt & 1, gg = ln >> 2, tt = ln & 3;
+      float b0, b1;
+      if (dir == 0) {
+        b0 = Ws[(8 * ks + 2 * tt) * 16 + 8 * nt + gg];
+        b1 = Ws[(8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg];
+      } else {
+        b0 = Ws[(8 * nt + gg) * 16 + 8 * ks + 2 * tt];
+        b1 = Ws[(8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1];
+      }
+      uint32_t h0, l0, h1, l1;
+      split_tf32(b0, h0, l0);
+      split_tf32(b1, h1, l1);
+      *reinterpret_cast<float4*>(smem + p.off_frag + mat * kFragFloats + dir * 512 + (ksnt * 32 + ln) * 4) =
+          make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void teardown() {}
+
+  __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
+
+  // ---- per-warp tiles: element (r, col) lives at r*16 + 4*((col>>2) ^ f(r)) + (col&3),
+  //      f(r) = ((r>>3)&3) ^ (2*bit1(r) + bit2(r))
+  __device__ __forceinline__ static void store_c(uint32_t tile, const MmaLane& ln, const float (&x)[2][2][4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+        sts64(tile + ln.cbase + q * 512 + 16 * (ln.cu ^ (2 * nt ^ q)), x[q >> 1][nt][2 * (q & 1)],
+              x[q >> 1][nt][2 * (q & 1) + 1]);
+  }
+  __device__ __forceinline__ static void load_c(uint32_t tile, const MmaLane& ln, float (&x)[2][2][4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float2 v = lds64(tile + ln.cbase + q * 512 + 16 * (ln.cu ^ (2 * nt ^ q)));
+        x[q >> 1][nt][2 * (q & 1)] = v.x;
+        x[q >> 1][nt][2 * (q & 1) + 1] = v.y;
+      }
+  }
+  __device__ __forceinline__ static void store_row(uint32_t tile, const MmaLane& ln, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      sts128(tile + ln.rbase + 16 * (ln.ru ^ c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  }
+  __device__ __forceinline__ static void load_row(uint32_t tile, const MmaLane& ln, float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 q = lds128(tile + ln.rbase + 16 * (ln.ru ^ c));
+      v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+    }
+  }
+
+  // x <- x * B (+ bias): 16 -> 16 for the warp's 32 rows; frag = the matrix' 512-float fragment
+  // block, bias = shared address of the 16 biases (0: none)
+  __device__ __forceinline__ static void dense16(float (&x)[2][2][4], uint32_t frag, uint32_t bias, const MmaLane& ln) {
+    float o[2][2][4];
+    float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+    if (bias) {
+      c0 = ldw64(bias + 8 * ln.t);
+      c1 = ldw64(bias + 32 + 8 * ln.t);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      o[mt][0][0] = c0.x; o[mt][0][1] = c0.y; o[mt][0][2] = c0.x; o[mt][0][3] = c0.y;
+      o[mt][1][0] = c1.x; o[mt][1][1] = c1.y; o[mt][1][2] = c1.x; o[mt][1][3] = c1.y;
+    }
+    const uint32_t fr = frag + ln.lane * 16;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        split_tf32(x[mt][ks][0], ahi[mt][0], alo[mt][0]);   // (row g,   k = t)   <- column 2t
+        split_tf32(x[mt][ks][2], ahi[mt][1], alo[mt][1]);   // (row g+8, k = t)
+        split_tf32(x[mt][ks][1], ahi[mt][2], alo[mt][2]);   // (row g,   k = t+4) <- column 2t+1
+        split_tf32(x[mt][ks][3], ahi[mt][3], alo[mt][3]);   // (row g+8, k = t+4)
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float4 f = ldw128(fr + (ks * 2 + nt) * 512);
+        const uint32_t bh0 = __float_as_uint(f.x), bh1 = __float_as_uint(f.y);
+        const uint32_t bl0 = __float_as_uint(f.z), bl1 = __float_as_uint(f.w);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_tf32(o[mt][nt], alo[mt], bh0, bh1);
+          mma_tf32(o[mt][nt], ahi[mt], bl0, bl1);
+          mma_tf32(o[mt][nt], ahi[mt], bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[mt][nt][e] = o[mt][nt][e];
+  }
+
+  __device__ __forceinline__ static void relu_c(float (&x)[2][2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[mt][nt][e] = fmaxf(x[mt][nt][e], 0.f);
+  }
+
+  // Conditioner forward for the warp's 32 rows: theta[0..16) of the calling thread's row.
+  // keep: store the hidden activations in the warp's tiles for cond_backward.
+  __device__ __forceinline__ void cond_forward(int D, int layer, int d, float tval, const float* cvec,
+                                               float* theta, bool keep) const {
+    const MmaLane ln;
+    const uint32_t wt = s_wt;
+    const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
+    const uint32_t W = s_w + mlp_offset<Net>(D, layer, d) * 4;
+    const uint32_t b0 = W + n_in * H * 4;
+    const uint32_t frag = s_frag + mlp * M * kFragFloats * 4;
+    float x[2][2][4];
+    {
+      const float2 c0 = ldw64(b0 + 8 * ln.t);
+      const float2 c1 = ldw64(b0 + 32 + 8 * ln.t);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        x[mt][0][0] = c0.x; x[mt][0][1] = c0.y; x[mt][0][2] = c0.x; x[mt][0][3] = c0.y;
+        x[mt][1][0] = c1.x; x[mt][1][1] = c1.y; x[mt][1][2] = c1.x; x[mt][1][3] = c1.y;
+      }
+    }
+    // layer 0 on the CUDA cores (n_in is 2..D): inputs come from the row owners in the quad
+#pragma unroll 1
+    for (int i = 0; i < n_in; ++i) {
+      const float xi = i == 0 ? tval : cvec[perm_at(layer, i - 1, D)];
+      const float2 w0 = ldw64(W + i * 64 + 8 * ln.t);
+      const float2 w1 = ldw64(W + i * 64 + 32 + 8 * ln.t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xq = __shfl_sync(0xffffffffu, xi, (ln.lane & ~3u) | q);
+        float* a0 = x[q >> 1][0] + 2 * (q & 1);
+        float* a1 = x[q >> 1][1] + 2 * (q & 1);
+        a0[0] = fmaf(xq, w0.x, a0[0]); a0[1] = fmaf(xq, w0.y, a0[1]);
+        a1[0] = fmaf(xq, w1.x, a1[0]); a1[1] = fmaf(xq, w1.y, a1[1]);
+      }
+    }
+    relu_c(x);
+    if (keep) {
+      __syncwarp();   // the previous conditioner's readers are done with the tiles
+      store_c(wt, ln, x);
+    }
+    uint32_t Wm = b0 + H * 4;
+#pragma unroll
+    for (int m = 1; m < M; ++m) {
+      dense16(x, frag + (m - 1) * kFragFloats * 4, Wm + H * H * 4, ln);
+      relu_c(x);
+      if (keep) store_c(wt + m * kWtFloats * 4, ln, x);
+      Wm += (H * H + H) * 4;
+    }
+    dense16(x, frag + (M - 1) * kFragFloats * 4, Wm + H * Pp * 4, ln);
+    const uint32_t scratch = wt + (keep ? M : 0) * kWtFloats * 4;
+    __syncwarp();
+    store_c(scratch, ln, x);
+    __syncwarp();
+    load_row(scratch, ln, theta);
+  }
+
+  // 4 per-thread partial sums (columns 2t, 2t+1, 8+2t, 9+2t of a 16-wide row) -> summed over the
+  // 8 lanes with the same t, then added to dst[column] (dst: shared address)
+  __device__ __forceinline__ static void colsum_add(const float (&v)[4], uint32_t dst, const MmaLane& ln) {
+    const bool hi = ln.lane & 16, b8 = ln.lane & 8;
+    float k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+    const float s0 = hi ? v[0] : v[2], s1 = hi ? v[1] : v[3];
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    float kk = b8 ? k1 : k0;
+    const float ss = b8 ? k0 : k1;
+    kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+    if (!(ln.lane & 4)) red_shared(dst + ((hi ? 8 : 0) + 2 * ln.t + (b8 ? 1 : 0)) * 4, kk);
+  }
+
+  // dst[i][j] += sum_r A[r][i] G[r][j] over the warp's 32 rows (A, G: swizzled tiles)
+  __device__ __forceinline__ static void wgrad16(uint32_t TA, uint32_t TG, uint32_t dst, const MmaLane& ln) {
+    float dw[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dw[nt][e] = 0.f;
+    const uint32_t ta = TA + ln.tbase, tg = TG + ln.tbase;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      // rows 8ks+t (chunk selector tu^ks) and 8ks+t+4 (selector tu^ks^1)
+      uint32_t ahi[4], alo[4];
+      split_tf32(lds32(ta + ks * 512 + 16 * (ln.tu ^ ks)), ahi[0], alo[0]);                  // (m = g,   k = t)
+      split_tf32(lds32(ta + ks * 512 + 16 * (ln.tu ^ ks ^ 2)), ahi[1], alo[1]);              // (m = g+8, k = t)
+      split_tf32(lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 1)), ahi[2], alo[2]);        // (m = g,   k = t+4)
+      split_tf32(lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 3)), ahi[3], alo[3]);        // (m = g+8, k = t+4)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(lds32(tg + ks * 512 + 16 * (ln.tu ^ ks ^ (2 * nt))), bh0, bl0);            // (k = t,   n = g)
+        split_tf32(lds32(tg + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ (2 * nt) ^ 1)), bh1, bl1);  // (k = t+4, n = g)
+        mma_tf32(dw[nt], alo, bh0, bh1);
+        mma_tf32(dw[nt], ahi, bl0, bl1);
+        mma_tf32(dw[nt], ahi, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const uint32_t q0 = dst + (ln.g * 16 + 8 * nt + 2 * ln.t) * 4;
+      red_shared(q0, dw[nt][0]);
+      red_shared(q0 + 4, dw[nt][1]);
+      red_shared(q0 + 512, dw[nt][2]);
+      red_shared(q0 + 516, dw[nt][3]);
+    }
+  }
+
+  // Conditioner backward for the warp's 32 rows.  cond_forward(..., keep = true) of the same
+  // conditioner must have run just before.  gtheta: adjoint of the row's spline parameters;
+  // gvec[coordinate] += adjoint of the conditioning coordinates; weight gradients -> accumulator.
+  __device__ __forceinline__ void cond_backward(int D, int layer, int d, float tval, const float* cvec,
+                                                const float* gtheta, float* gvec) const {
+    const MmaLane ln;
+    const uint32_t wt = s_wt;
+    const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
+    const int w_off = mlp_offset<Net>(D, layer, d);
+    const uint32_t W = s_w + w_off * 4;
+    const uint32_t A = s_acc + w_off * 4;
+    const uint32_t frag = s_frag + (mlp * M * kFragFloats + 512) * 4;
+    const uint32_t tg = wt + M * kWtFloats * 4;
+    __syncwarp();
+    store_row(tg, ln, gtheta);
+    __syncwarp();
+    float G[2][2][4];
+    load_c(tg, ln, G);
+#pragma unroll
+    for (int slot = M - 1; slot >= 0; --slot) {
+      // dense matrix `slot`: input = hidden activations `slot`, output adjoint = G
+      const uint32_t moff = (n_in * H + H + slot * (H * H + H)) * 4;
+      wgrad16(wt + slot * kWtFloats * 4, tg, A + moff, ln);
+      {
+        float s[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[e] = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          s[0] += G[mt][0][0] + G[mt][0][2]; s[1] += G[mt][0][1] + G[mt][0][3];
+          s[2] += G[mt][1][0] + G[mt][1][2]; s[3] += G[mt][1][1] + G[mt][1][3];
+        }
+        colsum_add(s, A + moff + H * 16 * 4, ln);
+      }
+      dense16(G, frag + slot * kFragFloats * 4, 0u, ln);
+      float hm[2][2][4];
+      load_c(wt + slot * kWtFloats * 4, ln, hm);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) G[mt][nt][e] = hm[mt][nt][e] > 0.f ? G[mt][nt][e] : 0.f;
+      if (slot > 0) {
+        __syncwarp();
+        store_c(tg, ln, G);
+        __syncwarp();
+      }
+    }
+    // layer 0: bias, input matrix, input adjoints
+    {
+      float s[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        s[0] += G[mt][0][0] + G[mt][0][2]; s[1] += G[mt][0][1] + G[mt][0][3];
+        s[2] += G[mt][1][0] + G[mt][1][2]; s[3] += G[mt][1][1] + G[mt][1][3];
+      }
+      colsum_add(s, A + n_in * H * 4, ln);
+    }
+#pragma unroll 1
+    for (int i = 0; i < n_in; ++i) {
+      const float xi = i == 0 ? tval : cvec[perm_at(layer, i - 1, D)];
+      const float2 w0 = ldw64(W + i * 64 + 8 * ln.t);
+      const float2 w1 = ldw64(W + i * 64 + 32 + 8 * ln.t);
+      float pw[4] = {0.f, 0.f, 0.f, 0.f}, pin[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xq = __shfl_sync(0xffffffffu, xi, (ln.lane & ~3u) | q);
+        const float* g0 = G[q >> 1][0] + 2 * (q & 1);
+        const float* g1 = G[q >> 1][1] + 2 * (q & 1);
+        pw[0] = fmaf(xq, g0[0], pw[0]); pw[1] = fmaf(xq, g0[1], pw[1]);
+        pw[2] = fmaf(xq, g1[0], pw[2]); pw[3] = fmaf(xq, g1[1], pw[3]);
+        pin[q] = g0[0] * w0.x + g0[1] * w0.y + g1[0] * w1.x + g1[1] * w1.y;
+      }
+      colsum_add(pw, A + i * 64, ln);
+      if (i >= 1) {
+        // sum over the quad; lane t ends up with the total of row 8t+g (its own row)
+        const bool t2 = ln.lane & 2, t1 = ln.lane & 1;
+        float k0 = t2 ? pin[2] : pin[0], k1 = t2 ? pin[3] : pin[1];
+        const float s0 = t2 ? pin[0] : pin[2], s1 = t2 ? pin[1] : pin[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        float kk = t1 ? k1 : k0;
+        const float ss = t1 ? k0 : k1;
+        kk += __shfl_xor_sync(0xffffffffu, ss, 1);
+        gvec[perm_at(layer, i - 1, D)] += kk;
+      }
+    }
+  }
+
+  // flush the per-thread adjoint of the shared `first` parameter (blob offset 0)
+  __device__ __forceinline__ void flush_first(const float* gfirst, const RowTiles<float, Net>&) const {
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < Pp; ++j) {
+      float v = gfirst[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red_shared(s_acc + j * 4, v);
+    }
+    __syncthreads();
+  }
+};
+
+}  // namespace cnfot

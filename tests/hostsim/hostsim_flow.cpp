@@ -29,6 +29,7 @@ struct HostTiles {
 
 template <typename T, class Net>
 struct HostSink {
+  static constexpr bool kWarpMlp = false;
   double* G;     // gradient blob (double accumulation)
   const T* Wb;   // weight blob
   const T* first_params() const { return Wb; }
