@@ -312,12 +312,11 @@ def run_ours(args):
   loss_dev = float(out[shape.blob_size])
 
   # ---- e2e: host buffers through the C ABI (N=1) / pinned copies + all-reduce (N>1)
-  n_host = 3
+  n_host = 8
   pin = lambda x: x.cpu().contiguous().pin_memory()
   hsets = [(pin(s[0]), pin(s[1]), pin(s[2])) for s in sets[:n_host]]
   hW = pin(W)
   hout = torch.empty(shape.blob_size + 8, dtype=torch.float32).pin_memory()
-  dsrc, dtgt, dsub = torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1]), torch.empty_like(sets[0][2])
   dW2 = torch.empty_like(W)
 
   def step_e2e(i):
@@ -325,9 +324,9 @@ def run_ours(args):
     if world == 1:
       ops.mfc_step_host(shape, problem, hW, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, hout, device=dev)
     else:
-      dW2.copy_(hW, non_blocking=True); dsrc.copy_(src, non_blocking=True)
-      dtgt.copy_(tgt, non_blocking=True); dsub.copy_(sub, non_blocking=True)
-      ops.mfc_step(shape, problem, dW2, None, dsub, dsrc, dtgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
+      # weights H2D; the pinned row buffers are read in place by the kernel (zero-copy over PCIe)
+      dW2.copy_(hW, non_blocking=True)
+      ops.mfc_step(shape, problem, dW2, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
       td.all_reduce(out)
       hout.copy_(out, non_blocking=True)
       torch.cuda.synchronize()
@@ -353,11 +352,14 @@ def run_ours(args):
     rows_evals = 2 * B + 3 * b
     flops = rows_evals * 3 * 2176.0
     fp32_peak = 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-    traffic = None
+    traffic, insts = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
       with open(tpath) as f:
-        traffic = json.load(f).get("mfc_step_kernel_dram_bytes_per_launch")
+        tj = json.load(f)
+      traffic = tj.get("mfc_step_kernel_dram_bytes_per_launch")
+      insts = tj.get("mfc_step_kernel_warp_insts_per_launch")
+    issue_peak = 148 * 4 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6  # warp instructions / s
     line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
       "warmup": max(args.warmup, 3), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
@@ -366,18 +368,28 @@ def run_ours(args):
                                       "loss_last_step": loss_dev}),
       "e2e": {"value": gB * args.steps / el_e, "unit": UNIT, "h2d_bytes_per_step": h2d,
               "d2h_bytes_per_step": d2h, "ms_per_step": el_e / args.steps * 1e3,
-              "api": "cnfot_mfc_step_host (C ABI, pinned host buffers)" if world == 1 else
-                     "pinned H2D + cnfot_mfc_step + NCCL all-reduce + D2H"},
+              "api": "cnfot_mfc_step_host (C ABI; pinned host rows read in place by the kernel over PCIe, "
+                     "weights H2D, [grad|loss] D2H)" if world == 1 else
+                     "weights H2D + cnfot_mfc_step on pinned host rows (zero-copy) + NCCL all-reduce + D2H"},
       "gpu_launches": 2 * args.steps,
       "clocks": clk.summary(),
       "roofline": {"bound": "hbm", "kernel": "mfc_step_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
                    "frac": ach / hbm, "traffic": traffic, "peak_source": pk_src,
-                   "note": "fused step kernel is fp32-issue bound, not HBM bound (SURVEY.md §8d): see roofline_fp32; "
-                           "the HBM-bound kernels of the path are the stand-alone spline kernels in roofline_spline"},
+                   "note": "the fused step kernel is bound by instruction issue, not by HBM or the tensor pipe "
+                           "(SURVEY.md §8d; ncu: profiles/): see roofline_issue / roofline_fp32; the HBM-bound kernels "
+                           "of the path are the stand-alone spline kernels in roofline_spline"},
+      "roofline_issue": {"bound": "issue", "kernel": "mfc_step_kernel",
+                         "achieved": (insts / t_launch / 1e9) if insts else None, "peak": issue_peak / 1e9,
+                         "unit": "G warp-inst/s", "frac": (insts / t_launch / issue_peak) if insts else None,
+                         "warp_insts_per_launch": insts,
+                         "note": "executed warp instructions per launch (ncu smsp__inst_executed.sum, profiles/) / "
+                                 "live launch time, against 148 SM x 4 schedulers x max clock"},
       "roofline_fp32": {"bound": "fp32", "kernel": "mfc_step_kernel", "achieved": flops / t_launch / 1e12,
                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / fp32_peak,
                         "flops_per_launch": flops,
-                        "note": "algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only; peak = 148 SM x 128 FMA x 2 x max clock"},
+                        "note": "algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only, against the CUDA-core fp32 peak "
+                                "148 SM x 128 FMA x 2 x max clock; the 16x16 layers run on the tensor pipe (mma.sync "
+                                "tf32, 3 MMAs per product for fp32 fidelity), the input layers and splines on CUDA cores"},
     }
     if world == 1:
       line["roofline_spline"] = spline_rooflines(hbm)

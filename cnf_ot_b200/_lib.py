@@ -110,8 +110,9 @@ def load() -> ctypes.CDLL:
 def last_launch_info() -> dict:
   vals = [c_int32(0) for _ in range(4)]
   load().cnfot_last_launch_info(*[ctypes.byref(v) for v in vals])
+  eng = vals[3].value  # 0 CUDA cores, 1 tcgen05 engine, 2 warp-level MMA engine
   return {"grid": vals[0].value, "smem_bytes": vals[1].value, "ctas_per_sm": vals[2].value,
-          "tensor_cores": bool(vals[3].value)}
+          "tensor_cores": bool(eng), "engine": {0: "cuda", 1: "tc", 2: "mma"}.get(eng, "?")}
 
 
 def check(rc: int) -> None:

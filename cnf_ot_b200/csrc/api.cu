@@ -650,48 +650,74 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
   float* dW = (float*)p; p += align256((int64_t)lay.total * sizeof(float));
   float* dOut = (float*)p; p += align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
   const int64_t bytesB = rows_B * lay.D * (int64_t)sizeof(float);
-  const int64_t bytesb = rows_b * lay.D * (int64_t)sizeof(float);
   float* dLat = (float*)p; p += align256(bytesB);
   float* dSrc = (float*)p; p += align256(bytesB);
   float* dTgt = (float*)p; p += align256(bytesB);
   float* dSub = (float*)p;
-  // Row chunks: the H2D copy of chunk k+1 (internal copy stream) overlaps the kernels of chunk k
-  // (caller's stream); every chunk adds into dOut.  The b-row sub-batch terms ride with chunk 0.
-  HostPipe* hp = nullptr;
-  if (int rc = host_pipe(&hp)) return rc;
-  // measured on B200 (tools/host_chunks.py, cfg 2): 1 chunk 540-580 us, 2: 575, 4: 675 -> no split by default
-  int nchunk = 1;
-  if (const char* ev = getenv("CNFOT_HOST_CHUNKS")) {  // tuning knob (1..4)
-    const int v = atoi(ev);
-    if (v >= 1 && v <= 4) nchunk = v;
-  }
   cudaError_t e;
-  if ((e = cudaEventRecord(hp->start, s)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-  if ((e = cudaStreamWaitEvent(hp->copy, hp->start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-  auto h2d = [&](cudaStream_t st, float* dst, const float* src, int64_t off_rows, int64_t n_rows) -> cudaError_t {
-    if (!src || n_rows == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst + off_rows * lay.D, src + off_rows * lay.D, (size_t)(n_rows * lay.D) * sizeof(float),
-                           cudaMemcpyHostToDevice, st);
-  };
+  // Zero-copy path: when every row buffer is pinned (page-locked and mapped: cudaHostAlloc /
+  // cudaHostRegister / torch pin_memory), the kernel reads the rows straight from host memory.
+  // Each row is read exactly once and the step is compute-bound (16 warps per SM hide the PCIe
+  // latency), so the transfer overlaps the math tile by tile instead of preceding it.
+  // CNFOT_HOST_ZEROCOPY=0 forces the staged copy.
+  bool zero_copy = true;
+  if (const char* ev = getenv("CNFOT_HOST_ZEROCOPY")) zero_copy = ev[0] != '0';
+  const float* mapped[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* hostp[4] = {latent_host, latent_sub_host, src_host, tgt_host};
+  for (int k = 0; k < 4 && zero_copy; ++k) {
+    if (!hostp[k]) continue;
+    cudaPointerAttributes at;
+    e = cudaPointerGetAttributes(&at, hostp[k]);
+    if (e != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+      cudaGetLastError();  // pageable memory: not an error, use the staged path
+      zero_copy = false;
+      break;
+    }
+    mapped[k] = (const float*)at.devicePointer;
+  }
   if ((e = cudaMemcpyAsync(dW, weights_host, (size_t)lay.total * sizeof(float), cudaMemcpyHostToDevice, s)) != cudaSuccess)
     return cuda_fail(e, "H2D weights");
-  if ((e = h2d(s, dSub, latent_sub_host, 0, rows_b)) != cudaSuccess) return cuda_fail(e, "H2D latent_sub");
-  for (int k = 0; k < nchunk; ++k) {
-    const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
-    if ((e = h2d(hp->copy, dLat, latent_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D latent");
-    if ((e = h2d(hp->copy, dSrc, src_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D src");
-    if ((e = h2d(hp->copy, dTgt, tgt_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D tgt");
-    if ((e = cudaEventRecord(hp->ready[k], hp->copy)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-  }
-  for (int k = 0; k < nchunk; ++k) {
-    const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
-    if ((e = cudaStreamWaitEvent(s, hp->ready[k], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-    int rc = mfc_step_impl(stream, flow, problem, dW, latent_host ? dLat + lo * lay.D : nullptr,
-                           latent_sub_host ? dSub : nullptr, src_host ? dSrc + lo * lay.D : nullptr,
-                           tgt_host ? dTgt + lo * lay.D : nullptr, t_batch_host, n_t, hi - lo,
-                           k == 0 ? rows_b : 0, global_B, global_b, lambda, dOut, ws,
-                           align256(partial_bytes(lay)), k > 0);
+  if (zero_copy) {
+    int rc = mfc_step_impl(stream, flow, problem, dW, mapped[0], mapped[1], mapped[2], mapped[3], t_batch_host,
+                           n_t, rows_B, rows_b, global_B, global_b, lambda, dOut, ws,
+                           align256(partial_bytes(lay)), false);
     if (rc) return rc;
+  } else {
+    // Staged path.  Row chunks: the H2D copy of chunk k+1 (internal copy stream) overlaps the kernels
+    // of chunk k (caller's stream); every chunk adds into dOut.  The b-row sub-batch terms ride with
+    // chunk 0.  Measured on B200 (tools/host_chunks.py, cfg 2): chunking does not pay, default 1.
+    HostPipe* hp = nullptr;
+    if (int rc = host_pipe(&hp)) return rc;
+    int nchunk = 1;
+    if (const char* ev = getenv("CNFOT_HOST_CHUNKS")) {  // tuning knob (1..4)
+      const int v = atoi(ev);
+      if (v >= 1 && v <= 4) nchunk = v;
+    }
+    if ((e = cudaEventRecord(hp->start, s)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+    if ((e = cudaStreamWaitEvent(hp->copy, hp->start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    auto h2d = [&](cudaStream_t st, float* dst, const float* src, int64_t off_rows, int64_t n_rows) -> cudaError_t {
+      if (!src || n_rows == 0) return cudaSuccess;
+      return cudaMemcpyAsync(dst + off_rows * lay.D, src + off_rows * lay.D, (size_t)(n_rows * lay.D) * sizeof(float),
+                             cudaMemcpyHostToDevice, st);
+    };
+    if ((e = h2d(s, dSub, latent_sub_host, 0, rows_b)) != cudaSuccess) return cuda_fail(e, "H2D latent_sub");
+    for (int k = 0; k < nchunk; ++k) {
+      const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
+      if ((e = h2d(hp->copy, dLat, latent_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D latent");
+      if ((e = h2d(hp->copy, dSrc, src_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D src");
+      if ((e = h2d(hp->copy, dTgt, tgt_host, lo, hi - lo)) != cudaSuccess) return cuda_fail(e, "H2D tgt");
+      if ((e = cudaEventRecord(hp->ready[k], hp->copy)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+    }
+    for (int k = 0; k < nchunk; ++k) {
+      const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
+      if ((e = cudaStreamWaitEvent(s, hp->ready[k], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+      int rc = mfc_step_impl(stream, flow, problem, dW, latent_host ? dLat + lo * lay.D : nullptr,
+                             latent_sub_host ? dSub : nullptr, src_host ? dSrc + lo * lay.D : nullptr,
+                             tgt_host ? dTgt + lo * lay.D : nullptr, t_batch_host, n_t, hi - lo,
+                             k == 0 ? rows_b : 0, global_B, global_b, lambda, dOut, ws,
+                             align256(partial_bytes(lay)), k > 0);
+      if (rc) return rc;
+    }
   }
   e = cudaMemcpyAsync(out_host, dOut, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float),
                       cudaMemcpyDeviceToHost, s);

@@ -135,6 +135,8 @@ template <class Net>
 struct DeviceCtx {
   using NetT = Net;
   static constexpr bool kWarpMlp = false;
+  static constexpr bool kAccInGlobal = false;
+  __device__ __forceinline__ void bind_partials(float*) {}
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   float* smem;
   const float* gW;   // the blob in global memory

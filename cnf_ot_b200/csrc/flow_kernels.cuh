@@ -15,6 +15,10 @@ namespace cnfot {
 // CTA context by engine: 0 CUDA-core dense layers, 1 the tcgen05 engine (tc_engine.cuh),
 // 2 the warp-level tensor-core engine (warp_mlp.cuh); 1 and 2 exist for 16-wide networks
 enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2 };
+#ifndef CNFOT_MMA_MIN_CTAS
+#define CNFOT_MMA_MIN_CTAS 4
+#endif
+constexpr int kMmaMinCtas = CNFOT_MMA_MIN_CTAS;   // register budget of the warp-MMA kernels: 65536 / (128 * n)
 template <class Net, int ENG>
 struct CtxSelect { using type = DeviceCtx<Net>; };
 template <class Net>
@@ -46,13 +50,14 @@ struct EvalArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile) flow_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_eval_kernel(EvalArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
   using Ctx = typename CtxSelect<Net, ENG>::type;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx.bind_partials(nullptr);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
@@ -83,12 +88,15 @@ struct PartialBuf {
   double* loss;    // [n_cta][kNumSlots]
 };
 
+// sAcc: the CTA's shared-memory gradient accumulator, or nullptr when the context adds straight
+// into the CTA's partial row (Ctx::kAccInGlobal)
 __device__ inline void flush_partials(const PartialBuf& pb, const float* sAcc, int total,
                                       const double* loss /* kNumSlots, thread-local */,
                                       double* scratch) {
   __syncthreads();
   float* dst = pb.grad + (int64_t)blockIdx.x * total;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = sAcc[i];
+  if (sAcc)
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = sAcc[i];
   for (int s = 0; s < kNumSlots; ++s) {
     double v = block_sum(loss[s], scratch);
     if (threadIdx.x == 0) pb.loss[(int64_t)blockIdx.x * kNumSlots + s] = v;
@@ -114,15 +122,16 @@ struct VjpArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile) flow_vjp_kernel(VjpArgs a) {
+__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_vjp_kernel(VjpArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
-  float* sAcc = smem + a.plan.off_acc;
   using Ctx = typename CtxSelect<Net, ENG>::type;
+  float* sAcc = Ctx::kAccInGlobal ? nullptr : smem + a.plan.off_acc;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
@@ -194,16 +203,17 @@ struct StepArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile) mfc_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ long long s_tile;
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
-  float* sAcc = smem + a.plan.off_acc;
   using Ctx = typename CtxSelect<Net, ENG>::type;
+  float* sAcc = Ctx::kAccInGlobal ? nullptr : smem + a.plan.off_acc;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};

@@ -21,8 +21,10 @@
 //   * the thread <-> row map inside a warp is  row = 8t + g, so the quad (same g) that holds a
 //     row's C-layout pieces also contains its owner: layer-0 inputs and the input gradients
 //     move with quad-local shuffles only.
-//   * weight gradients: per-warp MMA over its 32 rows, then added to the CTA's shared-memory
-//     accumulator (atomicAdd; warps are otherwise independent -- no CTA barrier in the loop).
+//   * weight gradients: per-warp MMA over its 32 rows, then added to the CTA's
+//     partial-gradient row
+//     in global memory with fire-and-forget red.global (L2); warps are otherwise independent --
+//     no CTA barrier in the loop.
 //
 // Reference semantics: the conditioner of /root/reference/cnf_ot/models/flows.py:46-86
 // (hk.nets.MLP([H]*M, activate_final=True) -> hk.Linear(P)), evaluated on [t, y[perm[:d]]]
@@ -47,20 +49,26 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   hi = __float_as_uint(v) & 0xFFFFE000u;
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
+// the tensor core reads only the tf32 bits of an operand register, so the "hi" operand of the split
+// is the fp32 value itself (ptxas drops an explicit mask for the same reason); this is the "lo" one
+__device__ __forceinline__ uint32_t tf32_residual(float v) {
+  return __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
+}
 
 // Shared-memory plan of the warp-MMA kernels (same struct as the CUDA-core plan; the row tiles
 // of the latter are not used).
 inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad) {
   SmemPlan p;
   p.total = f.total;
-  p.w_in_smem = 1;
+  p.w_in_smem = 1;  // the blob (input layers, biases, `first`) + the hi/lo fragments of the 16x16 matrices
+                    // (measured: reading the input layers from global/L1 instead costs ~3 %, and a fifth
+                    //  CTA per SM at <= 102 registers is slower than four at 128)
   const int tot4 = (f.total + 3) / 4 * 4;
   p.ld_in = p.ld_h = p.ld_p = 0;
   p.off_w = 0;
   p.w_stage = 0;
   int o = tot4;
-  p.off_acc = with_grad ? o : -1;
-  if (with_grad) o += tot4;
+  p.off_acc = -1;   // weight gradients go straight to the CTA's partial row in global memory
   p.off_in = p.off_hid = p.off_gh = p.off_gth = p.off_lo = p.off_wmma = -1;
   o = align_up(o, 32);
   p.off_frag = o;
@@ -101,14 +109,22 @@ __device__ __forceinline__ float4 ldw128(uint32_t a) {
   asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts32(uint32_t a, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void red_shared(uint32_t a, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+// fire-and-forget float adds into the CTA's partial-gradient row in global memory (resolved in L2;
+// shared-memory float atomics would be compare-and-swap loops)
+__device__ __forceinline__ void red_global(float* q, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_global2(float* q, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(x), "f"(y) : "memory");
 }
 
 // per-thread constants of the engine (recomputed from threadIdx.x where needed: cheaper than
@@ -139,13 +155,17 @@ template <class Net>
 struct DeviceCtxMma {
   using NetT = Net;
   static constexpr bool kWarpMlp = true;
+  static constexpr bool kAccInGlobal = true;
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   static_assert(H == 16 && Pp == 16, "the warp-MMA engine is written for 16-wide layers");
   float* smem;
   const float* gW;
   SmemPlan p;
+  float* gacc;   // this CTA's partial-gradient row (blob layout) in global memory; nullptr: forward only
   // shared-window byte addresses, filled by setup()
-  uint32_t s_w, s_acc, s_frag, s_wt;   // blob, accumulators, fragments, this warp's tiles
+  uint32_t s_w, s_frag, s_wt;   // blob, fragments, this warp's tiles
+
+  __device__ __forceinline__ void bind_partials(float* q) { gacc = q; }
 
   // row of the CTA tile owned by the calling thread
   __device__ __forceinline__ int row_in_tile() const {
@@ -156,12 +176,11 @@ struct DeviceCtxMma {
   __device__ __forceinline__ void setup(int D, int L, uint64_t*, uint32_t*) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     s_w = s0 + p.off_w * 4;
-    s_acc = s0 + (p.off_acc >= 0 ? p.off_acc : 0) * 4;
     s_frag = s0 + p.off_frag * 4;
     s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
     load_weights(smem + p.off_w, gW, p.total);
-    if (p.off_acc >= 0)
-      for (int i = threadIdx.x; i < p.total; i += blockDim.x) smem[p.off_acc + i] = 0.f;
+    if (gacc)
+      for (int i = threadIdx.x; i < p.total; i += blockDim.x) gacc[i] = 0.f;
     __syncthreads();
     // weight fragments, hi/lo split: element e = ((mat * 2 + dir) * 4 + ks * 2 + nt) * 32 + lane
     //   dir 0 (y = x W):    b0 = W[8ks+2t][8nt+g]   b1 = W[8ks+2t+1][8nt+g]
@@ -171,15 +190,15 @@ struct DeviceCtxMma {
       const int ln = e & 31, ksnt = (e >> 5) & 3, dir = (e >> 7) & 1, mat = e >> 8;
       const int mlp = mat / M, slot = mat - mlp * M;
       const int layer = mlp / (D - 1), d = mlp - layer * (D - 1) + 1;
-      const float* Ws = smem + p.off_w + mlp_offset<Net>(D, layer, d) + (d + 1) * H + H + slot * (H * H + H);
+      const float* Ws = gW + mlp_offset<Net>(D, layer, d) + (d + 1) * H + H + slot * (H * H + H);
       const int ks = ksnt >> 1, nt = ksnt & 1, gg = ln >> 2, tt = ln & 3;
       float b0, b1;
       if (dir == 0) {
-        b0 = Ws[(8 * ks + 2 * tt) * 16 + 8 * nt + gg];
-        b1 = Ws[(8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg];
+        b0 = __ldg(Ws + (8 * ks + 2 * tt) * 16 + 8 * nt + gg);
+        b1 = __ldg(Ws + (8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg);
       } else {
-        b0 = Ws[(8 * nt + gg) * 16 + 8 * ks + 2 * tt];
-        b1 = Ws[(8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1];
+        b0 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt);
+        b1 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1);
       }
       uint32_t h0, l0, h1, l1;
       split_tf32(b0, h0, l0);
@@ -193,6 +212,13 @@ struct DeviceCtxMma {
 
   __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
 
+  // ---- register layouts of a [32 x 16] matrix (thread (g, t); mt = m-tile, nt / ks = 8-column block)
+  //   C order  c[mt][nt] = { (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) }     MMA accumulator
+  //   A order  a[mt][ks] = { (g, 2t), (g+8, 2t), (g, 2t+1), (g+8, 2t+1) }     MMA A operand
+  // element (row 8q+g, column 8nt+2t+e):  c[q>>1][nt][2*(q&1)+e]  =  a[q>>1][nt][(q&1)+2e]
+  // Every elementwise step between two layers (ReLU, ReLU mask) writes its result in A order, so the
+  // accumulator -> operand permutation costs no instruction.
+  //
   // ---- per-warp tiles: element (r, col) lives at r*16 + 4*((col>>2) ^ f(r)) + (col&3),
   //      f(r) = ((r>>3)&3) ^ (2*bit1(r) + bit2(r))
   __device__ __forceinline__ static void store_c(uint32_t tile, const MmaLane& ln, const float (&x)[2][2][4]) {
@@ -202,6 +228,16 @@ struct DeviceCtxMma {
       for (int nt = 0; nt < 2; ++nt)
         sts64(tile + ln.cbase + q * 512 + 16 * (ln.cu ^ (2 * nt ^ q)), x[q >> 1][nt][2 * (q & 1)],
               x[q >> 1][nt][2 * (q & 1) + 1]);
+  }
+  __device__ __forceinline__ static void store_a(uint32_t tile, const MmaLane& ln, const float (&a)[2][2][4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint32_t ad = tile + ln.cbase + q * 512 + 16 * (ln.cu ^ (2 * nt ^ q));
+        sts32(ad, a[q >> 1][nt][q & 1]);
+        sts32(ad + 4, a[q >> 1][nt][(q & 1) + 2]);
+      }
   }
   __device__ __forceinline__ static void load_c(uint32_t tile, const MmaLane& ln, float (&x)[2][2][4]) {
 #pragma unroll
@@ -226,10 +262,10 @@ struct DeviceCtxMma {
     }
   }
 
-  // x <- x * B (+ bias): 16 -> 16 for the warp's 32 rows; frag = the matrix' 512-float fragment
-  // block, bias = shared address of the 16 biases (0: none)
-  __device__ __forceinline__ static void dense16(float (&x)[2][2][4], uint32_t frag, uint32_t bias, const MmaLane& ln) {
-    float o[2][2][4];
+  // o (C order) = a (A order) * B (+ bias): 16 -> 16 for the warp's 32 rows; frag = the matrix'
+  // 512-float fragment block, bias = shared address of the 16 biases (0: none)
+  __device__ __forceinline__ static void dense16(const float (&a)[2][2][4], uint32_t frag, uint32_t bias,
+                                                 const MmaLane& ln, float (&o)[2][2][4]) {
     float2 c0 = make_float2(0.f, 0.f), c1 = c0;
     if (bias) {
       c0 = ldw64(bias + 8 * ln.t);
@@ -245,12 +281,12 @@ struct DeviceCtxMma {
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        split_tf32(x[mt][ks][0], ahi[mt][0], alo[mt][0]);   // (row g,   k = t)   <- column 2t
-        split_tf32(x[mt][ks][2], ahi[mt][1], alo[mt][1]);   // (row g+8, k = t)
-        split_tf32(x[mt][ks][1], ahi[mt][2], alo[mt][2]);   // (row g,   k = t+4) <- column 2t+1
-        split_tf32(x[mt][ks][3], ahi[mt][3], alo[mt][3]);   // (row g+8, k = t+4)
-      }
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ahi[mt][e] = __float_as_uint(a[mt][ks][e]);
+          alo[mt][e] = tf32_residual(a[mt][ks][e]);
+        }
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         const float4 f = ldw128(fr + (ks * 2 + nt) * 512);
@@ -264,21 +300,19 @@ struct DeviceCtxMma {
         }
       }
     }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[mt][nt][e] = o[mt][nt][e];
   }
 
-  __device__ __forceinline__ static void relu_c(float (&x)[2][2][4]) {
+  // a (A order) = relu(c) (C order)
+  __device__ __forceinline__ static void relu_to_a(const float (&c)[2][2][4], float (&a)[2][2][4]) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[mt][nt][e] = fmaxf(x[mt][nt][e], 0.f);
+      for (int nt = 0; nt < 2; ++nt) {
+        a[mt][nt][0] = fmaxf(c[mt][nt][0], 0.f);
+        a[mt][nt][1] = fmaxf(c[mt][nt][2], 0.f);
+        a[mt][nt][2] = fmaxf(c[mt][nt][1], 0.f);
+        a[mt][nt][3] = fmaxf(c[mt][nt][3], 0.f);
+      }
   }
 
   // Conditioner forward for the warp's 32 rows: theta[0..16) of the calling thread's row.
@@ -291,7 +325,7 @@ struct DeviceCtxMma {
     const uint32_t W = s_w + mlp_offset<Net>(D, layer, d) * 4;
     const uint32_t b0 = W + n_in * H * 4;
     const uint32_t frag = s_frag + mlp * M * kFragFloats * 4;
-    float x[2][2][4];
+    float x[2][2][4], a[2][2][4];
     {
       const float2 c0 = ldw64(b0 + 8 * ln.t);
       const float2 c1 = ldw64(b0 + 32 + 8 * ln.t);
@@ -316,20 +350,20 @@ struct DeviceCtxMma {
         a1[0] = fmaf(xq, w1.x, a1[0]); a1[1] = fmaf(xq, w1.y, a1[1]);
       }
     }
-    relu_c(x);
+    relu_to_a(x, a);
     if (keep) {
       __syncwarp();   // the previous conditioner's readers are done with the tiles
-      store_c(wt, ln, x);
+      store_a(wt, ln, a);
     }
     uint32_t Wm = b0 + H * 4;
 #pragma unroll
     for (int m = 1; m < M; ++m) {
-      dense16(x, frag + (m - 1) * kFragFloats * 4, Wm + H * H * 4, ln);
-      relu_c(x);
-      if (keep) store_c(wt + m * kWtFloats * 4, ln, x);
+      dense16(a, frag + (m - 1) * kFragFloats * 4, Wm + H * H * 4, ln, x);
+      relu_to_a(x, a);
+      if (keep) store_a(wt + m * kWtFloats * 4, ln, a);
       Wm += (H * H + H) * 4;
     }
-    dense16(x, frag + (M - 1) * kFragFloats * 4, Wm + H * Pp * 4, ln);
+    dense16(a, frag + (M - 1) * kFragFloats * 4, Wm + H * Pp * 4, ln, x);
     const uint32_t scratch = wt + (keep ? M : 0) * kWtFloats * 4;
     __syncwarp();
     store_c(scratch, ln, x);
@@ -338,8 +372,8 @@ struct DeviceCtxMma {
   }
 
   // 4 per-thread partial sums (columns 2t, 2t+1, 8+2t, 9+2t of a 16-wide row) -> summed over the
-  // 8 lanes with the same t, then added to dst[column] (dst: shared address)
-  __device__ __forceinline__ static void colsum_add(const float (&v)[4], uint32_t dst, const MmaLane& ln) {
+  // 8 lanes with the same t, then added to dst[column]
+  __device__ __forceinline__ static void colsum_add(const float (&v)[4], float* dst, const MmaLane& ln) {
     const bool hi = ln.lane & 16, b8 = ln.lane & 8;
     float k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
     const float s0 = hi ? v[0] : v[2], s1 = hi ? v[1] : v[3];
@@ -349,11 +383,21 @@ struct DeviceCtxMma {
     const float ss = b8 ? k0 : k1;
     kk += __shfl_xor_sync(0xffffffffu, ss, 8);
     kk += __shfl_xor_sync(0xffffffffu, kk, 4);
-    if (!(ln.lane & 4)) red_shared(dst + ((hi ? 8 : 0) + 2 * ln.t + (b8 ? 1 : 0)) * 4, kk);
+    if (!(ln.lane & 4)) red_global(dst + (hi ? 8 : 0) + 2 * ln.t + (b8 ? 1 : 0), kk);
+  }
+  // column sums of an A-order matrix
+  __device__ __forceinline__ static void colsum_a(const float (&a)[2][2][4], float* dst, const MmaLane& ln) {
+    float s[4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      s[2 * nt] = (a[0][nt][0] + a[0][nt][1]) + (a[1][nt][0] + a[1][nt][1]);
+      s[2 * nt + 1] = (a[0][nt][2] + a[0][nt][3]) + (a[1][nt][2] + a[1][nt][3]);
+    }
+    colsum_add(s, dst, ln);
   }
 
   // dst[i][j] += sum_r A[r][i] G[r][j] over the warp's 32 rows (A, G: swizzled tiles)
-  __device__ __forceinline__ static void wgrad16(uint32_t TA, uint32_t TG, uint32_t dst, const MmaLane& ln) {
+  __device__ __forceinline__ static void wgrad16(uint32_t TA, uint32_t TG, float* dst, const MmaLane& ln) {
     float dw[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -363,34 +407,38 @@ struct DeviceCtxMma {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       // rows 8ks+t (chunk selector tu^ks) and 8ks+t+4 (selector tu^ks^1)
+      float av[4];
+      av[0] = lds32(ta + ks * 512 + 16 * (ln.tu ^ ks));              // (m = g,   k = t)
+      av[1] = lds32(ta + ks * 512 + 16 * (ln.tu ^ ks ^ 2));          // (m = g+8, k = t)
+      av[2] = lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 1));    // (m = g,   k = t+4)
+      av[3] = lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 3));    // (m = g+8, k = t+4)
       uint32_t ahi[4], alo[4];
-      split_tf32(lds32(ta + ks * 512 + 16 * (ln.tu ^ ks)), ahi[0], alo[0]);                  // (m = g,   k = t)
-      split_tf32(lds32(ta + ks * 512 + 16 * (ln.tu ^ ks ^ 2)), ahi[1], alo[1]);              // (m = g+8, k = t)
-      split_tf32(lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 1)), ahi[2], alo[2]);        // (m = g,   k = t+4)
-      split_tf32(lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 3)), ahi[3], alo[3]);        // (m = g+8, k = t+4)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ahi[e] = __float_as_uint(av[e]);
+        alo[e] = tf32_residual(av[e]);
+      }
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(lds32(tg + ks * 512 + 16 * (ln.tu ^ ks ^ (2 * nt))), bh0, bl0);            // (k = t,   n = g)
-        split_tf32(lds32(tg + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ (2 * nt) ^ 1)), bh1, bl1);  // (k = t+4, n = g)
-        mma_tf32(dw[nt], alo, bh0, bh1);
+        const float b0 = lds32(tg + ks * 512 + 16 * (ln.tu ^ ks ^ (2 * nt)));            // (k = t,   n = g)
+        const float b1 = lds32(tg + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ (2 * nt) ^ 1));  // (k = t+4, n = g)
+        const uint32_t bl0 = tf32_residual(b0), bl1 = tf32_residual(b1);
+        mma_tf32(dw[nt], alo, __float_as_uint(b0), __float_as_uint(b1));
         mma_tf32(dw[nt], ahi, bl0, bl1);
-        mma_tf32(dw[nt], ahi, bh0, bh1);
+        mma_tf32(dw[nt], ahi, __float_as_uint(b0), __float_as_uint(b1));
       }
     }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      const uint32_t q0 = dst + (ln.g * 16 + 8 * nt + 2 * ln.t) * 4;
-      red_shared(q0, dw[nt][0]);
-      red_shared(q0 + 4, dw[nt][1]);
-      red_shared(q0 + 512, dw[nt][2]);
-      red_shared(q0 + 516, dw[nt][3]);
+      float* q0 = dst + ln.g * 16 + 8 * nt + 2 * ln.t;
+      red_global2(q0, dw[nt][0], dw[nt][1]);
+      red_global2(q0 + 128, dw[nt][2], dw[nt][3]);
     }
   }
 
   // Conditioner backward for the warp's 32 rows.  cond_forward(..., keep = true) of the same
   // conditioner must have run just before.  gtheta: adjoint of the row's spline parameters;
-  // gvec[coordinate] += adjoint of the conditioning coordinates; weight gradients -> accumulator.
+  // gvec[coordinate] += adjoint of the conditioning coordinates; weight gradients -> gacc.
   __device__ __forceinline__ void cond_backward(int D, int layer, int d, float tval, const float* cvec,
                                                 const float* gtheta, float* gvec) const {
     const MmaLane ln;
@@ -398,57 +446,50 @@ struct DeviceCtxMma {
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
     const int w_off = mlp_offset<Net>(D, layer, d);
     const uint32_t W = s_w + w_off * 4;
-    const uint32_t A = s_acc + w_off * 4;
+    float* A = gacc + w_off;
     const uint32_t frag = s_frag + (mlp * M * kFragFloats + 512) * 4;
     const uint32_t tg = wt + M * kWtFloats * 4;
     __syncwarp();
     store_row(tg, ln, gtheta);
     __syncwarp();
-    float G[2][2][4];
-    load_c(tg, ln, G);
+    float G[2][2][4];   // A order
+    {
+      float c[2][2][4];
+      load_c(tg, ln, c);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          G[mt][nt][0] = c[mt][nt][0]; G[mt][nt][1] = c[mt][nt][2];
+          G[mt][nt][2] = c[mt][nt][1]; G[mt][nt][3] = c[mt][nt][3];
+        }
+    }
 #pragma unroll
     for (int slot = M - 1; slot >= 0; --slot) {
       // dense matrix `slot`: input = hidden activations `slot`, output adjoint = G
-      const uint32_t moff = (n_in * H + H + slot * (H * H + H)) * 4;
+      const int moff = n_in * H + H + slot * (H * H + H);
       wgrad16(wt + slot * kWtFloats * 4, tg, A + moff, ln);
-      {
-        float s[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s[e] = 0.f;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          s[0] += G[mt][0][0] + G[mt][0][2]; s[1] += G[mt][0][1] + G[mt][0][3];
-          s[2] += G[mt][1][0] + G[mt][1][2]; s[3] += G[mt][1][1] + G[mt][1][3];
-        }
-        colsum_add(s, A + moff + H * 16 * 4, ln);
-      }
-      dense16(G, frag + slot * kFragFloats * 4, 0u, ln);
-      float hm[2][2][4];
+      colsum_a(G, A + moff + H * 16, ln);
+      float dh[2][2][4], hm[2][2][4];
+      dense16(G, frag + slot * kFragFloats * 4, 0u, ln, dh);
       load_c(wt + slot * kWtFloats * 4, ln, hm);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) G[mt][nt][e] = hm[mt][nt][e] > 0.f ? G[mt][nt][e] : 0.f;
+        for (int nt = 0; nt < 2; ++nt) {
+          G[mt][nt][0] = hm[mt][nt][0] > 0.f ? dh[mt][nt][0] : 0.f;
+          G[mt][nt][1] = hm[mt][nt][2] > 0.f ? dh[mt][nt][2] : 0.f;
+          G[mt][nt][2] = hm[mt][nt][1] > 0.f ? dh[mt][nt][1] : 0.f;
+          G[mt][nt][3] = hm[mt][nt][3] > 0.f ? dh[mt][nt][3] : 0.f;
+        }
       if (slot > 0) {
         __syncwarp();
-        store_c(tg, ln, G);
+        store_a(tg, ln, G);
         __syncwarp();
       }
     }
     // layer 0: bias, input matrix, input adjoints
-    {
-      float s[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[e] = 0.f;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        s[0] += G[mt][0][0] + G[mt][0][2]; s[1] += G[mt][0][1] + G[mt][0][3];
-        s[2] += G[mt][1][0] + G[mt][1][2]; s[3] += G[mt][1][1] + G[mt][1][3];
-      }
-      colsum_add(s, A + n_in * H * 4, ln);
-    }
+    colsum_a(G, A + n_in * H, ln);
 #pragma unroll 1
     for (int i = 0; i < n_in; ++i) {
       const float xi = i == 0 ? tval : cvec[perm_at(layer, i - 1, D)];
@@ -458,13 +499,14 @@ struct DeviceCtxMma {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float xq = __shfl_sync(0xffffffffu, xi, (ln.lane & ~3u) | q);
-        const float* g0 = G[q >> 1][0] + 2 * (q & 1);
-        const float* g1 = G[q >> 1][1] + 2 * (q & 1);
-        pw[0] = fmaf(xq, g0[0], pw[0]); pw[1] = fmaf(xq, g0[1], pw[1]);
-        pw[2] = fmaf(xq, g1[0], pw[2]); pw[3] = fmaf(xq, g1[1], pw[3]);
-        pin[q] = g0[0] * w0.x + g0[1] * w0.y + g1[0] * w1.x + g1[1] * w1.y;
+        // row 8q+g: columns 2t, 2t+1 (nt = 0) and 8+2t, 9+2t (nt = 1)
+        const float g00 = G[q >> 1][0][q & 1], g01 = G[q >> 1][0][(q & 1) + 2];
+        const float g10 = G[q >> 1][1][q & 1], g11 = G[q >> 1][1][(q & 1) + 2];
+        pw[0] = fmaf(xq, g00, pw[0]); pw[1] = fmaf(xq, g01, pw[1]);
+        pw[2] = fmaf(xq, g10, pw[2]); pw[3] = fmaf(xq, g11, pw[3]);
+        pin[q] = g00 * w0.x + g01 * w0.y + g10 * w1.x + g11 * w1.y;
       }
-      colsum_add(pw, A + i * 64, ln);
+      colsum_add(pw, A + i * 16, ln);
       if (i >= 1) {
         // sum over the quad; lane t ends up with the total of row 8t+g (its own row)
         const bool t2 = ln.lane & 2, t1 = ln.lane & 1;
@@ -488,7 +530,7 @@ struct DeviceCtxMma {
       float v = gfirst[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red_shared(s_acc + j * 4, v);
+      if (lane == 0) red_global(gacc + j, v);
     }
     __syncthreads();
   }

@@ -32,6 +32,16 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
   return 0 if t is None else t.data_ptr()
 
 
+def _rows(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+  """Row buffers of the train step: CUDA tensors, or PINNED host tensors, which the kernel reads in
+  place over PCIe (unified addressing: each row is read once, so no staging copy is needed)."""
+  if t is not None and not t.is_cuda and t.is_pinned():
+    if t.dtype != torch.float32 or not t.is_contiguous():
+      raise _lib.CnfotError(f"{name}: expected a contiguous float32 tensor")
+    return t
+  return _dev(t, name)
+
+
 # ---------------------------------------------------------------- seam 2: splines
 def _rqs(inverse: bool, v, params, num_bins, range_min, range_max, min_bin_size, min_knot_slope,
          want_bins):
@@ -179,10 +189,10 @@ def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, laten
   lib = _lib.load()
   weights = _dev(weights, "weights")
   device = weights.device
-  latent = _dev(latent, "latent")
-  latent_sub = _dev(latent_sub, "latent_sub")
-  src = _dev(src, "src")
-  tgt = _dev(tgt, "tgt")
+  latent = _rows(latent, "latent")
+  latent_sub = _rows(latent_sub, "latent_sub")
+  src = _rows(src, "src")
+  tgt = _rows(tgt, "tgt")
   rows_B = 0
   for t in (src, latent):
     if t is not None:
@@ -207,7 +217,8 @@ def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, laten
 def mfc_step_host(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, latent_sub, src,
                   tgt, t_batch: Sequence[float], lam: float, global_B: int, global_b: int,
                   out: torch.Tensor, device=None) -> torch.Tensor:
-  """Same step with HOST (ideally pinned) tensors in and out; copies are inside the call."""
+  """Same step with HOST tensors in and out; transfers are inside the call.  Pinned row buffers are
+  read in place by the kernel (zero-copy), pageable ones are staged with cudaMemcpyAsync."""
   lib = _lib.load()
   device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
   for name, t in (("weights", weights), ("latent", latent), ("latent_sub", latent_sub),

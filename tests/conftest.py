@@ -21,3 +21,12 @@ def pytest_collection_modifyitems(config, items):
   for item in items:
     if "gpu" in item.keywords:
       item.add_marker(skip)
+
+
+@pytest.fixture(params=["mma", "cuda"])
+def engine(request, monkeypatch):
+  """Conditioner engine of the fused kernels (CNFOT_ENGINE): the warp-level tensor-core engine is
+  the default for 16-wide networks, the CUDA-core engine covers every other shape; shapes the
+  requested engine does not support fall back to the CUDA-core one inside the library."""
+  monkeypatch.setenv("CNFOT_ENGINE", request.param)
+  return request.param

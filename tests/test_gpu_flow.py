@@ -28,7 +28,7 @@ def close(a, b, tol=TOL, tol_max=TOL_MAX):
 
 
 @pytest.mark.parametrize("D,L,M,H,K,sigma", SHAPES)
-def test_forward_inverse_logprob(D, L, M, H, K, sigma):
+def test_forward_inverse_logprob(D, L, M, H, K, sigma, engine):
   cfg = make_cfg(dim=D, L=L, M=M, H=H, K=K)
   shape = shape_of(cfg)
   spec, params = make_params(cfg, sigma)
@@ -72,7 +72,7 @@ def test_identity_at_reference_init():
 
 @pytest.mark.parametrize("D,L,M,H,K,sigma", SHAPES[:4])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_vjp(D, L, M, H, K, sigma, inverse):
+def test_vjp(D, L, M, H, K, sigma, inverse, engine):
   cfg = make_cfg(dim=D, L=L, M=M, H=H, K=K)
   shape = shape_of(cfg)
   spec, params = make_params(cfg, sigma)
