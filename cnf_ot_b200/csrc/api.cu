@@ -105,8 +105,9 @@ struct LaunchCfg {
 static thread_local int g_last_launch[4] = {0, 0, 0, 0};
 
 // Shared-memory plan and engine choice.
-//   warp-MMA engine (warp_mlp.cuh)  16-wide networks whose weights + hi/lo fragments + per-warp
-//                                   tiles leave room for >= 2 CTAs per SM: the default there
+//   warp-MMA engine (warp_mlp.cuh)  16-wide networks: the default there.  Weights + hi/lo fragments resident
+//                                   in shared memory when that leaves room for >= 2 CTAs per SM, otherwise
+//                                   streamed from global memory (fragments built into the workspace)
 //   CUDA-core engine                everything else; weights live in shared memory when weights +
 //                                   accumulators + row tiles leave room for two CTAs per SM, otherwise
 //                                   one conditioner at a time is staged from L2
@@ -125,7 +126,7 @@ static int engine_override() {
   return -1;
 }
 
-static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, int* engine) {
+static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, int* engine, bool has_ws = true) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int want = engine_override();
@@ -143,6 +144,12 @@ static int make_plan(const FlowLayout& lay, bool with_grad, SmemPlan* sp, int* e
     if ((int64_t)m.floats * 4 * 2 <= di.max_smem_optin) {
       *sp = m;
       *engine = kEngMma;
+      return 0;
+    }
+    // larger flows: fragments in the caller's workspace (entry points that have one)
+    if (has_ws) {
+      *sp = plan_smem_mma(lay, with_grad, false);
+      *engine = kEngMmaStream;
       return 0;
     }
   }
@@ -200,14 +207,31 @@ static int configure(const void* kernel, const SmemPlan& sp, int64_t tiles, Laun
   g_last_launch[0] = cfg->grid;
   g_last_launch[1] = (int)smem;
   g_last_launch[2] = occ;
-  g_last_launch[3] = sp.off_wmma >= 0 ? kEngTc : (sp.off_frag >= 0 ? kEngMma : kEngCuda);
+  g_last_launch[3] = sp.off_wmma >= 0 ? kEngTc : (sp.off_frag >= 0 ? kEngMma : kEngCuda);  // 2 also for the streamed plan
   return 0;
 }
 
+static int64_t frag_bytes(const FlowLayout& lay) {
+  if (!tc_available(lay)) return 0;
+  return (int64_t)lay.L * (lay.D - 1) * lay.M * kFragFloats * sizeof(float);
+}
+// [tile counter | per-CTA loss partials | per-CTA gradient partials | weight fragments (streamed warp-MMA plan)]
 static int64_t partial_bytes(const FlowLayout& lay) {
   int64_t loss = (int64_t)kMaxGrid * kNumSlots * sizeof(double);
-  int64_t grad = (int64_t)kMaxGrid * lay.total * sizeof(float);
-  return kCounterBytes + loss + grad;
+  int64_t grad = ((int64_t)kMaxGrid * lay.total * sizeof(float) + 255) / 256 * 256;
+  return kCounterBytes + loss + grad + frag_bytes(lay);
+}
+static float* carve_frags(void* ws, const FlowLayout& lay) {
+  return (float*)((char*)ws + partial_bytes(lay) - frag_bytes(lay));
+}
+// streamed warp-MMA plan: fill the fragment buffer (stream-ordered before the main kernel)
+static int launch_build_frags(cudaStream_t s, const FlowLayout& lay, const float* weights, float* frags) {
+  const int n_mat = lay.L * (lay.D - 1) * lay.M;
+  const int blocks = (n_mat * 256 + 255) / 256;
+  build_frags_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, s>>>(weights, frags, lay.D, lay.M, n_mat);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "build_frags_kernel launch");
+  return 0;
 }
 
 static PartialBuf carve_partials(void* ws, unsigned long long** counter) {
@@ -418,12 +442,12 @@ static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, co
   if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
   SmemPlan sp;
   int engine;
-  if (int rc = make_plan(lay, false, &sp, &engine)) return rc;
+  if (int rc = make_plan(lay, false, &sp, &engine, false)) return rc;
   const void* kernel = find_flow_eval_kernel(lay, engine);
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   EvalArgs a;
-  a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
+  a.W = weights; a.frags = nullptr; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
   a.out = out; a.logdet = logdet; a.dir = dir; a.add_base = add_base;
   a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
@@ -478,7 +502,12 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
   if (int rc = configure(kernel, sp, (rows + kTile - 1) / kTile, &cfg)) return rc;
   unsigned long long* counter;
   VjpArgs a;
-  a.W = weights; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
+  a.W = weights; a.frags = nullptr; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
+  if (engine == kEngMmaStream) {
+    float* fr = carve_frags(workspace, lay);
+    if (int rc = launch_build_frags(s, lay, weights, fr)) return rc;
+    a.frags = fr;
+  }
   a.g_out = g_out; a.g_logdet = g_logdet; a.g_in = g_in; a.dir = dir; a.add_base = add_base;
   a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
@@ -573,6 +602,12 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   LaunchCfg cfg;
   if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
   a.W = weights;
+  a.frags = nullptr;
+  if (engine == kEngMmaStream) {
+    float* fr = carve_frags(workspace, lay);
+    if (int rc = launch_build_frags(s, lay, weights, fr)) return rc;
+    a.frags = fr;
+  }
   a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.sc = spline_consts(flow);
   a.pb = carve_partials(workspace, &a.tile_counter);

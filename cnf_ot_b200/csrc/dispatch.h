@@ -9,8 +9,9 @@ namespace cnfot {
 // when no instantiation exists for the network shape.  Shapes with a
 // compile-time (dim, layers) specialisation keep the per-row state in registers;
 // all others use the runtime-shape kernel (state in local memory).
-// engine: 0 CUDA cores, 1 tcgen05 (tc_engine.cuh), 2 warp-level MMA (warp_mlp.cuh); engines 1 and 2
-// exist for hidden == 16 and num_bins == 5 only (tc_available()).
+// engine: 0 CUDA cores, 1 tcgen05 (tc_engine.cuh), 2 warp-level MMA with weights + fragments resident in
+// shared memory (warp_mlp.cuh), 3 warp-level MMA streaming them from global memory; engines 1-3 exist
+// for hidden == 16 and num_bins == 5 only (tc_available()).
 const void* find_flow_eval_kernel(const FlowLayout& f, int engine = 0);
 const void* find_flow_vjp_kernel(const FlowLayout& f, int engine = 0);
 const void* find_mfc_step_kernel(const FlowLayout& f, int engine = 0);

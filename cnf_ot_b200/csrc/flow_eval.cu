@@ -26,6 +26,10 @@ const void* find_flow_eval_kernel(const FlowLayout& f, int engine) {
     EVAL_ENG_CASE(1, kEngMma) EVAL_ENG_CASE(2, kEngMma) EVAL_ENG_CASE(3, kEngMma)
     return nullptr;
   }
+  if (engine == kEngMmaStream && tc_available(f)) {
+    EVAL_ENG_CASE(1, kEngMmaStream) EVAL_ENG_CASE(2, kEngMmaStream) EVAL_ENG_CASE(3, kEngMmaStream)
+    return nullptr;
+  }
   if (f.H == 16 && f.K == 5 && f.M == 2 && f.D == 2 && f.L == 2)
     return (const void*)&flow_eval_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, kEngCuda>;
   CNFOT_NET_LIST(EVAL_CASE)
@@ -41,6 +45,10 @@ const void* find_flow_vjp_kernel(const FlowLayout& f, int engine) {
     if (f.M == 2 && f.D == 2 && f.L == 2)
       return (const void*)&flow_vjp_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, kEngMma>;
     VJP_ENG_CASE(1, kEngMma) VJP_ENG_CASE(2, kEngMma) VJP_ENG_CASE(3, kEngMma)
+    return nullptr;
+  }
+  if (engine == kEngMmaStream && tc_available(f)) {
+    VJP_ENG_CASE(1, kEngMmaStream) VJP_ENG_CASE(2, kEngMmaStream) VJP_ENG_CASE(3, kEngMmaStream)
     return nullptr;
   }
   if (f.H == 16 && f.K == 5 && f.M == 2 && f.D == 2 && f.L == 2)

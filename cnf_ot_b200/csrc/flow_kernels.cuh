@@ -14,7 +14,7 @@ namespace cnfot {
 
 // CTA context by engine: 0 CUDA-core dense layers, 1 the tcgen05 engine (tc_engine.cuh),
 // 2 the warp-level tensor-core engine (warp_mlp.cuh); 1 and 2 exist for 16-wide networks
-enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2 };
+enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2, kEngMmaStream = 3 };
 #ifndef CNFOT_MMA_MIN_CTAS
 #define CNFOT_MMA_MIN_CTAS 4
 #endif
@@ -24,7 +24,9 @@ struct CtxSelect { using type = DeviceCtx<Net>; };
 template <class Net>
 struct CtxSelect<Net, kEngTc> { using type = DeviceCtxTC<Net>; };
 template <class Net>
-struct CtxSelect<Net, kEngMma> { using type = DeviceCtxMma<Net>; };
+struct CtxSelect<Net, kEngMma> { using type = DeviceCtxMma<Net, true>; };
+template <class Net>
+struct CtxSelect<Net, kEngMmaStream> { using type = DeviceCtxMma<Net, false>; };
 
 template <class Ctx>
 __device__ __forceinline__ void ctx_setup(Ctx& ctx, int D, int L, uint64_t* mbar, uint32_t* slot) {
@@ -36,6 +38,7 @@ __device__ __forceinline__ void ctx_teardown(Ctx& ctx) { ctx.teardown(); }
 // ---- forward-only evaluation (model API: sample / forward / inverse / log_prob) ----
 struct EvalArgs {
   const float* W;
+  const float* frags;   // streamed warp-MMA plan: global fragment buffer (else nullptr)
   const float* in;
   const float* cond;
   int64_t cond_stride;
@@ -50,7 +53,7 @@ struct EvalArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_eval_kernel(EvalArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
@@ -58,6 +61,7 @@ __global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx.bind_partials(nullptr);
+  ctx.bind_frags(a.frags);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
@@ -106,6 +110,7 @@ __device__ inline void flush_partials(const PartialBuf& pb, const float* sAcc, i
 // ---- generic VJP of one flow pass (what a custom_vjp backward rule calls) ----------
 struct VjpArgs {
   const float* W;
+  const float* frags;
   const float* in;
   const float* cond;
   int64_t cond_stride;
@@ -122,7 +127,7 @@ struct VjpArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_vjp_kernel(VjpArgs a) {
+__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_vjp_kernel(VjpArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ __align__(8) uint64_t tc_mbar;
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) flow_
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
+  ctx.bind_frags(a.frags);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
@@ -191,6 +197,7 @@ constexpr int kMaxSegments = 40;
 
 struct StepArgs {
   const float* W;
+  const float* frags;
   int D, L;
   SmemPlan plan;
   SplineConsts<float> sc;
@@ -203,7 +210,7 @@ struct StepArgs {
 };
 
 template <class Net, class DimsT, int ENG>
-__global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch[kWarps];
   __shared__ long long s_tile;
@@ -214,6 +221,7 @@ __global__ void __launch_bounds__(kTile, ENG == kEngMma ? kMmaMinCtas : 1) mfc_s
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
+  ctx.bind_frags(a.frags);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};

@@ -23,6 +23,10 @@ const void* find_mfc_step_kernel(const FlowLayout& f, int engine) {
     STEP_ENG_CASE(1, kEngMma) STEP_ENG_CASE(2, kEngMma) STEP_ENG_CASE(3, kEngMma)
     return nullptr;
   }
+  if (engine == kEngMmaStream && tc_available(f)) {
+    STEP_ENG_CASE(1, kEngMmaStream) STEP_ENG_CASE(2, kEngMmaStream) STEP_ENG_CASE(3, kEngMmaStream)
+    return nullptr;
+  }
   if (f.H == 16 && f.K == 5 && f.M == 2 && f.D == 2 && f.L == 2)
     return (const void*)&mfc_step_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, kEngCuda>;
   CNFOT_NET_LIST(STEP_CASE)

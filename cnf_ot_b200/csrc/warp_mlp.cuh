@@ -57,22 +57,26 @@ __device__ __forceinline__ uint32_t tf32_residual(float v) {
 
 // Shared-memory plan of the warp-MMA kernels (same struct as the CUDA-core plan; the row tiles
 // of the latter are not used).
-inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad) {
+// resident: the blob (input layers, biases, `first`) and the hi/lo fragments of the 16x16 matrices
+// live in shared memory (measured on cfg 2: reading the input layers from global/L1 instead costs
+// ~3 %, and a fifth CTA per SM at <= 102 registers is slower than four at 128).
+// streamed (larger flows, e.g. dim 10): only `first` is resident; input layers / biases are read
+// from the blob and the fragments from a buffer a prep kernel fills (build_frags_kernel), both in
+// global memory through L1.
+inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad, bool resident = true) {
   SmemPlan p;
   p.total = f.total;
-  p.w_in_smem = 1;  // the blob (input layers, biases, `first`) + the hi/lo fragments of the 16x16 matrices
-                    // (measured: reading the input layers from global/L1 instead costs ~3 %, and a fifth
-                    //  CTA per SM at <= 102 registers is slower than four at 128)
+  p.w_in_smem = resident ? 1 : 0;
   const int tot4 = (f.total + 3) / 4 * 4;
   p.ld_in = p.ld_h = p.ld_p = 0;
   p.off_w = 0;
   p.w_stage = 0;
-  int o = tot4;
+  int o = resident ? tot4 : f.Pp;
   p.off_acc = -1;   // weight gradients go straight to the CTA's partial row in global memory
   p.off_in = p.off_hid = p.off_gh = p.off_gth = p.off_lo = p.off_wmma = -1;
   o = align_up(o, 32);
   p.off_frag = o;
-  o += f.L * (f.D - 1) * f.M * kFragFloats;
+  if (resident) o += f.L * (f.D - 1) * f.M * kFragFloats;
   p.off_wt = o;
   p.wt_stride = (with_grad ? f.M + 1 : 1) * kWtFloats;
   o += kWarps * p.wt_stride;
@@ -127,6 +131,65 @@ __device__ __forceinline__ void red_global2(float* q, float x, float y) {
   asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(x), "f"(y) : "memory");
 }
 
+// A float-indexed reference to read-only weights: a shared-window address (resident plan) or a
+// pointer into global memory (streamed plan).
+template <bool RES>
+struct WRef;
+template <>
+struct WRef<true> {
+  uint32_t a;
+  __device__ __forceinline__ WRef operator+(int floats) const { return WRef{a + (uint32_t)floats * 4u}; }
+  __device__ __forceinline__ float2 ld2() const { return ldw64(a); }
+  __device__ __forceinline__ float4 ld4() const { return ldw128(a); }
+  __device__ __forceinline__ bool valid() const { return a != 0u; }
+  __device__ __forceinline__ static WRef none() { return WRef{0u}; }
+};
+template <>
+struct WRef<false> {
+  const float* q;
+  __device__ __forceinline__ WRef operator+(int floats) const { return WRef{q + floats}; }
+  __device__ __forceinline__ float2 ld2() const { return __ldg(reinterpret_cast<const float2*>(q)); }
+  __device__ __forceinline__ float4 ld4() const { return __ldg(reinterpret_cast<const float4*>(q)); }
+  __device__ __forceinline__ bool valid() const { return q != nullptr; }
+  __device__ __forceinline__ static WRef none() { return WRef{nullptr}; }
+};
+
+// One float4 of the hi/lo weight fragments of a 16-wide flow (hidden = Pp = 16):
+//   element e = ((mat * 2 + dir) * 4 + ks * 2 + nt) * 32 + lane,  mat = mlp * M + slot
+//   dir 0 (y = x W):    b0 = W[8ks+2t][8nt+g]   b1 = W[8ks+2t+1][8nt+g]
+//   dir 1 (y = g W^T):  b0 = W[8nt+g][8ks+2t]   b1 = W[8nt+g][8ks+2t+1]
+//   value = { b0_hi, b1_hi, b0_lo, b1_lo }
+__device__ __forceinline__ float4 frag_element(const float* __restrict__ blob, int D, int M, int e) {
+  constexpr int H = 16, Pp = 16;
+  const int ln = e & 31, ksnt = (e >> 5) & 3, dir = (e >> 7) & 1, mat = e >> 8;
+  const int mlp = mat / M, slot = mat - mlp * M;
+  const int layer = mlp / (D - 1), d = mlp - layer * (D - 1) + 1;
+  const int mlp_const = H + (M - 1) * (H * H + H) + H * Pp + Pp;
+  const int layer_stride = (D - 1) * mlp_const + H * ((D - 1) * (D + 2) / 2);
+  const float* Ws = blob + Pp + layer * layer_stride + (d - 1) * mlp_const + H * ((d - 1) * (d + 2) / 2) +
+                    (d + 1) * H + H + slot * (H * H + H);
+  const int ks = ksnt >> 1, nt = ksnt & 1, gg = ln >> 2, tt = ln & 3;
+  float b0, b1;
+  if (dir == 0) {
+    b0 = __ldg(Ws + (8 * ks + 2 * tt) * 16 + 8 * nt + gg);
+    b1 = __ldg(Ws + (8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg);
+  } else {
+    b0 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt);
+    b1 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1);
+  }
+  uint32_t h0, l0, h1, l1;
+  split_tf32(b0, h0, l0);
+  split_tf32(b1, h1, l1);
+  return make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+}
+
+// streamed plan: fragments of every dense matrix into a global buffer (n_mat * kFragFloats floats)
+static __global__ void build_frags_kernel(const float* __restrict__ blob, float* __restrict__ frags, int D, int M,
+                                   int n_mat) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_mat * 256; e += gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(frags)[e] = frag_element(blob, D, M, e);
+}
+
 // per-thread constants of the engine (recomputed from threadIdx.x where needed: cheaper than
 // re-loading them from a context that lives in local memory)
 struct MmaLane {
@@ -151,9 +214,10 @@ struct MmaLane {
   }
 };
 
-template <class Net>
+template <class Net, bool RES>
 struct DeviceCtxMma {
   using NetT = Net;
+  using Ref = WRef<RES>;
   static constexpr bool kWarpMlp = true;
   static constexpr bool kAccInGlobal = true;
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
@@ -162,10 +226,12 @@ struct DeviceCtxMma {
   const float* gW;
   SmemPlan p;
   float* gacc;   // this CTA's partial-gradient row (blob layout) in global memory; nullptr: forward only
-  // shared-window byte addresses, filled by setup()
-  uint32_t s_w, s_frag, s_wt;   // blob, fragments, this warp's tiles
+  const float* gfrag;   // streamed plan: the fragment buffer in global memory
+  Ref w_ref, frag_ref;  // blob and fragments (shared-window address or global pointer)
+  uint32_t s_wt;        // shared-window address of this warp's tiles
 
   __device__ __forceinline__ void bind_partials(float* q) { gacc = q; }
+  __device__ __forceinline__ void bind_frags(const float* q) { gfrag = q; }
 
   // row of the CTA tile owned by the calling thread
   __device__ __forceinline__ int row_in_tile() const {
@@ -175,36 +241,19 @@ struct DeviceCtxMma {
 
   __device__ __forceinline__ void setup(int D, int L, uint64_t*, uint32_t*) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
-    s_w = s0 + p.off_w * 4;
-    s_frag = s0 + p.off_frag * 4;
     s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
-    load_weights(smem + p.off_w, gW, p.total);
+    load_weights(smem + p.off_w, gW, RES ? p.total : Pp);
     if (gacc)
       for (int i = threadIdx.x; i < p.total; i += blockDim.x) gacc[i] = 0.f;
-    __syncthreads();
-    // weight fragments, hi/lo split: element e = ((mat * 2 + dir) * 4 + ks * 2 + nt) * 32 + lane
-    //   dir 0 (y = x W):    b0 = W[8ks+2t][8nt+g]   b1 = W[8ks+2t+1][8nt+g]
-    //   dir 1 (y = g W^T):  b0 = W[8nt+g][8ks+2t]   b1 = W[8nt+g][8ks+2t+1]
-    const int n_mat = L * (D - 1) * M;
-    for (int e = threadIdx.x; e < n_mat * 256; e += blockDim.x) {
-      const int ln = e & 31, ksnt = (e >> 5) & 3, dir = (e >> 7) & 1, mat = e >> 8;
-      const int mlp = mat / M, slot = mat - mlp * M;
-      const int layer = mlp / (D - 1), d = mlp - layer * (D - 1) + 1;
-      const float* Ws = gW + mlp_offset<Net>(D, layer, d) + (d + 1) * H + H + slot * (H * H + H);
-      const int ks = ksnt >> 1, nt = ksnt & 1, gg = ln >> 2, tt = ln & 3;
-      float b0, b1;
-      if (dir == 0) {
-        b0 = __ldg(Ws + (8 * ks + 2 * tt) * 16 + 8 * nt + gg);
-        b1 = __ldg(Ws + (8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg);
-      } else {
-        b0 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt);
-        b1 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1);
-      }
-      uint32_t h0, l0, h1, l1;
-      split_tf32(b0, h0, l0);
-      split_tf32(b1, h1, l1);
-      *reinterpret_cast<float4*>(smem + p.off_frag + mat * kFragFloats + dir * 512 + (ksnt * 32 + ln) * 4) =
-          make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    if constexpr (RES) {
+      w_ref = Ref{s0 + (uint32_t)p.off_w * 4u};
+      frag_ref = Ref{s0 + (uint32_t)p.off_frag * 4u};
+      const int n_mat = L * (D - 1) * M;
+      for (int e = threadIdx.x; e < n_mat * 256; e += blockDim.x)
+        reinterpret_cast<float4*>(smem + p.off_frag)[e] = frag_element(gW, D, M, e);
+    } else {
+      w_ref = Ref{gW};
+      frag_ref = Ref{gfrag};
     }
     __syncthreads();
   }
@@ -263,20 +312,20 @@ struct DeviceCtxMma {
   }
 
   // o (C order) = a (A order) * B (+ bias): 16 -> 16 for the warp's 32 rows; frag = the matrix'
-  // 512-float fragment block, bias = shared address of the 16 biases (0: none)
-  __device__ __forceinline__ static void dense16(const float (&a)[2][2][4], uint32_t frag, uint32_t bias,
+  // 512-float fragment block, bias = the 16 biases (Ref::none(): no bias)
+  __device__ __forceinline__ static void dense16(const float (&a)[2][2][4], Ref frag, Ref bias,
                                                  const MmaLane& ln, float (&o)[2][2][4]) {
     float2 c0 = make_float2(0.f, 0.f), c1 = c0;
-    if (bias) {
-      c0 = ldw64(bias + 8 * ln.t);
-      c1 = ldw64(bias + 32 + 8 * ln.t);
+    if (bias.valid()) {
+      c0 = (bias + 2 * ln.t).ld2();
+      c1 = (bias + 8 + 2 * ln.t).ld2();
     }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       o[mt][0][0] = c0.x; o[mt][0][1] = c0.y; o[mt][0][2] = c0.x; o[mt][0][3] = c0.y;
       o[mt][1][0] = c1.x; o[mt][1][1] = c1.y; o[mt][1][2] = c1.x; o[mt][1][3] = c1.y;
     }
-    const uint32_t fr = frag + ln.lane * 16;
+    const Ref fr = frag + ln.lane * 4;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t ahi[2][4], alo[2][4];
@@ -289,7 +338,7 @@ struct DeviceCtxMma {
         }
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const float4 f = ldw128(fr + (ks * 2 + nt) * 512);
+        const float4 f = (fr + (ks * 2 + nt) * 128).ld4();
         const uint32_t bh0 = __float_as_uint(f.x), bh1 = __float_as_uint(f.y);
         const uint32_t bl0 = __float_as_uint(f.z), bl1 = __float_as_uint(f.w);
 #pragma unroll
@@ -322,13 +371,13 @@ struct DeviceCtxMma {
     const MmaLane ln;
     const uint32_t wt = s_wt;
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
-    const uint32_t W = s_w + mlp_offset<Net>(D, layer, d) * 4;
-    const uint32_t b0 = W + n_in * H * 4;
-    const uint32_t frag = s_frag + mlp * M * kFragFloats * 4;
+    const Ref W = w_ref + mlp_offset<Net>(D, layer, d);
+    const Ref b0 = W + n_in * H;
+    const Ref frag = frag_ref + mlp * M * kFragFloats;
     float x[2][2][4], a[2][2][4];
     {
-      const float2 c0 = ldw64(b0 + 8 * ln.t);
-      const float2 c1 = ldw64(b0 + 32 + 8 * ln.t);
+      const float2 c0 = (b0 + 2 * ln.t).ld2();
+      const float2 c1 = (b0 + 8 + 2 * ln.t).ld2();
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         x[mt][0][0] = c0.x; x[mt][0][1] = c0.y; x[mt][0][2] = c0.x; x[mt][0][3] = c0.y;
@@ -339,8 +388,8 @@ struct DeviceCtxMma {
 #pragma unroll 1
     for (int i = 0; i < n_in; ++i) {
       const float xi = i == 0 ? tval : cvec[perm_at(layer, i - 1, D)];
-      const float2 w0 = ldw64(W + i * 64 + 8 * ln.t);
-      const float2 w1 = ldw64(W + i * 64 + 32 + 8 * ln.t);
+      const float2 w0 = (W + i * 16 + 2 * ln.t).ld2();
+      const float2 w1 = (W + i * 16 + 8 + 2 * ln.t).ld2();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float xq = __shfl_sync(0xffffffffu, xi, (ln.lane & ~3u) | q);
@@ -355,15 +404,15 @@ struct DeviceCtxMma {
       __syncwarp();   // the previous conditioner's readers are done with the tiles
       store_a(wt, ln, a);
     }
-    uint32_t Wm = b0 + H * 4;
+    Ref Wm = b0 + H;
 #pragma unroll
     for (int m = 1; m < M; ++m) {
-      dense16(a, frag + (m - 1) * kFragFloats * 4, Wm + H * H * 4, ln, x);
+      dense16(a, frag + (m - 1) * kFragFloats, Wm + H * H, ln, x);
       relu_to_a(x, a);
       if (keep) store_a(wt + m * kWtFloats * 4, ln, a);
-      Wm += (H * H + H) * 4;
+      Wm = Wm + (H * H + H);
     }
-    dense16(a, frag + (M - 1) * kFragFloats * 4, Wm + H * Pp * 4, ln, x);
+    dense16(a, frag + (M - 1) * kFragFloats, Wm + H * Pp, ln, x);
     const uint32_t scratch = wt + (keep ? M : 0) * kWtFloats * 4;
     __syncwarp();
     store_c(scratch, ln, x);
@@ -445,9 +494,9 @@ struct DeviceCtxMma {
     const uint32_t wt = s_wt;
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
     const int w_off = mlp_offset<Net>(D, layer, d);
-    const uint32_t W = s_w + w_off * 4;
+    const Ref W = w_ref + w_off;
     float* A = gacc + w_off;
-    const uint32_t frag = s_frag + (mlp * M * kFragFloats + 512) * 4;
+    const Ref frag = frag_ref + (mlp * M * kFragFloats + 512);
     const uint32_t tg = wt + M * kWtFloats * 4;
     __syncwarp();
     store_row(tg, ln, gtheta);
@@ -471,7 +520,7 @@ struct DeviceCtxMma {
       wgrad16(wt + slot * kWtFloats * 4, tg, A + moff, ln);
       colsum_a(G, A + moff + H * 16, ln);
       float dh[2][2][4], hm[2][2][4];
-      dense16(G, frag + slot * kFragFloats * 4, 0u, ln, dh);
+      dense16(G, frag + slot * kFragFloats, Ref::none(), ln, dh);
       load_c(wt + slot * kWtFloats * 4, ln, hm);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -493,8 +542,8 @@ struct DeviceCtxMma {
 #pragma unroll 1
     for (int i = 0; i < n_in; ++i) {
       const float xi = i == 0 ? tval : cvec[perm_at(layer, i - 1, D)];
-      const float2 w0 = ldw64(W + i * 64 + 8 * ln.t);
-      const float2 w1 = ldw64(W + i * 64 + 32 + 8 * ln.t);
+      const float2 w0 = (W + i * 16 + 2 * ln.t).ld2();
+      const float2 w1 = (W + i * 16 + 8 + 2 * ln.t).ld2();
       float pw[4] = {0.f, 0.f, 0.f, 0.f}, pin[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

@@ -10,7 +10,7 @@ from util import make_cfg, make_inputs, make_params, shape_of
 from test_gpu_step import run_gpu
 engines = sys.argv[1].split(",") if len(sys.argv) > 1 else ["cuda", "mma"]
 cases = [("ot","obstacle",{}),("rwpo","double_well",{}),("fp","nongradient",{}),("ot","free",dict(M=3)),("ot","obstacle",dict(M=1)),
-         ("fp","lorenz",dict(dim=3,L=3,sigma=0.1)),("fp","nongradient",dict(dim=6,sigma=0.05,B=320))]
+         ("fp","lorenz",dict(dim=3,L=3,sigma=0.1)),("fp","nongradient",dict(dim=6,sigma=0.05,B=320)),("fp","nongradient",dict(dim=10,sigma=0.05,B=320))]
 for typ, sub, kw in cases:
     kw = dict(kw); sigma = kw.pop("sigma", 0.3)
     cfg = make_cfg(typ, sub, Tn=2, lam=500.0, **({"B": 1088} | kw)); shape = shape_of(cfg)
@@ -26,10 +26,11 @@ for typ, sub, kw in cases:
 # timing on the bench workload
 import bench
 dev = torch.device("cuda", 0)
-for name, typ, D, B in [("ot/obstacle", "ot", 2, 1 << 18), ("rwpo/double_well", "rwpo", 2, 1 << 20), ("fp/nongradient", "fp", 2, 1 << 19)]:
-    shape = FlowShape(D, 2, 2, 16, 5); cfg = bench.workload_cfg(B); cfg["general"]["type"] = typ
+for name, typ, D, B in [("ot/obstacle", "ot", 2, 1 << 18), ("rwpo/double_well", "rwpo", 2, 1 << 20), ("fp/nongradient", "fp", 2, 1 << 19),
+                        ("fp/nongradient D10 (cfg 4 per GPU)", "fp", 10, 1 << 19)]:
+    shape = FlowShape(D, 2, 2, 16, 5); cfg = bench.workload_cfg(B); cfg["general"]["type"] = typ; cfg["general"]["dim"] = D
     b = B // 32
-    W = bench.make_blob(shape, dev)
+    W = bench.make_blob(shape, dev) if D == 2 else torch.randn(shape.blob_size, device=dev) * 0.05
     g = torch.Generator(device=dev).manual_seed(1)
     lat = torch.randn(B, D, device=dev, generator=g); sub = torch.randn(b, D, device=dev, generator=g)
     src = lat + 3.0; tgt = torch.randn(B, D, device=dev, generator=g)
