@@ -79,6 +79,9 @@ SIGNATURES = {
   "cnfot_mfc_step": (c_int32, _STEP),
   "cnfot_mfc_step_host_workspace_bytes": (c_int64, [_F, c_int64, c_int64, c_int32]),
   "cnfot_mfc_step_host": (c_int32, _STEP),
+  "cnfot_kinetic_energy_workspace_bytes": (c_int64, [_F, c_int32]),
+  "cnfot_kinetic_energy": (c_int32, [c_void_p, _F, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32,
+                                     c_float, c_int32, c_float, c_float, c_void_p, c_void_p, c_int64]),
   "cnfot_adam_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_int64]),
 }

@@ -291,6 +291,15 @@ static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int 
   return 0;
 }
 
+// ---- energy finalize: sum the CTAs' kinetic partials into one double ----------------------
+__global__ void energy_finalize_kernel(const double* __restrict__ ploss, int n_cta, double* __restrict__ out) {
+  double v = 0.0;
+  for (int c = threadIdx.x; c < n_cta; c += 32) v += ploss[(int64_t)c * kNumSlots + kSlotKinetic];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
 // ---- Adam ----------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
@@ -759,6 +768,64 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
   if (e != cudaSuccess) return cuda_fail(e, "D2H out");
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int64_t cnfot_kinetic_energy_workspace_bytes(const cnfot_flow_desc* flow, int32_t n_t) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return partial_bytes(lay) + ((int64_t)(n_t > 0 ? n_t : 0) * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
+
+int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* latent,
+                         int64_t batch, int32_t latent_blocks, const float* t_host, int32_t n_t, float dt,
+                         int32_t with_score, float kappa, float dx, double* out, void* workspace,
+                         int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (int rc = check_fused(flow, lay)) return rc;
+  if (batch < 1 || n_t < 1 || latent_blocks < 1) return fail(CNFOT_ERR_ARG, "batch, n_t and latent_blocks must be >= 1");
+  if (!weights || !latent || !t_host || !out || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (!(dt > 0.f) || (with_score && !(dx > 0.f))) return fail(CNFOT_ERR_ARG, "dt and dx must be positive");
+  const int64_t need = cnfot_kinetic_energy_workspace_bytes(flow, n_t);
+  if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                          (long long)workspace_bytes, (long long)need);
+  cudaStream_t s = (cudaStream_t)stream;
+  EnergyArgs a;
+  float* t_dev = (float*)((char*)workspace + partial_bytes(lay));
+  cudaError_t e = cudaMemcpyAsync(t_dev, t_host, (size_t)n_t * sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D times");
+  SmemPlan sp;
+  int engine;
+  if (int rc = make_plan(lay, false, &sp, &engine)) return rc;
+  const void* kernel = find_energy_kernel(lay, engine);
+  if (!kernel) return fail(CNFOT_ERR_ARG, "no energy kernel for this network shape");
+  a.tiles_per_t = (batch + kTile - 1) / kTile;
+  a.n_tiles = a.tiles_per_t * n_t;
+  LaunchCfg cfg;
+  if (int rc = configure(kernel, sp, a.n_tiles, &cfg)) return rc;
+  a.W = weights;
+  a.frags = nullptr;
+  if (engine == kEngMmaStream) {
+    float* fr = carve_frags(workspace, lay);
+    if (int rc = launch_build_frags(s, lay, weights, fr)) return rc;
+    a.frags = fr;
+  }
+  a.D = lay.D; a.L = lay.L; a.plan = sp;
+  a.sc = spline_consts(flow);
+  a.latent = latent; a.batch = batch; a.latent_blocks = latent_blocks;
+  a.t_dev = t_dev; a.n_t = n_t; a.with_score = with_score;
+  a.dt = dt; a.dx = dx; a.kappa = kappa;
+  a.weight = 1.0 / (2.0 * (double)batch * (double)n_t);
+  a.pb = carve_partials(workspace, &a.tile_counter);
+  e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  void* args[] = {&a};
+  e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  if (e != cudaSuccess) return cuda_fail(e, "energy_kernel launch");
+  energy_finalize_kernel<<<1, 32, 0, s>>>(a.pb.loss, cfg.grid, out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "energy_finalize_kernel launch");
   return 0;
 }
 

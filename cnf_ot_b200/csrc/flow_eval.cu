@@ -57,4 +57,25 @@ const void* find_flow_vjp_kernel(const FlowLayout& f, int engine) {
   return nullptr;
 }
 
+#define ENERGY_CASE(H_, K_, M_)                                                          \
+  if (f.H == H_ && f.K == K_ && f.M == M_)                                               \
+    return (const void*)&energy_kernel<NetCfg<H_, K_, M_>, Dims<0, 0>, kEngCuda>;
+#define ENERGY_ENG_CASE(M_, E_)                                                          \
+  if (f.M == M_) return (const void*)&energy_kernel<NetCfg<16, 5, M_>, Dims<0, 0>, E_>;
+
+const void* find_energy_kernel(const FlowLayout& f, int engine) {
+  if (engine == kEngMma && tc_available(f)) {
+    if (f.M == 2 && f.D == 2 && f.L == 2)
+      return (const void*)&energy_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, kEngMma>;
+    ENERGY_ENG_CASE(1, kEngMma) ENERGY_ENG_CASE(2, kEngMma) ENERGY_ENG_CASE(3, kEngMma)
+    return nullptr;
+  }
+  if (engine == kEngMmaStream && tc_available(f)) {
+    ENERGY_ENG_CASE(1, kEngMmaStream) ENERGY_ENG_CASE(2, kEngMmaStream) ENERGY_ENG_CASE(3, kEngMmaStream)
+    return nullptr;
+  }
+  CNFOT_NET_LIST(ENERGY_CASE)
+  return nullptr;
+}
+
 }  // namespace cnfot

@@ -177,6 +177,66 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
   ctx_teardown(ctx);
 }
 
+// ---- evaluation energies: kinetic energy over a time grid (forward only) --------------------
+// tile = (time index, 128-row tile); latent block (ti % latent_blocks) feeds time ti.
+struct EnergyArgs {
+  const float* W;
+  const float* frags;
+  int D, L;
+  SmemPlan plan;
+  SplineConsts<float> sc;
+  const float* latent;     // (latent_blocks * batch, D)
+  int64_t batch;
+  int latent_blocks;
+  const float* t_dev;      // (n_t) times, device
+  int n_t;
+  int with_score;
+  float dt, dx, kappa;
+  double weight;           // 1 / (2 batch n_t)
+  int64_t tiles_per_t, n_tiles;
+  unsigned long long* tile_counter;
+  PartialBuf pb;
+};
+
+template <class Net, class DimsT, int ENG>
+__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) energy_kernel(const __grid_constant__ EnergyArgs a) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ double scratch[kWarps];
+  __shared__ long long s_tile;
+  __shared__ __align__(8) uint64_t tc_mbar;
+  __shared__ uint32_t tc_slot;
+  using Ctx = typename CtxSelect<Net, ENG>::type;
+  Ctx ctx;
+  ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx.bind_partials(nullptr);
+  ctx.bind_frags(a.frags);
+  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
+  const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
+  const DimsT dm{a.D, a.L};
+  const int D = dm.D();
+  double loss[kNumSlots];
+#pragma unroll
+  for (int s = 0; s < kNumSlots; ++s) loss[s] = 0.0;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(a.tile_counter, 1ULL);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= a.n_tiles) break;
+    const int ti = (int)(tile / a.tiles_per_t);
+    const int64_t r = (tile - (long long)ti * a.tiles_per_t) * kTile + ctx.row_in_tile();
+    const bool live = r < a.batch;
+    const float* src = a.latent + ((int64_t)(ti % a.latent_blocks) * a.batch + r) * D;
+    float row[kMaxDim];
+    for (int i = 0; i < D; ++i) row[i] = live ? src[i] : 0.f;
+    const float v2 = row_kinetic_value<float, Net, DimsT, Ctx>(dm, a.sc, a.t_dev[ti], row, a.dt, a.with_score != 0,
+                                                               a.kappa, a.dx, tl, ctx);
+    if (live) loss[kSlotKinetic] += (double)v2 * a.weight;
+  }
+  flush_partials(a.pb, nullptr, 0, loss, scratch);
+  ctx_teardown(ctx);
+}
+
 // ---- the fused train step ---------------------------------------------------------------
 // One persistent kernel evaluates every term of the configured loss: the work is a list
 // of segments (one per loss term and time), cut into 128-row tiles handed out by an

@@ -259,4 +259,41 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const SplineConsts<T>& sc, T t, const
   if (need_r3) flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, s3, g3, (T)0, gfirst, tl, ctx);
 }
 
+// ---- evaluation energies (forward only) --------------------------------------------------
+// One row's  sum_i v_i^2  of utils.calc_kinetic_energy (with_score = false,
+// /root/reference/cnf_ot/utils.py:311-340: v = (r(t+dt/2) - r(t-dt/2)) / dt) or of
+// utils.calc_score_kinetic_energy (with_score, utils.py:343-389: v += kappa * score, the score by
+// central differences of log_prob with step dx).  All passes start from the same latent row.
+template <typename T, class Net, class DimsT, class Ctx>
+CNFOT_HD T row_kinetic_value(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* latent, T dt,
+                             bool with_score, T kappa, T dx, const RowTiles<T, Net>& tl, Ctx& ctx) {
+  const int D = dm.D(), L = dm.L();
+  T s1[kMaxStateFloats], s2[kMaxStateFloats];
+  for (int i = 0; i < D; ++i) { s1[i] = latent[i]; s2[i] = latent[i]; }
+  flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t - dt / (T)2, s1, tl, ctx);
+  flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t + dt / (T)2, s2, tl, ctx);
+  T v[kMaxDim];
+  for (int i = 0; i < D; ++i) v[i] = (s2[L * D + i] - s1[L * D + i]) / dt;
+  if (with_score) {
+    T s3[kMaxStateFloats];
+    for (int i = 0; i < D; ++i) s3[i] = latent[i];
+    flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t, s3, tl, ctx);
+    const T* r3 = s3 + L * D;
+    for (int i = 0; i < D; ++i) {
+      T sp[kMaxStateFloats];
+      T lp[2];
+      for (int side = 0; side < 2; ++side) {
+        for (int j = 0; j < D; ++j) sp[j] = r3[j];
+        sp[i] = r3[i] + (side == 0 ? dx : -dx) / (T)2;
+        T ld = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, sp, tl, ctx);
+        lp[side] = base_log_prob<T>(sp + L * D, D) + ld;
+      }
+      v[i] += kappa * (lp[0] - lp[1]) / dx;
+    }
+  }
+  T acc = (T)0;
+  for (int i = 0; i < D; ++i) acc += v[i] * v[i];
+  return acc;
+}
+
 }  // namespace cnfot

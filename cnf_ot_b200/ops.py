@@ -243,6 +243,30 @@ def mfc_step_host(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, 
   return out
 
 
+def kinetic_energy(shape: FlowShape, weights, latent, t_values: Sequence[float], dt: float = 0.01,
+                   with_score: bool = False, kappa: float = 0.0, dx: float = 0.01,
+                   latent_blocks: int = 1) -> torch.Tensor:
+  """(1/n_t) sum_t mean(v_t^2)/2 * dim over a time grid in ONE forward-only kernel
+  (utils.calc_kinetic_energy / calc_score_kinetic_energy, cnf_ot/utils.py:311-389).
+  latent: (latent_blocks * batch, D); time i uses block i % latent_blocks.  Returns a 0-d float64
+  CUDA tensor."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  latent = _dev(latent, "latent").reshape(-1, shape.dim)
+  if latent.shape[0] % latent_blocks:
+    raise _lib.CnfotError("latent rows must be a multiple of latent_blocks")
+  batch = latent.shape[0] // latent_blocks
+  tb = torch.as_tensor(list(t_values), dtype=torch.float32)
+  out = torch.empty(1, dtype=torch.float64, device=weights.device)
+  desc = _lib.flow_desc(shape)
+  ws = _workspace(lib.cnfot_kinetic_energy_workspace_bytes(desc, tb.numel()), weights.device)
+  with torch.cuda.device(weights.device):
+    _lib.check(lib.cnfot_kinetic_energy(_stream(), desc, _ptr(weights), _ptr(latent), batch, latent_blocks,
+                                        tb.data_ptr(), tb.numel(), float(dt), int(with_score), float(kappa),
+                                        float(dx), _ptr(out), ws.data_ptr(), ws.numel()))
+  return out[0]
+
+
 def adam_update(params, grads, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8) -> None:
   """In-place optax.adam(lr) update of the parameter blob."""
   lib = _lib.load()

@@ -1,7 +1,8 @@
 """Host-side mirror of the training part of /root/reference/cnf_ot/mfc/solvers.py
 (:26-129): model construction, loss selection by `general.type`, the `update`
-step (value_and_grad + Adam) and the training loop.  The evaluation / plotting
-tail of the reference's `main` (:131-493) is out of scope.
+step (value_and_grad + Adam) and the training loop, plus the energy part of the evaluation
+tail (:138-172, `evaluate`).  The plotting / grid-density part of the reference's `main`
+(:173-493) is out of scope.
 
     from cnf_ot_b200 import solvers
     params, loss_hist = solvers.main(yaml.safe_load(open("cnf_ot_b200/config/mfc.yaml")))
@@ -13,7 +14,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from . import applications, ops, random
+from . import applications, ops, random, utils
 from .flows import ParamTree, RQSFlow, multi_transform, without_apply_rng
 
 
@@ -101,10 +102,54 @@ def main(config_dict: Dict, progress: bool = False):
   return params, loss_hist
 
 
+def evaluate(config: Dict, model, params, rng, batch_size: int = 65536, t_size: int = 10000, T=None,
+             verbose: bool = True) -> Dict[str, float]:
+  """Energy part of the evaluation tail, solvers.py:138-172.
+  ot:   the kinetic energy with more / fewer samples (utils.calc_kinetic_energy)
+  rwpo: T * score-corrected kinetic energy + potential energy at t = T; for the quadratic potential
+        the closed-form total dim (1 + log(T + 1)) / beta and the relative error in percent."""
+  import math
+  g = config["general"]
+  _type, dim = g["type"], g["dim"]
+  sample_fn, log_prob_fn = model.apply.sample, model.apply.log_prob
+  eval_rng, rng = random.split(random.as_key(rng))
+  out: Dict[str, float] = {}
+  if _type == "ot":
+    out["kinetic_more"] = float(utils.calc_kinetic_energy(sample_fn, params, eval_rng, batch_size=batch_size,
+                                                          t_size=t_size, dim=dim))
+    out["kinetic_less"] = float(utils.calc_kinetic_energy(sample_fn, params, eval_rng,
+                                                          batch_size=max(batch_size // 16, 1),
+                                                          t_size=max(t_size // 10, 1), dim=dim))
+    if verbose:
+      print("kinetic energy with more samples: {:.3e}".format(out["kinetic_more"]))
+      print("kinetic energy with less samples: {:.3e}".format(out["kinetic_less"]))
+  elif _type == "rwpo":
+    r = config["rwpo"]
+    T = r["T"] if T is None else T
+    beta, a, subtype = r["beta"], r["a"], r["pot_type"]
+    out["e_kin"] = T * float(utils.calc_score_kinetic_energy(sample_fn, log_prob_fn, params, T, beta, dim, eval_rng,
+                                                             batch_size=batch_size, t_size=t_size))
+    out["e_pot"] = float(applications.potential_loss_fn(model, dim, a, subtype, params, T, eval_rng, batch_size))
+    if verbose:
+      print(f"kinetic energy: {out['e_kin']:.3e}")
+      print(f"potential energy: {out['e_pot']:.3e}")
+    if subtype == "quadratic":
+      # the true value for the quadratic potential and Gaussian initial condition (solvers.py:170-172)
+      true_val = dim * (1 + math.log(T + 1)) / beta
+      out["true_val"] = true_val
+      out["relative_err_percent"] = (out["e_kin"] + out["e_pot"] - true_val) / true_val * 100
+      if verbose:
+        print("total energy: {:.3e}|relative err: {:.3e}".format(out["e_kin"] + out["e_pot"],
+                                                                out["relative_err_percent"]))
+  return out
+
+
 if __name__ == "__main__":
   import os
   import yaml
   here = os.path.dirname(os.path.abspath(__file__))
   with open(os.path.join(here, "config", "mfc.yaml"), "r") as file:
     config_dict = yaml.safe_load(file)
-  main(config_dict, progress=True)
+  params, _ = main(config_dict, progress=True)
+  model, _, _ = build(config_dict)
+  evaluate(config_dict, model, params, random.PRNGKey(config_dict["general"]["seed"] + 1))

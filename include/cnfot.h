@@ -86,7 +86,8 @@ CNFOT_API int cnfot_abi_version(void);
 CNFOT_API const char* cnfot_last_error(void);
 /* Launch configuration of the calling thread's most recent fused-kernel launch (diagnostics for
  * bench.py / profiles): persistent grid size, dynamic shared memory per CTA in bytes, resident
- * CTAs per SM the grid was sized for, and whether the tcgen05 engine variant was selected. */
+ * CTAs per SM the grid was sized for, and the conditioner engine that ran (0 CUDA cores,
+ * 1 tcgen05 engine, 2 warp-level tensor-core engine). */
 CNFOT_API void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm,
                                       int32_t* tensor_cores);
 
@@ -189,6 +190,23 @@ CNFOT_API int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow,
                         int32_t n_t, int64_t rows_B, int64_t rows_b, int64_t global_B,
                         int64_t global_b, float lambda, float* out_host, void* workspace,
                         int64_t workspace_bytes);
+
+/* ---- evaluation energies (the callers after the step: cnf_ot/mfc/solvers.py:141-164) ------
+ * utils.calc_kinetic_energy (cnf_ot/utils.py:311-340; with_score = 0) and
+ * utils.calc_score_kinetic_energy (cnf_ot/utils.py:343-389; with_score != 0, kappa = 1/beta) as ONE
+ * forward-only kernel over the whole time grid:
+ *   out[0] = (1/n_t) sum_t mean_{rows,dims}(v_t^2) / 2 * dim,
+ *   v_t = (r(t+dt/2) - r(t-dt/2)) / dt  [+ kappa * score_t, score by central differences of
+ *   log_prob with step dx], r(.) = the flow's samples of the SAME latent rows.
+ * latent: (latent_blocks * batch, D); time index i uses block i % latent_blocks (the reference
+ * draws a fresh batch per time: latent_blocks = n_t; 1 reuses one batch).  t_host: n_t times on
+ * the host.  out: ONE double on the device.  The multiplication by T the rwpo caller applies
+ * (solvers.py:154) is left to the caller. */
+CNFOT_API int64_t cnfot_kinetic_energy_workspace_bytes(const cnfot_flow_desc* flow, int32_t n_t);
+CNFOT_API int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                         const float* latent, int64_t batch, int32_t latent_blocks, const float* t_host,
+                         int32_t n_t, float dt, int32_t with_score, float kappa, float dx, double* out,
+                         void* workspace, int64_t workspace_bytes);
 
 /* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
  * element-wise update; step is the 1-based update count. */
