@@ -289,10 +289,22 @@ def run_ours(args):
   t_vals = torch.rand(4096, generator=tgen).tolist()
   out = torch.empty(shape.blob_size + 8, dtype=torch.float32, device=dev)
 
+  # N > 1: the step's final reduction kernel also does the all-reduce of [gradient | loss] over
+  # peer-mapped memory (NVLink / NVSwitch; cnfot_mfc_step_dp).  NCCL is the fallback transport.
+  px, transport = None, "none"
+  if world > 1:
+    try:
+      from cnf_ot_b200 import dist
+      px = dist.PeerExchange(shape, dev)
+      transport = "fused in the step's reduction kernel over peer-mapped memory (NVLink/NVSwitch)"
+    except Exception as exc:  # symmetric memory unavailable
+      print(f"[bench] PeerExchange unavailable ({exc!r}); using NCCL all-reduce", file=sys.stderr)
+      transport = "NCCL all-reduce"
+
   def step(i):
     src, tgt, sub = sets[i % n_sets]
-    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
-    if world > 1:
+    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out, peers=px)
+    if world > 1 and px is None:
       td.all_reduce(out)
 
   def sync():
@@ -326,8 +338,9 @@ def run_ours(args):
     else:
       # weights H2D; the pinned row buffers are read in place by the kernel (zero-copy over PCIe)
       dW2.copy_(hW, non_blocking=True)
-      ops.mfc_step(shape, problem, dW2, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out)
-      td.all_reduce(out)
+      ops.mfc_step(shape, problem, dW2, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out, peers=px)
+      if px is None:
+        td.all_reduce(out)
       hout.copy_(out, non_blocking=True)
       torch.cuda.synchronize()
 
@@ -364,14 +377,14 @@ def run_ours(args):
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
       "warmup": max(args.warmup, 3), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": config_block(n_gpus, {"l2_policy": f"{n_sets} rotating input sets ({n_sets * bytes_per_set >> 20} MiB > 2x L2)",
+      "config": config_block(n_gpus, {"all_reduce": transport, "l2_policy": f"{n_sets} rotating input sets ({n_sets * bytes_per_set >> 20} MiB > 2x L2)",
                                       "loss_last_step": loss_dev}),
       "e2e": {"value": gB * args.steps / el_e, "unit": UNIT, "h2d_bytes_per_step": h2d,
               "d2h_bytes_per_step": d2h, "ms_per_step": el_e / args.steps * 1e3,
               "api": "cnfot_mfc_step_host (C ABI; pinned host rows read in place by the kernel over PCIe, "
                      "weights H2D, [grad|loss] D2H)" if world == 1 else
-                     "weights H2D + cnfot_mfc_step on pinned host rows (zero-copy) + NCCL all-reduce + D2H"},
-      "gpu_launches": 2 * args.steps,
+                     "weights H2D + cnfot_mfc_step[_dp] on pinned host rows (zero-copy) + all-reduce + D2H"},
+      "gpu_launches": 2 * args.steps,  # mfc_step_kernel + finalize[_allreduce]_kernel per step
       "clocks": clk.summary(),
       "roofline": {"bound": "hbm", "kernel": "mfc_step_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
                    "frac": ach / hbm, "traffic": traffic, "peak_source": pk_src,

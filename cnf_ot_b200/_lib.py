@@ -44,6 +44,12 @@ class ProblemDesc(Structure):
   ]
 
 
+class PeerDesc(Structure):
+  """cnfot_peer_desc: peer-mapped exchange buffers of the fused step + all-reduce."""
+  _fields_ = [("rank", c_int32), ("world", c_int32), ("epoch", ctypes.c_uint32),
+              ("xbuf", c_void_p * 8), ("flags", c_void_p * 8)]
+
+
 _F = POINTER(FlowDesc)
 _P = POINTER(ProblemDesc)
 _RQS = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_float, c_float,
@@ -82,6 +88,10 @@ SIGNATURES = {
   "cnfot_kinetic_energy_workspace_bytes": (c_int64, [_F, c_int32]),
   "cnfot_kinetic_energy": (c_int32, [c_void_p, _F, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32,
                                      c_float, c_int32, c_float, c_float, c_void_p, c_void_p, c_int64]),
+  "cnfot_dp_exchange_stride": (c_int64, [_F]),
+  "cnfot_dp_exchange_floats": (c_int64, [_F, c_int32]),
+  "cnfot_dp_flag_count": (c_int64, [_F, c_int32]),
+  "cnfot_mfc_step_dp": (c_int32, _STEP + [POINTER(PeerDesc)]),
   "cnfot_adam_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_int64]),
 }

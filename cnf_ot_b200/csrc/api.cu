@@ -291,6 +291,87 @@ static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int 
   return 0;
 }
 
+// ---- finalize fused with the data-parallel all-reduce ---------------------
+// One kernel per rank does: (1) the rank's own reduction of its CTAs' partials (as finalize_kernel),
+// (2) pushes the result into every peer's exchange buffer with peer-to-peer stores over
+// NVLink / NVSwitch, (3) raises a per-block flag on every peer, (4) waits for the same block of
+// every peer, (5) sums the W contributions in rank order (bit-identical on all ranks) into `out`.
+// Block b of every rank owns outputs [32 b, 32 b + 32): no grid-wide synchronisation, and the
+// <= 38 + ... blocks of a launch are always co-resident.  Exchange buffers are double-buffered by
+// the parity of `epoch` (a rank cannot run two steps ahead of a peer: it needs the peer's flag of
+// the step in between); flags carry the epoch and never need resetting.
+struct PeerArgs {
+  int rank, world;
+  uint32_t epoch;
+  int stride;          // floats per rank slot in an exchange buffer (>= total + kNumSlots)
+  int nblk;            // blocks per launch = flags per rank
+  float* xbuf[8];
+  uint32_t* flags[8];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kFinWarps)
+finalize_allreduce_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss, int n_cta,
+                          int total, float* __restrict__ out, const PeerArgs pa) {
+  __shared__ double part[kFinWarps][32];
+  __shared__ int timed_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int n_out = total + kNumSlots;
+  double acc = 0.0;
+  if (i < total) {
+    for (int c = warp; c < n_cta; c += kFinWarps) acc += (double)pgrad[(int64_t)c * total + i];
+  } else if (i < n_out) {
+    // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
+    const int sl = i - total;
+    for (int c = warp; c < n_cta; c += kFinWarps) {
+      const double* q = ploss + (int64_t)c * kNumSlots;
+      if (sl == 0) acc += q[0] + q[1] + q[2] + q[3];
+      else if (sl <= 4) acc += q[sl - 1];
+    }
+  }
+  part[warp][lane] = acc;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (warp != 0) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
+  const float mine = (float)t;
+  const int par = pa.epoch & 1u;
+  if (i < n_out)
+    for (int p = 0; p < pa.world; ++p) pa.xbuf[p][((int64_t)par * pa.world + pa.rank) * pa.stride + i] = mine;
+  __threadfence_system();
+  __syncwarp();
+  if (lane < pa.world) st_release_sys(pa.flags[lane] + pa.rank * pa.nblk + blockIdx.x, pa.epoch);
+  if (lane < pa.world) {
+    const uint32_t* f = pa.flags[pa.rank] + lane * pa.nblk + blockIdx.x;
+    const long long t0 = clock64();
+    // epochs are compared modulo 2^32 (a peer is never more than one step ahead)
+    while ((int32_t)(ld_acquire_sys(f) - pa.epoch) < 0) {
+      if (clock64() - t0 > (4LL << 30)) {  // ~2 s: a peer never arrived; poison the result instead of hanging
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (i < n_out) {
+    const float* mybuf = pa.xbuf[pa.rank] + (int64_t)par * pa.world * pa.stride + i;
+    float sum = 0.f;
+    for (int q = 0; q < pa.world; ++q) sum += __ldcg(mybuf + (int64_t)q * pa.stride);
+    out[i] = *(volatile int*)&timed_out ? __int_as_float(0x7fc00000) : sum;
+  }
+}
+
 // ---- energy finalize: sum the CTAs' kinetic partials into one double ----------------------
 __global__ void energy_finalize_kernel(const double* __restrict__ ploss, int n_cta, double* __restrict__ out) {
   double v = 0.0;
@@ -555,11 +636,25 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
                          const float* weights, const float* latent, const float* latent_sub,
                          const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
                          int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b, float lambda,
-                         float* out, void* workspace, int64_t workspace_bytes, bool accumulate) {
+                         float* out, void* workspace, int64_t workspace_bytes, bool accumulate,
+                         const cnfot_peer_desc* peers = nullptr) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
   if (int rc = check_fused(flow, lay)) return rc;
   if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");
+  PeerArgs pa;
+  if (peers) {
+    if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world)
+      return fail(CNFOT_ERR_ARG, "peer descriptor: need 1 <= world <= 8 and 0 <= rank < world");
+    if (peers->epoch == 0) return fail(CNFOT_ERR_ARG, "peer descriptor: epoch starts at 1");
+    pa.rank = peers->rank; pa.world = peers->world; pa.epoch = peers->epoch;
+    pa.stride = (int)cnfot_dp_exchange_stride(flow);
+    pa.nblk = (lay.total + kNumSlots + 31) / 32;
+    for (int k = 0; k < peers->world; ++k) {
+      if (!peers->xbuf[k] || !peers->flags[k]) return fail(CNFOT_ERR_ARG, "peer descriptor: NULL peer buffer");
+      pa.xbuf[k] = peers->xbuf[k]; pa.flags[k] = peers->flags[k];
+    }
+  }
   if (rows_B < 0 || rows_b < 0 || global_B < 1 || global_b < 1 || rows_B > global_B || rows_b > global_b)
     return fail(CNFOT_ERR_ARG, "bad row counts");
   if (n_t < 1 || n_t > kMaxSegments - 4) return fail(CNFOT_ERR_ARG, "t_batch_size must be in [1, %d]", kMaxSegments - 4);
@@ -598,10 +693,18 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   a.n_seg = ns;
   a.n_tiles = tiles;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tiles == 0) {
+  if (tiles == 0 && !peers) {
     if (accumulate) return 0;
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return 0;
+  }
+  if (tiles == 0) {  // an empty shard still takes part in the all-reduce
+    PartialBuf none;
+    none.grad = nullptr; none.loss = nullptr;
+    finalize_allreduce_kernel<<<pa.nblk, 32 * kFinWarps, 0, s>>>(none.grad, none.loss, 0, lay.total, out, pa);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "finalize_allreduce_kernel launch");
     return 0;
   }
   SmemPlan sp;
@@ -625,7 +728,37 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   void* args[] = {&a};
   e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
   if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
+  if (peers) {
+    finalize_allreduce_kernel<<<pa.nblk, 32 * kFinWarps, 0, s>>>(a.pb.grad, a.pb.loss, cfg.grid, lay.total, out, pa);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "finalize_allreduce_kernel launch");
+    return 0;
+  }
   return launch_finalize(s, a.pb, cfg.grid, lay.total, out, out + lay.total, accumulate);
+}
+
+int64_t cnfot_dp_exchange_stride(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  return (lay.total + kNumSlots + 31) / 32 * 32;
+}
+int64_t cnfot_dp_exchange_floats(const cnfot_flow_desc* flow, int32_t world) {
+  const int64_t st = cnfot_dp_exchange_stride(flow);
+  return st < 0 ? -1 : 2 * (int64_t)world * st;
+}
+int64_t cnfot_dp_flag_count(const cnfot_flow_desc* flow, int32_t world) {
+  const int64_t st = cnfot_dp_exchange_stride(flow);
+  return st < 0 ? -1 : (int64_t)world * (st / 32);
+}
+
+int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                      const float* weights, const float* latent, const float* latent_sub, const float* src,
+                      const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
+                      int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
+                      void* workspace, int64_t workspace_bytes, const cnfot_peer_desc* peers) {
+  if (!peers) return fail(CNFOT_ERR_ARG, "peer descriptor is NULL");
+  return mfc_step_impl(stream, flow, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t,
+                       rows_B, rows_b, global_B, global_b, lambda, out, workspace, workspace_bytes, false, peers);
 }
 
 int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,

@@ -6,6 +6,7 @@ tensors (they raise otherwise -- there is no CPU path).
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -181,11 +182,13 @@ def problem_desc(cfg: dict) -> _lib.ProblemDesc:
 
 def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, latent_sub, src, tgt,
              t_batch: Sequence[float], lam: float, global_B: int, global_b: int,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, peers=None) -> torch.Tensor:
   """value_and_grad of the configured loss on this GPU's shard.
 
   Returns the fp32 buffer [gradient (blob_size) | 8 loss slots] (see include/cnfot.h);
-  buffers of different ranks sum to the whole-batch result."""
+  buffers of different ranks sum to the whole-batch result.  With `peers` (a
+  dist.PeerExchange) the final reduction kernel also all-reduces the buffer over peer-mapped
+  memory (cnfot_mfc_step_dp): the returned buffer is already the whole-batch result."""
   lib = _lib.load()
   weights = _dev(weights, "weights")
   device = weights.device
@@ -207,10 +210,17 @@ def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, laten
   nbytes = lib.cnfot_mfc_step_workspace_bytes(desc, rows_B, rows_b, n_t)
   ws = _workspace(nbytes, device)
   with torch.cuda.device(device):
-    _lib.check(lib.cnfot_mfc_step(_stream(), desc, problem, _ptr(weights), _ptr(latent),
-                                  _ptr(latent_sub), _ptr(src), _ptr(tgt), tb.data_ptr(), n_t, rows_B,
-                                  rows_b, global_B, global_b, float(lam), _ptr(out), ws.data_ptr(),
-                                  ws.numel()))
+    if peers is None:
+      _lib.check(lib.cnfot_mfc_step(_stream(), desc, problem, _ptr(weights), _ptr(latent),
+                                    _ptr(latent_sub), _ptr(src), _ptr(tgt), tb.data_ptr(), n_t, rows_B,
+                                    rows_b, global_B, global_b, float(lam), _ptr(out), ws.data_ptr(),
+                                    ws.numel()))
+    else:
+      pd = peers.next_desc(shape)
+      _lib.check(lib.cnfot_mfc_step_dp(_stream(), desc, problem, _ptr(weights), _ptr(latent),
+                                       _ptr(latent_sub), _ptr(src), _ptr(tgt), tb.data_ptr(), n_t, rows_B,
+                                       rows_b, global_B, global_b, float(lam), _ptr(out), ws.data_ptr(),
+                                       ws.numel(), ctypes.byref(pd)))
   return out
 
 

@@ -177,6 +177,34 @@ CNFOT_API int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cn
                    const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
                    int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
                    float lambda, float* out, void* workspace, int64_t workspace_bytes);
+/* ---- data-parallel step: the train step fused with its all-reduce -------
+ * Same as cnfot_mfc_step on this rank's shard, but the final reduction kernel also exchanges the
+ * [gradient | loss slots] buffer with the peer GPUs of the node through peer-mapped memory
+ * (NVLink / NVSwitch, no NCCL call): on return (stream-ordered) `out` holds the SUM over all ranks,
+ * bit-identical on every rank.  The caller owns the exchange memory and maps it across processes
+ * (e.g. torch.distributed._symmetric_memory, CUDA IPC or VMM handles):
+ *   xbuf[k]   rank k's exchange buffer, cnfot_dp_exchange_floats() floats, as addressable from THIS
+ *             process (k == rank: the local allocation)
+ *   flags[k]  rank k's flag array, cnfot_dp_flag_count() uint32, zero-initialised once
+ *   epoch     1, 2, 3, ... : must increase by one per call, identically on all ranks
+ * Every rank must make the call (an empty shard passes rows_B = rows_b = 0).  A peer that never
+ * arrives makes the wait time out after ~2 s and `out` is filled with NaN (no hang). */
+typedef struct cnfot_peer_desc {
+  int32_t rank, world;   /* world <= 8 (one node) */
+  uint32_t epoch;
+  float* xbuf[8];
+  uint32_t* flags[8];
+} cnfot_peer_desc;
+CNFOT_API int64_t cnfot_dp_exchange_stride(const cnfot_flow_desc* flow);
+CNFOT_API int64_t cnfot_dp_exchange_floats(const cnfot_flow_desc* flow, int32_t world);
+CNFOT_API int64_t cnfot_dp_flag_count(const cnfot_flow_desc* flow, int32_t world);
+CNFOT_API int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                      const float* weights, const float* latent, const float* latent_sub,
+                      const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
+                      int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
+                      float lambda, float* out, void* workspace, int64_t workspace_bytes,
+                      const cnfot_peer_desc* peers);
+
 /* Same step with HOST buffers in and out (weights, latent, latent_sub, src, tgt, out are host
  * pointers): copies inputs to the device workspace, runs the step, copies `out` back and
  * synchronises the stream.  The workspace must be

@@ -1,0 +1,65 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): the fused step + all-reduce
+(cnfot_mfc_step_dp over peer-mapped memory) against cnfot_mfc_step + NCCL all-reduce, and timing."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as td
+import bench
+from cnf_ot_b200 import ops, dist
+from cnf_ot_b200.layout import FlowShape
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+td.init_process_group("nccl", device_id=dev)
+shape = FlowShape(2, 2, 2, 16, 5)
+B = 1 << 16; b = B // 32
+cfg = bench.workload_cfg(B * world)
+pd = ops.problem_desc(cfg)
+W = bench.make_blob(shape, dev); td.broadcast(W, 0)
+g = torch.Generator(device=dev).manual_seed(100 + rank)
+src = torch.randn(B, 2, device=dev, generator=g) + 3; tgt = torch.randn(B, 2, device=dev, generator=g)
+sub = torch.randn(b, 2, device=dev, generator=g)
+px = dist.PeerExchange(shape, dev)
+ok = True
+for it in range(6):
+  t = [0.1 + 0.1 * it]
+  ref = ops.mfc_step(shape, pd, W, None, sub, src, tgt, t, 5000.0, B * world, b * world).clone()
+  td.all_reduce(ref)
+  if it == 3 and rank == world - 1:   # an empty shard still takes part
+    got = ops.mfc_step(shape, pd, W, None, sub[:0], src[:0], tgt[:0], t, 5000.0, B * world, b * world, peers=px).clone()
+  else:
+    got = ops.mfc_step(shape, pd, W, None, sub, src, tgt, t, 5000.0, B * world, b * world, peers=px).clone()
+  if it == 3:
+    # reference for the empty-shard step: ranks 0..W-2 only
+    part = ops.mfc_step(shape, pd, W, None, sub, src, tgt, t, 5000.0, B * world, b * world).clone()
+    if rank == world - 1: part.zero_()
+    td.all_reduce(part); ref = part
+  err = float((got - ref).abs().max() / ref.abs().max())
+  # every rank must hold the bit-identical result
+  gathered = [torch.empty_like(got) for _ in range(world)]
+  td.all_gather(gathered, got)
+  same = all(torch.equal(gathered[0], x) for x in gathered)
+  if rank == 0: print(f"step {it}: fused vs NCCL rel err {err:.2e}; identical on all ranks: {same}", flush=True)
+  ok = ok and err < 2e-6 and same
+out = torch.empty(shape.blob_size + 8, device=dev)
+def timed(fn, n=100):
+  for _ in range(5): fn()
+  td.barrier(); torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(n): fn()
+  e1.record(); torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / n * 1e3
+def nccl_step():
+  ops.mfc_step(shape, pd, W, None, sub, src, tgt, [0.3], 5000.0, B * world, b * world, out=out); td.all_reduce(out)
+def fused_step():
+  ops.mfc_step(shape, pd, W, None, sub, src, tgt, [0.3], 5000.0, B * world, b * world, out=out, peers=px)
+def local_step():
+  ops.mfc_step(shape, pd, W, None, sub, src, tgt, [0.3], 5000.0, B * world, b * world, out=out)
+a, c, l = timed(nccl_step), timed(fused_step), timed(local_step)
+if rank == 0:
+  print(f"B/GPU={B}: local step {l:.1f} us, + NCCL all-reduce {a:.1f} us, fused step+all-reduce {c:.1f} us", flush=True)
+  print("CHECK_DP", "PASS" if ok else "FAIL", flush=True)
+td.barrier(); td.destroy_process_group()
