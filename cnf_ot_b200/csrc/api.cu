@@ -248,7 +248,23 @@ static PartialBuf carve_partials(void* ws, unsigned long long** counter) {
 // One block reduces 32 consecutive parameters: warp w sums partials w, w+8, ... (coalesced
 // 128-byte reads), the 8 warps are folded through shared memory.  Fixed order => the
 // result is bit-reproducible for a given grid size.
-constexpr int kFinWarps = 8;
+constexpr int kFinWarps = 32;  // 1024 threads: the per-CTA partials are read with many loads in flight
+// sum over the CTAs c = warp, warp + kFinWarps, ... of pgrad[c][i], four independent loads in flight
+__device__ __forceinline__ double column_partial(const float* __restrict__ pgrad, int n_cta, int total, int i,
+                                                 int warp) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int c = warp;
+  for (; c + 3 * kFinWarps < n_cta; c += 4 * kFinWarps) {
+    const float v0 = __ldcg(pgrad + (int64_t)c * total + i);
+    const float v1 = __ldcg(pgrad + (int64_t)(c + kFinWarps) * total + i);
+    const float v2 = __ldcg(pgrad + (int64_t)(c + 2 * kFinWarps) * total + i);
+    const float v3 = __ldcg(pgrad + (int64_t)(c + 3 * kFinWarps) * total + i);
+    a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
+  }
+  for (; c < n_cta; c += kFinWarps) a0 += (double)__ldcg(pgrad + (int64_t)c * total + i);
+  return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(32 * kFinWarps)
 finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss, int n_cta,
                 int total, float* __restrict__ out_grad, float* __restrict__ out_slots,
@@ -257,8 +273,7 @@ finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ plos
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   double acc = 0.0;
-  if (i < total)
-    for (int c = warp; c < n_cta; c += kFinWarps) acc += (double)pgrad[(int64_t)c * total + i];
+  if (i < total) acc = column_partial(pgrad, n_cta, total, i, warp);
   part[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && i < total) {
@@ -267,17 +282,28 @@ finalize_kernel(const float* __restrict__ pgrad, const double* __restrict__ plos
     for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
     out_grad[i] = accumulate ? out_grad[i] + (float)t : (float)t;
   }
-  if (out_slots && blockIdx.x == 0 && warp == 1) {
-    // lanes 0..7 <-> internal slots (fit0, fitT, potential, kinetic, unused...)
+  if (out_slots && blockIdx.x == gridDim.x - 1) {
+    // loss slots (the last block: it has the fewest gradient columns): 4 CTAs x 8 slots per warp pass
+    __syncthreads();
+    const int sl = lane & 7, sub = lane >> 3;
     double v = 0.0;
-    if (lane < kNumSlots)
-      for (int c = 0; c < n_cta; ++c) v += ploss[(int64_t)c * kNumSlots + lane];
-    double tot = v;
-    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 2);  // lanes 0..3 now hold the sum of slots 0..3
-    if (lane == 0) out_slots[0] = accumulate ? out_slots[0] + (float)tot : (float)tot;
-    if (lane < 4) out_slots[1 + lane] = accumulate ? out_slots[1 + lane] + (float)v : (float)v;
-    if (lane >= 5 && lane < kNumSlots) out_slots[lane] = 0.f;
+    for (int c = warp * 4 + sub; c < n_cta; c += 4 * kFinWarps) v += ploss[(int64_t)c * kNumSlots + sl];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    part[warp][lane] = v;
+    __syncthreads();
+    if (warp == 0) {
+      // lanes 0..7 <-> internal slots (fit0, fitT, potential, kinetic, unused...)
+      double t = 0.0;
+      if (lane < kNumSlots)
+        for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
+      double tot = t;
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 2);  // lanes 0..3 now hold the sum of slots 0..3
+      if (lane == 0) out_slots[0] = accumulate ? out_slots[0] + (float)tot : (float)tot;
+      if (lane < 4) out_slots[1 + lane] = accumulate ? out_slots[1 + lane] + (float)t : (float)t;
+      if (lane >= 5 && lane < kNumSlots) out_slots[lane] = 0.f;
+    }
   }
 }
 
@@ -328,7 +354,7 @@ finalize_allreduce_kernel(const float* __restrict__ pgrad, const double* __restr
   const int n_out = total + kNumSlots;
   double acc = 0.0;
   if (i < total) {
-    for (int c = warp; c < n_cta; c += kFinWarps) acc += (double)pgrad[(int64_t)c * total + i];
+    acc = column_partial(pgrad, n_cta, total, i, warp);
   } else if (i < n_out) {
     // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
     const int sl = i - total;
