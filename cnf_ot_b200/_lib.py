@@ -92,6 +92,10 @@ SIGNATURES = {
   "cnfot_dp_exchange_floats": (c_int64, [_F, c_int32]),
   "cnfot_dp_flag_count": (c_int64, [_F, c_int32]),
   "cnfot_mfc_step_dp": (c_int32, _STEP + [POINTER(PeerDesc)]),
+  "cnfot_dense_prepared_floats": (c_int64, [c_int32, c_int32]),
+  "cnfot_dense_prepare": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+  "cnfot_dense_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                    c_void_p, c_int32, c_int32, c_void_p, c_int32]),
   "cnfot_adam_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_int64]),
 }

@@ -10,6 +10,7 @@
 
 #include "../../include/cnfot.h"
 #include "device_common.cuh"
+#include "dense_tc.h"
 #include "dispatch.h"
 #include "flow_kernels.cuh"
 #include "step_host.h"
@@ -985,6 +986,40 @@ int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float*
   energy_finalize_kernel<<<1, 32, 0, s>>>(a.pb.loss, cfg.grid, out);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "energy_finalize_kernel launch");
+  return 0;
+}
+
+// ---- wide conditioner layers on tcgen05 (dense_tc.cu) ----------------------------------------
+int64_t cnfot_dense_prepared_floats(int32_t K, int32_t N) {
+  if (K < 16 || N < 16 || K % 16 || N % 16) return -1;
+  return 2 * (int64_t)K * N;
+}
+
+int cnfot_dense_prepare(void* stream, const float* W, int32_t K, int32_t N, int32_t ldw, int32_t transpose,
+                        float* prepared) {
+  if (!W || !prepared) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (cnfot_dense_prepared_floats(K, N) < 0) return fail(CNFOT_ERR_ARG, "dense layers need K and N to be multiples of 16");
+  cudaError_t e = dense_prep((cudaStream_t)stream, W, K, N, ldw, transpose != 0, prepared);
+  if (e != cudaSuccess) return cuda_fail(e, "dense_prep_kernel launch");
+  return 0;
+}
+
+int cnfot_dense_forward(void* stream, const float* X, int64_t rows, int32_t K, int32_t ldx, const float* prepared,
+                        int32_t N, const float* bias, const float* mask_src, int32_t ldm, int32_t epilogue,
+                        float* Y, int32_t ldy) {
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (rows == 0) return 0;
+  if (!X || !prepared || !Y) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (cnfot_dense_prepared_floats(K, N) < 0) return fail(CNFOT_ERR_ARG, "dense layers need K and N to be multiples of 16");
+  if (epilogue < 0 || epilogue > 3) return fail(CNFOT_ERR_ARG, "unknown epilogue");
+  if ((epilogue == 0 || epilogue == 1) && !bias) return fail(CNFOT_ERR_ARG, "bias is NULL");
+  if (epilogue == 2 && !mask_src) return fail(CNFOT_ERR_ARG, "mask_src is NULL");
+  if (ldx % 4 || ldy % 4 || (epilogue == 2 && ldm % 4)) return fail(CNFOT_ERR_ARG, "row strides must be multiples of 4 floats");
+  bool ok = false;
+  cudaError_t e = dense_forward((cudaStream_t)stream, X, rows, K, ldx, prepared, N, bias, mask_src, ldm, epilogue,
+                                Y, ldy, &ok);
+  if (!ok) return fail(CNFOT_ERR_ARG, "no dense kernel for N = %d", N);
+  if (e != cudaSuccess) return cuda_fail(e, "dense_tc_kernel launch");
   return 0;
 }
 

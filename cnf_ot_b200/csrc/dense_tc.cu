@@ -1,0 +1,279 @@
+// Wide conditioner layers on tcgen05: Y = epilogue(X W + b) for X (rows x K), W (K x N), fp32 in
+// and out with fp32 fidelity (3xTF32), for the H = 512 conditioners of BASELINE config 5
+// (/root/reference/cnf_ot/models/flows.py:65-81: hk.nets.MLP([H]*M) -> hk.Linear(P)).
+//
+// One CTA = one 128-row x NT-column output tile, accumulator in TMEM (NT fp32 columns x 128 lanes).
+// The contraction runs in chunks of 16 (one 64-byte swizzled row per operand row):
+//   A stage  [128 rows][16 k]  K-major, SWIZZLE_64B -- written by the CTA's threads from X, twice:
+//            the values themselves (the tensor core reads their tf32 bits = x_hi) and the exact
+//            residuals x_lo = x - x_hi;
+//   B stage  [NT n][16 k] hi | lo, same layout -- the weights are prepared ONCE per call into exactly
+//            this tile order (dense_prep_kernel), so a stage is one contiguous block that a single
+//            thread fetches with a 1-D bulk TMA copy (cp.async.bulk -> mbarrier complete_tx).
+//   per chunk: 2 k-steps x { x_lo*w_hi, x_hi*w_lo, x_hi*w_hi } = 6 tcgen05.mma.kind::tf32
+//            (M = 128, N = NT, K = 8) issued by one thread, tcgen05.commit -> "stage free" mbarrier.
+// Two stages: the loads of chunk i+1 overlap the MMAs of chunk i.  Epilogue: every warp reads its 32
+// TMEM lanes with tcgen05.ld (32 columns at a time), adds the bias, applies ReLU or a ReLU mask,
+// and writes full 128-byte row segments.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dense_tc.h"
+
+namespace cnfot {
+
+namespace {
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void commit_to(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float residual_tf32(float v) {
+  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+}
+
+// element (row n, k) of a [rows][16] SWIZZLE_64B tile, in floats
+__device__ __forceinline__ int sw64_pos(int n, int k) {
+  return n * 16 + ((((k >> 2) ^ ((n >> 1) & 3)) << 2) | (k & 3));
+}
+
+}  // namespace
+
+// out[(kc * 2 + part) * N * 16 + sw64_pos(n, kk)] = hi / lo of  Wv(kc * 16 + kk, n),
+// Wv(k, n) = transpose ? W[n * ldw + k] : W[k * ldw + n];  K % 16 == 0.
+__global__ void dense_prep_kernel(const float* __restrict__ W, int K, int N, int ldw, int transpose,
+                                  float* __restrict__ out) {
+  const int64_t total = (int64_t)K * N;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int k, n;
+    if (transpose) { k = (int)(e % K); n = (int)(e / K); }   // consecutive threads read consecutive memory
+    else { n = (int)(e % N); k = (int)(e / N); }
+    const float v = transpose ? W[(int64_t)n * ldw + k] : W[(int64_t)k * ldw + n];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const int kc = k >> 4, kk = k & 15;
+    float* t = out + (int64_t)kc * 2 * N * 16;
+    const int p = sw64_pos(n, kk);
+    t[p] = hi;
+    t[N * 16 + p] = v - hi;
+  }
+}
+
+template <int NT>
+struct DenseSmem {
+  static constexpr int kAFloats = 128 * 16;
+  static constexpr int kBFloats = NT * 16;
+  static constexpr int kStageFloats = 2 * kAFloats + 2 * kBFloats;   // A_hi | A_lo | B_hi | B_lo
+  static constexpr int kBytes = 2 * kStageFloats * 4 + 1024;
+};
+
+// EPI: 0 = bias, 1 = bias + ReLU, 2 = ReLU mask (Y = mask_src > 0 ? acc : 0), 3 = none
+template <int NT, int EPI>
+__global__ void __launch_bounds__(128)
+dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const float* __restrict__ Bt,
+                int N_total, const float* __restrict__ bias, const float* __restrict__ mask_src, int ldm,
+                float* __restrict__ Y, int ldy) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  using S = DenseSmem<NT>;
+  constexpr int kTmemCols = NT < 32 ? 32 : NT;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * 128;
+  const int n0 = blockIdx.y * NT;
+  const int64_t r = row0 + tid;
+  const bool live = r < rows;
+
+  if (tid == 0) {
+    mbar_init(s_u32(&bar_full[0]), 1); mbar_init(s_u32(&bar_full[1]), 1);
+    mbar_init(s_u32(&bar_free[0]), 1); mbar_init(s_u32(&bar_free[1]), 1);
+    mbar_init(s_u32(&bar_done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = idesc_tf32(NT);
+  const int n_chunks = K >> 4;
+  const int sw = (tid >> 1) & 3;
+  const float* xrow = X + r * ldx;
+
+  for (int i = 0; i < n_chunks; ++i) {
+    const int s = i & 1;
+    float* stage = smem + s * S::kStageFloats;
+    // the A chunk of this thread's row (issued before any wait: the loads fly while the stage drains)
+    float4 xa[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      xa[c] = live ? __ldg(reinterpret_cast<const float4*>(xrow + i * 16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= 2) mbar_wait(s_u32(&bar_free[s]), ((i >> 1) - 1) & 1);   // MMAs of chunk i-2 are done with the stage
+    if (tid == 0) {
+      // weights: one contiguous [hi | lo] block per (chunk, NT columns)
+      const float* src = Bt + ((int64_t)i * 2 * N_total + n0) * 16;
+      mbar_expect_tx(s_u32(&bar_full[s]), 2 * S::kBFloats * 4);
+      bulk_g2s(s_u32(stage + 2 * S::kAFloats), src, S::kBFloats * 4, s_u32(&bar_full[s]));
+      bulk_g2s(s_u32(stage + 2 * S::kAFloats + S::kBFloats), src + (int64_t)N_total * 16, S::kBFloats * 4,
+               s_u32(&bar_full[s]));
+    }
+    float* ah = stage + tid * 16;
+    float* al = stage + S::kAFloats + tid * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      *reinterpret_cast<float4*>(ah + ((c ^ sw) << 2)) = xa[c];
+      *reinterpret_cast<float4*>(al + ((c ^ sw) << 2)) =
+          make_float4(residual_tf32(xa[c].x), residual_tf32(xa[c].y), residual_tf32(xa[c].z), residual_tf32(xa[c].w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      mbar_wait(s_u32(&bar_full[s]), (i >> 1) & 1);
+      const uint32_t a_hi = s_u32(stage), a_lo = a_hi + S::kAFloats * 4;
+      const uint32_t b_hi = a_hi + 2 * S::kAFloats * 4, b_lo = b_hi + S::kBFloats * 4;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t o = ks * 32;
+        umma(tmem, desc_sw64(a_lo + o), desc_sw64(b_hi + o), idesc, (i | ks) != 0);
+        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_lo + o), idesc, 1);
+        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_hi + o), idesc, 1);
+      }
+      commit_to(s_u32(&bar_free[s]));
+      if (i == n_chunks - 1) commit_to(s_u32(&bar_done));
+    }
+  }
+  mbar_wait(s_u32(&bar_done), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;");
+
+  // epilogue: thread = row (TMEM lane), 16 columns per tcgen05.ld
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    uint32_t v[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr + c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (live) {
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(v[j]);
+        if (EPI == 0 || EPI == 1) a += __ldg(bias + n0 + c0 + j);
+        if (EPI == 1) a = fmaxf(a, 0.f);
+        o[j] = a;
+      }
+      if (EPI == 2) {
+        const float4* m4 = reinterpret_cast<const float4*>(mask_src + r * ldm + n0 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 m = __ldg(m4 + q);
+          o[4 * q] = m.x > 0.f ? o[4 * q] : 0.f;
+          o[4 * q + 1] = m.y > 0.f ? o[4 * q + 1] : 0.f;
+          o[4 * q + 2] = m.z > 0.f ? o[4 * q + 2] : 0.f;
+          o[4 * q + 3] = m.w > 0.f ? o[4 * q + 3] : 0.f;
+        }
+      }
+      float4* y4 = reinterpret_cast<float4*>(Y + r * ldy + n0 + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y4[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+template <int NT, int EPI>
+static cudaError_t launch_dense(cudaStream_t s, const float* X, int64_t rows, int K, int ldx, const float* Bt,
+                                int N, const float* bias, const float* mask_src, int ldm, float* Y, int ldy) {
+  auto kern = dense_tc_kernel<NT, EPI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((rows + 127) / 128), (unsigned)(N / NT));
+  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_prep(cudaStream_t s, const float* W, int K, int N, int ldw, bool transpose, float* out) {
+  const int64_t total = (int64_t)K * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dense_prep_kernel<<<blocks, 256, 0, s>>>(W, K, N, ldw, transpose ? 1 : 0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_forward(cudaStream_t s, const float* X, int64_t rows, int K, int ldx, const float* Bt, int N,
+                          const float* bias, const float* mask_src, int ldm, int epilogue, float* Y, int ldy,
+                          bool* supported) {
+  *supported = true;
+  if (rows == 0) return cudaSuccess;
+#define DENSE_CASE(NT_)                                                                                   \
+  switch (epilogue) {                                                                                    \
+    case 0: return launch_dense<NT_, 0>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
+    case 1: return launch_dense<NT_, 1>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
+    case 2: return launch_dense<NT_, 2>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
+    case 3: return launch_dense<NT_, 3>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
+  }
+  if (N % 256 == 0) { DENSE_CASE(256) }
+  else if (N % 128 == 0) { DENSE_CASE(128) }
+  else if (N % 64 == 0) { DENSE_CASE(64) }
+  else if (N % 16 == 0 && N <= 64) {
+    if (N == 16) { DENSE_CASE(16) }
+    else if (N == 32) { DENSE_CASE(32) }
+    else if (N == 48) { DENSE_CASE(16) }
+  }
+#undef DENSE_CASE
+  *supported = false;
+  return cudaSuccess;
+}
+
+}  // namespace cnfot

@@ -277,6 +277,46 @@ def kinetic_energy(shape: FlowShape, weights, latent, t_values: Sequence[float],
   return out[0]
 
 
+class PreparedDense:
+  """Weights of one dense layer in the tcgen05 kernels' tile order (hi / lo tf32 split)."""
+
+  def __init__(self, W: torch.Tensor, transpose: bool = False):
+    lib = _lib.load()
+    W = _dev(W, "W")
+    if W.dim() != 2:
+      raise _lib.CnfotError("W must be a matrix")
+    self.K, self.N = (W.shape[1], W.shape[0]) if transpose else (W.shape[0], W.shape[1])
+    n = lib.cnfot_dense_prepared_floats(self.K, self.N)
+    if n < 0:
+      raise _lib.CnfotError("dense layers need both sizes to be multiples of 16")
+    self.buf = torch.empty(n, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+      _lib.check(lib.cnfot_dense_prepare(_stream(), _ptr(W), self.K, self.N, W.stride(0), int(transpose),
+                                         _ptr(self.buf)))
+
+
+_EPILOGUES = {"bias": 0, "bias_relu": 1, "relu_mask": 2, "none": 3}
+
+
+def dense_forward(X, prepared: PreparedDense, bias=None, mask_src=None, epilogue: str = "bias", out=None):
+  """Y = epilogue(X W + b) on tcgen05 (3xTF32): see include/cnfot.h, cnfot_dense_forward."""
+  lib = _lib.load()
+  X = _dev(X, "X")
+  rows = X.shape[0]
+  if X.dim() != 2 or X.shape[1] != prepared.K or X.stride(1) != 1:
+    raise _lib.CnfotError("X must be (rows, K) with unit inner stride")
+  bias = _dev(bias, "bias")
+  mask_src = _dev(mask_src, "mask_src")
+  if out is None:
+    out = torch.empty(rows, prepared.N, dtype=torch.float32, device=X.device)
+  with torch.cuda.device(X.device):
+    _lib.check(lib.cnfot_dense_forward(_stream(), _ptr(X), rows, prepared.K, X.stride(0), _ptr(prepared.buf),
+                                       prepared.N, _ptr(bias), _ptr(mask_src),
+                                       0 if mask_src is None else mask_src.stride(0), _EPILOGUES[epilogue],
+                                       _ptr(out), out.stride(0)))
+  return out
+
+
 def adam_update(params, grads, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8) -> None:
   """In-place optax.adam(lr) update of the parameter blob."""
   lib = _lib.load()

@@ -236,6 +236,23 @@ CNFOT_API int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, co
                          int32_t n_t, float dt, int32_t with_score, float kappa, float dx, double* out,
                          void* workspace, int64_t workspace_bytes);
 
+/* ---- wide conditioner layers on tcgen05 (BASELINE config 5: hidden = 512) -----------------------
+ * Y (rows x N) = epilogue(X (rows x K) * W (K x N) [+ bias]), fp32 in / out with fp32 fidelity (3xTF32):
+ * the dense layers of the conditioner MLP (cnf_ot/models/flows.py:65-81) and, with transpose != 0 at
+ * prepare time, their data gradients (G * W^T).  tcgen05.mma.kind::tf32 with the accumulator in TMEM,
+ * weights staged by 1-D bulk TMA copies from a buffer prepared once per weight update:
+ *   cnfot_dense_prepare      W (row stride ldw) -> `prepared` (cnfot_dense_prepared_floats(K, N) floats);
+ *                            transpose != 0 prepares W^T, i.e. W is then (N x K) and the call computes X * W^T
+ *   cnfot_dense_forward      epilogue 0: + bias, 1: + bias then ReLU, 2: ReLU mask (Y = mask_src > 0 ? acc : 0,
+ *                            mask_src (rows x N, row stride ldm)), 3: none
+ * K and N must be multiples of 16; ldx, ldy, ldm multiples of 4. */
+CNFOT_API int64_t cnfot_dense_prepared_floats(int32_t K, int32_t N);
+CNFOT_API int cnfot_dense_prepare(void* stream, const float* W, int32_t K, int32_t N, int32_t ldw,
+                        int32_t transpose, float* prepared);
+CNFOT_API int cnfot_dense_forward(void* stream, const float* X, int64_t rows, int32_t K, int32_t ldx,
+                        const float* prepared, int32_t N, const float* bias, const float* mask_src,
+                        int32_t ldm, int32_t epilogue, float* Y, int32_t ldy);
+
 /* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
  * element-wise update; step is the 1-based update count. */
 CNFOT_API int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v,
