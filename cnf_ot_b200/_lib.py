@@ -96,6 +96,8 @@ SIGNATURES = {
   "cnfot_dense_prepare": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
   "cnfot_dense_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p,
                                     c_void_p, c_int32, c_int32, c_void_p, c_int32]),
+  "cnfot_dense_wgrad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32,
+                                  c_void_p, c_int32, c_void_p]),
   "cnfot_adam_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_int64]),
 }

@@ -1023,6 +1023,18 @@ int cnfot_dense_forward(void* stream, const float* X, int64_t rows, int32_t K, i
   return 0;
 }
 
+int cnfot_dense_wgrad(void* stream, const float* A, int32_t lda, const float* G, int32_t ldg, int64_t rows,
+                      int32_t Ka, int32_t Nb, float* dW, int32_t ldw, float* db) {
+  if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+  if (rows == 0) return 0;
+  if (!A || !G || !dW) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (Ka < 1 || Nb < 4 || Nb % 4 || ldw % 4 || ((uintptr_t)dW & 15))
+    return fail(CNFOT_ERR_ARG, "dense_wgrad: Nb and ldw must be multiples of 4 and dW 16-byte aligned");
+  cudaError_t e = dense_wgrad((cudaStream_t)stream, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, db);
+  if (e != cudaSuccess) return cuda_fail(e, "dense_wgrad_kernel launch");
+  return 0;
+}
+
 int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v, int64_t count,
                       float lr, float b1, float b2, float eps, int64_t step) {
   if (count < 0 || step < 1) return fail(CNFOT_ERR_ARG, "bad count/step");

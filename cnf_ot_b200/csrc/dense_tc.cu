@@ -232,6 +232,192 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
+// ---- weight gradient: dW (Ka x Nb) += A^T G over a range of rows, A (rows x Ka), G (rows x Nb) --------
+// tcgen05.kind::tf32 takes K-major operands only (tools/tc_probe.cu: MN-major descriptors are not
+// executed), so the contraction index -- the sample rows -- must be contiguous inside a stage row.
+// Thread t owns operand row t of the stage (feature m0+t of A, features n0+t and n0+128+t of G) and
+// gathers its 16 values of a chunk with 16 loads that are coalesced across the warp (consecutive
+// features of one sample row), then writes its 64-byte stage row (values and residuals) with the same
+// swizzle as the forward kernel.  Same MMA schedule; the 128 x NT accumulator of the CTA's row range
+// is added to dW with red.global.add.v4.f32 (split over row ranges: grid.z).
+template <int NT>
+__global__ void __launch_bounds__(128)
+dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ G, int ldg, int64_t rows,
+                   int Ka, int Nb, float* __restrict__ dW, int ldw) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  using S = DenseSmem<NT>;
+  constexpr int kTmemCols = NT < 32 ? 32 : NT;
+  constexpr int NB = NT / 128 > 0 ? NT / 128 : 1;   // G features per thread (NT = 128 or 256), or < 128 features
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
+  // this CTA's row range, in whole chunks of 16
+  const int64_t chunks_total = (rows + 15) / 16;
+  const int64_t per = (chunks_total + gridDim.z - 1) / gridDim.z;
+  const int64_t c_lo = blockIdx.z * per, c_hi = c_lo + per < chunks_total ? c_lo + per : chunks_total;
+  if (c_lo >= c_hi) return;
+
+  if (tid == 0) {
+    mbar_init(s_u32(&bar_free[0]), 1); mbar_init(s_u32(&bar_free[1]), 1);
+    mbar_init(s_u32(&bar_done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = idesc_tf32(NT);
+  const int sw = (tid >> 1) & 3;
+  const bool a_ok = m0 + tid < Ka;
+  const float* acol = A + m0 + tid;
+
+  for (int64_t c = c_lo; c < c_hi; ++c) {
+    const int i = (int)(c - c_lo), s = i & 1;
+    float* stage = smem + s * S::kStageFloats;
+    const int64_t r0 = c * 16;
+    float av[16], gv[NB][16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const bool in = r0 + k < rows;
+      av[k] = (in && a_ok) ? __ldg(acol + (r0 + k) * lda) : 0.f;
+#pragma unroll
+      for (int h = 0; h < NB; ++h) {
+        const int n = n0 + h * 128 + tid;
+        gv[h][k] = (in && tid + h * 128 < NT && n < Nb) ? __ldg(G + (r0 + k) * ldg + n) : 0.f;
+      }
+    }
+    if (i >= 2) mbar_wait(s_u32(&bar_free[s]), ((i >> 1) - 1) & 1);
+    float* ah = stage + tid * 16;
+    float* al = stage + S::kAFloats + tid * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      *reinterpret_cast<float4*>(ah + ((q ^ sw) << 2)) = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
+      *reinterpret_cast<float4*>(al + ((q ^ sw) << 2)) =
+          make_float4(residual_tf32(av[4 * q]), residual_tf32(av[4 * q + 1]), residual_tf32(av[4 * q + 2]),
+                      residual_tf32(av[4 * q + 3]));
+    }
+#pragma unroll
+    for (int h = 0; h < NB; ++h) {
+      const int row = h * 128 + tid;
+      if (row < NT) {
+        float* bh = stage + 2 * S::kAFloats + row * 16;
+        float* bl = bh + S::kBFloats;
+        const int swb = (row >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(bh + ((q ^ swb) << 2)) =
+              make_float4(gv[h][4 * q], gv[h][4 * q + 1], gv[h][4 * q + 2], gv[h][4 * q + 3]);
+          *reinterpret_cast<float4*>(bl + ((q ^ swb) << 2)) =
+              make_float4(residual_tf32(gv[h][4 * q]), residual_tf32(gv[h][4 * q + 1]), residual_tf32(gv[h][4 * q + 2]),
+                          residual_tf32(gv[h][4 * q + 3]));
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t a_hi = s_u32(stage), a_lo = a_hi + S::kAFloats * 4;
+      const uint32_t b_hi = a_hi + 2 * S::kAFloats * 4, b_lo = b_hi + S::kBFloats * 4;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t o = ks * 32;
+        umma(tmem, desc_sw64(a_lo + o), desc_sw64(b_hi + o), idesc, (i | ks) != 0);
+        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_lo + o), idesc, 1);
+        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_hi + o), idesc, 1);
+      }
+      commit_to(s_u32(&bar_free[s]));
+      if (c == c_hi - 1) commit_to(s_u32(&bar_done));
+    }
+  }
+  mbar_wait(s_u32(&bar_done), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  float* wrow = dW + (int64_t)(m0 + tid) * ldw + n0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    uint32_t v[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr + c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (a_ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (n0 + c0 + 4 * q < Nb)
+          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(wrow + c0 + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                       "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                       "f"(__uint_as_float(v[4 * q + 3]))
+                       : "memory");
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+// db[n] += sum_r G[r][n]
+__global__ void __launch_bounds__(256) dense_colsum_kernel(const float* __restrict__ G, int ldg, int64_t rows, int Nb,
+                                                           float* __restrict__ db) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sub = threadIdx.x >> 5;   // 8 row phases per block
+  const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = blockIdx.y * per, hi = lo + per < rows ? lo + per : rows;
+  float acc = 0.f;
+  if (n < Nb)
+    for (int64_t r = lo + sub; r < hi; r += 8) acc += __ldg(G + r * ldg + n);
+  __shared__ float part[8][32];
+  part[sub][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (sub == 0 && n < Nb) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    atomicAdd(db + n, t);
+  }
+}
+
+template <int NT>
+static cudaError_t launch_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka,
+                                int Nb, float* dW, int ldw) {
+  auto kern = dense_wgrad_kernel<NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
+  if (e != cudaSuccess) return e;
+  const int mt = (Ka + 127) / 128, nt = (Nb + NT - 1) / NT;
+  const int64_t chunks = (rows + 15) / 16;
+  int64_t z = (148 * 2 + mt * nt - 1) / (mt * nt);   // about one wave of 2 CTAs per SM
+  if (z > chunks) z = chunks;
+  if (z > 65535) z = 65535;
+  if (z < 1) z = 1;
+  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)z);
+  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  return cudaGetLastError();
+}
+
+cudaError_t dense_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka, int Nb,
+                        float* dW, int ldw, float* db) {
+  if (rows == 0) return cudaSuccess;
+  cudaError_t e;
+  if (Nb > 128) e = launch_wgrad<256>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  else if (Nb > 64) e = launch_wgrad<128>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  else if (Nb > 16) e = launch_wgrad<64>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  else e = launch_wgrad<16>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  if (e != cudaSuccess || !db) return e;
+  int64_t zy = rows / 4096 + 1;
+  if (zy > 1024) zy = 1024;
+  dense_colsum_kernel<<<dim3((unsigned)((Nb + 31) / 32), (unsigned)zy), 256, 0, s>>>(G, ldg, rows, Nb, db);
+  return cudaGetLastError();
+}
+
 template <int NT, int EPI>
 static cudaError_t launch_dense(cudaStream_t s, const float* X, int64_t rows, int K, int ldx, const float* Bt,
                                 int N, const float* bias, const float* mask_src, int ldm, float* Y, int ldy) {

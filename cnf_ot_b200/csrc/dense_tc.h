@@ -13,4 +13,8 @@ cudaError_t dense_forward(cudaStream_t s, const float* X, int64_t rows, int K, i
                           const float* bias, const float* mask_src, int ldm, int epilogue, float* Y, int ldy,
                           bool* supported);
 
+// dW (Ka x Nb, row stride ldw) += A^T G over `rows` sample rows, db (Nb, may be NULL) += column sums of G
+cudaError_t dense_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka, int Nb,
+                        float* dW, int ldw, float* db);
+
 }  // namespace cnfot

@@ -317,6 +317,20 @@ def dense_forward(X, prepared: PreparedDense, bias=None, mask_src=None, epilogue
   return out
 
 
+def dense_wgrad(A, G, dW, db=None) -> None:
+  """dW += A^T G, db += column sums of G (tcgen05, 3xTF32): see include/cnfot.h, cnfot_dense_wgrad.
+  dW may be a strided view (rows contiguous) of a gradient blob."""
+  lib = _lib.load()
+  A, G = _dev(A, "A"), _dev(G, "G")
+  if not dW.is_cuda or dW.dtype != torch.float32 or dW.stride(1) != 1:
+    raise _lib.CnfotError("dW must be a CUDA float32 matrix with unit inner stride")
+  if A.shape[0] != G.shape[0] or dW.shape != (A.shape[1], G.shape[1]):
+    raise _lib.CnfotError("dense_wgrad: shape mismatch")
+  with torch.cuda.device(A.device):
+    _lib.check(lib.cnfot_dense_wgrad(_stream(), _ptr(A), A.stride(0), _ptr(G), G.stride(0), A.shape[0], A.shape[1],
+                                     G.shape[1], _ptr(dW), dW.stride(0), _ptr(db)))
+
+
 def adam_update(params, grads, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8) -> None:
   """In-place optax.adam(lr) update of the parameter blob."""
   lib = _lib.load()

@@ -252,6 +252,12 @@ CNFOT_API int cnfot_dense_prepare(void* stream, const float* W, int32_t K, int32
 CNFOT_API int cnfot_dense_forward(void* stream, const float* X, int64_t rows, int32_t K, int32_t ldx,
                         const float* prepared, int32_t N, const float* bias, const float* mask_src,
                         int32_t ldm, int32_t epilogue, float* Y, int32_t ldy);
+/* Weight gradient of the same layer, ACCUMULATED: dW (Ka x Nb, row stride ldw) += A^T G over `rows` rows
+ * (A (rows x Ka, stride lda) the layer input, G (rows x Nb, stride ldg) the adjoint of its
+ * pre-activation), db (Nb, may be NULL) += column sums of G.  tcgen05 with both operands gathered
+ * K-major (sample rows contiguous) by the CTA, 3xTF32, split over row ranges, red.global adds. */
+CNFOT_API int cnfot_dense_wgrad(void* stream, const float* A, int32_t lda, const float* G, int32_t ldg,
+                      int64_t rows, int32_t Ka, int32_t Nb, float* dW, int32_t ldw, float* db);
 
 /* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
  * element-wise update; step is the 1-based update count. */

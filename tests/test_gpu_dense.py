@@ -55,3 +55,23 @@ def test_dense_rejects_bad_shapes():
     ops.dense_forward(torch.zeros(4, 32, device="cuda"), P, epilogue="none")
   with pytest.raises(CnfotError):
     ops.dense_forward(torch.zeros(4, 16, device="cuda"), P, epilogue="bias")
+
+
+@pytest.mark.parametrize("rows,Ka,Nb", [(5000, 512, 512), (777, 512, 16), (100, 33, 512), (4096, 64, 128), (17, 16, 64)])
+def test_dense_wgrad_matches_float64(rows, Ka, Nb):
+  g = torch.Generator().manual_seed(rows + Ka + Nb)
+  A = torch.randn(rows, Ka, generator=g).cuda()
+  G = torch.randn(rows, Nb, generator=g).cuda()
+  dW0 = torch.randn(Ka, Nb, generator=g).cuda()
+  db0 = torch.randn(Nb, generator=g).cuda()
+  dW, db = dW0.clone(), db0.clone()
+  ops.dense_wgrad(A, G, dW, db)
+  ref = dW0.double() + A.double().T @ G.double()
+  refb = db0.double() + G.double().sum(0)
+  assert float((dW.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+  assert float((db.double() - refb).abs().max()) <= 1e-5 * float(refb.abs().max())
+  # a strided destination (a matrix inside a larger blob) and inputs that are column slices
+  blob = torch.zeros(Ka, Nb + 16, device="cuda")
+  ops.dense_wgrad(A, G, blob[:, 16:])
+  assert float((blob[:, 16:].double() - A.double().T @ G.double()).abs().max()) <= 1e-5 * float(ref.abs().max())
+  assert float(blob[:, :16].abs().max()) == 0.0

@@ -22,3 +22,10 @@ for rows, K, N in ((1 << 18, 512, 512), (1 << 20, 512, 512), (1 << 20, 512, 16))
   for _ in range(5): torch.relu(torch.addmm(b, X, W))
   e1.record(); torch.cuda.synchronize()
   print(f"   torch fp32 addmm+relu (cuBLAS): {e0.elapsed_time(e1)/5:.3f} ms", flush=True)
+for rows, Ka, Nb in ((1 << 20, 512, 512),):
+  A = torch.randn(rows, Ka, device="cuda"); G = torch.randn(rows, Nb, device="cuda"); dW = torch.zeros(Ka, Nb, device="cuda"); db = torch.zeros(Nb, device="cuda")
+  for _ in range(2): ops.dense_wgrad(A, G, dW, db)
+  torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+  for _ in range(5): ops.dense_wgrad(A, G, dW, db)
+  e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 5
+  print(f"wgrad rows={rows} {Ka}x{Nb}: {ms:.3f} ms  {2.0*rows*Ka*Nb/ms/1e9:.1f} TFLOP/s algorithmic", flush=True)
