@@ -78,6 +78,9 @@ SIGNATURES = {
   "cnfot_rqs_inverse_vjp": (c_int32, _RQS_VJP),
   "cnfot_flow_forward": (c_int32, _FLOW),
   "cnfot_flow_inverse": (c_int32, _FLOW),
+  "cnfot_flow_workspace_bytes": (c_int64, [_F, c_int64]),
+  "cnfot_flow_forward_ws": (c_int32, _FLOW + [c_void_p, c_int64]),
+  "cnfot_flow_inverse_ws": (c_int32, _FLOW + [c_void_p, c_int64]),
   "cnfot_flow_vjp_workspace_bytes": (c_int64, [_F, c_int64]),
   "cnfot_flow_forward_vjp": (c_int32, _FLOW_VJP),
   "cnfot_flow_inverse_vjp": (c_int32, _FLOW_VJP),
@@ -129,9 +132,9 @@ def load() -> ctypes.CDLL:
 def last_launch_info() -> dict:
   vals = [c_int32(0) for _ in range(4)]
   load().cnfot_last_launch_info(*[ctypes.byref(v) for v in vals])
-  eng = vals[3].value  # 0 CUDA cores, 1 tcgen05 engine, 2 warp-level MMA engine
+  eng = vals[3].value  # 0 CUDA cores, 1 tcgen05 engine, 2 warp-level MMA engine, 4 wide-conditioner engine
   return {"grid": vals[0].value, "smem_bytes": vals[1].value, "ctas_per_sm": vals[2].value,
-          "tensor_cores": bool(eng), "engine": {0: "cuda", 1: "tc", 2: "mma"}.get(eng, "?")}
+          "tensor_cores": bool(eng), "engine": {0: "cuda", 1: "tc", 2: "mma", 4: "wide"}.get(eng, "?")}
 
 
 def check(rc: int) -> None:

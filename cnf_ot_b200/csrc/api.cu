@@ -14,6 +14,7 @@
 #include "dispatch.h"
 #include "flow_kernels.cuh"
 #include "step_host.h"
+#include "wide.h"
 
 namespace cnfot {
 
@@ -92,6 +93,19 @@ static int check_fused(const cnfot_flow_desc* f, const FlowLayout& lay) {
                 "(see CNFOT_NET_LIST in cnf_ot_b200/csrc/dispatch.h)",
                 f->hidden, f->num_bins, f->mlp_layers);
   return 0;
+}
+
+// shapes the fused per-row kernels cover (no error message: callers fall through to the wide engine)
+static bool fused_ok(const cnfot_flow_desc* f, const FlowLayout& lay) {
+  return f->dim <= kMaxDim && (f->num_layers + 1) * f->dim <= kMaxStateFloats && find_flow_eval_kernel(lay) != nullptr;
+}
+// the wide-conditioner engine (wide.cu) takes every shape the fused kernels do not, when it can
+// (CNFOT_ENGINE=wide forces it for shapes both cover: used by the cross-engine parity tests)
+static bool use_wide(const cnfot_flow_desc* f, const FlowLayout& lay) {
+  if (!wide_supported(lay, nullptr)) return false;
+  if (!fused_ok(f, lay)) return true;
+  const char* e = getenv("CNFOT_ENGINE");
+  return e && !strcmp(e, "wide");
 }
 
 static SplineConsts<float> spline_consts(const cnfot_flow_desc* f) {
@@ -477,6 +491,7 @@ int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t 
 int cnfot_flow_supported(const cnfot_flow_desc* flow) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay)) return 0;
   return check_fused(flow, lay);
 }
 
@@ -549,9 +564,28 @@ int cnfot_rqs_inverse_vjp(void* stream, const float* y, const float* params, con
 // ---- seam 1 ---------------------------------------------------------------------------
 static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, const float* weights,
                           const float* in, const float* cond, int64_t cond_stride, int64_t rows,
-                          float* out, float* logdet, int32_t add_base) {
+                          float* out, float* logdet, int32_t add_base, void* workspace = nullptr,
+                          int64_t workspace_bytes = 0) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay)) {
+    if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+    if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
+    if (rows == 0) return 0;
+    if (!weights || !in || !cond || !out) return fail(CNFOT_ERR_ARG, "NULL buffer");
+    const int64_t need = wide_flow_workspace_bytes(lay, rows, false);
+    if (!workspace)
+      return fail(CNFOT_ERR_WORKSPACE, "this flow runs on the wide-conditioner engine, which needs a workspace: "
+                                       "call cnfot_flow_forward_ws / cnfot_flow_inverse_ws");
+    if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                            (long long)workspace_bytes, (long long)need);
+    const char* what = "";
+    cudaError_t e = wide_flow_eval((cudaStream_t)stream, lay, spline_consts(flow), weights, dir, in, cond, cond_stride,
+                                   rows, out, logdet, add_base, workspace, &what);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    g_last_launch[0] = 0; g_last_launch[1] = 0; g_last_launch[2] = 0; g_last_launch[3] = kEngWide;
+    return 0;
+  }
   if (int rc = check_fused(flow, lay)) return rc;
   if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
   if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
@@ -585,10 +619,28 @@ int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* w
   return flow_eval_call(1, stream, flow, weights, in, cond, cond_stride, rows, out, logdet, add_base);
 }
 
-int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows) {
-  (void)rows;
+int64_t cnfot_flow_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows) {
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
+  return use_wide(flow, lay) ? wide_flow_workspace_bytes(lay, rows, false) : 0;
+}
+int cnfot_flow_forward_ws(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* in,
+                          const float* cond, int64_t cond_stride, int64_t rows, float* out, float* logdet,
+                          int32_t add_base, void* workspace, int64_t workspace_bytes) {
+  return flow_eval_call(0, stream, flow, weights, in, cond, cond_stride, rows, out, logdet, add_base, workspace,
+                        workspace_bytes);
+}
+int cnfot_flow_inverse_ws(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* in,
+                          const float* cond, int64_t cond_stride, int64_t rows, float* out, float* logdet,
+                          int32_t add_base, void* workspace, int64_t workspace_bytes) {
+  return flow_eval_call(1, stream, flow, weights, in, cond, cond_stride, rows, out, logdet, add_base, workspace,
+                        workspace_bytes);
+}
+
+int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  if (use_wide(flow, lay)) return wide_flow_workspace_bytes(lay, rows, true);
   return partial_bytes(lay);
 }
 
@@ -598,6 +650,21 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
                          float* g_weights, void* workspace, int64_t workspace_bytes) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay)) {
+    if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
+    if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
+    if (!weights || !g_weights || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+    if (rows > 0 && (!in || !cond || !g_out)) return fail(CNFOT_ERR_ARG, "NULL buffer");
+    const int64_t need = wide_flow_workspace_bytes(lay, rows, true);
+    if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                            (long long)workspace_bytes, (long long)need);
+    const char* what = "";
+    cudaError_t e = wide_flow_vjp((cudaStream_t)stream, lay, spline_consts(flow), weights, dir, in, cond, cond_stride,
+                                  rows, g_out, g_logdet, add_base, g_in, g_weights, workspace, &what);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    g_last_launch[0] = 0; g_last_launch[1] = 0; g_last_launch[2] = 0; g_last_launch[3] = kEngWide;
+    return 0;
+  }
   if (int rc = check_fused(flow, lay)) return rc;
   if (rows < 0) return fail(CNFOT_ERR_ARG, "rows < 0");
   if (cond_stride != 0 && cond_stride != 1) return fail(CNFOT_ERR_ARG, "cond_stride must be 0 or 1");
@@ -651,12 +718,50 @@ int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const floa
 }
 
 // ---- seam 3 ---------------------------------------------------------------------------
+static int64_t step_ws_bytes(const cnfot_flow_desc* flow, const FlowLayout& lay, int64_t rows_B, int64_t rows_b) {
+  return use_wide(flow, lay) ? wide_step_workspace_bytes(lay, rows_B, rows_b) : partial_bytes(lay);
+}
+
 int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B, int64_t rows_b,
                                        int32_t n_t) {
-  (void)rows_B; (void)rows_b; (void)n_t;
+  (void)n_t;
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
-  return partial_bytes(lay);
+  return step_ws_bytes(flow, lay, rows_B, rows_b);
+}
+
+// The step on the wide-conditioner engine (wide.cu): hidden >= 64, e.g. BASELINE config 5.
+static int mfc_step_wide(void* stream, const cnfot_flow_desc* flow, const FlowLayout& lay,
+                         const cnfot_problem_desc* problem, const float* weights, const float* latent_sub,
+                         const float* src, const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
+                         int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out, void* workspace,
+                         int64_t workspace_bytes, bool accumulate, const cnfot_peer_desc* peers) {
+  if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");
+  if (peers)
+    return fail(CNFOT_ERR_ARG, "the wide-conditioner engine has no fused all-reduce (its gradient is hundreds of MB): "
+                               "call cnfot_mfc_step and all-reduce `out` with NCCL");
+  if (accumulate) return fail(CNFOT_ERR_ARG, "the wide-conditioner engine does not take chunked host input");
+  if (problem->type != CNFOT_OT)
+    return fail(CNFOT_ERR_ARG, "the wide-conditioner engine implements general.type == ot (free / obstacle) only");
+  if (rows_B < 0 || rows_b < 0 || global_B < 1 || global_b < 1 || rows_B > global_B || rows_b > global_b)
+    return fail(CNFOT_ERR_ARG, "bad row counts");
+  if (n_t < 1) return fail(CNFOT_ERR_ARG, "t_batch_size must be >= 1");
+  if (!weights || !out || !workspace || !t_batch_host) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (rows_B > 0 && (!src || !tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
+  if (rows_b > 0 && !latent_sub) return fail(CNFOT_ERR_ARG, "latent_sub is NULL");
+  const int64_t need = wide_step_workspace_bytes(lay, rows_B, rows_b);
+  if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                          (long long)workspace_bytes, (long long)need);
+  StepConsts<float> pc;
+  const char* err = nullptr;
+  if (make_step_consts<float>(*problem, lay.D, (double)lambda, global_B, global_b, n_t, &pc, &err))
+    return fail(CNFOT_ERR_ARG, "%s", err);
+  const char* what = "";
+  cudaError_t e = wide_mfc_step((cudaStream_t)stream, lay, spline_consts(flow), pc, weights, latent_sub, src, tgt,
+                                t_batch_host, n_t, rows_B, rows_b, out, workspace, &what);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  g_last_launch[0] = 0; g_last_launch[1] = 0; g_last_launch[2] = 0; g_last_launch[3] = kEngWide;
+  return 0;
 }
 
 static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
@@ -667,6 +772,9 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
                          const cnfot_peer_desc* peers = nullptr) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay))
+    return mfc_step_wide(stream, flow, lay, problem, weights, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b,
+                         global_B, global_b, lambda, out, workspace, workspace_bytes, accumulate, peers);
   if (int rc = check_fused(flow, lay)) return rc;
   if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");
   PeerArgs pa;
@@ -832,7 +940,7 @@ int64_t cnfot_mfc_step_host_workspace_bytes(const cnfot_flow_desc* flow, int64_t
   int64_t rowsb = align256(rows_b * lay.D * (int64_t)sizeof(float));
   int64_t w = align256((int64_t)lay.total * sizeof(float));
   int64_t o = align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
-  return align256(partial_bytes(lay)) + w + o + 3 * rowsB + rowsb;
+  return align256(step_ws_bytes(flow, lay, rows_B, rows_b)) + w + o + 3 * rowsB + rowsb;
 }
 
 int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
@@ -850,7 +958,8 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
                                           (long long)workspace_bytes, (long long)need);
   cudaStream_t s = (cudaStream_t)stream;
   char* p = (char*)workspace;
-  void* ws = p; p += align256(partial_bytes(lay));
+  const int64_t ws_bytes = align256(step_ws_bytes(flow, lay, rows_B, rows_b));
+  void* ws = p; p += ws_bytes;
   float* dW = (float*)p; p += align256((int64_t)lay.total * sizeof(float));
   float* dOut = (float*)p; p += align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
   const int64_t bytesB = rows_B * lay.D * (int64_t)sizeof(float);
@@ -884,7 +993,7 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
   if (zero_copy) {
     int rc = mfc_step_impl(stream, flow, problem, dW, mapped[0], mapped[1], mapped[2], mapped[3], t_batch_host,
                            n_t, rows_B, rows_b, global_B, global_b, lambda, dOut, ws,
-                           align256(partial_bytes(lay)), false);
+                           ws_bytes, false);
     if (rc) return rc;
   } else {
     // Staged path.  Row chunks: the H2D copy of chunk k+1 (internal copy stream) overlaps the kernels
@@ -919,7 +1028,7 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
                              latent_sub_host ? dSub : nullptr, src_host ? dSrc + lo * lay.D : nullptr,
                              tgt_host ? dTgt + lo * lay.D : nullptr, t_batch_host, n_t, hi - lo,
                              k == 0 ? rows_b : 0, global_B, global_b, lambda, dOut, ws,
-                             align256(partial_bytes(lay)), k > 0);
+                             ws_bytes, k > 0);
       if (rc) return rc;
     }
   }
@@ -1011,7 +1120,7 @@ int cnfot_dense_forward(void* stream, const float* X, int64_t rows, int32_t K, i
   if (rows == 0) return 0;
   if (!X || !prepared || !Y) return fail(CNFOT_ERR_ARG, "NULL buffer");
   if (cnfot_dense_prepared_floats(K, N) < 0) return fail(CNFOT_ERR_ARG, "dense layers need K and N to be multiples of 16");
-  if (epilogue < 0 || epilogue > 3) return fail(CNFOT_ERR_ARG, "unknown epilogue");
+  if (epilogue < 0 || epilogue > 4) return fail(CNFOT_ERR_ARG, "unknown epilogue");
   if ((epilogue == 0 || epilogue == 1) && !bias) return fail(CNFOT_ERR_ARG, "bias is NULL");
   if (epilogue == 2 && !mask_src) return fail(CNFOT_ERR_ARG, "mask_src is NULL");
   if (ldx % 4 || ldy % 4 || (epilogue == 2 && ldm % 4)) return fail(CNFOT_ERR_ARG, "row strides must be multiples of 4 floats");

@@ -17,6 +17,7 @@
 // and writes full 128-byte row segments.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dense_tc.h"
 
@@ -70,13 +71,16 @@ __device__ __forceinline__ void commit_to(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ float residual_tf32(float v) {
-  return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+// 3xTF32 split with round-to-nearest parts (zero-mean errors; a truncating split is biased and the bias adds
+// up over the contraction): hi = rn_tf32(v), lo = rn_tf32(v - hi); v - hi is exact in fp32.
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r & 0xFFFFE000u);
 }
-
-// element (row n, k) of a [rows][16] SWIZZLE_64B tile, in floats
-__device__ __forceinline__ int sw64_pos(int n, int k) {
-  return n * 16 + ((((k >> 2) ^ ((n >> 1) & 3)) << 2) | (k & 3));
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
 }
 
 }  // namespace
@@ -91,12 +95,12 @@ __global__ void dense_prep_kernel(const float* __restrict__ W, int K, int N, int
     if (transpose) { k = (int)(e % K); n = (int)(e / K); }   // consecutive threads read consecutive memory
     else { n = (int)(e % N); k = (int)(e / N); }
     const float v = transpose ? W[(int64_t)n * ldw + k] : W[(int64_t)k * ldw + n];
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float hi = tf32_rn(v);
     const int kc = k >> 4, kk = k & 15;
     float* t = out + (int64_t)kc * 2 * N * 16;
     const int p = sw64_pos(n, kk);
     t[p] = hi;
-    t[N * 16 + p] = v - hi;
+    t[N * 16 + p] = tf32_rn(v - hi);
   }
 }
 
@@ -108,17 +112,21 @@ struct DenseSmem {
   static constexpr int kBytes = 2 * kStageFloats * 4 + 1024;
 };
 
-// EPI: 0 = bias, 1 = bias + ReLU, 2 = ReLU mask (Y = mask_src > 0 ? acc : 0), 3 = none
+__host__ __device__ constexpr int tmem_cols(int nt) { return nt <= 32 ? 32 : nt <= 64 ? 64 : nt <= 128 ? 128 : 256; }
+
+// EPI: 0 = bias, 1 = bias + ReLU, 2 = ReLU mask (Y = mask_src > 0 ? acc : 0), 3 = none, 4 = accumulate (Y += acc)
 template <int NT, int EPI>
 __global__ void __launch_bounds__(128)
 dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const float* __restrict__ Bt,
                 int N_total, const float* __restrict__ bias, const float* __restrict__ mask_src, int ldm,
-                float* __restrict__ Y, int ldy) {
+                float* __restrict__ Y, int ldy, int acc2) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done;
   __shared__ uint32_t tmem_slot;
   using S = DenseSmem<NT>;
-  constexpr int kTmemCols = NT < 32 ? 32 : NT;
+  // acc2: the two small products (x_lo w_hi, x_hi w_lo) go to a second accumulator, NT columns further
+  const int kTmemCols = acc2 ? tmem_cols(2 * NT) : tmem_cols(NT);
+  const uint32_t lo_off = acc2 ? (uint32_t)NT : 0u;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * 128;
   const int n0 = blockIdx.y * NT;
@@ -165,9 +173,10 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
     float* al = stage + S::kAFloats + tid * 16;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      *reinterpret_cast<float4*>(ah + ((c ^ sw) << 2)) = xa[c];
-      *reinterpret_cast<float4*>(al + ((c ^ sw) << 2)) =
-          make_float4(residual_tf32(xa[c].x), residual_tf32(xa[c].y), residual_tf32(xa[c].z), residual_tf32(xa[c].w));
+      float4 hi, lo;
+      split4(xa[c], hi, lo);
+      *reinterpret_cast<float4*>(ah + ((c ^ sw) << 2)) = hi;
+      *reinterpret_cast<float4*>(al + ((c ^ sw) << 2)) = lo;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -180,9 +189,9 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const uint32_t o = ks * 32;
-        umma(tmem, desc_sw64(a_lo + o), desc_sw64(b_hi + o), idesc, (i | ks) != 0);
-        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_lo + o), idesc, 1);
-        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_hi + o), idesc, 1);
+        umma(tmem + lo_off, desc_sw64(a_lo + o), desc_sw64(b_hi + o), idesc, (i | ks) != 0);
+        umma(tmem + lo_off, desc_sw64(a_hi + o), desc_sw64(b_lo + o), idesc, 1);
+        umma(tmem, desc_sw64(a_hi + o), desc_sw64(b_hi + o), idesc, acc2 ? (i | ks) != 0 : 1);
       }
       commit_to(s_u32(&bar_free[s]));
       if (i == n_chunks - 1) commit_to(s_u32(&bar_done));
@@ -202,6 +211,17 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr + c0));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (acc2) {
+      uint32_t u[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+            "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+          : "r"(taddr + lo_off + c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+    }
     if (live) {
       float o[16];
 #pragma unroll
@@ -224,7 +244,14 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
       }
       float4* y4 = reinterpret_cast<float4*>(Y + r * ldy + n0 + c0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) y4[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      for (int q = 0; q < 4; ++q) {
+        float4 w = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        if (EPI == 4) {
+          const float4 old = y4[q];
+          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        y4[q] = w;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -243,12 +270,12 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
 template <int NT>
 __global__ void __launch_bounds__(128)
 dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ G, int ldg, int64_t rows,
-                   int Ka, int Nb, float* __restrict__ dW, int ldw) {
+                   int Ka, int Nb, float* __restrict__ dW, int ldw, const WgradMap map, float* __restrict__ db) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t bar_free[2], bar_done;
   __shared__ uint32_t tmem_slot;
   using S = DenseSmem<NT>;
-  constexpr int kTmemCols = NT < 32 ? 32 : NT;
+  constexpr int kTmemCols = tmem_cols(NT);
   constexpr int NB = NT / 128 > 0 ? NT / 128 : 1;   // G features per thread (NT = 128 or 256), or < 128 features
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
@@ -275,6 +302,10 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
   const int sw = (tid >> 1) & 3;
   const bool a_ok = m0 + tid < Ka;
   const float* acol = A + m0 + tid;
+  float bsum[NB];
+#pragma unroll
+  for (int h = 0; h < NB; ++h) bsum[h] = 0.f;
+  if (map.mode == 0 ? blockIdx.x != 0 : blockIdx.y != 0) db = nullptr;
 
   for (int64_t c = c_lo; c < c_hi; ++c) {
     const int i = (int)(c - c_lo), s = i & 1;
@@ -291,15 +322,28 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
         gv[h][k] = (in && tid + h * 128 < NT && n < Nb) ? __ldg(G + (r0 + k) * ldg + n) : 0.f;
       }
     }
+    // bias gradient on the side: column sums of G (mode 0, by the CTAs of the first feature tile) or of A
+    // (mode 1: the operands are swapped there, by the CTAs of the first state-column tile)
+    if (db) {
+      if (map.mode == 0) {
+#pragma unroll
+        for (int h = 0; h < NB; ++h)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) bsum[h] += gv[h][k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bsum[0] += av[k];
+      }
+    }
     if (i >= 2) mbar_wait(s_u32(&bar_free[s]), ((i >> 1) - 1) & 1);
     float* ah = stage + tid * 16;
     float* al = stage + S::kAFloats + tid * 16;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      *reinterpret_cast<float4*>(ah + ((q ^ sw) << 2)) = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
-      *reinterpret_cast<float4*>(al + ((q ^ sw) << 2)) =
-          make_float4(residual_tf32(av[4 * q]), residual_tf32(av[4 * q + 1]), residual_tf32(av[4 * q + 2]),
-                      residual_tf32(av[4 * q + 3]));
+      float4 hi, lo;
+      split4(make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]), hi, lo);
+      *reinterpret_cast<float4*>(ah + ((q ^ sw) << 2)) = hi;
+      *reinterpret_cast<float4*>(al + ((q ^ sw) << 2)) = lo;
     }
 #pragma unroll
     for (int h = 0; h < NB; ++h) {
@@ -310,11 +354,10 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
         const int swb = (row >> 1) & 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<float4*>(bh + ((q ^ swb) << 2)) =
-              make_float4(gv[h][4 * q], gv[h][4 * q + 1], gv[h][4 * q + 2], gv[h][4 * q + 3]);
-          *reinterpret_cast<float4*>(bl + ((q ^ swb) << 2)) =
-              make_float4(residual_tf32(gv[h][4 * q]), residual_tf32(gv[h][4 * q + 1]), residual_tf32(gv[h][4 * q + 2]),
-                          residual_tf32(gv[h][4 * q + 3]));
+          float4 hi, lo;
+          split4(make_float4(gv[h][4 * q], gv[h][4 * q + 1], gv[h][4 * q + 2], gv[h][4 * q + 3]), hi, lo);
+          *reinterpret_cast<float4*>(bh + ((q ^ swb) << 2)) = hi;
+          *reinterpret_cast<float4*>(bl + ((q ^ swb) << 2)) = lo;
         }
       }
     }
@@ -336,6 +379,17 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
       if (c == c_hi - 1) commit_to(s_u32(&bar_done));
     }
   }
+  if (db) {
+    if (map.mode == 0) {
+#pragma unroll
+      for (int h = 0; h < NB; ++h) {
+        const int n = n0 + h * 128 + tid;
+        if (tid + h * 128 < NT && n < Nb) atomicAdd(db + n, bsum[h]);
+      }
+    } else if (a_ok) {
+      atomicAdd(db + m0 + tid, bsum[0]);
+    }
+  }
   mbar_wait(s_u32(&bar_done), 0);
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -349,7 +403,18 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr + c0));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (a_ok) {
+    if (a_ok && map.mode == 1) {
+      // transposed destination with the conditioner-input row map: accumulator (m, n) = sum_r A[r][m] G[r][n]
+      // is the gradient of W0[w0_row(n)][m] (G = the state rows, A = the adjoint of the first hidden layer)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + c0 + j;
+        const int row = n < Nb ? w0_row(n, map.D, map.d, map.rev) : -1;
+        if (row >= 0)
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dW + (int64_t)row * ldw + m0 + tid), "f"(__uint_as_float(v[j]))
+                       : "memory");
+      }
+    } else if (a_ok) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (n0 + c0 + 4 * q < Nb)
@@ -365,30 +430,9 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
-// db[n] += sum_r G[r][n]
-__global__ void __launch_bounds__(256) dense_colsum_kernel(const float* __restrict__ G, int ldg, int64_t rows, int Nb,
-                                                           float* __restrict__ db) {
-  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int sub = threadIdx.x >> 5;   // 8 row phases per block
-  const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
-  const int64_t lo = blockIdx.y * per, hi = lo + per < rows ? lo + per : rows;
-  float acc = 0.f;
-  if (n < Nb)
-    for (int64_t r = lo + sub; r < hi; r += 8) acc += __ldg(G + r * ldg + n);
-  __shared__ float part[8][32];
-  part[sub][threadIdx.x & 31] = acc;
-  __syncthreads();
-  if (sub == 0 && n < Nb) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
-    atomicAdd(db + n, t);
-  }
-}
-
 template <int NT>
 static cudaError_t launch_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka,
-                                int Nb, float* dW, int ldw) {
+                                int Nb, float* dW, int ldw, const WgradMap& map, float* db) {
   auto kern = dense_wgrad_kernel<NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
   if (e != cudaSuccess) return e;
@@ -399,23 +443,20 @@ static cudaError_t launch_wgrad(cudaStream_t s, const float* A, int lda, const f
   if (z > 65535) z = 65535;
   if (z < 1) z = 1;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)z);
-  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
+  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(A, lda, G, ldg, rows, Ka, Nb, dW, ldw, map, db);
   return cudaGetLastError();
 }
 
 cudaError_t dense_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka, int Nb,
-                        float* dW, int ldw, float* db) {
+                        float* dW, int ldw, float* db, const WgradMap* mapp) {
   if (rows == 0) return cudaSuccess;
-  cudaError_t e;
-  if (Nb > 128) e = launch_wgrad<256>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
-  else if (Nb > 64) e = launch_wgrad<128>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
-  else if (Nb > 16) e = launch_wgrad<64>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
-  else e = launch_wgrad<16>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw);
-  if (e != cudaSuccess || !db) return e;
-  int64_t zy = rows / 4096 + 1;
-  if (zy > 1024) zy = 1024;
-  dense_colsum_kernel<<<dim3((unsigned)((Nb + 31) / 32), (unsigned)zy), 256, 0, s>>>(G, ldg, rows, Nb, db);
-  return cudaGetLastError();
+  WgradMap map;
+  map.mode = 0; map.D = 0; map.d = 0; map.rev = 0;
+  if (mapp) map = *mapp;
+  if (Nb > 128) return launch_wgrad<256>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, map, db);
+  if (Nb > 64) return launch_wgrad<128>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, map, db);
+  if (Nb > 16) return launch_wgrad<64>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, map, db);
+  return launch_wgrad<16>(s, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, map, db);
 }
 
 template <int NT, int EPI>
@@ -425,7 +466,10 @@ static cudaError_t launch_dense(cudaStream_t s, const float* X, int64_t rows, in
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((rows + 127) / 128), (unsigned)(N / NT));
-  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);
+  // CNFOT_DENSE_ACC2=1: separate accumulator for the small 3xTF32 terms (needs 2 NT <= 512 TMEM columns)
+  int acc2 = 0;
+  if (const char* ev = getenv("CNFOT_DENSE_ACC2")) acc2 = ev[0] == '1' && 2 * NT <= 512;
+  kern<<<grid, 128, DenseSmem<NT>::kBytes, s>>>(X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy, acc2);
   return cudaGetLastError();
 }
 
@@ -448,6 +492,7 @@ cudaError_t dense_forward(cudaStream_t s, const float* X, int64_t rows, int K, i
     case 1: return launch_dense<NT_, 1>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
     case 2: return launch_dense<NT_, 2>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
     case 3: return launch_dense<NT_, 3>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
+    case 4: return launch_dense<NT_, 4>(s, X, rows, K, ldx, Bt, N, bias, mask_src, ldm, Y, ldy);         \
   }
   if (N % 256 == 0) { DENSE_CASE(256) }
   else if (N % 128 == 0) { DENSE_CASE(128) }
@@ -455,7 +500,7 @@ cudaError_t dense_forward(cudaStream_t s, const float* X, int64_t rows, int K, i
   else if (N % 16 == 0 && N <= 64) {
     if (N == 16) { DENSE_CASE(16) }
     else if (N == 32) { DENSE_CASE(32) }
-    else if (N == 48) { DENSE_CASE(16) }
+    else if (N == 48) { DENSE_CASE(48) }
   }
 #undef DENSE_CASE
   *supported = false;

@@ -14,7 +14,7 @@ namespace cnfot {
 
 // CTA context by engine: 0 CUDA-core dense layers, 1 the tcgen05 engine (tc_engine.cuh),
 // 2 the warp-level tensor-core engine (warp_mlp.cuh); 1 and 2 exist for 16-wide networks
-enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2, kEngMmaStream = 3 };
+enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2, kEngMmaStream = 3, kEngWide = 4 };
 #ifndef CNFOT_MMA_MIN_CTAS
 #define CNFOT_MMA_MIN_CTAS 4
 #endif

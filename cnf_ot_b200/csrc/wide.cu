@@ -1,0 +1,731 @@
+// Wide-conditioner engine: the train step (and the flow passes under it) for flows whose conditioner
+// MLPs are too large for the fused per-row kernels -- BASELINE config 5: D = 32, 16 layers, hidden 512,
+// 139 M parameters.  Same semantics as flow_pass / flow_pass_bwd in flow_math.cuh
+// (/root/reference/cnf_ot/models/autoregressive.py:76-136, flows.py:46-86,138-175), restructured
+// around the batch instead of the row:
+//
+//   * the batch is cut into chunks of R rows (default 4 x 148 x 128 = 75 776: every hidden-layer GEMM is exactly
+//     four waves of 128 x 256 tiles at two CTAs per SM, and the narrow layers (N = 16 / 48), whose grids are
+//     one CTA per 128 rows, get four resident CTAs per SM to hide their load latency -- measured 1.7x faster
+//     per row than single-wave chunks whose activations would stay in L2);
+//   * a chunk's flow state is a matrix S (R x Kx), row = [x_0 .. x_{D-1} | t | 0 ..], one per flow
+//     layer boundary.  The conditioner of (layer, d) reads it DIRECTLY as the A operand of its input
+//     GEMM: its (d+1) x H input matrix is scattered once per step into a Kx x H matrix whose row k is
+//     the weight row of state column k (zero where the conditioner does not look), so the
+//     autoregressive masking and the alternating permutation cost nothing per row;
+//   * every dense layer runs on tcgen05 (dense_tc.cu: 3xTF32, TMEM accumulators, TMA-staged prepared
+//     weights), the spline + log-det is a per-row kernel on the 16 raw parameters the last GEMM wrote;
+//   * backward re-computes a conditioner's activations, differentiates the spline, and runs
+//     dgrad (prepared W^T, ReLU mask fused in the epilogue) and wgrad (K-major gathered A^T G,
+//     red.global into the gradient blob) per layer; the input adjoints of the first layer are
+//     accumulated straight into the chunk's adjoint state G (R x Kx) by the GEMM epilogue.
+//
+// Loss heads (kl_loss_fn, kinetic_loss_fn, potential_loss_fn; applications.py:11-86,176-242) are small
+// per-row kernels between the forward and the backward sweep of a chunk.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "dense_tc.h"
+#include "wide.h"
+
+namespace cnfot {
+
+namespace {
+
+constexpr int kMaxM = 4;
+constexpr int kThreads = 256;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+struct WideDims {
+  int D, L, M, H, Pp, Kx;
+  int64_t prep_mlp;   // prepared floats of one conditioner (one direction)
+};
+
+WideDims make_dims(const FlowLayout& lay) {
+  WideDims w;
+  w.D = lay.D; w.L = lay.L; w.M = lay.M; w.H = lay.H; w.Pp = lay.Pp;
+  w.Kx = round_up(lay.D + 1, 16);
+  w.prep_mlp = 2 * ((int64_t)w.Kx * w.H + (int64_t)(w.M - 1) * w.H * w.H + (int64_t)w.H * w.Pp);
+  return w;
+}
+
+__host__ __device__ inline int64_t mlp_blob_offset(const FlowLayout& lay, int layer, int d) {
+  return lay.Pp + (int64_t)layer * lay.layer_stride + (int64_t)(d - 1) * lay.mlp_const +
+         (int64_t)lay.H * ((d - 1) * (d + 2) / 2);
+}
+
+// ---- weight preparation: every matrix of every conditioner into tcgen05 tile order, hi / lo split ----
+// blockIdx.y = conditioner (layer * (D-1) + d - 1).  `pf` serves X * W, `pt` (may be NULL) serves G * W^T.
+__device__ __forceinline__ void put_split(float* tile_base, int64_t n_cols, int k, int n, float v) {
+  // round-to-nearest 3xTF32 split, as dense_prep_kernel
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  const float hi = __uint_as_float(r & 0xFFFFE000u);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - hi));
+  float* t = tile_base + (int64_t)(k >> 4) * 2 * n_cols * 16;
+  const int p = sw64_pos(n, k & 15);
+  t[p] = hi;
+  t[n_cols * 16 + p] = __uint_as_float(r & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(kThreads)
+wide_prep_kernel(const float* __restrict__ W, FlowLayout lay, WideDims wd, float* __restrict__ prep_fwd,
+                 float* __restrict__ prep_T) {
+  const int mlp = blockIdx.y;
+  const int layer = mlp / (wd.D - 1), d = mlp % (wd.D - 1) + 1, rev = layer & 1;
+  const int H = wd.H, Kx = wd.Kx, Pp = wd.Pp;
+  const float* w = W + mlp_blob_offset(lay, layer, d);
+  float* pf = prep_fwd + (int64_t)mlp * wd.prep_mlp;
+  float* pt = prep_T ? prep_T + (int64_t)mlp * wd.prep_mlp : nullptr;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  // input layer: state column k -> weight row w0_row(k)
+  for (int e = t0; e < Kx * H; e += stride) {
+    const int k = e / H, h = e - k * H;
+    const int row = w0_row(k, wd.D, d, rev);
+    const float v = row >= 0 ? w[(int64_t)row * H + h] : 0.f;
+    put_split(pf, H, k, h, v);
+    if (pt) put_split(pt, Kx, h, k, v);
+  }
+  pf += 2 * (int64_t)Kx * H;
+  if (pt) pt += 2 * (int64_t)Kx * H;
+  w += (int64_t)(d + 1) * H + H;
+  for (int m = 1; m < wd.M; ++m) {
+    for (int e = t0; e < H * H; e += stride) {
+      const int i = e / H, j = e - i * H;
+      const float v = w[e];
+      put_split(pf, H, i, j, v);
+      if (pt) put_split(pt, H, j, i, v);
+    }
+    pf += 2 * (int64_t)H * H;
+    if (pt) pt += 2 * (int64_t)H * H;
+    w += (int64_t)H * H + H;
+  }
+  for (int e = t0; e < H * Pp; e += stride) {
+    const int i = e / Pp, j = e - i * Pp;
+    const float v = w[e];
+    put_split(pf, Pp, i, j, v);
+    if (pt) put_split(pt, H, j, i, v);
+  }
+}
+
+// ---- chunk state initialisation: S[0] = [rows | t | 0], S[1..L] = [0 | t | 0] ---------------------------
+__global__ void __launch_bounds__(kThreads)
+wide_init_kernel(const float* __restrict__ rows, int64_t n, int D, int Kx, int L, int64_t state_stride, float t,
+                 const float* __restrict__ cond, int64_t cond_stride, float* __restrict__ S) {
+  const int64_t per = n * Kx;
+  const int64_t total = per * (L + 1);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e / per);
+    const int64_t q = e - (int64_t)s * per;
+    const int64_t r = q / Kx;
+    const int c = (int)(q - r * Kx);
+    float v = 0.f;
+    if (c < D) v = s == 0 ? rows[r * D + c] : 0.f;
+    else if (c == D) v = cond ? cond[r * cond_stride] : t;
+    S[(int64_t)s * state_stride + q] = v;
+  }
+}
+
+// ---- spline kernels: one row per thread, raw parameters from the last GEMM (or the shared `first`) ----
+template <int K>
+__device__ __forceinline__ void load_theta(const float* __restrict__ theta, int64_t r, int bcast, float* th) {
+  constexpr int Pp = (3 * K + 1 + 3) / 4 * 4;
+  const float4* p = reinterpret_cast<const float4*>(theta + (bcast ? 0 : r * Pp));
+#pragma unroll
+  for (int j = 0; j < Pp / 4; ++j) {
+    const float4 v = __ldg(p + j);
+    th[4 * j] = v.x; th[4 * j + 1] = v.y; th[4 * j + 2] = v.z; th[4 * j + 3] = v.w;
+  }
+}
+
+// DIR 0: spline inverse formula (sample direction); DIR 1: forward formula (log-prob direction)
+template <int K, int DIR>
+__global__ void __launch_bounds__(kThreads)
+wide_spline_kernel(const float* __restrict__ theta, int bcast, const float* __restrict__ Sin, float* __restrict__ Sout,
+                   int Kx, int col, float* __restrict__ LD, int ld_accumulate, int64_t n, SplineConsts<float> sc) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  constexpr int Pp = (3 * K + 1 + 3) / 4 * 4;
+  float th[Pp];
+  load_theta<K>(theta, r, bcast, th);
+  const float v = Sin[r * Kx + col];
+  SplineState<float, K> st;
+  float out, ld;
+  if (DIR == 0) rqs_inverse<float, K>(v, th, sc, st, out, ld);
+  else rqs_forward<float, K>(v, th, sc, st, out, ld);
+  Sout[r * Kx + col] = out;
+  LD[r] = ld_accumulate ? LD[r] + ld : ld;
+}
+
+// Reverse mode: G[r][col] (adjoint of the spline output) is replaced by the adjoint of its input;
+// GTheta (n x Pp) receives the adjoint of the raw parameters.  gld = gld_scalar (+ gld_rows[r]).
+template <int K, int DIR>
+__global__ void __launch_bounds__(kThreads)
+wide_spline_vjp_kernel(const float* __restrict__ theta, int bcast, const float* __restrict__ Sin, int Kx, int col,
+                       float* __restrict__ G, float gld_scalar, const float* __restrict__ gld_rows,
+                       float* __restrict__ GTheta, int64_t n, SplineConsts<float> sc) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  constexpr int Pp = (3 * K + 1 + 3) / 4 * 4;
+  float th[Pp], gth[Pp];
+  load_theta<K>(theta, r, bcast, th);
+  const float v = Sin[r * Kx + col];
+  const float go = G[r * Kx + col];
+  const float gl = gld_scalar + (gld_rows ? gld_rows[r] : 0.f);
+  SplineState<float, K> st;
+  float out, ld, gi;
+#pragma unroll
+  for (int j = 0; j < Pp; ++j) gth[j] = 0.f;
+  if (DIR == 0) {
+    rqs_inverse<float, K>(v, th, sc, st, out, ld);
+    gi = rqs_inverse_bwd<float, K>(v, st, sc, go, gl, gth);
+  } else {
+    rqs_forward<float, K>(v, th, sc, st, out, ld);
+    gi = rqs_forward_bwd<float, K>(v, st, sc, go, gl, gth);
+  }
+  G[r * Kx + col] = gi;
+  float4* q = reinterpret_cast<float4*>(GTheta + r * Pp);
+#pragma unroll
+  for (int j = 0; j < Pp / 4; ++j) q[j] = make_float4(gth[4 * j], gth[4 * j + 1], gth[4 * j + 2], gth[4 * j + 3]);
+}
+
+// ---- column sums (bias gradients, gradient of `first`): dst[c] += sum_r G[r][c] ------------------------
+__global__ void __launch_bounds__(kThreads)
+wide_colsum_kernel(const float* __restrict__ G, int ldg, int64_t rows, int N, float* __restrict__ dst) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sub = threadIdx.x >> 5;
+  const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = blockIdx.y * per, hi = lo + per < rows ? lo + per : rows;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    int64_t r = lo + sub;
+    for (; r + 8 < hi; r += 16) {
+      a0 += __ldg(G + r * ldg + c);
+      a1 += __ldg(G + (r + 8) * ldg + c);
+    }
+    if (r < hi) a0 += __ldg(G + r * ldg + c);
+  }
+  __shared__ float part[8][32];
+  part[sub][threadIdx.x & 31] = a0 + a1;
+  __syncthreads();
+  if (sub == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    atomicAdd(dst + c, t);
+  }
+}
+
+// ---- loss heads ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_add(double v, double* dst) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+}
+
+// kl_loss_fn row: -w log p(data | t) = -w (log N(z) + ld); G = w z (applications.py:85)
+__global__ void __launch_bounds__(kThreads)
+wide_nll_head_kernel(const float* __restrict__ Z, const float* __restrict__ LD, int64_t n, int D, int Kx, float w,
+                     float* __restrict__ G, double* __restrict__ slot) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double loss = 0.0;
+  if (r < n) {
+    float acc = 0.f;
+    for (int c = 0; c < Kx; ++c) {
+      const float z = c < D ? Z[r * Kx + c] : 0.f;
+      acc += z * z;
+      G[r * Kx + c] = w * z;
+    }
+    const float lp = -0.5f * acc - 0.91893853320467274178f * (float)D + LD[r];
+    loss = -(double)w * (double)lp;
+  }
+  block_add(loss, slot);
+}
+
+// kinetic_loss_fn rows (applications.py:220-242) + the ot/obstacle potential at r(t) (:190-191, :398-401)
+__global__ void __launch_bounds__(kThreads)
+wide_kinetic_head_kernel(const float* __restrict__ R1, const float* __restrict__ R2, const float* __restrict__ R3,
+                         int64_t n, int D, int Kx, float dt, float w_kin, float w_pot, float* __restrict__ G1,
+                         float* __restrict__ G2, float* __restrict__ G3, double* __restrict__ slot_kin,
+                         double* __restrict__ slot_pot) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double lk = 0.0, lp = 0.0;
+  if (r < n) {
+    const float idt = 1.f / dt;
+    float acc = 0.f;
+    for (int c = 0; c < Kx; ++c) {
+      float g = 0.f;
+      if (c < D) {
+        const float v = (R2[r * Kx + c] - R1[r * Kx + c]) * idt;
+        acc += v * v;
+        g = 2.f * w_kin * v * idt;
+      }
+      G2[r * Kx + c] = g;
+      G1[r * Kx + c] = -g;
+    }
+    lk = (double)w_kin * (double)acc;
+    if (R3) {
+      float q = 0.f;
+      for (int c = 0; c < D; ++c) q += R3[r * Kx + c] * R3[r * Kx + c];
+      const float pv = 50.f * __expf(-0.5f * q);
+      for (int c = 0; c < Kx; ++c) G3[r * Kx + c] = c < D ? -w_pot * pv * R3[r * Kx + c] : 0.f;
+      lp = (double)w_pot * (double)pv;
+    }
+  }
+  block_add(lk, slot_kin);
+  if (R3) block_add(lp, slot_pot);
+}
+
+// out slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic, 5-7 zero
+__global__ void wide_finalize_kernel(const double* __restrict__ slots, float* __restrict__ out_slots) {
+  if (threadIdx.x == 0) {
+    const double t = slots[kSlotFit0] + slots[kSlotFitT] + slots[kSlotPotential] + slots[kSlotKinetic];
+    out_slots[0] = (float)t;
+    out_slots[1] = (float)slots[kSlotFit0];
+    out_slots[2] = (float)slots[kSlotFitT];
+    out_slots[3] = (float)slots[kSlotPotential];
+    out_slots[4] = (float)slots[kSlotKinetic];
+    out_slots[5] = out_slots[6] = out_slots[7] = 0.f;
+  }
+}
+
+// copy the D coordinates of a state to a dense (n x D) buffer
+__global__ void __launch_bounds__(kThreads)
+wide_extract_kernel(const float* __restrict__ S, int64_t n, int D, int Kx, float* __restrict__ out) {
+  const int64_t total = n * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / D;
+    const int c = (int)(e - r * D);
+    out[e] = S[r * Kx + c];
+  }
+}
+
+// logdet output of the model API: ld, or the density ConditionalTransformed returns
+// (conditional.py:316-321,382-402): forward: log N(in) - ld ; inverse: log N(out) + ld
+__global__ void __launch_bounds__(kThreads)
+wide_logdet_out_kernel(const float* __restrict__ LD, const float* __restrict__ base_rows, int ld_base, int64_t n, int D,
+                       int add_base, float sign, float* __restrict__ out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float v = LD[r];
+  if (add_base) {
+    float acc = 0.f;
+    for (int c = 0; c < D; ++c) acc += base_rows[r * ld_base + c] * base_rows[r * ld_base + c];
+    v = -0.5f * acc - 0.91893853320467274178f * (float)D + sign * v;
+  }
+  out[r] = v;
+}
+
+// model-API VJP: seed the adjoint state from (g_out, g_logdet) -- see flow_vjp_kernel in flow_kernels.cuh
+__global__ void __launch_bounds__(kThreads)
+wide_vjp_seed_kernel(const float* __restrict__ g_out, const float* __restrict__ g_logdet, const float* __restrict__ Zout,
+                     int64_t n, int D, int Kx, int dir, int add_base, float* __restrict__ G, float* __restrict__ GL) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float gl = g_logdet ? g_logdet[r] : 0.f;
+  for (int c = 0; c < Kx; ++c) {
+    float g = c < D ? g_out[r * D + c] : 0.f;
+    if (add_base && dir == 1 && c < D) g -= gl * Zout[r * Kx + c];
+    G[r * Kx + c] = g;
+  }
+  GL[r] = (add_base && dir == 0) ? -gl : gl;
+}
+__global__ void __launch_bounds__(kThreads)
+wide_vjp_out_kernel(const float* __restrict__ G, const float* __restrict__ g_logdet, const float* __restrict__ Zin,
+                    int64_t n, int D, int Kx, int dir, int add_base, float* __restrict__ g_in) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float gl = g_logdet ? g_logdet[r] : 0.f;
+  for (int c = 0; c < D; ++c) {
+    float g = G[r * Kx + c];
+    if (add_base && dir == 0) g -= gl * Zin[r * Kx + c];
+    g_in[r * D + c] = g;
+  }
+}
+
+// ---- the engine --------------------------------------------------------------------------------------------
+struct WideEngine {
+  cudaStream_t s;
+  FlowLayout lay;
+  WideDims wd;
+  SplineConsts<float> sc;
+  const float* W;
+  float* grad;            // blob layout, accumulated (may be NULL: forward only)
+  float* prep_fwd;
+  float* prep_T;
+  int64_t R;              // chunk capacity (rows)
+  float* S[3];            // (L+1) x R x Kx each
+  float* LD[3];
+  float* G[3];            // R x Kx each
+  float* A[kMaxM];        // R x H each
+  float* Ga;
+  float* Gb;
+  float* Theta;           // R x Pp
+  float* GTheta;
+  float* GL;              // R: per-row adjoint of the log-det (model-API VJP)
+  double* slots;
+  cudaError_t err = cudaSuccess;
+  const char* what = "";
+
+  bool ok() const { return err == cudaSuccess; }
+  void check(cudaError_t e, const char* w) {
+    if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; }
+  }
+  void check_launch(const char* w) { check(cudaGetLastError(), w); }
+  int64_t state_stride() const { return R * wd.Kx; }
+  float* state(int p, int s_) const { return S[p] + (int64_t)s_ * state_stride(); }
+  static unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+  void dense(const float* X, int64_t n, int K, int ldx, const float* P, int N, const float* bias, const float* mask,
+             int ldm, int epi, float* Y, int ldy) {
+    if (!ok()) return;
+    bool sup = false;
+    check(dense_forward(s, X, n, K, ldx, P, N, bias, mask, ldm, epi, Y, ldy, &sup), "dense_tc_kernel launch");
+    if (ok() && !sup) { err = cudaErrorInvalidValue; what = "no dense kernel for this layer width"; }
+  }
+
+  // conditioner (layer, d >= 1) on the state rows `cst`: fills A[0..M-1] and Theta
+  void mlp_forward(int layer, int d, const float* cst, int64_t n) {
+    const int H = wd.H, Kx = wd.Kx, Pp = wd.Pp, M = wd.M;
+    const int mlp = layer * (wd.D - 1) + d - 1;
+    const float* pf = prep_fwd + (int64_t)mlp * wd.prep_mlp;
+    const float* w = W + mlp_blob_offset(lay, layer, d);
+    const float* bias = w + (int64_t)(d + 1) * H;
+    dense(cst, n, Kx, Kx, pf, H, bias, nullptr, 0, 1, A[0], H);
+    pf += 2 * (int64_t)Kx * H;
+    w = bias + H;
+    for (int m = 1; m < M; ++m) {
+      bias = w + (int64_t)H * H;
+      dense(A[m - 1], n, H, H, pf, H, bias, nullptr, 0, 1, A[m], H);
+      pf += 2 * (int64_t)H * H;
+      w = bias + H;
+    }
+    bias = w + (int64_t)H * Pp;
+    dense(A[M - 1], n, H, H, pf, Pp, bias, nullptr, 0, 0, Theta, Pp);
+  }
+
+  void colsum(const float* Gm, int ldg, int64_t n, int N, float* dst) {
+    if (!ok()) return;
+    int64_t zy = n / 2048 + 1;
+    if (zy > 296) zy = 296;
+    wide_colsum_kernel<<<dim3((unsigned)((N + 31) / 32), (unsigned)zy), kThreads, 0, s>>>(Gm, ldg, n, N, dst);
+    check_launch("wide_colsum_kernel launch");
+  }
+
+  void wgrad(const float* Am, int lda, const float* Gm, int ldg, int64_t n, int Ka, int Nb, float* dW, int ldw,
+             float* db, const WgradMap* map = nullptr) {
+    if (!ok()) return;
+    check(dense_wgrad(s, Am, lda, Gm, ldg, n, Ka, Nb, dW, ldw, db, map), "dense_wgrad_kernel launch");
+  }
+
+  // backward of the conditioner whose activations mlp_forward just left in A[], given GTheta;
+  // adds the input adjoints into Gst (R x Kx) and the weight gradients into grad
+  void mlp_backward(int layer, int d, const float* cst, float* Gst, int64_t n) {
+    const int H = wd.H, Kx = wd.Kx, Pp = wd.Pp, M = wd.M;
+    const int mlp = layer * (wd.D - 1) + d - 1;
+    const int64_t off = mlp_blob_offset(lay, layer, d);
+    const float* pt = prep_T + (int64_t)mlp * wd.prep_mlp;
+    const int64_t off_w0 = off, off_b0 = off + (int64_t)(d + 1) * H;
+    const int64_t off_out = off_b0 + H + (int64_t)(M - 1) * ((int64_t)H * H + H);
+    const float* pt_out = pt + 2 * (int64_t)Kx * H + (int64_t)(M - 1) * 2 * H * H;
+    // output layer
+    wgrad(A[M - 1], H, GTheta, Pp, n, H, Pp, grad + off_out, Pp, grad + off_out + (int64_t)H * Pp);
+    float* gc = Ga;
+    float* gn = Gb;
+    dense(GTheta, n, Pp, Pp, pt_out, H, nullptr, A[M - 1], H, 2, gc, H);
+    for (int m = M - 1; m >= 1; --m) {
+      const int64_t off_m = off_b0 + H + (int64_t)(m - 1) * ((int64_t)H * H + H);
+      wgrad(A[m - 1], H, gc, H, n, H, H, grad + off_m, H, grad + off_m + (int64_t)H * H);
+      const float* pt_m = pt + 2 * (int64_t)Kx * H + (int64_t)(m - 1) * 2 * H * H;
+      dense(gc, n, H, H, pt_m, H, nullptr, A[m - 1], H, 2, gn, H);
+      float* tmp = gc; gc = gn; gn = tmp;
+    }
+    // input layer: dW0[w0_row(k)][h] += sum_r S[r][k] gc[r][h]
+    WgradMap map;
+    map.mode = 1; map.D = wd.D; map.d = d; map.rev = layer & 1;
+    wgrad(gc, H, cst, Kx, n, H, wd.D + 1, grad + off_w0, H, grad + off_b0, &map);
+    dense(gc, n, H, H, pt, Kx, nullptr, nullptr, 0, 4, Gst, Kx);
+  }
+
+  template <int K>
+  void spline(int dir, const float* theta, int bcast, const float* Sin, float* Sout, int col, float* LDp, int accumulate,
+              int64_t n) {
+    if (!ok()) return;
+    if (dir == 0)
+      wide_spline_kernel<K, 0><<<blocks_for(n), kThreads, 0, s>>>(theta, bcast, Sin, Sout, wd.Kx, col, LDp, accumulate, n, sc);
+    else
+      wide_spline_kernel<K, 1><<<blocks_for(n), kThreads, 0, s>>>(theta, bcast, Sin, Sout, wd.Kx, col, LDp, accumulate, n, sc);
+    check_launch("wide_spline_kernel launch");
+  }
+  template <int K>
+  void spline_vjp(int dir, const float* theta, int bcast, const float* Sin, int col, float* Gst, float gld,
+                  const float* gld_rows, int64_t n) {
+    if (!ok()) return;
+    if (dir == 0)
+      wide_spline_vjp_kernel<K, 0><<<blocks_for(n), kThreads, 0, s>>>(theta, bcast, Sin, wd.Kx, col, Gst, gld, gld_rows,
+                                                                      GTheta, n, sc);
+    else
+      wide_spline_vjp_kernel<K, 1><<<blocks_for(n), kThreads, 0, s>>>(theta, bcast, Sin, wd.Kx, col, Gst, gld, gld_rows,
+                                                                      GTheta, n, sc);
+    check_launch("wide_spline_vjp_kernel launch");
+  }
+
+  void init_states(int p, const float* rows, int64_t n, float t, const float* cond = nullptr, int64_t cond_stride = 0) {
+    if (!ok()) return;
+    int64_t total = n * wd.Kx * (wd.L + 1);
+    int64_t b = (total + kThreads - 1) / kThreads;
+    if (b > 148 * 16) b = 148 * 16;
+    wide_init_kernel<<<(unsigned)b, kThreads, 0, s>>>(rows, n, wd.D, wd.Kx, wd.L, state_stride(), t, cond, cond_stride, S[p]);
+    check_launch("wide_init_kernel launch");
+  }
+
+  // one pass through the flow (flow_pass<DIR> of flow_math.cuh on a chunk); result in state(p, L), LD[p]
+  template <int K>
+  void flow_pass(int dir, int p, int64_t n) {
+    const int D = wd.D, L = wd.L;
+    for (int st = 0; st < L && ok(); ++st) {
+      const int layer = dir == 0 ? st : L - 1 - st;
+      const float* Sin = state(p, st);
+      float* Sout = state(p, st + 1);
+      const float* cst = dir == 0 ? Sin : Sout;
+      for (int d = 0; d < D && ok(); ++d) {
+        const int col = perm_at(layer, d, D);
+        if (d > 0) mlp_forward(layer, d, cst, n);
+        spline<K>(dir, d == 0 ? W : Theta, d == 0, Sin, Sout, col, LD[p], !(st == 0 && d == 0), n);
+      }
+    }
+  }
+
+  // reverse mode of flow_pass: G[p] holds the adjoint of state(p, L) on entry, of state(p, 0) on exit
+  template <int K>
+  void flow_bwd(int dir, int p, int64_t n, float gld, const float* gld_rows) {
+    const int D = wd.D, L = wd.L;
+    for (int st = L - 1; st >= 0 && ok(); --st) {
+      const int layer = dir == 0 ? st : L - 1 - st;
+      const float* Sin = state(p, st);
+      const float* cst = dir == 0 ? Sin : state(p, st + 1);
+      for (int dd = 0; dd < D && ok(); ++dd) {
+        const int d = dir == 0 ? dd : D - 1 - dd;
+        const int col = perm_at(layer, d, D);
+        if (d > 0) mlp_forward(layer, d, cst, n);
+        spline_vjp<K>(dir, d == 0 ? W : Theta, d == 0, Sin, col, G[p], gld, gld_rows, n);
+        if (d == 0) colsum(GTheta, wd.Pp, n, wd.Pp, grad);
+        else mlp_backward(layer, d, cst, G[p], n);
+      }
+    }
+  }
+};
+
+int64_t chunk_rows() {
+  int64_t r = 4 * 148 * 128;
+  if (const char* e = getenv("CNFOT_WIDE_CHUNK")) {
+    const long v = atol(e);
+    if (v >= 128 && v <= (1 << 20)) r = round_up64(v, 128);
+  }
+  return r;
+}
+
+struct Carve {
+  char* p;
+  int64_t used = 0;
+  explicit Carve(void* base) : p((char*)base) {}
+  template <typename T>
+  T* take(int64_t count) {
+    T* out = p ? (T*)(p + used) : nullptr;
+    used += round_up64(count * (int64_t)sizeof(T), 256);
+    return out;
+  }
+};
+
+// carve (or, with base == NULL, just size) the workspace
+int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_grad, int n_pass, WideEngine* e) {
+  WideDims wd = make_dims(lay);
+  int64_t R = chunk_rows();
+  if (max_rows < R) R = round_up64(max_rows > 0 ? max_rows : 1, 128);
+  Carve c(base);
+  const int64_t n_mlp = (int64_t)lay.L * (lay.D - 1);
+  double* slots = c.take<double>(kNumSlots);
+  float* pf = c.take<float>(n_mlp * wd.prep_mlp);
+  float* pt = with_grad ? c.take<float>(n_mlp * wd.prep_mlp) : nullptr;
+  float *S[3] = {nullptr, nullptr, nullptr}, *LDp[3] = {nullptr, nullptr, nullptr}, *G[3] = {nullptr, nullptr, nullptr};
+  for (int p = 0; p < n_pass; ++p) {
+    S[p] = c.take<float>((int64_t)(lay.L + 1) * R * wd.Kx);
+    LDp[p] = c.take<float>(R);
+    if (with_grad) G[p] = c.take<float>(R * wd.Kx);
+  }
+  float* A[kMaxM];
+  for (int m = 0; m < kMaxM; ++m) A[m] = m < lay.M ? c.take<float>(R * lay.H) : nullptr;
+  float* Ga = with_grad ? c.take<float>(R * lay.H) : nullptr;
+  float* Gb = with_grad && lay.M > 1 ? c.take<float>(R * lay.H) : nullptr;
+  float* Theta = c.take<float>(R * lay.Pp);
+  float* GTheta = with_grad ? c.take<float>(R * lay.Pp) : nullptr;
+  float* GL = with_grad ? c.take<float>(R) : nullptr;
+  if (e) {
+    e->lay = lay; e->wd = wd; e->R = R; e->slots = slots; e->prep_fwd = pf; e->prep_T = pt;
+    for (int p = 0; p < 3; ++p) { e->S[p] = S[p]; e->LD[p] = LDp[p]; e->G[p] = G[p]; }
+    for (int m = 0; m < kMaxM; ++m) e->A[m] = A[m];
+    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL;
+  }
+  return c.used;
+}
+
+void launch_prep(WideEngine& e, bool with_T) {
+  if (!e.ok()) return;
+  const int n_mlp = e.lay.L * (e.lay.D - 1);
+  if (n_mlp == 0) return;
+  int bx = (e.wd.H * e.wd.H + kThreads - 1) / kThreads;
+  if (bx > 64) bx = 64;
+  wide_prep_kernel<<<dim3((unsigned)bx, (unsigned)n_mlp), kThreads, 0, e.s>>>(e.W, e.lay, e.wd, e.prep_fwd,
+                                                                               with_T ? e.prep_T : nullptr);
+  e.check_launch("wide_prep_kernel launch");
+}
+
+template <int K>
+void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent_sub, const float* src, const float* tgt,
+              const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b) {
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  const bool obstacle = pc.potential == kPotObstacle;
+  // kinetic terms: the b-row sub-batch at every sampled time
+  for (int it = 0; it < n_t && e.ok(); ++it) {
+    const float t = t_batch_host[it];
+    for (int64_t r0 = 0; r0 < rows_b && e.ok(); r0 += e.R) {
+      const int64_t n = rows_b - r0 < e.R ? rows_b - r0 : e.R;
+      const float* rows = latent_sub + r0 * D;
+      e.init_states(0, rows, n, t - pc.dt / 2.f);
+      e.init_states(1, rows, n, t + pc.dt / 2.f);
+      e.flow_pass<K>(0, 0, n);
+      e.flow_pass<K>(0, 1, n);
+      if (obstacle) {
+        e.init_states(2, rows, n, t);
+        e.flow_pass<K>(0, 2, n);
+      }
+      if (!e.ok()) break;
+      wide_kinetic_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+          e.state(0, L), e.state(1, L), obstacle ? e.state(2, L) : nullptr, n, D, Kx, pc.dt, pc.w_kin, pc.w_pot, e.G[0],
+          e.G[1], e.G[2], e.slots + kSlotKinetic, e.slots + kSlotPotential);
+      e.check_launch("wide_kinetic_head_kernel launch");
+      e.flow_bwd<K>(0, 1, n, 0.f, nullptr);
+      e.flow_bwd<K>(0, 0, n, 0.f, nullptr);
+      if (obstacle) e.flow_bwd<K>(0, 2, n, 0.f, nullptr);
+    }
+  }
+  // density-fit terms: -lambda mean log p(data | t) at t = 0 (source) and t = T (target)
+  for (int side = 0; side < 2 && e.ok(); ++side) {
+    const float* data = side == 0 ? src : tgt;
+    const float t = side == 0 ? 0.f : pc.horizon;
+    double* slot = e.slots + (side == 0 ? kSlotFit0 : kSlotFitT);
+    for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += e.R) {
+      const int64_t n = rows_B - r0 < e.R ? rows_B - r0 : e.R;
+      e.init_states(0, data + r0 * D, n, t);
+      e.flow_pass<K>(1, 0, n);
+      if (!e.ok()) break;
+      wide_nll_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(e.state(0, L), e.LD[0], n, D, Kx, pc.w_fit, e.G[0],
+                                                                        slot);
+      e.check_launch("wide_nll_head_kernel launch");
+      e.flow_bwd<K>(1, 0, n, -pc.w_fit, nullptr);
+    }
+  }
+}
+
+}  // namespace
+
+bool wide_supported(const FlowLayout& lay, const char** why) {
+  const char* w = nullptr;
+  if (lay.D < 2) w = "wide engine needs dim >= 2";
+  else if (lay.H < 16 || lay.H % 16 || (lay.H > 64 && lay.H % 64)) w = "wide engine needs hidden in {16, 32, 48} or a multiple of 64";
+  else if (lay.M < 1 || lay.M > kMaxM) w = "wide engine supports 1..4 hidden layers";
+  else if (lay.K != 5) w = "wide engine is instantiated for num_bins == 5";
+  else if (lay.D + 1 > 64) w = "wide engine supports dim <= 63";
+  if (why) *why = w;
+  return w == nullptr;
+}
+
+int64_t wide_step_workspace_bytes(const FlowLayout& lay, int64_t rows_B, int64_t rows_b) {
+  return carve(nullptr, lay, rows_B > rows_b ? rows_B : rows_b, true, 3, nullptr);
+}
+
+int64_t wide_flow_workspace_bytes(const FlowLayout& lay, int64_t rows, bool with_grad) {
+  return carve(nullptr, lay, rows, with_grad, 1, nullptr);
+}
+
+cudaError_t wide_mfc_step(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const StepConsts<float>& pc,
+                          const float* weights, const float* latent_sub, const float* src, const float* tgt,
+                          const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b, float* out, void* workspace,
+                          const char** what) {
+  WideEngine e;
+  e.s = s; e.sc = sc; e.W = weights; e.grad = out;
+  carve(workspace, lay, rows_B > rows_b ? rows_B : rows_b, true, 3, &e);
+  e.check(cudaMemsetAsync(out, 0, ((size_t)lay.total + kNumSlots) * sizeof(float), s), "cudaMemsetAsync");
+  e.check(cudaMemsetAsync(e.slots, 0, kNumSlots * sizeof(double), s), "cudaMemsetAsync");
+  launch_prep(e, true);
+  run_step<5>(e, pc, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b);
+  if (e.ok()) {
+    wide_finalize_kernel<<<1, 32, 0, s>>>(e.slots, out + lay.total);
+    e.check_launch("wide_finalize_kernel launch");
+  }
+  if (what) *what = e.what;
+  return e.err;
+}
+
+cudaError_t wide_flow_eval(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const float* weights,
+                           int dir, const float* in, const float* cond, int64_t cond_stride, int64_t rows, float* out,
+                           float* logdet, int add_base, void* workspace, const char** what) {
+  WideEngine e;
+  e.s = s; e.sc = sc; e.W = weights; e.grad = nullptr;
+  carve(workspace, lay, rows, false, 1, &e);
+  launch_prep(e, false);
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  for (int64_t r0 = 0; r0 < rows && e.ok(); r0 += e.R) {
+    const int64_t n = rows - r0 < e.R ? rows - r0 : e.R;
+    e.init_states(0, in + r0 * D, n, 0.f, cond + r0 * cond_stride, cond_stride);
+    e.flow_pass<5>(dir, 0, n);
+    if (!e.ok()) break;
+    int64_t b = (n * D + kThreads - 1) / kThreads;
+    if (b > 148 * 16) b = 148 * 16;
+    wide_extract_kernel<<<(unsigned)b, kThreads, 0, s>>>(e.state(0, L), n, D, Kx, out + r0 * D);
+    e.check_launch("wide_extract_kernel launch");
+    if (logdet) {
+      // forward: log N(latent input) - fldj ; inverse: log N(latent output) + ildj
+      const float* base = dir == 0 ? e.state(0, 0) : e.state(0, L);
+      wide_logdet_out_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(e.LD[0], base, Kx, n, D, add_base,
+                                                                        dir == 0 ? -1.f : 1.f, logdet + r0);
+      e.check_launch("wide_logdet_out_kernel launch");
+    }
+  }
+  if (what) *what = e.what;
+  return e.err;
+}
+
+cudaError_t wide_flow_vjp(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const float* weights,
+                          int dir, const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                          const float* g_out, const float* g_logdet, int add_base, float* g_in, float* g_weights,
+                          void* workspace, const char** what) {
+  WideEngine e;
+  e.s = s; e.sc = sc; e.W = weights; e.grad = g_weights;
+  carve(workspace, lay, rows, true, 1, &e);
+  e.check(cudaMemsetAsync(g_weights, 0, (size_t)lay.total * sizeof(float), s), "cudaMemsetAsync");
+  launch_prep(e, true);
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  for (int64_t r0 = 0; r0 < rows && e.ok(); r0 += e.R) {
+    const int64_t n = rows - r0 < e.R ? rows - r0 : e.R;
+    e.init_states(0, in + r0 * D, n, 0.f, cond + r0 * cond_stride, cond_stride);
+    e.flow_pass<5>(dir, 0, n);
+    if (!e.ok()) break;
+    wide_vjp_seed_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(g_out + r0 * D, g_logdet ? g_logdet + r0 : nullptr,
+                                                                    e.state(0, L), n, D, Kx, dir, add_base, e.G[0], e.GL);
+    e.check_launch("wide_vjp_seed_kernel launch");
+    e.flow_bwd<5>(dir, 0, n, 0.f, e.GL);
+    if (g_in && e.ok()) {
+      wide_vjp_out_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(e.G[0], g_logdet ? g_logdet + r0 : nullptr,
+                                                                     e.state(0, 0), n, D, Kx, dir, add_base, g_in + r0 * D);
+      e.check_launch("wide_vjp_out_kernel launch");
+    }
+  }
+  if (what) *what = e.what;
+  return e.err;
+}
+
+}  // namespace cnfot

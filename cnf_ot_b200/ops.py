@@ -116,11 +116,13 @@ def flow_eval(shape: FlowShape, weights, x, cond, inverse: bool, want_logdet=Tru
   c, cs = _cond(cond, rows, x.device)
   out = torch.empty_like(x)
   ld = torch.empty(rows, dtype=torch.float32, device=x.device) if want_logdet else None
-  fn = lib.cnfot_flow_inverse if inverse else lib.cnfot_flow_forward
+  fn = lib.cnfot_flow_inverse_ws if inverse else lib.cnfot_flow_forward_ws
   desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_flow_workspace_bytes(desc, rows)  # 0 unless the wide-conditioner engine runs
+  ws = _workspace(nbytes, x.device) if nbytes > 0 else None
   with torch.cuda.device(x.device):
     _lib.check(fn(_stream(), desc, _ptr(weights), _ptr(x), _ptr(c), cs, rows, _ptr(out), _ptr(ld),
-                  1 if add_base else 0))
+                  1 if add_base else 0, _ptr(ws), 0 if ws is None else ws.numel()))
   return out, ld
 
 

@@ -87,7 +87,8 @@ CNFOT_API const char* cnfot_last_error(void);
 /* Launch configuration of the calling thread's most recent fused-kernel launch (diagnostics for
  * bench.py / profiles): persistent grid size, dynamic shared memory per CTA in bytes, resident
  * CTAs per SM the grid was sized for, and the conditioner engine that ran (0 CUDA cores,
- * 1 tcgen05 engine, 2 warp-level tensor-core engine). */
+ * 1 tcgen05 engine, 2 warp-level tensor-core engine, 4 wide-conditioner engine: batched tcgen05
+ * GEMMs, the other three fields are 0). */
 CNFOT_API void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm,
                                       int32_t* tensor_cores);
 
@@ -101,7 +102,8 @@ CNFOT_API int64_t cnfot_offset_first(const cnfot_flow_desc* flow);              
  * m == mlp_layers, "linear_out_layer{l}_d{d}"; bias != 0 selects "b" instead of "w". */
 CNFOT_API int64_t cnfot_offset_linear(const cnfot_flow_desc* flow, int32_t layer, int32_t d, int32_t m,
                             int32_t bias);
-/* 0 if the fused kernels support this shape, else CNFOT_ERR_ARG (message says why). */
+/* 0 if the fused per-row kernels or the wide-conditioner engine support this shape, else
+ * CNFOT_ERR_ARG (message says why). */
 CNFOT_API int cnfot_flow_supported(const cnfot_flow_desc* flow);
 
 /* ---- seam 2: one scalar spline per row (distrax.RationalQuadraticSpline) ------------
@@ -140,6 +142,20 @@ CNFOT_API int cnfot_flow_forward(void* stream, const cnfot_flow_desc* flow, cons
 CNFOT_API int cnfot_flow_inverse(void* stream, const cnfot_flow_desc* flow, const float* weights,
                        const float* in, const float* cond, int64_t cond_stride, int64_t rows,
                        float* out, float* logdet, int32_t add_base);
+/* The same two calls with a caller-owned workspace of cnfot_flow_workspace_bytes(flow, rows) bytes
+ * (0 for flows the fused per-row kernels cover).  Flows with wide conditioners (hidden a multiple of
+ * 64, e.g. BASELINE config 5: dim 32, 16 layers, hidden 512) run on the wide-conditioner engine --
+ * batched tcgen05 GEMMs over row chunks -- which needs scratch memory; for those the two calls
+ * above fail with CNFOT_ERR_WORKSPACE and these must be used. */
+CNFOT_API int64_t cnfot_flow_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows);
+CNFOT_API int cnfot_flow_forward_ws(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                          const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                          float* out, float* logdet, int32_t add_base, void* workspace,
+                          int64_t workspace_bytes);
+CNFOT_API int cnfot_flow_inverse_ws(void* stream, const cnfot_flow_desc* flow, const float* weights,
+                          const float* in, const float* cond, int64_t cond_stride, int64_t rows,
+                          float* out, float* logdet, int32_t add_base, void* workspace,
+                          int64_t workspace_bytes);
 /* VJPs of the two calls above (what a jax.custom_vjp backward rule calls): given g_out (rows,D)
  * and g_logdet (rows, may be NULL = zeros; it is the adjoint of the `logdet` OUTPUT, so it
  * honours add_base) writes g_in (rows,D, may be NULL) and writes the parameter gradient,
@@ -244,7 +260,7 @@ CNFOT_API int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, co
  *   cnfot_dense_prepare      W (row stride ldw) -> `prepared` (cnfot_dense_prepared_floats(K, N) floats);
  *                            transpose != 0 prepares W^T, i.e. W is then (N x K) and the call computes X * W^T
  *   cnfot_dense_forward      epilogue 0: + bias, 1: + bias then ReLU, 2: ReLU mask (Y = mask_src > 0 ? acc : 0,
- *                            mask_src (rows x N, row stride ldm)), 3: none
+ *                            mask_src (rows x N, row stride ldm)), 3: none, 4: accumulate (Y += X * W)
  * K and N must be multiples of 16; ldx, ldy, ldm multiples of 4. */
 CNFOT_API int64_t cnfot_dense_prepared_floats(int32_t K, int32_t N);
 CNFOT_API int cnfot_dense_prepare(void* stream, const float* W, int32_t K, int32_t N, int32_t ldw,
