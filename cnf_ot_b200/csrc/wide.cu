@@ -219,6 +219,230 @@ wide_colsum_kernel(const float* __restrict__ G, int ldg, int64_t rows, int N, fl
   }
 }
 
+// ---- the narrow ends of a conditioner on CUDA cores -----------------------------------------------------------
+// The output layer (H -> Pp = 16) and the input layer's weight gradient (<= 33 state columns) have one tiny GEMM
+// dimension: as 128-row tensor-core tiles they were latency-bound one-CTA-per-128-rows pipelines (100-145 us per
+// 75 776 rows, ncu launch list r01); as streaming FFMA kernels they run at the speed their one pass over the
+// (rows x H) activation allows.  Exact fp32 FMAs, no split.
+
+// Shared-memory operands are read as warp-wide broadcasts; a broadcast still costs the load unit one cycle per
+// 128 bytes of REGISTERS written (32 lanes x 16 B = 4 cycles per LDS.128), so every kernel re-uses each broadcast
+// value for several rows / hidden units held in registers.
+
+// Theta (n x PP) = A (n x H) * Wout (H x PP) + bout.  A warp takes 16 rows as 4 row groups x 8 k-phases: a load
+// instruction reads 32 contiguous bytes of 4 rows, the weights come from a padded shared tile (row stride 20
+// floats: the 8 phases hit 8 distinct 16-byte bank groups) and serve 4 rows each, the 8 partial sums are folded
+// with 3 butterfly steps.
+template <int PP>
+__global__ void __launch_bounds__(kThreads)
+wide_out_fwd_kernel(const float* __restrict__ A, const float* __restrict__ Wout, const float* __restrict__ bout, int64_t n,
+                    int H, float* __restrict__ Theta) {
+  extern __shared__ __align__(16) float wsm[];   // [H][PP + 4]
+  constexpr int WS = PP + 4;
+  constexpr int RT = 4;                          // row groups per warp pass
+  for (int e = threadIdx.x; e < H * (PP / 4); e += blockDim.x) {
+    const int k = e / (PP / 4), q = e - k * (PP / 4);
+    *reinterpret_cast<float4*>(wsm + k * WS + 4 * q) = __ldg(reinterpret_cast<const float4*>(Wout + (int64_t)k * PP) + q);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, rg = lane >> 3;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * (4 * RT); base < n; base += n_warps * (4 * RT)) {
+    const float* arow[RT];
+    bool live[RT];
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+      const int64_t r = base + 4 * t + rg;
+      live[t] = r < n;
+      arow[t] = A + (live[t] ? r : 0) * H + sub;
+    }
+    float acc[RT][PP];
+#pragma unroll
+    for (int t = 0; t < RT; ++t)
+#pragma unroll
+      for (int p = 0; p < PP; ++p) acc[t][p] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < H; k += 8) {
+      float a[RT];
+#pragma unroll
+      for (int t = 0; t < RT; ++t) a[t] = live[t] ? __ldg(arow[t] + k) : 0.f;
+      const float* w = wsm + (k + sub) * WS;
+#pragma unroll
+      for (int q = 0; q < PP / 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + 4 * q);
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+          acc[t][4 * q] += a[t] * w4.x; acc[t][4 * q + 1] += a[t] * w4.y;
+          acc[t][4 * q + 2] += a[t] * w4.z; acc[t][4 * q + 3] += a[t] * w4.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+#pragma unroll
+      for (int p = 0; p < PP; ++p) {
+        acc[t][p] += __shfl_xor_sync(0xffffffffu, acc[t][p], 1);
+        acc[t][p] += __shfl_xor_sync(0xffffffffu, acc[t][p], 2);
+        acc[t][p] += __shfl_xor_sync(0xffffffffu, acc[t][p], 4);
+      }
+      // phase `sub` writes outputs [2 sub, 2 sub + 2) (PP = 16)
+      if (live[t] && 2 * sub < PP) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PP; p += 2) {
+          o0 = (p >> 1) == sub ? acc[t][p] : o0;
+          o1 = (p >> 1) == sub ? acc[t][p + 1] : o1;
+        }
+        *reinterpret_cast<float2*>(Theta + (base + 4 * t + rg) * PP + 2 * sub) =
+            make_float2(o0 + __ldg(bout + 2 * sub), o1 + __ldg(bout + 2 * sub + 1));
+      }
+    }
+  }
+}
+
+// Backward of the output layer in ONE pass over A (n x H): a thread owns TH hidden units h (128 apart),
+//   G2[r][h]     = A[r][h] > 0 ? sum_p GTheta[r][p] Wout[h][p] : 0     (adjoint of the last hidden pre-activation)
+//   dWout[h][p] += sum_r A[r][h] GTheta[r][p],   dbout[p] += sum_r GTheta[r][p]
+// GTheta rows are staged 64 at a time in shared memory and read as broadcasts.
+constexpr int kOutBwdThreads = 128;
+constexpr int kOutBwdTH = 4;
+template <int PP>
+__global__ void __launch_bounds__(kOutBwdThreads)
+wide_out_bwd_kernel(const float* __restrict__ A, const float* __restrict__ GTheta, const float* __restrict__ Wout, int64_t n,
+                    int H, float* __restrict__ G2, float* __restrict__ dWout, float* __restrict__ dbout) {
+  constexpr int NT_ = kOutBwdThreads, TH = kOutBwdTH;
+  __shared__ __align__(16) float gt[64 * PP];
+  const int tid = threadIdx.x;
+  const int h0 = blockIdx.x * (NT_ * TH) + tid;
+  const int64_t per = ((n + gridDim.y - 1) / gridDim.y + 63) / 64 * 64;
+  const int64_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+  float w[TH][PP], acc[TH][PP];
+  bool hv[TH];
+#pragma unroll
+  for (int j = 0; j < TH; ++j) {
+    hv[j] = h0 + NT_ * j < H;
+#pragma unroll
+    for (int q = 0; q < PP / 4; ++q) {
+      const float4 v = hv[j] ? __ldg(reinterpret_cast<const float4*>(Wout + (int64_t)(h0 + NT_ * j) * PP) + q)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[j][4 * q] = v.x; w[j][4 * q + 1] = v.y; w[j][4 * q + 2] = v.z; w[j][4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int p = 0; p < PP; ++p) acc[j][p] = 0.f;
+  }
+  float bsum = 0.f;   // thread p < PP of the blocks with blockIdx.x == 0: column p of this block's GTheta rows
+  for (int64_t r0 = lo; r0 < hi; r0 += 64) {
+    __syncthreads();
+    for (int e = tid; e < 64 * PP / 4; e += NT_) {
+      const int64_t r = r0 + e / (PP / 4);
+      *reinterpret_cast<float4*>(gt + 4 * e) =
+          r < hi ? __ldg(reinterpret_cast<const float4*>(GTheta + r * PP) + e % (PP / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int cnt = hi - r0 < 64 ? (int)(hi - r0) : 64;
+    if (blockIdx.x == 0 && tid < PP)
+      for (int rr = 0; rr < cnt; ++rr) bsum += gt[rr * PP + tid];
+#pragma unroll 2
+    for (int rr = 0; rr < cnt; ++rr) {
+      float a[TH], sacc[TH];
+#pragma unroll
+      for (int j = 0; j < TH; ++j) {
+        a[j] = hv[j] ? __ldg(A + (r0 + rr) * H + h0 + NT_ * j) : 0.f;
+        sacc[j] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < PP / 4; ++q) {
+        const float4 g = *reinterpret_cast<const float4*>(gt + rr * PP + 4 * q);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+          sacc[j] += g.x * w[j][4 * q] + g.y * w[j][4 * q + 1] + g.z * w[j][4 * q + 2] + g.w * w[j][4 * q + 3];
+          acc[j][4 * q] += a[j] * g.x; acc[j][4 * q + 1] += a[j] * g.y;
+          acc[j][4 * q + 2] += a[j] * g.z; acc[j][4 * q + 3] += a[j] * g.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TH; ++j)
+        if (hv[j]) G2[(r0 + rr) * H + h0 + NT_ * j] = a[j] > 0.f ? sacc[j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TH; ++j)
+    if (hv[j]) {
+#pragma unroll
+      for (int q = 0; q < PP / 4; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dWout + (int64_t)(h0 + NT_ * j) * PP + 4 * q),
+                     "f"(acc[j][4 * q]), "f"(acc[j][4 * q + 1]), "f"(acc[j][4 * q + 2]), "f"(acc[j][4 * q + 3]) : "memory");
+    }
+  if (blockIdx.x == 0 && tid < PP) atomicAdd(dbout + tid, bsum);
+}
+
+// Weight gradient of the input layer: dW0[w0_row(k)][h] += sum_r S[r][k] G1[r][h], db0[h] += sum_r G1[r][h];
+// a thread owns 2 hidden units (256 apart), 4 KV4 state columns accumulated in registers for each, state rows
+// staged 64 at a time.
+constexpr int kInWgradTH = 2;
+template <int KV4>
+__global__ void __launch_bounds__(kThreads)
+wide_in_wgrad_kernel(const float* __restrict__ S, int Kx, const float* __restrict__ G1, int64_t n, int H, int D, int d, int rev,
+                     float* __restrict__ dW0, float* __restrict__ db0) {
+  constexpr int KV = 4 * KV4, TH = kInWgradTH;
+  __shared__ __align__(16) float st[64 * KV];
+  const int tid = threadIdx.x;
+  const int h0 = blockIdx.x * (kThreads * TH) + tid;
+  bool hv[TH];
+#pragma unroll
+  for (int j = 0; j < TH; ++j) hv[j] = h0 + kThreads * j < H;
+  const int64_t per = ((n + gridDim.y - 1) / gridDim.y + 63) / 64 * 64;
+  const int64_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+  float acc[TH][KV], bsum[TH];
+#pragma unroll
+  for (int j = 0; j < TH; ++j) {
+    bsum[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KV; ++k) acc[j][k] = 0.f;
+  }
+  for (int64_t r0 = lo; r0 < hi; r0 += 64) {
+    __syncthreads();
+    for (int e = tid; e < 64 * KV4; e += kThreads) {
+      const int rr = e / KV4, q = e - rr * KV4;
+      const int64_t r = r0 + rr;
+      *reinterpret_cast<float4*>(st + 4 * e) =
+          r < hi ? __ldg(reinterpret_cast<const float4*>(S + r * Kx) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int cnt = hi - r0 < 64 ? (int)(hi - r0) : 64;
+#pragma unroll 2
+    for (int rr = 0; rr < cnt; ++rr) {
+      float g[TH];
+#pragma unroll
+      for (int j = 0; j < TH; ++j) {
+        g[j] = hv[j] ? __ldg(G1 + (r0 + rr) * H + h0 + kThreads * j) : 0.f;
+        bsum[j] += g[j];
+      }
+#pragma unroll
+      for (int q = 0; q < KV4; ++q) {
+        const float4 sv = *reinterpret_cast<const float4*>(st + rr * KV + 4 * q);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+          acc[j][4 * q] += g[j] * sv.x; acc[j][4 * q + 1] += g[j] * sv.y;
+          acc[j][4 * q + 2] += g[j] * sv.z; acc[j][4 * q + 3] += g[j] * sv.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TH; ++j)
+    if (hv[j]) {
+      const int h = h0 + kThreads * j;
+#pragma unroll
+      for (int k = 0; k < KV; ++k) {
+        const int row = w0_row(k, D, d, rev);
+        if (row >= 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dW0 + (int64_t)row * H + h), "f"(acc[j][k]) : "memory");
+      }
+      atomicAdd(db0 + h, bsum[j]);
+    }
+}
+
 // ---- loss heads ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_add(double v, double* dst) {
 #pragma unroll
@@ -366,6 +590,8 @@ struct WideEngine {
   float* Theta;           // R x Pp
   float* GTheta;
   float* GL;              // R: per-row adjoint of the log-det (model-API VJP)
+  float* stashA;          // n_mlp x R x H: last hidden activations of pass 0, kept for its backward sweep (or NULL)
+  float* stashT;          // n_mlp x R x Pp: raw spline parameters of pass 0
   double* slots;
   cudaError_t err = cudaSuccess;
   const char* what = "";
@@ -387,24 +613,36 @@ struct WideEngine {
     if (ok() && !sup) { err = cudaErrorInvalidValue; what = "no dense kernel for this layer width"; }
   }
 
-  // conditioner (layer, d >= 1) on the state rows `cst`: fills A[0..M-1] and Theta
-  void mlp_forward(int layer, int d, const float* cst, int64_t n) {
+  // conditioner (layer, d >= 1) on the state rows `cst`: hidden activations into A[0..M-2] and `a_last`, raw spline
+  // parameters into `theta`; with skip_last only the layers below the last hidden one are evaluated (the rest is
+  // taken from the stash by the caller)
+  void mlp_forward(int layer, int d, const float* cst, int64_t n, float* a_last, float* theta, bool skip_last = false) {
     const int H = wd.H, Kx = wd.Kx, Pp = wd.Pp, M = wd.M;
     const int mlp = layer * (wd.D - 1) + d - 1;
     const float* pf = prep_fwd + (int64_t)mlp * wd.prep_mlp;
     const float* w = W + mlp_blob_offset(lay, layer, d);
     const float* bias = w + (int64_t)(d + 1) * H;
-    dense(cst, n, Kx, Kx, pf, H, bias, nullptr, 0, 1, A[0], H);
+    if (!(skip_last && M == 1)) dense(cst, n, Kx, Kx, pf, H, bias, nullptr, 0, 1, M == 1 ? a_last : A[0], H);
     pf += 2 * (int64_t)Kx * H;
     w = bias + H;
     for (int m = 1; m < M; ++m) {
       bias = w + (int64_t)H * H;
-      dense(A[m - 1], n, H, H, pf, H, bias, nullptr, 0, 1, A[m], H);
+      if (!(skip_last && m == M - 1)) dense(A[m - 1], n, H, H, pf, H, bias, nullptr, 0, 1, m == M - 1 ? a_last : A[m], H);
       pf += 2 * (int64_t)H * H;
       w = bias + H;
     }
+    if (skip_last || !ok()) return;
     bias = w + (int64_t)H * Pp;
-    dense(A[M - 1], n, H, H, pf, Pp, bias, nullptr, 0, 0, Theta, Pp);
+    int64_t nb = (n + 127) / 128;   // 8 warps x 16 rows per block pass
+    if (nb > 148 * 4) nb = 148 * 4;
+    const size_t smem = (size_t)H * (Pp + 4) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(wide_out_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    wide_out_fwd_kernel<16><<<(unsigned)nb, kThreads, smem, s>>>(a_last, w, bias, n, H, theta);
+    check_launch("wide_out_fwd_kernel launch");
   }
 
   void colsum(const float* Gm, int ldg, int64_t n, int N, float* dst) {
@@ -421,21 +659,28 @@ struct WideEngine {
     check(dense_wgrad(s, Am, lda, Gm, ldg, n, Ka, Nb, dW, ldw, db, map), "dense_wgrad_kernel launch");
   }
 
-  // backward of the conditioner whose activations mlp_forward just left in A[], given GTheta;
-  // adds the input adjoints into Gst (R x Kx) and the weight gradients into grad
-  void mlp_backward(int layer, int d, const float* cst, float* Gst, int64_t n) {
+  // backward of a conditioner given its activations (A[0..M-2], a_last) and GTheta: adds the input adjoints into
+  // Gst (R x Kx) and the weight gradients into grad
+  void mlp_backward(int layer, int d, const float* cst, float* Gst, int64_t n, const float* a_last) {
     const int H = wd.H, Kx = wd.Kx, Pp = wd.Pp, M = wd.M;
     const int mlp = layer * (wd.D - 1) + d - 1;
     const int64_t off = mlp_blob_offset(lay, layer, d);
     const float* pt = prep_T + (int64_t)mlp * wd.prep_mlp;
     const int64_t off_w0 = off, off_b0 = off + (int64_t)(d + 1) * H;
     const int64_t off_out = off_b0 + H + (int64_t)(M - 1) * ((int64_t)H * H + H);
-    const float* pt_out = pt + 2 * (int64_t)Kx * H + (int64_t)(M - 1) * 2 * H * H;
-    // output layer
-    wgrad(A[M - 1], H, GTheta, Pp, n, H, Pp, grad + off_out, Pp, grad + off_out + (int64_t)H * Pp);
+    if (!ok()) return;
+    // output layer: G2, dWout, dbout in one pass over the last hidden activations
     float* gc = Ga;
     float* gn = Gb;
-    dense(GTheta, n, Pp, Pp, pt_out, H, nullptr, A[M - 1], H, 2, gc, H);
+    {
+      const int hb = (H + kOutBwdThreads * kOutBwdTH - 1) / (kOutBwdThreads * kOutBwdTH);
+      int64_t ny = (n + 63) / 64;   // >= 64 rows per block, about 4 blocks per SM
+      if (ny * hb > 148 * 4) ny = (148 * 4) / hb;
+      if (ny < 1) ny = 1;
+      wide_out_bwd_kernel<16><<<dim3((unsigned)hb, (unsigned)ny), kOutBwdThreads, 0, s>>>(
+          a_last, GTheta, W + off_out, n, H, gc, grad + off_out, grad + off_out + (int64_t)H * Pp);
+      check_launch("wide_out_bwd_kernel launch");
+    }
     for (int m = M - 1; m >= 1; --m) {
       const int64_t off_m = off_b0 + H + (int64_t)(m - 1) * ((int64_t)H * H + H);
       wgrad(A[m - 1], H, gc, H, n, H, H, grad + off_m, H, grad + off_m + (int64_t)H * H);
@@ -443,10 +688,22 @@ struct WideEngine {
       dense(gc, n, H, H, pt_m, H, nullptr, A[m - 1], H, 2, gn, H);
       float* tmp = gc; gc = gn; gn = tmp;
     }
-    // input layer: dW0[w0_row(k)][h] += sum_r S[r][k] gc[r][h]
-    WgradMap map;
-    map.mode = 1; map.D = wd.D; map.d = d; map.rev = layer & 1;
-    wgrad(gc, H, cst, Kx, n, H, wd.D + 1, grad + off_w0, H, grad + off_b0, &map);
+    if (!ok()) return;
+    // input layer: dW0 / db0 on CUDA cores, the input adjoints accumulated into the adjoint state by the GEMM epilogue
+    const int kv4 = (wd.D + 1 + 3) / 4;
+    const int hb = (H + kThreads * kInWgradTH - 1) / (kThreads * kInWgradTH);
+    int64_t ny = (n + 63) / 64;
+    if (ny * hb > 148 * 2) ny = (148 * 2) / hb;
+    if (ny < 1) ny = 1;
+    dim3 grid((unsigned)hb, (unsigned)ny);
+    switch (kv4) {
+#define CNFOT_IN_WGRAD(Q) case Q: wide_in_wgrad_kernel<Q><<<grid, kThreads, 0, s>>>(cst, Kx, gc, n, H, wd.D, d, layer & 1, grad + off_w0, grad + off_b0); break;
+      CNFOT_IN_WGRAD(1) CNFOT_IN_WGRAD(2) CNFOT_IN_WGRAD(3) CNFOT_IN_WGRAD(4) CNFOT_IN_WGRAD(5) CNFOT_IN_WGRAD(6)
+      CNFOT_IN_WGRAD(7) CNFOT_IN_WGRAD(8) CNFOT_IN_WGRAD(9) CNFOT_IN_WGRAD(10) CNFOT_IN_WGRAD(11) CNFOT_IN_WGRAD(12)
+      CNFOT_IN_WGRAD(13) CNFOT_IN_WGRAD(14) CNFOT_IN_WGRAD(15) CNFOT_IN_WGRAD(16)
+#undef CNFOT_IN_WGRAD
+    }
+    check_launch("wide_in_wgrad_kernel launch");
     dense(gc, n, H, H, pt, Kx, nullptr, nullptr, 0, 4, Gst, Kx);
   }
 
@@ -482,10 +739,17 @@ struct WideEngine {
     check_launch("wide_init_kernel launch");
   }
 
-  // one pass through the flow (flow_pass<DIR> of flow_math.cuh on a chunk); result in state(p, L), LD[p]
+  bool stashing(int p) const { return p == 0 && stashA != nullptr; }
+  float* stash_a(int st, int d) const { return stashA + ((int64_t)st * (wd.D - 1) + d - 1) * R * wd.H; }
+  float* stash_t(int st, int d) const { return stashT + ((int64_t)st * (wd.D - 1) + d - 1) * R * wd.Pp; }
+
+  // one pass through the flow (flow_pass<DIR> of flow_math.cuh on a chunk); result in state(p, L), LD[p].
+  // keep: pass 0 leaves every conditioner's last hidden activations and raw spline parameters in the stash
+  // (when the workspace has one) so that flow_bwd does not re-run the hidden GEMMs.
   template <int K>
-  void flow_pass(int dir, int p, int64_t n) {
+  void flow_pass(int dir, int p, int64_t n, bool keep = false) {
     const int D = wd.D, L = wd.L;
+    keep = keep && stashing(p);
     for (int st = 0; st < L && ok(); ++st) {
       const int layer = dir == 0 ? st : L - 1 - st;
       const float* Sin = state(p, st);
@@ -493,16 +757,18 @@ struct WideEngine {
       const float* cst = dir == 0 ? Sin : Sout;
       for (int d = 0; d < D && ok(); ++d) {
         const int col = perm_at(layer, d, D);
-        if (d > 0) mlp_forward(layer, d, cst, n);
-        spline<K>(dir, d == 0 ? W : Theta, d == 0, Sin, Sout, col, LD[p], !(st == 0 && d == 0), n);
+        float* th = keep && d > 0 ? stash_t(st, d) : Theta;
+        if (d > 0) mlp_forward(layer, d, cst, n, keep ? stash_a(st, d) : A[wd.M - 1], th);
+        spline<K>(dir, d == 0 ? W : th, d == 0, Sin, Sout, col, LD[p], !(st == 0 && d == 0), n);
       }
     }
   }
 
   // reverse mode of flow_pass: G[p] holds the adjoint of state(p, L) on entry, of state(p, 0) on exit
   template <int K>
-  void flow_bwd(int dir, int p, int64_t n, float gld, const float* gld_rows) {
+  void flow_bwd(int dir, int p, int64_t n, float gld, const float* gld_rows, bool kept = false) {
     const int D = wd.D, L = wd.L;
+    kept = kept && stashing(p);
     for (int st = L - 1; st >= 0 && ok(); --st) {
       const int layer = dir == 0 ? st : L - 1 - st;
       const float* Sin = state(p, st);
@@ -510,10 +776,12 @@ struct WideEngine {
       for (int dd = 0; dd < D && ok(); ++dd) {
         const int d = dir == 0 ? dd : D - 1 - dd;
         const int col = perm_at(layer, d, D);
-        if (d > 0) mlp_forward(layer, d, cst, n);
-        spline_vjp<K>(dir, d == 0 ? W : Theta, d == 0, Sin, col, G[p], gld, gld_rows, n);
+        const float* a_last = kept && d > 0 ? stash_a(st, d) : A[wd.M - 1];
+        const float* th = kept && d > 0 ? stash_t(st, d) : Theta;
+        if (d > 0) mlp_forward(layer, d, cst, n, A[wd.M - 1], Theta, kept);
+        spline_vjp<K>(dir, d == 0 ? W : th, d == 0, Sin, col, G[p], gld, gld_rows, n);
         if (d == 0) colsum(GTheta, wd.Pp, n, wd.Pp, grad);
-        else mlp_backward(layer, d, cst, G[p], n);
+        else mlp_backward(layer, d, cst, G[p], n, a_last);
       }
     }
   }
@@ -563,11 +831,20 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
   float* Theta = c.take<float>(R * lay.Pp);
   float* GTheta = with_grad ? c.take<float>(R * lay.Pp) : nullptr;
   float* GL = with_grad ? c.take<float>(R) : nullptr;
+  // stash of pass 0 (last hidden activations + raw spline parameters of every conditioner): skips the re-computation
+  // of the hidden GEMMs in the backward sweep.  Taken when it fits the budget (CNFOT_WIDE_STASH_GB, default 96;
+  // 0 disables): BASELINE config 5 needs 79 GB at the default chunk -- this is what 180 GB of HBM3e are for.
+  const int64_t stash_floats = with_grad ? n_mlp * R * (int64_t)(lay.H + lay.Pp) : 0;
+  double budget_gb = 96.0;
+  if (const char* ev = getenv("CNFOT_WIDE_STASH_GB")) budget_gb = atof(ev);
+  const bool stash = stash_floats > 0 && (double)stash_floats * 4.0 <= budget_gb * 1e9;
+  float* stashA = stash ? c.take<float>(n_mlp * R * (int64_t)lay.H) : nullptr;
+  float* stashT = stash ? c.take<float>(n_mlp * R * (int64_t)lay.Pp) : nullptr;
   if (e) {
     e->lay = lay; e->wd = wd; e->R = R; e->slots = slots; e->prep_fwd = pf; e->prep_T = pt;
     for (int p = 0; p < 3; ++p) { e->S[p] = S[p]; e->LD[p] = LDp[p]; e->G[p] = G[p]; }
     for (int m = 0; m < kMaxM; ++m) e->A[m] = A[m];
-    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL;
+    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL; e->stashA = stashA; e->stashT = stashT;
   }
   return c.used;
 }
@@ -620,12 +897,12 @@ void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent_su
     for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += e.R) {
       const int64_t n = rows_B - r0 < e.R ? rows_B - r0 : e.R;
       e.init_states(0, data + r0 * D, n, t);
-      e.flow_pass<K>(1, 0, n);
+      e.flow_pass<K>(1, 0, n, true);
       if (!e.ok()) break;
       wide_nll_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(e.state(0, L), e.LD[0], n, D, Kx, pc.w_fit, e.G[0],
                                                                         slot);
       e.check_launch("wide_nll_head_kernel launch");
-      e.flow_bwd<K>(1, 0, n, -pc.w_fit, nullptr);
+      e.flow_bwd<K>(1, 0, n, -pc.w_fit, nullptr, true);
     }
   }
 }
@@ -712,12 +989,12 @@ cudaError_t wide_flow_vjp(cudaStream_t s, const FlowLayout& lay, const SplineCon
   for (int64_t r0 = 0; r0 < rows && e.ok(); r0 += e.R) {
     const int64_t n = rows - r0 < e.R ? rows - r0 : e.R;
     e.init_states(0, in + r0 * D, n, 0.f, cond + r0 * cond_stride, cond_stride);
-    e.flow_pass<5>(dir, 0, n);
+    e.flow_pass<5>(dir, 0, n, true);
     if (!e.ok()) break;
     wide_vjp_seed_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(g_out + r0 * D, g_logdet ? g_logdet + r0 : nullptr,
                                                                     e.state(0, L), n, D, Kx, dir, add_base, e.G[0], e.GL);
     e.check_launch("wide_vjp_seed_kernel launch");
-    e.flow_bwd<5>(dir, 0, n, 0.f, e.GL);
+    e.flow_bwd<5>(dir, 0, n, 0.f, e.GL, true);
     if (g_in && e.ok()) {
       wide_vjp_out_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(e.G[0], g_logdet ? g_logdet + r0 : nullptr,
                                                                      e.state(0, 0), n, D, Kx, dir, add_base, g_in + r0 * D);
