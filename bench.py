@@ -413,15 +413,136 @@ def run_ours(args):
     td.destroy_process_group()
 
 
+# ---------------------------------------------------------------- BASELINE configs[4] on the wide-conditioner engine
+def run_cfg5(args):
+  """Synthetic scale-out workload (BASELINE configs[4]): d = 32, 16 layers, conditioner 2 x 512, ot/free structure,
+  Gaussian source N(-3, I) -> target N(0, I), rows sharded over the GPUs, ONE NCCL all-reduce of the 556 MB
+  [gradient | loss] buffer per step.  Not the driver's default line (that is configs[1]); run with
+  --workload cfg5 [--rows-per-gpu R] (BASELINE: 2^24 / 8 = 2^21 rows per GPU)."""
+  import torch.distributed as td
+  from cnf_ot_b200 import _lib, ops
+  from cnf_ot_b200.layout import FlowShape
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    td.init_process_group("nccl", device_id=dev)
+  D, L, H = 32, args.layers, 512
+  shape = FlowShape(D, L, 2, H, 5)
+  B = args.rows_per_gpu
+  b = B // 32
+  gB, gb = B * world, b * world
+  cfg = {"general": {"type": "ot", "dim": D, "dx": 0.01, "dt": 0.01}, "ot": {"subtype": "free"}}
+  problem = ops.problem_desc(cfg)
+  g = torch.Generator(device=dev).manual_seed(43)
+  # haiku-like scale for the hidden matrices (1/sqrt(fan_in) ~ 0.04 at 512), small output layers: a well-conditioned flow
+  W = torch.randn(shape.blob_size, device=dev, generator=g) * 0.02
+  if world > 1:
+    td.broadcast(W, 0)
+  g = torch.Generator(device=dev).manual_seed(42 + rank)
+  n_sets = 2
+  sets = [(torch.randn(B, D, device=dev, generator=g) - 3.0, torch.randn(B, D, device=dev, generator=g),
+           torch.randn(b, D, device=dev, generator=g)) for _ in range(n_sets)]
+  out = torch.empty(shape.blob_size + 8, dtype=torch.float32, device=dev)
+  t_vals = torch.rand(64, generator=torch.Generator().manual_seed(42)).tolist()
+
+  def step(i):
+    src, tgt, sub = sets[i % n_sets]
+    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 64]], 5000.0, gB, gb, out=out)
+    if world > 1:
+      td.all_reduce(out)
+
+  def sync():
+    if world > 1:
+      td.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(max(args.warmup, 1)):
+    step(i)
+  with ClockSampler(local) as clk:
+    el = time_region(step, args.steps, sync)
+  t = torch.tensor([el], dtype=torch.float64, device=dev)
+  if world > 1:
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+  el = float(t)
+  # e2e: pinned host rows read in place, weights H2D, [gradient | loss] D2H
+  pin = lambda x: x.cpu().contiguous().pin_memory()
+  hsrc, htgt, hsub = (pin(x) for x in sets[0])
+  hW, hout = pin(W), torch.empty(shape.blob_size + 8, dtype=torch.float32).pin_memory()
+  dW2 = torch.empty_like(W)
+
+  def step_e2e(i):
+    dW2.copy_(hW, non_blocking=True)
+    ops.mfc_step(shape, problem, dW2, None, hsub, hsrc, htgt, [t_vals[i % 64]], 5000.0, gB, gb, out=out)
+    if world > 1:
+      td.all_reduce(out)
+    hout.copy_(out, non_blocking=True)
+    torch.cuda.synchronize()
+
+  step_e2e(0)
+  el_e = time_region(step_e2e, max(1, args.steps // 2), sync) / max(1, args.steps // 2) * args.steps
+  t = torch.tensor([el_e], dtype=torch.float64, device=dev)
+  if world > 1:
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+  el_e = float(t)
+  if rank == 0:
+    pk, pk_src = peaks()
+    # dominant kernel: the hidden-layer GEMM (rows x 512 x 512, 3xTF32), timed alone on one chunk of rows
+    rows = 4 * 148 * 128
+    X = torch.randn(rows, H, device=dev)
+    P = ops.PreparedDense(torch.randn(H, H, device=dev) / H**0.5)
+    bias = torch.zeros(H, device=dev)
+    Y = torch.empty(rows, H, device=dev)
+    fn = lambda i: ops.dense_forward(X, P, bias=bias, epilogue="bias_relu", out=Y)
+    for i in range(3):
+      fn(i)
+    tk = time_region(fn, 20, torch.cuda.synchronize) / 20
+    tf32_peak = float(pk.get("bf16_tflops_sustained", 1392.5)) / 2.0
+    pipe = 3 * 2.0 * rows * H * H / tk / 1e12   # tf32 MMA flops issued (3 per fp32-fidelity product)
+    per_pass = 2 * L * sum((d + 1) * H + H * H + 16 * H for d in range(1, D))
+    line = {
+      "metric": METRIC, "value": gB * args.steps / el, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+      "warmup": max(args.warmup, 1), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
+      "config": {"workload": "synthetic scale-out, ot/free structure (BASELINE configs[4])", "dim": D, "flow_num_layers": L,
+                 "mlp": "2x512", "num_bins": 5, "params": shape.blob_size, "batch_per_gpu": B, "global_batch": gB,
+                 "sub_batch": "batch//32", "engine": _lib.last_launch_info()["engine"],
+                 "parallelism": f"dp{world} (rows sharded, one NCCL all-reduce of [grad|loss], {shape.blob_size * 4 >> 20} MiB)",
+                 "l2_policy": "inputs and activations far larger than L2", "loss_last_step": float(out[shape.blob_size])},
+      "e2e": {"value": gB * args.steps / el_e, "unit": UNIT, "h2d_bytes_per_step": (2 * B + b) * D * 4 + shape.blob_size * 4,
+              "d2h_bytes_per_step": (shape.blob_size + 8) * 4,
+              "api": "weights H2D + cnfot_mfc_step on pinned host rows (read in place) + all-reduce + D2H"},
+      "gpu_launches": None, "clocks": clk.summary(),
+      "roofline": {"bound": "tensor", "kernel": "dense_tc_kernel<256,1> (hidden layer, rows x 512 x 512, timed alone)",
+                   "achieved": pipe, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pipe / tf32_peak, "traffic": None,
+                   "peak_source": pk_src + ": bf16_tflops_sustained / 2 (tf32)",
+                   "fp32_fidelity_tflops": pipe / 3, "us_per_launch": tk * 1e6,
+                   "step_algorithmic_tflops": 3 * per_pass * (2 * B + 2 * b) / (el / args.steps) / 1e12},
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    td.barrier()
+    td.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=50)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                  help="cfg2 = BASELINE configs[1] (the driver's line); cfg5 = configs[4] on the wide-conditioner engine")
+  ap.add_argument("--rows-per-gpu", type=int, default=1 << 17, help="cfg5 only (BASELINE: 2^21)")
+  ap.add_argument("--layers", type=int, default=16, help="cfg5 only: flow layers (BASELINE: 16)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.workload == "cfg5":
+    run_cfg5(args)
   else:
     run_ours(args)
 

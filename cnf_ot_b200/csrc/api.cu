@@ -732,7 +732,7 @@ int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows
 
 // The step on the wide-conditioner engine (wide.cu): hidden >= 64, e.g. BASELINE config 5.
 static int mfc_step_wide(void* stream, const cnfot_flow_desc* flow, const FlowLayout& lay,
-                         const cnfot_problem_desc* problem, const float* weights, const float* latent_sub,
+                         const cnfot_problem_desc* problem, const float* weights, const float* latent, const float* latent_sub,
                          const float* src, const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
                          int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out, void* workspace,
                          int64_t workspace_bytes, bool accumulate, const cnfot_peer_desc* peers) {
@@ -741,13 +741,15 @@ static int mfc_step_wide(void* stream, const cnfot_flow_desc* flow, const FlowLa
     return fail(CNFOT_ERR_ARG, "the wide-conditioner engine has no fused all-reduce (its gradient is hundreds of MB): "
                                "call cnfot_mfc_step and all-reduce `out` with NCCL");
   if (accumulate) return fail(CNFOT_ERR_ARG, "the wide-conditioner engine does not take chunked host input");
-  if (problem->type != CNFOT_OT)
-    return fail(CNFOT_ERR_ARG, "the wide-conditioner engine implements general.type == ot (free / obstacle) only");
   if (rows_B < 0 || rows_b < 0 || global_B < 1 || global_b < 1 || rows_B > global_B || rows_b > global_b)
     return fail(CNFOT_ERR_ARG, "bad row counts");
   if (n_t < 1) return fail(CNFOT_ERR_ARG, "t_batch_size must be >= 1");
   if (!weights || !out || !workspace || !t_batch_host) return fail(CNFOT_ERR_ARG, "NULL buffer");
-  if (rows_B > 0 && (!src || !tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
+  if (problem->type == CNFOT_OT) {
+    if (rows_B > 0 && (!src || !tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
+  } else if (rows_B > 0 && !latent) {
+    return fail(CNFOT_ERR_ARG, "latent is NULL");
+  }
   if (rows_b > 0 && !latent_sub) return fail(CNFOT_ERR_ARG, "latent_sub is NULL");
   const int64_t need = wide_step_workspace_bytes(lay, rows_B, rows_b);
   if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
@@ -757,7 +759,7 @@ static int mfc_step_wide(void* stream, const cnfot_flow_desc* flow, const FlowLa
   if (make_step_consts<float>(*problem, lay.D, (double)lambda, global_B, global_b, n_t, &pc, &err))
     return fail(CNFOT_ERR_ARG, "%s", err);
   const char* what = "";
-  cudaError_t e = wide_mfc_step((cudaStream_t)stream, lay, spline_consts(flow), pc, weights, latent_sub, src, tgt,
+  cudaError_t e = wide_mfc_step((cudaStream_t)stream, lay, spline_consts(flow), pc, weights, latent, latent_sub, src, tgt,
                                 t_batch_host, n_t, rows_B, rows_b, out, workspace, &what);
   if (e != cudaSuccess) return cuda_fail(e, what);
   g_last_launch[0] = 0; g_last_launch[1] = 0; g_last_launch[2] = 0; g_last_launch[3] = kEngWide;
@@ -773,7 +775,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
   if (use_wide(flow, lay))
-    return mfc_step_wide(stream, flow, lay, problem, weights, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b,
+    return mfc_step_wide(stream, flow, lay, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b,
                          global_B, global_b, lambda, out, workspace, workspace_bytes, accumulate, peers);
   if (int rc = check_fused(flow, lay)) return rc;
   if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");

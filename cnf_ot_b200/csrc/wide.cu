@@ -34,6 +34,7 @@ namespace cnfot {
 namespace {
 
 constexpr int kMaxM = 4;
+constexpr int kMaxPass = 5;   // flow passes alive at once: r(t-dt/2), r(t+dt/2), r(t), and the two shifted log-prob passes
 constexpr int kThreads = 256;
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -113,8 +114,8 @@ wide_prep_kernel(const float* __restrict__ W, FlowLayout lay, WideDims wd, float
 
 // ---- chunk state initialisation: S[0] = [rows | t | 0], S[1..L] = [0 | t | 0] ---------------------------
 __global__ void __launch_bounds__(kThreads)
-wide_init_kernel(const float* __restrict__ rows, int64_t n, int D, int Kx, int L, int64_t state_stride, float t,
-                 const float* __restrict__ cond, int64_t cond_stride, float* __restrict__ S) {
+wide_init_kernel(const float* __restrict__ rows, int ld_rows, int64_t n, int D, int Kx, int L, int64_t state_stride, float t,
+                 const float* __restrict__ cond, int64_t cond_stride, int shift_col, float shift, float* __restrict__ S) {
   const int64_t per = n * Kx;
   const int64_t total = per * (L + 1);
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -123,7 +124,7 @@ wide_init_kernel(const float* __restrict__ rows, int64_t n, int D, int Kx, int L
     const int64_t r = q / Kx;
     const int c = (int)(q - r * Kx);
     float v = 0.f;
-    if (c < D) v = s == 0 ? rows[r * D + c] : 0.f;
+    if (c < D) v = s == 0 ? rows[r * ld_rows + c] + (c == shift_col ? shift : 0.f) : 0.f;
     else if (c == D) v = cond ? cond[r * cond_stride] : t;
     S[(int64_t)s * state_stride + q] = v;
   }
@@ -503,6 +504,118 @@ wide_kinetic_head_kernel(const float* __restrict__ R1, const float* __restrict__
   if (R3) block_add(lp, slot_pot);
 }
 
+constexpr int kMaxWideDim = 64;
+
+// Rows pushed through the sample direction at time t (row_sample_terms of step_math.cuh):
+// do_fit: reverse_kl_loss_fn (applications.py:129-163)  w_fit (log p(y) - log q_t(y));  do_pot: potential_loss_fn (:176-205)
+__global__ void __launch_bounds__(kThreads)
+wide_sample_head_kernel(const float* __restrict__ Z0, const float* __restrict__ Y, const float* __restrict__ LD, int64_t n,
+                        int D, int Kx, float t, int do_fit, int do_pot, StepConsts<float> pc, float* __restrict__ G,
+                        double* __restrict__ slot_fit, double* __restrict__ slot_pot) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double lf = 0.0, lpot = 0.0;
+  if (r < n) {
+    float y[kMaxWideDim], g[kMaxWideDim];
+    float r2 = 0.f, z2 = 0.f;
+    for (int c = 0; c < D; ++c) {
+      y[c] = Y[r * Kx + c];
+      g[c] = 0.f;
+      r2 += y[c] * y[c];
+      z2 += Z0[r * Kx + c] * Z0[r * Kx + c];
+    }
+    if (do_fit) {
+      const float half_log_2pi = 0.91893853320467274178f;
+      const float lp = -0.5f * z2 - half_log_2pi * (float)D - LD[r];
+      const float w1 = (pc.horizon - t) / pc.horizon, w2 = t / pc.horizon;
+      const float l1 = -0.5f * r2 / pc.var_src - (float)D * (half_log_2pi + 0.5f * logf(pc.var_src));
+      const float l2 = -0.5f * r2 / pc.var_tgt - (float)D * (half_log_2pi + 0.5f * logf(pc.var_tgt));
+      float logq, coef;   // coef = -d log q / d y_i / y_i
+      if (w2 <= 0.f) { logq = l1 + logf(w1); coef = 1.f / pc.var_src; }
+      else if (w1 <= 0.f) { logq = l2 + logf(w2); coef = 1.f / pc.var_tgt; }
+      else {
+        const float a1 = l1 + logf(w1), a2 = l2 + logf(w2);
+        const float m = fmaxf(a1, a2);
+        const float e1 = expf(a1 - m), e2 = expf(a2 - m);
+        logq = m + logf(e1 + e2);
+        coef = (e1 / pc.var_src + e2 / pc.var_tgt) / (e1 + e2);
+      }
+      lf = (double)pc.w_fit * (double)(lp - logq);
+      for (int c = 0; c < D; ++c) g[c] += pc.w_fit * coef * y[c];
+    }
+    if (do_pot) {
+      float gp[kMaxWideDim];
+      const float v = potential_value_grad<float>(pc.potential, pc.a, y, D, gp);
+      lpot = (double)pc.w_pot * (double)v;
+      for (int c = 0; c < D; ++c) g[c] += pc.w_pot * gp[c];
+    }
+    for (int c = 0; c < Kx; ++c) G[r * Kx + c] = c < D ? g[c] : 0.f;
+  }
+  block_add(lf, slot_fit);
+  block_add(lpot, slot_pot);
+}
+
+// Coordinate i of kinetic_with_score_loss_fn / flow_matching_loss_fn (applications.py:245-374; row_kinetic of
+// step_math.cuh): score_i from the two shifted log-prob passes, resid_i = (r2_i - r1_i)/dt + kappa score_i - truth_i,
+// loss += w_kin resid_i^2; seeds the adjoints of the five passes.
+__global__ void __launch_bounds__(kThreads)
+wide_score_head_kernel(int i, const float* __restrict__ R1, const float* __restrict__ R2, const float* __restrict__ R3,
+                       const float* __restrict__ Zp, const float* __restrict__ LDp, const float* __restrict__ Zm,
+                       const float* __restrict__ LDm, int64_t n, int D, int Kx, StepConsts<float> pc, float* __restrict__ G1,
+                       float* __restrict__ G2, float* __restrict__ Gp, float* __restrict__ Gm, float* __restrict__ GLp,
+                       float* __restrict__ GLm, float* __restrict__ GRES, double* __restrict__ slot_kin) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double lk = 0.0;
+  if (r < n) {
+    float zp2 = 0.f, zm2 = 0.f;
+    for (int c = 0; c < D; ++c) {
+      zp2 += Zp[r * Kx + c] * Zp[r * Kx + c];
+      zm2 += Zm[r * Kx + c] * Zm[r * Kx + c];
+    }
+    // base log-densities: the -D log(2 pi)/2 terms cancel in the difference
+    const float score = ((-0.5f * zp2 + LDp[r]) - (-0.5f * zm2 + LDm[r])) / pc.dx;
+    float truth_i = 0.f;
+    if (pc.type == kFP) {
+      float r3[kMaxWideDim], truth[kMaxWideDim];
+      for (int c = 0; c < D; ++c) { r3[c] = R3[r * Kx + c]; truth[c] = 0.f; }
+      drift_value<float>(pc.drift, pc.a, r3, D, truth);
+      truth_i = truth[i];
+    }
+    const float resid = (R2[r * Kx + i] - R1[r * Kx + i]) / pc.dt + pc.kappa * score - truth_i;
+    lk = (double)pc.w_kin * (double)resid * (double)resid;
+    const float gres = 2.f * pc.w_kin * resid;
+    GRES[r * Kx + i] = gres;
+    G2[r * Kx + i] = gres / pc.dt;
+    G1[r * Kx + i] = -gres / pc.dt;
+    const float glp = gres * pc.kappa / pc.dx;
+    for (int c = 0; c < Kx; ++c) {
+      Gp[r * Kx + c] = c < D ? -glp * Zp[r * Kx + c] : 0.f;   // d log N(z) / dz = -z
+      Gm[r * Kx + c] = c < D ? glp * Zm[r * Kx + c] : 0.f;
+    }
+    GLp[r] = glp;
+    GLm[r] = -glp;
+  }
+  block_add(lk, slot_kin);
+}
+
+// G3 += Gp + Gm (the input adjoints of the two shifted passes are adjoints of r3)
+__global__ void __launch_bounds__(kThreads)
+wide_add2_kernel(float* __restrict__ G3, const float* __restrict__ Gp, const float* __restrict__ Gm, int64_t count) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    G3[e] += Gp[e] + Gm[e];
+}
+
+// fp: resid = v - truth(r3): pull the residual adjoints back through the drift target (applications.py:308-372)
+__global__ void __launch_bounds__(kThreads)
+wide_drift_pullback_kernel(const float* __restrict__ R3, const float* __restrict__ GRES, int64_t n, int D, int Kx,
+                           StepConsts<float> pc, float* __restrict__ G3) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float r3[kMaxWideDim], gres[kMaxWideDim], g3[kMaxWideDim];
+  for (int c = 0; c < D; ++c) { r3[c] = R3[r * Kx + c]; gres[c] = GRES[r * Kx + c]; g3[c] = G3[r * Kx + c]; }
+  drift_pullback<float>(pc.drift, pc.a, r3, D, gres, g3);
+  for (int c = 0; c < D; ++c) G3[r * Kx + c] = g3[c];
+}
+
 // out slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic, 5-7 zero
 __global__ void wide_finalize_kernel(const double* __restrict__ slots, float* __restrict__ out_slots) {
   if (threadIdx.x == 0) {
@@ -581,15 +694,17 @@ struct WideEngine {
   float* prep_fwd;
   float* prep_T;
   int64_t R;              // chunk capacity (rows)
-  float* S[3];            // (L+1) x R x Kx each
-  float* LD[3];
-  float* G[3];            // R x Kx each
+  float* S[kMaxPass];     // (L+1) x R x Kx each
+  float* LD[kMaxPass];
+  float* G[kMaxPass];     // R x Kx each
   float* A[kMaxM];        // R x H each
   float* Ga;
   float* Gb;
   float* Theta;           // R x Pp
   float* GTheta;
-  float* GL;              // R: per-row adjoint of the log-det (model-API VJP)
+  float* GL;              // R: per-row adjoint of the log-det (model-API VJP; score passes: GL and GL2)
+  float* GL2;
+  float* GRES;            // R x Kx: d loss / d residual_i of the score-kinetic rows (drift pull-back)
   float* stashA;          // n_mlp x R x H: last hidden activations of pass 0, kept for its backward sweep (or NULL)
   float* stashT;          // n_mlp x R x Pp: raw spline parameters of pass 0
   double* slots;
@@ -730,12 +845,15 @@ struct WideEngine {
     check_launch("wide_spline_vjp_kernel launch");
   }
 
-  void init_states(int p, const float* rows, int64_t n, float t, const float* cond = nullptr, int64_t cond_stride = 0) {
+  // state 0 of pass p = [rows (+ shift on one coordinate) | t | 0]; ld_rows = row stride of `rows` (0: dense, D)
+  void init_states(int p, const float* rows, int64_t n, float t, const float* cond = nullptr, int64_t cond_stride = 0,
+                   int ld_rows = 0, int shift_col = -1, float shift = 0.f) {
     if (!ok()) return;
     int64_t total = n * wd.Kx * (wd.L + 1);
     int64_t b = (total + kThreads - 1) / kThreads;
     if (b > 148 * 16) b = 148 * 16;
-    wide_init_kernel<<<(unsigned)b, kThreads, 0, s>>>(rows, n, wd.D, wd.Kx, wd.L, state_stride(), t, cond, cond_stride, S[p]);
+    wide_init_kernel<<<(unsigned)b, kThreads, 0, s>>>(rows, ld_rows ? ld_rows : wd.D, n, wd.D, wd.Kx, wd.L, state_stride(), t, cond,
+                                                      cond_stride, shift_col, shift, S[p]);
     check_launch("wide_init_kernel launch");
   }
 
@@ -818,7 +936,7 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
   double* slots = c.take<double>(kNumSlots);
   float* pf = c.take<float>(n_mlp * wd.prep_mlp);
   float* pt = with_grad ? c.take<float>(n_mlp * wd.prep_mlp) : nullptr;
-  float *S[3] = {nullptr, nullptr, nullptr}, *LDp[3] = {nullptr, nullptr, nullptr}, *G[3] = {nullptr, nullptr, nullptr};
+  float *S[kMaxPass] = {}, *LDp[kMaxPass] = {}, *G[kMaxPass] = {};
   for (int p = 0; p < n_pass; ++p) {
     S[p] = c.take<float>((int64_t)(lay.L + 1) * R * wd.Kx);
     LDp[p] = c.take<float>(R);
@@ -831,6 +949,8 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
   float* Theta = c.take<float>(R * lay.Pp);
   float* GTheta = with_grad ? c.take<float>(R * lay.Pp) : nullptr;
   float* GL = with_grad ? c.take<float>(R) : nullptr;
+  float* GL2 = with_grad && n_pass > 3 ? c.take<float>(R) : nullptr;
+  float* GRES = with_grad && n_pass > 3 ? c.take<float>(R * wd.Kx) : nullptr;
   // stash of pass 0 (last hidden activations + raw spline parameters of every conditioner): skips the re-computation
   // of the hidden GEMMs in the backward sweep.  Taken when it fits the budget (CNFOT_WIDE_STASH_GB, default 96;
   // 0 disables): BASELINE config 5 needs 79 GB at the default chunk -- this is what 180 GB of HBM3e are for.
@@ -842,9 +962,9 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
   float* stashT = stash ? c.take<float>(n_mlp * R * (int64_t)lay.Pp) : nullptr;
   if (e) {
     e->lay = lay; e->wd = wd; e->R = R; e->slots = slots; e->prep_fwd = pf; e->prep_T = pt;
-    for (int p = 0; p < 3; ++p) { e->S[p] = S[p]; e->LD[p] = LDp[p]; e->G[p] = G[p]; }
+    for (int p = 0; p < kMaxPass; ++p) { e->S[p] = S[p]; e->LD[p] = LDp[p]; e->G[p] = G[p]; }
     for (int m = 0; m < kMaxM; ++m) e->A[m] = A[m];
-    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL; e->stashA = stashA; e->stashT = stashT;
+    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL; e->GL2 = GL2; e->GRES = GRES; e->stashA = stashA; e->stashT = stashT;
   }
   return c.used;
 }
@@ -860,49 +980,103 @@ void launch_prep(WideEngine& e, bool with_T) {
   e.check_launch("wide_prep_kernel launch");
 }
 
+// kinetic terms of one chunk of the b-row sub-batch at time t (row_kinetic of step_math.cuh)
 template <int K>
-void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent_sub, const float* src, const float* tgt,
-              const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b) {
+void kinetic_chunk(WideEngine& e, const StepConsts<float>& pc, const float* rows, int64_t n, float t) {
   const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
-  const bool obstacle = pc.potential == kPotObstacle;
-  // kinetic terms: the b-row sub-batch at every sampled time
-  for (int it = 0; it < n_t && e.ok(); ++it) {
-    const float t = t_batch_host[it];
-    for (int64_t r0 = 0; r0 < rows_b && e.ok(); r0 += e.R) {
-      const int64_t n = rows_b - r0 < e.R ? rows_b - r0 : e.R;
-      const float* rows = latent_sub + r0 * D;
-      e.init_states(0, rows, n, t - pc.dt / 2.f);
-      e.init_states(1, rows, n, t + pc.dt / 2.f);
-      e.flow_pass<K>(0, 0, n);
-      e.flow_pass<K>(0, 1, n);
-      if (obstacle) {
-        e.init_states(2, rows, n, t);
-        e.flow_pass<K>(0, 2, n);
-      }
-      if (!e.ok()) break;
-      wide_kinetic_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
-          e.state(0, L), e.state(1, L), obstacle ? e.state(2, L) : nullptr, n, D, Kx, pc.dt, pc.w_kin, pc.w_pot, e.G[0],
-          e.G[1], e.G[2], e.slots + kSlotKinetic, e.slots + kSlotPotential);
-      e.check_launch("wide_kinetic_head_kernel launch");
-      e.flow_bwd<K>(0, 1, n, 0.f, nullptr);
-      e.flow_bwd<K>(0, 0, n, 0.f, nullptr);
-      if (obstacle) e.flow_bwd<K>(0, 2, n, 0.f, nullptr);
+  const bool with_score = pc.type != kOT;
+  const bool obstacle = pc.potential == kPotObstacle && !with_score;
+  e.init_states(0, rows, n, t - pc.dt / 2.f);
+  e.init_states(1, rows, n, t + pc.dt / 2.f);
+  e.flow_pass<K>(0, 0, n);
+  e.flow_pass<K>(0, 1, n);
+  if (obstacle || with_score) {
+    e.init_states(2, rows, n, t);
+    e.flow_pass<K>(0, 2, n);
+  }
+  if (!e.ok()) return;
+  if (!with_score) {
+    wide_kinetic_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+        e.state(0, L), e.state(1, L), obstacle ? e.state(2, L) : nullptr, n, D, Kx, pc.dt, pc.w_kin, pc.w_pot, e.G[0], e.G[1],
+        e.G[2], e.slots + kSlotKinetic, e.slots + kSlotPotential);
+    e.check_launch("wide_kinetic_head_kernel launch");
+  } else {
+    const size_t gbytes = (size_t)n * Kx * sizeof(float);
+    e.check(cudaMemsetAsync(e.G[0], 0, gbytes, e.s), "cudaMemsetAsync");
+    e.check(cudaMemsetAsync(e.G[1], 0, gbytes, e.s), "cudaMemsetAsync");
+    e.check(cudaMemsetAsync(e.G[2], 0, gbytes, e.s), "cudaMemsetAsync");
+    e.check(cudaMemsetAsync(e.GRES, 0, gbytes, e.s), "cudaMemsetAsync");
+    int64_t ab = (n * Kx + kThreads - 1) / kThreads;
+    if (ab > 148 * 16) ab = 148 * 16;
+    for (int i = 0; i < D && e.ok(); ++i) {
+      // the two log-prob passes of coordinate i start from r3 -+ e_i dx/2: forward both, then back-propagate both
+      e.init_states(3, e.state(2, L), n, t, nullptr, 0, Kx, i, pc.dx / 2.f);
+      e.init_states(4, e.state(2, L), n, t, nullptr, 0, Kx, i, -pc.dx / 2.f);
+      e.flow_pass<K>(1, 3, n);
+      e.flow_pass<K>(1, 4, n);
+      if (!e.ok()) return;
+      wide_score_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+          i, e.state(0, L), e.state(1, L), e.state(2, L), e.state(3, L), e.LD[3], e.state(4, L), e.LD[4], n, D, Kx, pc, e.G[0],
+          e.G[1], e.G[3], e.G[4], e.GL, e.GL2, e.GRES, e.slots + kSlotKinetic);
+      e.check_launch("wide_score_head_kernel launch");
+      e.flow_bwd<K>(1, 3, n, 0.f, e.GL);
+      e.flow_bwd<K>(1, 4, n, 0.f, e.GL2);
+      if (!e.ok()) return;
+      wide_add2_kernel<<<(unsigned)ab, kThreads, 0, e.s>>>(e.G[2], e.G[3], e.G[4], n * Kx);
+      e.check_launch("wide_add2_kernel launch");
+    }
+    if (pc.type == kFP && e.ok()) {
+      wide_drift_pullback_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(e.state(2, L), e.GRES, n, D, Kx, pc, e.G[2]);
+      e.check_launch("wide_drift_pullback_kernel launch");
     }
   }
-  // density-fit terms: -lambda mean log p(data | t) at t = 0 (source) and t = T (target)
-  for (int side = 0; side < 2 && e.ok(); ++side) {
-    const float* data = side == 0 ? src : tgt;
-    const float t = side == 0 ? 0.f : pc.horizon;
-    double* slot = e.slots + (side == 0 ? kSlotFit0 : kSlotFitT);
+  e.flow_bwd<K>(0, 1, n, 0.f, nullptr);
+  e.flow_bwd<K>(0, 0, n, 0.f, nullptr);
+  if (obstacle || with_score) e.flow_bwd<K>(0, 2, n, 0.f, nullptr);
+}
+
+template <int K>
+void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent, const float* latent_sub, const float* src,
+              const float* tgt, const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b) {
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  // kinetic terms: the b-row sub-batch at every sampled time
+  for (int it = 0; it < n_t && e.ok(); ++it)
+    for (int64_t r0 = 0; r0 < rows_b && e.ok(); r0 += e.R)
+      kinetic_chunk<K>(e, pc, latent_sub + r0 * D, rows_b - r0 < e.R ? rows_b - r0 : e.R, t_batch_host[it]);
+  if (pc.type == kOT) {
+    // density-fit terms: -lambda mean log p(data | t) at t = 0 (source) and t = T (target)
+    for (int side = 0; side < 2 && e.ok(); ++side) {
+      const float* data = side == 0 ? src : tgt;
+      const float t = side == 0 ? 0.f : pc.horizon;
+      double* slot = e.slots + (side == 0 ? kSlotFit0 : kSlotFitT);
+      for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += e.R) {
+        const int64_t n = rows_B - r0 < e.R ? rows_B - r0 : e.R;
+        e.init_states(0, data + r0 * D, n, t);
+        e.flow_pass<K>(1, 0, n, true);
+        if (!e.ok()) break;
+        wide_nll_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(e.state(0, L), e.LD[0], n, D, Kx, pc.w_fit,
+                                                                          e.G[0], slot);
+        e.check_launch("wide_nll_head_kernel launch");
+        e.flow_bwd<K>(1, 0, n, -pc.w_fit, nullptr, true);
+      }
+    }
+    return;
+  }
+  // rwpo / fp: reverse-KL fit at t = 0 on the B latent rows; rwpo adds the terminal potential at t = T
+  const int n_seg = pc.type == kRWPO ? 2 : 1;
+  for (int seg = 0; seg < n_seg && e.ok(); ++seg) {
+    const int do_fit = seg == 0, do_pot = seg == 1;
+    const float t = seg == 0 ? 0.f : pc.horizon;
     for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += e.R) {
       const int64_t n = rows_B - r0 < e.R ? rows_B - r0 : e.R;
-      e.init_states(0, data + r0 * D, n, t);
-      e.flow_pass<K>(1, 0, n, true);
+      e.init_states(0, latent + r0 * D, n, t);
+      e.flow_pass<K>(0, 0, n, true);
       if (!e.ok()) break;
-      wide_nll_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(e.state(0, L), e.LD[0], n, D, Kx, pc.w_fit, e.G[0],
-                                                                        slot);
-      e.check_launch("wide_nll_head_kernel launch");
-      e.flow_bwd<K>(1, 0, n, -pc.w_fit, nullptr, true);
+      wide_sample_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+          e.state(0, 0), e.state(0, L), e.LD[0], n, D, Kx, t, do_fit, do_pot, pc, e.G[0], e.slots + kSlotFit0,
+          e.slots + kSlotPotential);
+      e.check_launch("wide_sample_head_kernel launch");
+      e.flow_bwd<K>(0, 0, n, do_fit ? -pc.w_fit : 0.f, nullptr, true);
     }
   }
 }
@@ -921,7 +1095,7 @@ bool wide_supported(const FlowLayout& lay, const char** why) {
 }
 
 int64_t wide_step_workspace_bytes(const FlowLayout& lay, int64_t rows_B, int64_t rows_b) {
-  return carve(nullptr, lay, rows_B > rows_b ? rows_B : rows_b, true, 3, nullptr);
+  return carve(nullptr, lay, rows_B > rows_b ? rows_B : rows_b, true, kMaxPass, nullptr);
 }
 
 int64_t wide_flow_workspace_bytes(const FlowLayout& lay, int64_t rows, bool with_grad) {
@@ -929,16 +1103,16 @@ int64_t wide_flow_workspace_bytes(const FlowLayout& lay, int64_t rows, bool with
 }
 
 cudaError_t wide_mfc_step(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const StepConsts<float>& pc,
-                          const float* weights, const float* latent_sub, const float* src, const float* tgt,
-                          const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b, float* out, void* workspace,
-                          const char** what) {
+                          const float* weights, const float* latent, const float* latent_sub, const float* src,
+                          const float* tgt, const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b, float* out,
+                          void* workspace, const char** what) {
   WideEngine e;
   e.s = s; e.sc = sc; e.W = weights; e.grad = out;
-  carve(workspace, lay, rows_B > rows_b ? rows_B : rows_b, true, 3, &e);
+  carve(workspace, lay, rows_B > rows_b ? rows_B : rows_b, true, kMaxPass, &e);
   e.check(cudaMemsetAsync(out, 0, ((size_t)lay.total + kNumSlots) * sizeof(float), s), "cudaMemsetAsync");
   e.check(cudaMemsetAsync(e.slots, 0, kNumSlots * sizeof(double), s), "cudaMemsetAsync");
   launch_prep(e, true);
-  run_step<5>(e, pc, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b);
+  run_step<5>(e, pc, latent, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b);
   if (e.ok()) {
     wide_finalize_kernel<<<1, 32, 0, s>>>(e.slots, out + lay.total);
     e.check_launch("wide_finalize_kernel launch");

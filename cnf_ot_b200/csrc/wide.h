@@ -15,11 +15,11 @@ bool wide_supported(const FlowLayout& lay, const char** why);
 int64_t wide_step_workspace_bytes(const FlowLayout& lay, int64_t rows_B, int64_t rows_b);
 int64_t wide_flow_workspace_bytes(const FlowLayout& lay, int64_t rows, bool with_grad);
 
-// ot_loss_fn's value_and_grad on this shard: out = [gradient (blob) | 8 loss slots], overwritten
+// value_and_grad of ot_loss_fn / rwpo_loss_fn / fp_loss_fn on this shard: out = [gradient (blob) | 8 loss slots], overwritten
 cudaError_t wide_mfc_step(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const StepConsts<float>& pc,
-                          const float* weights, const float* latent_sub, const float* src, const float* tgt,
-                          const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b, float* out, void* workspace,
-                          const char** what);
+                          const float* weights, const float* latent, const float* latent_sub, const float* src,
+                          const float* tgt, const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b, float* out,
+                          void* workspace, const char** what);
 // flow.bijector.forward / inverse (dir 0 / 1) with log-det (or the density with add_base)
 cudaError_t wide_flow_eval(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const float* weights,
                            int dir, const float* in, const float* cond, int64_t cond_stride, int64_t rows, float* out,

@@ -114,21 +114,26 @@ def run_step(cfg, shape, params, inputs, lam, rows=None, sub_rows=None):
   f = lambda t: t.float().cuda()
   rs = slice(0, B) if rows is None else rows
   ss = slice(0, b) if sub_rows is None else sub_rows
-  out = ops.mfc_step(shape, ops.problem_desc(cfg), W, None, f(inputs["latent"][:b][ss]), f(inputs["src"][rs]),
-                     f(inputs["tgt"][rs]), inputs["t_batch"].tolist(), lam, B, b)
+  ot = cfg["general"]["type"] == "ot"
+  out = ops.mfc_step(shape, ops.problem_desc(cfg), W, None if ot else f(inputs["latent"][rs]), f(inputs["latent"][:b][ss]),
+                     f(inputs["src"][rs]) if ot else None, f(inputs["tgt"][rs]) if ot else None,
+                     inputs["t_batch"].tolist(), lam, B, b)
   return out.cpu().double()
 
 
-STEP_CASES = [("free", dict(dim=4, H=64, sigma=0.05)), ("obstacle", dict(dim=2, H=64, sigma=0.1)),
-              ("free", dict(dim=3, H=128, M=1, sigma=0.02)), ("obstacle", dict(dim=5, H=64, M=3, L=3, sigma=0.05)),
-              ("free", dict(dim=3, H=512, B=384, sigma=0.01))]
+STEP_CASES = [("ot", "free", dict(dim=4, H=64, sigma=0.05)), ("ot", "obstacle", dict(dim=2, H=64, sigma=0.1)),
+              ("ot", "free", dict(dim=3, H=128, M=1, sigma=0.02)), ("ot", "obstacle", dict(dim=5, H=64, M=3, L=3, sigma=0.05)),
+              ("ot", "free", dict(dim=3, H=512, B=384, sigma=0.01)),
+              ("rwpo", "quadratic", dict(dim=2, H=64, sigma=0.1)), ("rwpo", "double_well", dict(dim=3, H=64, M=1, sigma=0.03)),
+              ("fp", "gradient", dict(dim=2, H=64, sigma=0.1)), ("fp", "nongradient", dict(dim=4, H=64, sigma=0.05)),
+              ("fp", "lorenz", dict(dim=3, H=128, L=3, sigma=0.02))]
 
 
-@pytest.mark.parametrize("sub,kw", STEP_CASES)
-def test_loss_and_gradient(sub, kw):
+@pytest.mark.parametrize("typ,sub,kw", STEP_CASES)
+def test_loss_and_gradient(typ, sub, kw):
   kw = dict(kw)
   sigma = kw.pop("sigma")
-  cfg = make_cfg("ot", sub, Tn=2, lam=500.0, **({"B": 640 + 64} | kw))
+  cfg = make_cfg(typ, sub, Tn=2, lam=500.0, **({"B": 640 + 64} | kw))
   shape = shape_of(cfg)
   spec, params = make_params(cfg, sigma)
   inputs = make_inputs(cfg)
@@ -169,17 +174,17 @@ def test_chunks_and_shards_sum_to_whole_batch(monkeypatch):
 
 def test_unsupported_requests_fail_loudly():
   from cnf_ot_b200._lib import CnfotError
-  cfg = make_cfg("rwpo", "double_well", dim=2, H=64, B=256)
+  from cnf_ot_b200.layout import FlowShape
+  cfg = make_cfg("ot", "free", dim=2, H=64, B=256)
   shape = shape_of(cfg)
   _, params = make_params(cfg, 0.1)
-  inputs = make_inputs(cfg)
   W = pack(shape, params).cuda()
-  with pytest.raises(CnfotError):   # the wide engine implements the ot losses only
-    ops.mfc_step(shape, ops.problem_desc(cfg), W, inputs["latent"].float().cuda(), inputs["latent"][:8].float().cuda(),
-                 None, None, inputs["t_batch"].tolist(), 1.0, 256, 8)
   lib = _lib.load()
   x = torch.zeros(4, 2, device="cuda")
   c = torch.zeros(1, device="cuda")
   with pytest.raises(CnfotError):   # the workspace-less entry cannot run a wide flow
     _lib.check(lib.cnfot_flow_forward(0, _lib.flow_desc(shape), W.data_ptr(), x.data_ptr(), c.data_ptr(), 0, 4,
                                       x.data_ptr(), 0, 0))
+  bad = FlowShape(2, 2, 2, 64, 8)   # neither engine is instantiated for 8 bins at hidden 64
+  with pytest.raises(CnfotError):
+    ops.flow_eval(bad, torch.zeros(bad.blob_size, device="cuda"), x, c, inverse=False)

@@ -8,9 +8,11 @@ from cnf_ot_b200.layout import pack
 from oracle import losses as olosses
 from util import make_cfg, make_inputs, make_params, shape_of
 
-for sub, kw, sigma in [("obstacle", dict(dim=5, H=64, M=3, L=3), 0.05), ("free", dict(dim=3, H=512, B=384), 0.01)]:
-  for lam in (500.0, 0.0):
-    cfg = make_cfg("ot", sub, Tn=2, lam=lam, **({"B": 704} | kw))
+CASES = [("rwpo", "double_well", dict(dim=3, H=64, M=1), 0.1), ("rwpo", "double_well", dict(dim=3, H=64, M=1), 0.03),
+         ("rwpo", "double_well", dict(dim=3, H=64, M=2), 0.1), ("rwpo", "quadratic", dict(dim=3, H=64, M=1), 0.1)]
+for typ, sub, kw, sigma in CASES:
+  for lam in (500.0,):
+    cfg = make_cfg(typ, sub, Tn=2, lam=lam, **({"B": 704} | kw))
     shape = shape_of(cfg)
     spec, params = make_params(cfg, sigma)
     inputs = make_inputs(cfg)
@@ -18,11 +20,13 @@ for sub, kw, sigma in [("obstacle", dict(dim=5, H=64, M=3, L=3), 0.05), ("free",
     Gor = pack(shape, grads, torch.float64)
     B = cfg["train"]["batch_size"]; b = B // 32
     f = lambda t: t.float().cuda()
-    out = ops.mfc_step(shape, ops.problem_desc(cfg), pack(shape, params).cuda(), None, f(inputs["latent"][:b]),
-                       f(inputs["src"]), f(inputs["tgt"]), inputs["t_batch"].tolist(), lam, B, b).cpu().double()
+    ot = typ == "ot"
+    out = ops.mfc_step(shape, ops.problem_desc(cfg), pack(shape, params).cuda(), None if ot else f(inputs["latent"]),
+                       f(inputs["latent"][:b]), f(inputs["src"]) if ot else None, f(inputs["tgt"]) if ot else None,
+                       inputs["t_batch"].tolist(), lam, B, b).cpu().double()
     n = shape.blob_size
     sc = float(Gor.abs().max())
-    print(sub, kw, "lam", lam, "loss or %.9g ours %.9g  slots %s  grad scale %.4g" % (float(loss), float(out[n]), out[n:n+5].tolist(), sc))
+    print(typ, sub, kw, "sigma", sigma, "lam", lam, "loss or %.9g ours %.9g  slots %s  grad scale %.4g" % (float(loss), float(out[n]), out[n:n+5].tolist(), sc))
     worst = []
     for mod, leaf, shp, off, stride in shape.leaves():
       rows = 1
