@@ -1045,6 +1045,7 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
 int64_t cnfot_kinetic_energy_workspace_bytes(const cnfot_flow_desc* flow, int32_t n_t) {
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
+  if (use_wide(flow, lay)) return wide_energy_workspace_bytes(lay);
   return partial_bytes(lay) + ((int64_t)(n_t > 0 ? n_t : 0) * (int64_t)sizeof(float) + 255) / 256 * 256;
 }
 
@@ -1054,13 +1055,22 @@ int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float*
                          int64_t workspace_bytes) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
-  if (int rc = check_fused(flow, lay)) return rc;
+  if (!use_wide(flow, lay))
+    if (int rc = check_fused(flow, lay)) return rc;
   if (batch < 1 || n_t < 1 || latent_blocks < 1) return fail(CNFOT_ERR_ARG, "batch, n_t and latent_blocks must be >= 1");
   if (!weights || !latent || !t_host || !out || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
   if (!(dt > 0.f) || (with_score && !(dx > 0.f))) return fail(CNFOT_ERR_ARG, "dt and dx must be positive");
   const int64_t need = cnfot_kinetic_energy_workspace_bytes(flow, n_t);
   if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
                                           (long long)workspace_bytes, (long long)need);
+  if (use_wide(flow, lay)) {
+    const char* what = "";
+    cudaError_t we = wide_kinetic_energy((cudaStream_t)stream, lay, spline_consts(flow), weights, latent, batch,
+                                         latent_blocks, t_host, n_t, dt, with_score, kappa, dx, out, workspace, &what);
+    if (we != cudaSuccess) return cuda_fail(we, what);
+    g_last_launch[0] = 0; g_last_launch[1] = 0; g_last_launch[2] = 0; g_last_launch[3] = kEngWide;
+    return 0;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   EnergyArgs a;
   float* t_dev = (float*)((char*)workspace + partial_bytes(lay));

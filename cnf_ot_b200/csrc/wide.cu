@@ -616,6 +616,40 @@ wide_drift_pullback_kernel(const float* __restrict__ R3, const float* __restrict
   for (int c = 0; c < D; ++c) G3[r * Kx + c] = g3[c];
 }
 
+// ---- evaluation energies (forward only; utils.calc_kinetic_energy / calc_score_kinetic_energy, cnf_ot/utils.py:311-389)
+__global__ void __launch_bounds__(kThreads)
+wide_velocity_kernel(const float* __restrict__ R1, const float* __restrict__ R2, int64_t n, int D, int Kx, float dt,
+                     float* __restrict__ V) {
+  const int64_t total = n * Kx;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Kx);
+    V[e] = c < D ? (R2[e] - R1[e]) / dt : 0.f;
+  }
+}
+// V[r][i] += kappa * score_i, score_i by central differences of log_prob (the -D log(2 pi)/2 terms cancel)
+__global__ void __launch_bounds__(kThreads)
+wide_score_add_kernel(int i, const float* __restrict__ Zp, const float* __restrict__ LDp, const float* __restrict__ Zm,
+                      const float* __restrict__ LDm, int64_t n, int D, int Kx, float kappa, float dx, float* __restrict__ V) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float zp2 = 0.f, zm2 = 0.f;
+  for (int c = 0; c < D; ++c) {
+    zp2 += Zp[r * Kx + c] * Zp[r * Kx + c];
+    zm2 += Zm[r * Kx + c] * Zm[r * Kx + c];
+  }
+  V[r * Kx + i] += kappa * ((-0.5f * zp2 + LDp[r]) - (-0.5f * zm2 + LDm[r])) / dx;
+}
+__global__ void __launch_bounds__(kThreads)
+wide_sumsq_kernel(const float* __restrict__ V, int64_t count, double weight, double* __restrict__ slot) {
+  double acc = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    acc += (double)V[e] * (double)V[e];
+  block_add(acc * weight, slot);
+}
+__global__ void wide_energy_out_kernel(const double* __restrict__ slots, double* __restrict__ out) {
+  if (threadIdx.x == 0) out[0] = slots[kSlotKinetic];
+}
+
 // out slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic, 5-7 zero
 __global__ void wide_finalize_kernel(const double* __restrict__ slots, float* __restrict__ out_slots) {
   if (threadIdx.x == 0) {
@@ -705,6 +739,7 @@ struct WideEngine {
   float* GL;              // R: per-row adjoint of the log-det (model-API VJP; score passes: GL and GL2)
   float* GL2;
   float* GRES;            // R x Kx: d loss / d residual_i of the score-kinetic rows (drift pull-back)
+  float* V;               // R x Kx: velocities of the evaluation energies
   float* stashA;          // n_mlp x R x H: last hidden activations of pass 0, kept for its backward sweep (or NULL)
   float* stashT;          // n_mlp x R x Pp: raw spline parameters of pass 0
   double* slots;
@@ -951,6 +986,7 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
   float* GL = with_grad ? c.take<float>(R) : nullptr;
   float* GL2 = with_grad && n_pass > 3 ? c.take<float>(R) : nullptr;
   float* GRES = with_grad && n_pass > 3 ? c.take<float>(R * wd.Kx) : nullptr;
+  float* V = !with_grad && n_pass > 3 ? c.take<float>(R * wd.Kx) : nullptr;
   // stash of pass 0 (last hidden activations + raw spline parameters of every conditioner): skips the re-computation
   // of the hidden GEMMs in the backward sweep.  Taken when it fits the budget (CNFOT_WIDE_STASH_GB, default 96;
   // 0 disables): BASELINE config 5 needs 79 GB at the default chunk -- this is what 180 GB of HBM3e are for.
@@ -964,7 +1000,7 @@ int64_t carve(void* base, const FlowLayout& lay, int64_t max_rows, bool with_gra
     e->lay = lay; e->wd = wd; e->R = R; e->slots = slots; e->prep_fwd = pf; e->prep_T = pt;
     for (int p = 0; p < kMaxPass; ++p) { e->S[p] = S[p]; e->LD[p] = LDp[p]; e->G[p] = G[p]; }
     for (int m = 0; m < kMaxM; ++m) e->A[m] = A[m];
-    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL; e->GL2 = GL2; e->GRES = GRES; e->stashA = stashA; e->stashT = stashT;
+    e->Ga = Ga; e->Gb = Gb; e->Theta = Theta; e->GTheta = GTheta; e->GL = GL; e->GL2 = GL2; e->GRES = GRES; e->V = V; e->stashA = stashA; e->stashT = stashT;
   }
   return c.used;
 }
@@ -1174,6 +1210,62 @@ cudaError_t wide_flow_vjp(cudaStream_t s, const FlowLayout& lay, const SplineCon
                                                                      e.state(0, 0), n, D, Kx, dir, add_base, g_in + r0 * D);
       e.check_launch("wide_vjp_out_kernel launch");
     }
+  }
+  if (what) *what = e.what;
+  return e.err;
+}
+
+int64_t wide_energy_workspace_bytes(const FlowLayout& lay) {
+  return carve(nullptr, lay, chunk_rows(), false, kMaxPass, nullptr);
+}
+
+cudaError_t wide_kinetic_energy(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const float* weights,
+                                const float* latent, int64_t batch, int latent_blocks, const float* t_host, int n_t, float dt,
+                                int with_score, float kappa, float dx, double* out, void* workspace, const char** what) {
+  WideEngine e;
+  e.s = s; e.sc = sc; e.W = weights; e.grad = nullptr;
+  carve(workspace, lay, chunk_rows(), false, kMaxPass, &e);
+  e.check(cudaMemsetAsync(e.slots, 0, kNumSlots * sizeof(double), s), "cudaMemsetAsync");
+  launch_prep(e, false);
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  const double weight = 1.0 / (2.0 * (double)batch * (double)n_t);
+  for (int it = 0; it < n_t && e.ok(); ++it) {
+    const float t = t_host[it];
+    const float* block = latent + (int64_t)(it % latent_blocks) * batch * D;
+    for (int64_t r0 = 0; r0 < batch && e.ok(); r0 += e.R) {
+      const int64_t n = batch - r0 < e.R ? batch - r0 : e.R;
+      const float* rows = block + r0 * D;
+      int64_t ab = (n * Kx + kThreads - 1) / kThreads;
+      if (ab > 148 * 16) ab = 148 * 16;
+      e.init_states(0, rows, n, t - dt / 2.f);
+      e.init_states(1, rows, n, t + dt / 2.f);
+      e.flow_pass<5>(0, 0, n);
+      e.flow_pass<5>(0, 1, n);
+      if (!e.ok()) break;
+      wide_velocity_kernel<<<(unsigned)ab, kThreads, 0, s>>>(e.state(0, L), e.state(1, L), n, D, Kx, dt, e.V);
+      e.check_launch("wide_velocity_kernel launch");
+      if (with_score) {
+        e.init_states(2, rows, n, t);
+        e.flow_pass<5>(0, 2, n);
+        for (int i = 0; i < D && e.ok(); ++i) {
+          e.init_states(3, e.state(2, L), n, t, nullptr, 0, Kx, i, dx / 2.f);
+          e.init_states(4, e.state(2, L), n, t, nullptr, 0, Kx, i, -dx / 2.f);
+          e.flow_pass<5>(1, 3, n);
+          e.flow_pass<5>(1, 4, n);
+          if (!e.ok()) break;
+          wide_score_add_kernel<<<WideEngine::blocks_for(n), kThreads, 0, s>>>(i, e.state(3, L), e.LD[3], e.state(4, L), e.LD[4],
+                                                                           n, D, Kx, kappa, dx, e.V);
+          e.check_launch("wide_score_add_kernel launch");
+        }
+      }
+      if (!e.ok()) break;
+      wide_sumsq_kernel<<<(unsigned)(ab > 592 ? 592 : ab), kThreads, 0, s>>>(e.V, n * Kx, weight, e.slots + kSlotKinetic);
+      e.check_launch("wide_sumsq_kernel launch");
+    }
+  }
+  if (e.ok()) {
+    wide_energy_out_kernel<<<1, 32, 0, s>>>(e.slots, out);
+    e.check_launch("wide_energy_out_kernel launch");
   }
   if (what) *what = e.what;
   return e.err;

@@ -29,4 +29,10 @@ cudaError_t wide_flow_vjp(cudaStream_t s, const FlowLayout& lay, const SplineCon
                           const float* g_out, const float* g_logdet, int add_base, float* g_in, float* g_weights,
                           void* workspace, const char** what);
 
+// utils.calc_kinetic_energy / calc_score_kinetic_energy over a time grid (forward only); out: one double on the device
+int64_t wide_energy_workspace_bytes(const FlowLayout& lay);
+cudaError_t wide_kinetic_energy(cudaStream_t s, const FlowLayout& lay, const SplineConsts<float>& sc, const float* weights,
+                                const float* latent, int64_t batch, int latent_blocks, const float* t_host, int n_t, float dt,
+                                int with_score, float kappa, float dx, double* out, void* workspace, const char** what);
+
 }  // namespace cnfot

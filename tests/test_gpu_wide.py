@@ -188,3 +188,47 @@ def test_unsupported_requests_fail_loudly():
   bad = FlowShape(2, 2, 2, 64, 8)   # neither engine is instantiated for 8 bins at hidden 64
   with pytest.raises(CnfotError):
     ops.flow_eval(bad, torch.zeros(bad.blob_size, device="cuda"), x, c, inverse=False)
+
+
+@pytest.mark.parametrize("with_score", [False, True])
+def test_kinetic_energy_matches_oracle(with_score):
+  """cnfot_kinetic_energy on the wide engine (utils.calc_kinetic_energy / calc_score_kinetic_energy,
+  cnf_ot/utils.py:311-389): same tolerance as the fused kernels (tests/test_gpu_energies.py)."""
+  from oracle import energies as oen
+  D = 3
+  cfg = make_cfg(dim=D, H=64)
+  shape = shape_of(cfg)
+  spec, params = make_params(cfg, 0.05)
+  W = pack(shape, params).cuda()
+  g = torch.Generator().manual_seed(21)
+  n_t, batch = 4, 300
+  latent = torch.randn(n_t, batch, D, generator=g, dtype=torch.float64).float()
+  ts = torch.linspace(0.0, 1.5, n_t, dtype=torch.float64).float().tolist()
+  if with_score:
+    ref = oen.score_kinetic_energy(spec, params, latent.double(), ts, beta=2.0)
+  else:
+    ref = oen.kinetic_energy(spec, params, latent.double(), ts)
+  got = ops.kinetic_energy(shape, W, latent.reshape(-1, D).cuda(), ts, with_score=with_score, kappa=0.5, latent_blocks=n_t)
+  assert _lib.last_launch_info()["engine"] == "wide"
+  assert abs(float(got) - float(ref)) <= 2e-4 * abs(float(ref)), (float(got), float(ref))
+
+
+def test_reference_api_on_a_wide_flow():
+  """The RQSFlow / applications mirror (flows.py:213-226, applications.py) runs unchanged on a flow the fused
+  kernels do not cover: model.apply.* and value_and_grad(loss_fn) reach the wide engine through the same C ABI."""
+  import functools
+  from cnf_ot_b200 import applications, random
+  from cnf_ot_b200.flows import RQSFlow
+  model = RQSFlow((3, ), 2, [64, 64], 5)
+  params = model.init(random.PRNGKey(0), torch.zeros(1, 3), torch.zeros(1))
+  x = torch.randn(500, 3, device="cuda")
+  lp = model.apply.log_prob(params, x, cond=torch.tensor([0.3]))
+  assert _lib.last_launch_info()["engine"] == "wide"
+  ref = oflow.base_log_prob(x.double().cpu())   # identity flow at the reference initialisation
+  assert float((lp.double().cpu() - ref).abs().max()) < 1e-4
+  y = model.apply.forward(params, x, torch.tensor([0.3]))
+  assert float((y - x).abs().max()) < 4e-6
+  loss_fn = functools.partial(applications.ot_loss_fn, model, 3, 1, 0.01, 1, "free")
+  loss, grads = applications.value_and_grad(loss_fn)(params, random.PRNGKey(1), 50.0, 1024)
+  assert torch.isfinite(torch.as_tensor(float(loss)))
+  assert float(grads.blob.abs().max()) > 0
