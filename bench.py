@@ -522,10 +522,29 @@ def run_cfg5(args):
                    "fp32_fidelity_tflops": pipe / 3, "us_per_launch": tk * 1e6,
                    "step_algorithmic_tflops": 3 * per_pass * (2 * B + 2 * b) / (el / args.steps) / 1e12},
     }
+    if world == 1 and not args.no_cpu_baseline:
+      line["cpu_baseline"] = cpu_baseline_cfg5(L)
     print(json.dumps(line), flush=True)
   if world > 1:
     td.barrier()
     td.destroy_process_group()
+
+
+def cpu_baseline_cfg5(L, rows=128):
+  """The CPU restatement (oracle/, torch f64, autograd) on a bounded sample of the configs[4] workload."""
+  from oracle import losses as olosses
+  from util import make_cfg, make_inputs, make_params
+  torch.set_num_threads(os.cpu_count() or 1)
+  cfg = make_cfg("ot", "free", dim=32, L=L, M=2, H=512, K=5, B=rows, Tn=1, lam=5000.0)
+  spec, params = make_params(cfg, 0.01)
+  inputs = make_inputs(cfg)
+  olosses.value_and_grad(cfg, spec, params, inputs)
+  t0 = time.perf_counter()
+  olosses.value_and_grad(cfg, spec, params, inputs)
+  dt = time.perf_counter() - t0
+  return {"value": rows / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"oracle (torch f64 restatement of the reference step) on {rows} rows of the same workload "
+                    f"(dim 32, {L} layers, 2x512), 1 timed step after 1 warm-up"}
 
 
 def main():
@@ -538,6 +557,7 @@ def main():
                   help="cfg2 = BASELINE configs[1] (the driver's line); cfg5 = configs[4] on the wide-conditioner engine")
   ap.add_argument("--rows-per-gpu", type=int, default=1 << 17, help="cfg5 only (BASELINE: 2^21)")
   ap.add_argument("--layers", type=int, default=16, help="cfg5 only: flow layers (BASELINE: 16)")
+  ap.add_argument("--no-cpu-baseline", action="store_true", help="cfg5 only: skip the CPU oracle timing")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -302,22 +302,72 @@ wide_out_fwd_kernel(const float* __restrict__ A, const float* __restrict__ Wout,
   }
 }
 
-// Backward of the output layer in ONE pass over A (n x H): a thread owns TH hidden units h (128 apart),
+// ---- bulk-copy ring shared by the two streaming kernels below ---------------------------------------------------
+// A CTA walks its row range in tiles of kRingRows rows; one thread fetches tile t + kRingStages - 1 with 1-D bulk
+// copies (cp.async.bulk -> mbarrier complete_tx) while everybody computes tile t, so ~100 KB per SM are in flight
+// without occupying registers (per-thread loads kept only ~8 KB per SM in flight: 194 us for 310 MB, r01 launch list).
+constexpr int kRingStages = 4;
+constexpr int kRingRows = 16;
+__device__ __forceinline__ uint32_t ring_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ring_s32(bar)), "r"(1));
+}
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(ring_s32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void ring_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ring_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ring_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ring_s32(dst)), "l"(src), "r"(bytes), "r"(ring_s32(bar)) : "memory");
+}
+
+// Backward of the output layer in ONE pass over A (n x H): a thread owns TH hidden units h (256 apart),
 //   G2[r][h]     = A[r][h] > 0 ? sum_p GTheta[r][p] Wout[h][p] : 0     (adjoint of the last hidden pre-activation)
 //   dWout[h][p] += sum_r A[r][h] GTheta[r][p],   dbout[p] += sum_r GTheta[r][p]
-// GTheta rows are staged 64 at a time in shared memory and read as broadcasts.
-constexpr int kOutBwdThreads = 128;
-constexpr int kOutBwdTH = 4;
+// A rows (the CTA's 512 columns) and GTheta rows arrive through the bulk-copy ring.
+constexpr int kOutBwdThreads = 256;
+constexpr int kOutBwdTH = 2;
+constexpr int kOutBwdCols = kOutBwdThreads * kOutBwdTH;
 template <int PP>
 __global__ void __launch_bounds__(kOutBwdThreads)
 wide_out_bwd_kernel(const float* __restrict__ A, const float* __restrict__ GTheta, const float* __restrict__ Wout, int64_t n,
                     int H, float* __restrict__ G2, float* __restrict__ dWout, float* __restrict__ dbout) {
   constexpr int NT_ = kOutBwdThreads, TH = kOutBwdTH;
-  __shared__ __align__(16) float gt[64 * PP];
+  extern __shared__ __align__(128) float ring[];   // [stage][kRingRows][kOutBwdCols] | [stage][kRingRows][PP]
+  __shared__ __align__(8) uint64_t full[kRingStages];
+  float* ringA = ring;
+  float* ringG = ring + kRingStages * kRingRows * kOutBwdCols;
   const int tid = threadIdx.x;
-  const int h0 = blockIdx.x * (NT_ * TH) + tid;
+  const int hbase = blockIdx.x * kOutBwdCols;
+  const int hcount = H - hbase < kOutBwdCols ? H - hbase : kOutBwdCols;
+  const int h0 = hbase + tid;
   const int64_t per = ((n + gridDim.y - 1) / gridDim.y + 63) / 64 * 64;
   const int64_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+  const int n_tiles = hi > lo ? (int)((hi - lo + kRingRows - 1) / kRingRows) : 0;
+  auto issue = [&](int t) {   // one thread
+    const int sidx = t % kRingStages;
+    const int64_t r0 = lo + (int64_t)t * kRingRows;
+    const int cnt = hi - r0 < kRingRows ? (int)(hi - r0) : kRingRows;
+    ring_expect(&full[sidx], (uint32_t)(cnt * (hcount + PP) * 4));
+    for (int rr = 0; rr < cnt; ++rr)
+      ring_copy(ringA + (sidx * kRingRows + rr) * kOutBwdCols, A + (r0 + rr) * H + hbase, (uint32_t)(hcount * 4), &full[sidx]);
+    ring_copy(ringG + sidx * kRingRows * PP, GTheta + r0 * PP, (uint32_t)(cnt * PP * 4), &full[sidx]);
+  };
+  if (tid == 0) {
+    for (int q = 0; q < kRingStages; ++q) ring_init(&full[q]);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < kRingStages && t < n_tiles; ++t) issue(t);
   float w[TH][PP], acc[TH][PP];
   bool hv[TH];
 #pragma unroll
@@ -333,28 +383,26 @@ wide_out_bwd_kernel(const float* __restrict__ A, const float* __restrict__ GThet
     for (int p = 0; p < PP; ++p) acc[j][p] = 0.f;
   }
   float bsum = 0.f;   // thread p < PP of the blocks with blockIdx.x == 0: column p of this block's GTheta rows
-  for (int64_t r0 = lo; r0 < hi; r0 += 64) {
-    __syncthreads();
-    for (int e = tid; e < 64 * PP / 4; e += NT_) {
-      const int64_t r = r0 + e / (PP / 4);
-      *reinterpret_cast<float4*>(gt + 4 * e) =
-          r < hi ? __ldg(reinterpret_cast<const float4*>(GTheta + r * PP) + e % (PP / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    const int cnt = hi - r0 < 64 ? (int)(hi - r0) : 64;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int sidx = t % kRingStages;
+    const int64_t r0 = lo + (int64_t)t * kRingRows;
+    const int cnt = hi - r0 < kRingRows ? (int)(hi - r0) : kRingRows;
+    ring_wait(&full[sidx], (uint32_t)((t / kRingStages) & 1));
+    const float* ta = ringA + sidx * kRingRows * kOutBwdCols + tid;
+    const float* tg = ringG + sidx * kRingRows * PP;
     if (blockIdx.x == 0 && tid < PP)
-      for (int rr = 0; rr < cnt; ++rr) bsum += gt[rr * PP + tid];
-#pragma unroll 2
+      for (int rr = 0; rr < cnt; ++rr) bsum += tg[rr * PP + tid];
+#pragma unroll 4
     for (int rr = 0; rr < cnt; ++rr) {
       float a[TH], sacc[TH];
 #pragma unroll
       for (int j = 0; j < TH; ++j) {
-        a[j] = hv[j] ? __ldg(A + (r0 + rr) * H + h0 + NT_ * j) : 0.f;
+        a[j] = hv[j] ? ta[rr * kOutBwdCols + NT_ * j] : 0.f;
         sacc[j] = 0.f;
       }
 #pragma unroll
       for (int q = 0; q < PP / 4; ++q) {
-        const float4 g = *reinterpret_cast<const float4*>(gt + rr * PP + 4 * q);
+        const float4 g = *reinterpret_cast<const float4*>(tg + rr * PP + 4 * q);
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           sacc[j] += g.x * w[j][4 * q] + g.y * w[j][4 * q + 1] + g.z * w[j][4 * q + 2] + g.w * w[j][4 * q + 3];
@@ -366,6 +414,8 @@ wide_out_bwd_kernel(const float* __restrict__ A, const float* __restrict__ GThet
       for (int j = 0; j < TH; ++j)
         if (hv[j]) G2[(r0 + rr) * H + h0 + NT_ * j] = a[j] > 0.f ? sacc[j] : 0.f;
     }
+    __syncthreads();   // everybody is done with the stage: refill it
+    if (tid == 0 && t + kRingStages < n_tiles) issue(t + kRingStages);
   }
 #pragma unroll
   for (int j = 0; j < TH; ++j)
@@ -377,24 +427,49 @@ wide_out_bwd_kernel(const float* __restrict__ A, const float* __restrict__ GThet
     }
   if (blockIdx.x == 0 && tid < PP) atomicAdd(dbout + tid, bsum);
 }
+template <int PP>
+constexpr size_t out_bwd_smem() { return (size_t)kRingStages * kRingRows * (kOutBwdCols + PP) * sizeof(float); }
 
 // Weight gradient of the input layer: dW0[w0_row(k)][h] += sum_r S[r][k] G1[r][h], db0[h] += sum_r G1[r][h];
-// a thread owns 2 hidden units (256 apart), 4 KV4 state columns accumulated in registers for each, state rows
-// staged 64 at a time.
+// a thread owns 2 hidden units (256 apart), 4 KV4 state columns accumulated in registers for each; G1 rows (the
+// CTA's 512 columns) and the state rows arrive through the bulk-copy ring.
 constexpr int kInWgradTH = 2;
+constexpr int kInWgradCols = kThreads * kInWgradTH;
 template <int KV4>
 __global__ void __launch_bounds__(kThreads)
 wide_in_wgrad_kernel(const float* __restrict__ S, int Kx, const float* __restrict__ G1, int64_t n, int H, int D, int d, int rev,
                      float* __restrict__ dW0, float* __restrict__ db0) {
   constexpr int KV = 4 * KV4, TH = kInWgradTH;
-  __shared__ __align__(16) float st[64 * KV];
+  extern __shared__ __align__(128) float ring[];   // [stage][kRingRows][kInWgradCols] | [stage][kRingRows][Kx]
+  __shared__ __align__(8) uint64_t full[kRingStages];
+  float* ringG = ring;
+  float* ringS = ring + kRingStages * kRingRows * kInWgradCols;
   const int tid = threadIdx.x;
-  const int h0 = blockIdx.x * (kThreads * TH) + tid;
+  const int hbase = blockIdx.x * kInWgradCols;
+  const int hcount = H - hbase < kInWgradCols ? H - hbase : kInWgradCols;
+  const int h0 = hbase + tid;
   bool hv[TH];
 #pragma unroll
   for (int j = 0; j < TH; ++j) hv[j] = h0 + kThreads * j < H;
   const int64_t per = ((n + gridDim.y - 1) / gridDim.y + 63) / 64 * 64;
   const int64_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+  const int n_tiles = hi > lo ? (int)((hi - lo + kRingRows - 1) / kRingRows) : 0;
+  auto issue = [&](int t) {   // one thread
+    const int sidx = t % kRingStages;
+    const int64_t r0 = lo + (int64_t)t * kRingRows;
+    const int cnt = hi - r0 < kRingRows ? (int)(hi - r0) : kRingRows;
+    ring_expect(&full[sidx], (uint32_t)(cnt * (hcount + Kx) * 4));
+    for (int rr = 0; rr < cnt; ++rr)
+      ring_copy(ringG + (sidx * kRingRows + rr) * kInWgradCols, G1 + (r0 + rr) * H + hbase, (uint32_t)(hcount * 4), &full[sidx]);
+    ring_copy(ringS + sidx * kRingRows * Kx, S + r0 * Kx, (uint32_t)(cnt * Kx * 4), &full[sidx]);
+  };
+  if (tid == 0) {
+    for (int q = 0; q < kRingStages; ++q) ring_init(&full[q]);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < kRingStages && t < n_tiles; ++t) issue(t);
   float acc[TH][KV], bsum[TH];
 #pragma unroll
   for (int j = 0; j < TH; ++j) {
@@ -402,27 +477,24 @@ wide_in_wgrad_kernel(const float* __restrict__ S, int Kx, const float* __restric
 #pragma unroll
     for (int k = 0; k < KV; ++k) acc[j][k] = 0.f;
   }
-  for (int64_t r0 = lo; r0 < hi; r0 += 64) {
-    __syncthreads();
-    for (int e = tid; e < 64 * KV4; e += kThreads) {
-      const int rr = e / KV4, q = e - rr * KV4;
-      const int64_t r = r0 + rr;
-      *reinterpret_cast<float4*>(st + 4 * e) =
-          r < hi ? __ldg(reinterpret_cast<const float4*>(S + r * Kx) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    const int cnt = hi - r0 < 64 ? (int)(hi - r0) : 64;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int sidx = t % kRingStages;
+    const int64_t r0 = lo + (int64_t)t * kRingRows;
+    const int cnt = hi - r0 < kRingRows ? (int)(hi - r0) : kRingRows;
+    ring_wait(&full[sidx], (uint32_t)((t / kRingStages) & 1));
+    const float* tg = ringG + sidx * kRingRows * kInWgradCols + tid;
+    const float* ts = ringS + sidx * kRingRows * Kx;
 #pragma unroll 2
     for (int rr = 0; rr < cnt; ++rr) {
       float g[TH];
 #pragma unroll
       for (int j = 0; j < TH; ++j) {
-        g[j] = hv[j] ? __ldg(G1 + (r0 + rr) * H + h0 + kThreads * j) : 0.f;
+        g[j] = hv[j] ? tg[rr * kInWgradCols + kThreads * j] : 0.f;
         bsum[j] += g[j];
       }
 #pragma unroll
       for (int q = 0; q < KV4; ++q) {
-        const float4 sv = *reinterpret_cast<const float4*>(st + rr * KV + 4 * q);
+        const float4 sv = *reinterpret_cast<const float4*>(ts + rr * Kx + 4 * q);
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           acc[j][4 * q] += g[j] * sv.x; acc[j][4 * q + 1] += g[j] * sv.y;
@@ -430,6 +502,8 @@ wide_in_wgrad_kernel(const float* __restrict__ S, int Kx, const float* __restric
         }
       }
     }
+    __syncthreads();
+    if (tid == 0 && t + kRingStages < n_tiles) issue(t + kRingStages);
   }
 #pragma unroll
   for (int j = 0; j < TH; ++j)
@@ -443,6 +517,7 @@ wide_in_wgrad_kernel(const float* __restrict__ S, int Kx, const float* __restric
       atomicAdd(db0 + h, bsum[j]);
     }
 }
+inline size_t in_wgrad_smem(int Kx) { return (size_t)kRingStages * kRingRows * (kInWgradCols + Kx) * sizeof(float); }
 
 // ---- loss heads ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_add(double v, double* dst) {
@@ -823,11 +898,16 @@ struct WideEngine {
     float* gc = Ga;
     float* gn = Gb;
     {
-      const int hb = (H + kOutBwdThreads * kOutBwdTH - 1) / (kOutBwdThreads * kOutBwdTH);
-      int64_t ny = (n + 63) / 64;   // >= 64 rows per block, about 4 blocks per SM
-      if (ny * hb > 148 * 4) ny = (148 * 4) / hb;
+      const int hb = (H + kOutBwdCols - 1) / kOutBwdCols;
+      int64_t ny = (n + 63) / 64;   // >= 64 rows per block, one block per SM (the ring takes 132 KB)
+      if (ny * hb > 148) ny = 148 / hb;
       if (ny < 1) ny = 1;
-      wide_out_bwd_kernel<16><<<dim3((unsigned)hb, (unsigned)ny), kOutBwdThreads, 0, s>>>(
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(wide_out_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out_bwd_smem<16>());
+        attr_done = true;
+      }
+      wide_out_bwd_kernel<16><<<dim3((unsigned)hb, (unsigned)ny), kOutBwdThreads, out_bwd_smem<16>(), s>>>(
           a_last, GTheta, W + off_out, n, H, gc, grad + off_out, grad + off_out + (int64_t)H * Pp);
       check_launch("wide_out_bwd_kernel launch");
     }
@@ -841,13 +921,19 @@ struct WideEngine {
     if (!ok()) return;
     // input layer: dW0 / db0 on CUDA cores, the input adjoints accumulated into the adjoint state by the GEMM epilogue
     const int kv4 = (wd.D + 1 + 3) / 4;
-    const int hb = (H + kThreads * kInWgradTH - 1) / (kThreads * kInWgradTH);
+    const int hb = (H + kInWgradCols - 1) / kInWgradCols;
     int64_t ny = (n + 63) / 64;
-    if (ny * hb > 148 * 2) ny = (148 * 2) / hb;
+    if (ny * hb > 148) ny = 148 / hb;
     if (ny < 1) ny = 1;
     dim3 grid((unsigned)hb, (unsigned)ny);
+    const size_t ring_bytes = in_wgrad_smem(Kx);
     switch (kv4) {
-#define CNFOT_IN_WGRAD(Q) case Q: wide_in_wgrad_kernel<Q><<<grid, kThreads, 0, s>>>(cst, Kx, gc, n, H, wd.D, d, layer & 1, grad + off_w0, grad + off_b0); break;
+#define CNFOT_IN_WGRAD(Q)                                                                                              \
+  case Q:                                                                                                              \
+    cudaFuncSetAttribute(wide_in_wgrad_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);       \
+    wide_in_wgrad_kernel<Q><<<grid, kThreads, ring_bytes, s>>>(cst, Kx, gc, n, H, wd.D, d, layer & 1, grad + off_w0,   \
+                                                               grad + off_b0);                                         \
+    break;
       CNFOT_IN_WGRAD(1) CNFOT_IN_WGRAD(2) CNFOT_IN_WGRAD(3) CNFOT_IN_WGRAD(4) CNFOT_IN_WGRAD(5) CNFOT_IN_WGRAD(6)
       CNFOT_IN_WGRAD(7) CNFOT_IN_WGRAD(8) CNFOT_IN_WGRAD(9) CNFOT_IN_WGRAD(10) CNFOT_IN_WGRAD(11) CNFOT_IN_WGRAD(12)
       CNFOT_IN_WGRAD(13) CNFOT_IN_WGRAD(14) CNFOT_IN_WGRAD(15) CNFOT_IN_WGRAD(16)
