@@ -128,8 +128,11 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
   const int kTmemCols = acc2 ? tmem_cols(2 * NT) : tmem_cols(NT);
   const uint32_t lo_off = acc2 ? (uint32_t)NT : 0u;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * 128;
-  const int n0 = blockIdx.y * NT;
+  // 1-D grid, column tile fastest: the CTAs that share a row tile are adjacent in launch order, so the second
+  // read of the A rows hits L2 (ncu r01: with the column tile on gridDim.y the A matrix came from HBM twice)
+  const int ntn = N_total / NT;
+  const int64_t row0 = (int64_t)(blockIdx.x / ntn) * 128;
+  const int n0 = (int)(blockIdx.x % ntn) * NT;
   const int64_t r = row0 + tid;
   const bool live = r < rows;
 
@@ -465,7 +468,7 @@ static cudaError_t launch_dense(cudaStream_t s, const float* X, int64_t rows, in
   auto kern = dense_tc_kernel<NT, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)((rows + 127) / 128), (unsigned)(N / NT));
+  dim3 grid((unsigned)(((rows + 127) / 128) * (N / NT)));
   // CNFOT_DENSE_ACC2=1: separate accumulator for the small 3xTF32 terms (needs 2 NT <= 512 TMEM columns)
   int acc2 = 0;
   if (const char* ev = getenv("CNFOT_DENSE_ACC2")) acc2 = ev[0] == '1' && 2 * NT <= 512;
