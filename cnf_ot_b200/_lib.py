@@ -101,6 +101,8 @@ SIGNATURES = {
                                     c_void_p, c_int32, c_int32, c_void_p, c_int32]),
   "cnfot_dense_wgrad": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32,
                                   c_void_p, c_int32, c_void_p]),
+  "cnfot_mask_tail": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32]),
+  "cnfot_recon_head": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p]),
   "cnfot_adam_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_float, c_float, c_float, c_float, c_int64]),
 }

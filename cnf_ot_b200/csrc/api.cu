@@ -438,6 +438,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ---- dimension-reduction loss head (cnf_ot/dr/trainers.py:91-111) -------------------------------------------
+// loss += weight * sum (x - xr)^2 ; g_xr = -2 weight (x - xr)
+__global__ void __launch_bounds__(256)
+recon_head_kernel(const float* __restrict__ x, const float* __restrict__ xr, int64_t count, float weight,
+                  float* __restrict__ g_xr, double* __restrict__ loss) {
+  double acc = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    const float dlt = x[e] - xr[e];
+    acc += (double)dlt * (double)dlt;
+    g_xr[e] = -2.f * weight * dlt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(loss, acc * (double)weight);
+}
+// y[:, sub_dim:] = 0
+__global__ void __launch_bounds__(256)
+mask_tail_kernel(float* __restrict__ y, int64_t rows, int dim, int sub_dim) {
+  const int64_t count = rows * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    if ((int)(e % dim) >= sub_dim) y[e] = 0.f;
+}
+
 }  // namespace cnfot
 
 using namespace cnfot;
@@ -1153,6 +1176,32 @@ int cnfot_dense_wgrad(void* stream, const float* A, int32_t lda, const float* G,
     return fail(CNFOT_ERR_ARG, "dense_wgrad: Nb and ldw must be multiples of 4 and dW 16-byte aligned");
   cudaError_t e = dense_wgrad((cudaStream_t)stream, A, lda, G, ldg, rows, Ka, Nb, dW, ldw, db);
   if (e != cudaSuccess) return cuda_fail(e, "dense_wgrad_kernel launch");
+  return 0;
+}
+
+int cnfot_recon_head(void* stream, const float* x, const float* xr, int64_t rows, int32_t dim, float weight,
+                     float* g_xr, double* loss) {
+  if (rows < 0 || dim < 1) return fail(CNFOT_ERR_ARG, "bad sizes");
+  if (rows == 0) return 0;
+  if (!x || !xr || !g_xr || !loss) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  const int64_t count = rows * dim;
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  recon_head_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, xr, count, weight, g_xr, loss);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "recon_head_kernel launch");
+  return 0;
+}
+
+int cnfot_mask_tail(void* stream, float* y, int64_t rows, int32_t dim, int32_t sub_dim) {
+  if (rows < 0 || dim < 1 || sub_dim < 0 || sub_dim > dim) return fail(CNFOT_ERR_ARG, "bad sizes");
+  if (rows == 0 || sub_dim == dim) return 0;
+  if (!y) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  int64_t blocks = (rows * dim + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mask_tail_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y, rows, dim, sub_dim);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "mask_tail_kernel launch");
   return 0;
 }
 

@@ -102,7 +102,7 @@ class FlowModel:
     k = 0
     for l in range(s.num_layers):
       for d in range(1, s.dim):
-        fan_in = d + 1
+        fan_in = d + 1 if s.conditional else d
         for m in range(s.mlp_layers):
           w = params[f"mlp_layer{l}_d{d}/~/linear_{m}"]["w"]
           w.copy_(_trunc_normal(keys[k], tuple(w.shape), 1.0 / math.sqrt(fan_in), self.device))
@@ -144,15 +144,23 @@ class FlowModel:
     x = self._latent(seed, sample_shape, latent)
     return ops.flow_eval(self.shape, W, x, cond, inverse=False, add_base=True)
 
-  def _forward(self, params, x, c):
+  def _cond(self, c):
+    # unconditional flows (cond_shape=(0,), dr/trainers.py:41-68) run the same kernels with t = 0 and zero t-weights
+    if not self.shape.conditional:
+      if c is not None:
+        raise TypeError("this flow is unconditional (cond_shape=(0,)): no condition argument")
+      return torch.zeros(1)
+    return c
+
+  def _forward(self, params, x, c=None):
     """flow.bijector.forward: latent -> physical."""
     W = _blob_of(self.shape, params, self.device)
-    return ops.flow_eval(self.shape, W, x, c, inverse=False, want_logdet=False)[0]
+    return ops.flow_eval(self.shape, W, x, self._cond(c), inverse=False, want_logdet=False)[0]
 
-  def _inverse(self, params, y, c):
+  def _inverse(self, params, y, c=None):
     """flow.bijector.inverse: physical -> latent."""
     W = _blob_of(self.shape, params, self.device)
-    return ops.flow_eval(self.shape, W, y, c, inverse=True, want_logdet=False)[0]
+    return ops.flow_eval(self.shape, W, y, self._cond(c), inverse=True, want_logdet=False)[0]
 
 
 def RQSFlow(
@@ -168,14 +176,15 @@ def RQSFlow(
   """Same arguments as cnf_ot.models.flows.RQSFlow (flows.py:178-186)."""
   if periodized:
     raise NotImplementedError("periodized flows are outside the MFC hot path (solvers.py:46 passes False)")
-  if tuple(cond_shape) != (1, ):
-    raise NotImplementedError("only the time-conditioned flow (cond_shape=(1,)) is on the hot path")
+  if tuple(cond_shape) not in ((1, ), (0, )):
+    raise NotImplementedError("cond_shape must be (1,) (time-conditioned, mfc/) or (0,) (unconditional, dr/)")
   if len(event_shape) != 1:
     raise ValueError("event_shape must be (dim,)")
   hs = [int(h) for h in hidden_sizes]
   if not hs or any(h != hs[0] for h in hs):
     raise ValueError("hidden_sizes must be [hidden_size] * mlp_num_layers (solvers.py:44)")
-  return FlowModel(FlowShape(int(event_shape[0]), int(num_layers), len(hs), hs[0], int(num_bins)), device)
+  return FlowModel(FlowShape(int(event_shape[0]), int(num_layers), len(hs), hs[0], int(num_bins),
+                             conditional=tuple(cond_shape) == (1, )), device)
 
 
 # haiku spellings used at solvers.py:48 -- the model above is already "transformed"

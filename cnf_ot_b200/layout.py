@@ -48,6 +48,10 @@ class FlowShape:
   range_max: float = 10.0
   min_bin_size: float = 1e-4
   min_knot_slope: float = 1e-4
+  # cond_shape == (1,) (time-conditioned, the MFC solvers) or (0,) (unconditional, cnf_ot/dr/trainers.py:41-68).
+  # An unconditional flow keeps the SAME blob layout: row 0 of every input matrix (the weights of t) exists but
+  # is zero and is not a leaf, and the kernels are called with t = 0, so its gradient is exactly zero too.
+  conditional: bool = True
 
   @property
   def P(self) -> int:
@@ -92,9 +96,10 @@ class FlowShape:
     """Number of reference parameters (un-padded), e.g. 1200 for mfc.yaml."""
     P, H, M = self.P, self.hidden, self.mlp_layers
     n = P
+    c = 1 if self.conditional else 0
     for _ in range(self.num_layers):
       for d in range(1, self.dim):
-        n += (d + 1) * H + H + (M - 1) * (H * H + H) + H * P + P
+        n += (d + c) * H + H + (M - 1) * (H * H + H) + H * P + P
     return n
 
   def leaves(self) -> Iterator[Tuple[str, str, Tuple[int, ...], int, int]]:
@@ -103,9 +108,10 @@ class FlowShape:
     yield "~", "first", (1, P), 0, Pp
     for l in range(self.num_layers):
       for d in range(1, self.dim):
-        fan_in = d + 1
+        fan_in = d + 1 if self.conditional else d
         for m in range(M):
-          yield mlp_key(l, d, m), "w", (fan_in, H), self.linear_offset(l, d, m, False), H
+          skip = H if (m == 0 and not self.conditional) else 0   # unconditional: the t row is not a leaf
+          yield mlp_key(l, d, m), "w", (fan_in, H), self.linear_offset(l, d, m, False) + skip, H
           yield mlp_key(l, d, m), "b", (H, ), self.linear_offset(l, d, m, True), H
           fan_in = H
         yield out_key(l, d), "w", (H, P), self.linear_offset(l, d, M, False), Pp

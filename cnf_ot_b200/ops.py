@@ -333,6 +333,28 @@ def dense_wgrad(A, G, dW, db=None) -> None:
                                      G.shape[1], _ptr(dW), dW.stride(0), _ptr(db)))
 
 
+def mask_tail(y: torch.Tensor, sub_dim: int) -> torch.Tensor:
+  """y[:, sub_dim:] = 0 in place (cnf_ot/dr/trainers.py:95,108)."""
+  lib = _lib.load()
+  y = _dev(y, "y")
+  with torch.cuda.device(y.device):
+    _lib.check(lib.cnfot_mask_tail(_stream(), _ptr(y), y.shape[0], y.shape[1], int(sub_dim)))
+  return y
+
+
+def recon_head(x: torch.Tensor, xr: torch.Tensor, global_rows: int):
+  """(loss contribution, g_xr) of mean_rows sum_dims (x - xr)^2 over this shard (trainers.py:97,110);
+  the loss is a 0-d float64 CUDA tensor."""
+  lib = _lib.load()
+  x, xr = _dev(x, "x"), _dev(xr, "xr")
+  g = torch.empty_like(xr)
+  loss = torch.zeros(1, dtype=torch.float64, device=x.device)
+  with torch.cuda.device(x.device):
+    _lib.check(lib.cnfot_recon_head(_stream(), _ptr(x), _ptr(xr), x.shape[0], x.shape[1], 1.0 / float(global_rows),
+                                    _ptr(g), _ptr(loss)))
+  return loss[0], g
+
+
 def adam_update(params, grads, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8) -> None:
   """In-place optax.adam(lr) update of the parameter blob."""
   lib = _lib.load()

@@ -275,6 +275,17 @@ CNFOT_API int cnfot_dense_forward(void* stream, const float* X, int64_t rows, in
 CNFOT_API int cnfot_dense_wgrad(void* stream, const float* A, int32_t lda, const float* G, int32_t ldg,
                       int64_t rows, int32_t Ka, int32_t Nb, float* dW, int32_t ldw, float* db);
 
+/* ---- dimension-reduction loss (cnf_ot/dr/trainers.py:91-111) -------------------------
+ * loss_fn(params, x) = mean_rows sum_dims (x - decoder.forward(mask(encoder.forward(x))))^2 with UNCONDITIONAL
+ * flows (cond_shape = (0,), trainers.py:41-68).  The flows are the cnfot_flow_* calls above on a blob whose
+ * t-rows (row 0 of every input matrix) are zero, with cond = 0; these two calls are the glue between them:
+ *   cnfot_mask_tail    y[:, sub_dim:] = 0                                   (trainers.py:95,108)
+ *   cnfot_recon_head   *loss += weight * sum (x - xr)^2, g_xr = -2 weight (x - xr)    (trainers.py:97,110;
+ *                      weight = 1 / global rows; loss: one double on the device, zeroed by the caller) */
+CNFOT_API int cnfot_mask_tail(void* stream, float* y, int64_t rows, int32_t dim, int32_t sub_dim);
+CNFOT_API int cnfot_recon_head(void* stream, const float* x, const float* xr, int64_t rows, int32_t dim,
+                     float weight, float* g_xr, double* loss);
+
 /* optax.adam(lr) defaults b1=0.9 b2=0.999 eps=1e-8 (cnf_ot/mfc/solvers.py:55,95-96), fused
  * element-wise update; step is the 1-based update count. */
 CNFOT_API int cnfot_adam_update(void* stream, float* params, const float* grads, float* m, float* v,

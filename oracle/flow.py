@@ -38,7 +38,10 @@ class FlowSpec:
   """Static description of a flow (what `RQSFlow(...)` closes over)."""
 
   def __init__(self, dim: int, num_layers: int, hidden_sizes: Sequence[int],
-               num_bins: int):
+               num_bins: int, conditional: bool = True):
+    # conditional=False: cond_shape=(0,), the unconditional flows of cnf_ot/dr/trainers.py:41-68
+    # (autoregressive.py:94-98: the condition is concatenated only `if self.is_conditional`)
+    self.conditional = bool(conditional)
     self.dim = int(dim)
     self.num_layers = int(num_layers)
     self.hidden_sizes = [int(h) for h in hidden_sizes]
@@ -56,7 +59,7 @@ class FlowSpec:
     n = p
     for _ in range(self.num_layers):
       for d in range(1, self.dim):
-        fan_in = d + 1
+        fan_in = d + 1 if self.conditional else d
         for h in self.hidden_sizes:
           n += fan_in * h + h
           fan_in = h
@@ -94,7 +97,7 @@ def init_params(spec: FlowSpec, seed: int = 0) -> Params:
   params: Params = {"~": {"first": torch.zeros(1, p, dtype=torch.float32)}}
   for l in range(spec.num_layers):
     for d in range(1, spec.dim):
-      fan_in = d + 1
+      fan_in = d + 1 if spec.conditional else d
       for m, h in enumerate(spec.hidden_sizes):
         params[mlp_key(l, d, m)] = {
           "w": _trunc_normal(gen, (fan_in, h), 1.0 / math.sqrt(fan_in)),
@@ -138,9 +141,11 @@ def conditioner(spec: FlowSpec, params: Params, layer: int, d: int,
   return h @ lin["w"] + lin["b"]
 
 
-def _cond_input(y: Tensor, c: Tensor, idx: List[int]) -> Tensor:
-  # [c, y[perm[:d]]] with c broadcast over rows (autoregressive.py:94-98)
+def _cond_input(y: Tensor, c: Optional[Tensor], idx: List[int]) -> Tensor:
+  # [c, y[perm[:d]]] with c broadcast over rows; no c for unconditional flows (autoregressive.py:94-98)
   cols = y[..., idx]
+  if c is None:
+    return cols
   c_ = c.expand(cols.shape[:-1] + c.shape[-1:])
   return torch.cat([c_, cols], dim=-1)
 
@@ -180,19 +185,21 @@ def layer_inverse(spec, params, layer, y, c):
   return torch.stack(xs, dim=-1), sum(lds)
 
 
-def _as_cond(c, rows_like: Tensor) -> Tensor:
+def _as_cond(c, rows_like: Tensor) -> Optional[Tensor]:
+  if c is None:   # unconditional flow
+    return None
   c = torch.as_tensor(c, dtype=rows_like.dtype)
   if c.dim() == 0:
     c = c.reshape(1)
   return c
 
 
-def flow_forward_and_log_det(spec, params, x, c):
+def flow_forward_and_log_det(spec, params, x, c=None):
   """flow.bijector.forward: latent -> physical ("sample direction").
 
   ConditionalInverse.forward = chain.inverse = layers in list order, each
   layer's inverse_and_log_det (conditional.py:153-157,169-177,233-237)."""
-  c = _as_cond(c, x)
+  c = _as_cond(c, x) if spec.conditional else None
   ld = torch.zeros(x.shape[:-1], dtype=x.dtype)
   for l in range(spec.num_layers):
     x, ld_l = layer_inverse(spec, params, l, x, c)
@@ -200,12 +207,12 @@ def flow_forward_and_log_det(spec, params, x, c):
   return x, ld
 
 
-def flow_inverse_and_log_det(spec, params, y, c):
+def flow_inverse_and_log_det(spec, params, y, c=None):
   """flow.bijector.inverse: physical -> latent ("log-prob direction").
 
   ConditionalInverse.inverse = chain.forward = reversed layers, each layer's
   forward_and_log_det (conditional.py:147-151,159-167,239-243)."""
-  c = _as_cond(c, y)
+  c = _as_cond(c, y) if spec.conditional else None
   ld = torch.zeros(y.shape[:-1], dtype=y.dtype)
   for l in reversed(range(spec.num_layers)):
     y, ld_l = layer_forward(spec, params, l, y, c)
