@@ -72,6 +72,30 @@ def step_case(typ, sub, B, lam, Tn, **kw):
           "grad": pack(shape, grads, torch.float64)}
 
 
+def dr_case(model, D, L, H, sub_dim, sigma, n, seed):
+  """Dimension-reduction loss (cnf_ot/dr/trainers.py:91-111) on unconditional flows (oracle/dr.py)."""
+  from cnf_ot_b200.layout import FlowShape
+  from oracle import dr as odr
+  spec = oflow.FlowSpec(D, L, [H, H], 5, conditional=False)
+  shape = FlowShape(D, L, 2, H, 5, conditional=False)
+
+  def mk(s):
+    p = oflow.perturb_params(oflow.init_params(spec, s), sigma, seed=s + 10)
+    return {m: {k: v.to(torch.float32).to(v.dtype) for k, v in lv.items()} for m, lv in p.items()}
+  g = torch.Generator().manual_seed(seed)
+  x = f32(torch.randn(n, D, generator=g, dtype=torch.float64) * 1.5)
+  dec = mk(2)
+  params = {"encoder": mk(1), "decoder": dec} if model == "enc_dec" else dec
+  loss, grads = odr.value_and_grad(model, spec, params, x, sub_dim)
+  out = {"shape": np.array([D, L, 2, H, 5]), "sub_dim": np.array(sub_dim), "x": x, "loss": loss,
+         "blob_decoder": pack(shape, dec, torch.float64),
+         "grad_decoder": pack(shape, grads["decoder"] if model == "enc_dec" else grads, torch.float64)}
+  if model == "enc_dec":
+    out["blob_encoder"] = pack(shape, params["encoder"], torch.float64)
+    out["grad_encoder"] = pack(shape, grads["encoder"], torch.float64)
+  return out
+
+
 def save(name, d):
   out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
@@ -79,6 +103,8 @@ def save(name, d):
 
 
 STEP_CASES = {
+  # hidden 64: outside the fused kernels, runs on the wide-conditioner engine (csrc/wide.cu)
+  "step_ot_free_d3_h64": ("ot", "free", 256, 500.0, 2, dict(dim=3, H=64, sigma=0.05)),
   "step_ot_obstacle": ("ot", "obstacle", 256, 500.0, 2, {}),
   "step_rwpo_double_well": ("rwpo", "double_well", 256, 500.0, 2, {}),
   "step_fp_nongradient_d4": ("fp", "nongradient", 128, 100.0, 1, dict(dim=4, sigma=0.1)),
@@ -89,5 +115,8 @@ if __name__ == "__main__":
   save("rqs_k8", spline_case(8, 256, 8))
   save("flow_d2", flow_case(2, 2, 2, 16, 5, 0.3, 384, 9))
   save("flow_d3_h8", flow_case(3, 3, 1, 8, 3, 0.1, 256, 10))
+  save("flow_d3_h64", flow_case(3, 2, 2, 64, 5, 0.05, 256, 11))
+  save("dr_enc_dec_d4", dr_case("enc_dec", 4, 2, 16, 2, 0.08, 320, 12))
+  save("dr_dec_only_d4", dr_case("dec_only", 4, 2, 16, 2, 0.08, 320, 13))
   for name, (typ, sub, B, lam, Tn, kw) in STEP_CASES.items():
     save(name, step_case(typ, sub, B, lam, Tn, **dict(kw)))
