@@ -17,7 +17,8 @@ TOL_LOSS, TOL_GRAD = 2e-5, 5e-5
 
 # (D, L, M, H, sigma)
 # sigma keeps the flows well conditioned (|log-det| < 8): the raw spline parameters scale with sigma * sqrt(H)
-SHAPES = [(4, 2, 2, 64, 0.05), (5, 3, 1, 128, 0.01), (3, 2, 3, 64, 0.1), (17, 2, 2, 64, 0.03), (3, 2, 2, 512, 0.01)]
+SHAPES = [(4, 2, 2, 64, 0.05), (5, 3, 1, 128, 0.01), (3, 2, 3, 64, 0.1), (17, 2, 2, 64, 0.03), (3, 2, 2, 512, 0.01),
+          (3, 2, 2, 32, 0.1), (3, 2, 4, 48, 0.1), (40, 2, 2, 64, 0.02)]   # narrow widths, 4 hidden layers, dim > 32
 
 
 def close(a, b, tol=TOL, tol_max=TOL_MAX):
@@ -126,7 +127,8 @@ STEP_CASES = [("ot", "free", dict(dim=4, H=64, sigma=0.05)), ("ot", "obstacle", 
               ("ot", "free", dict(dim=3, H=512, B=384, sigma=0.01)),
               ("rwpo", "quadratic", dict(dim=2, H=64, sigma=0.1)), ("rwpo", "double_well", dict(dim=3, H=64, M=1, sigma=0.03)),
               ("fp", "gradient", dict(dim=2, H=64, sigma=0.1)), ("fp", "nongradient", dict(dim=4, H=64, sigma=0.05)),
-              ("fp", "lorenz", dict(dim=3, H=128, L=3, sigma=0.02))]
+              ("fp", "lorenz", dict(dim=3, H=128, L=3, sigma=0.02)),
+              ("ot", "obstacle", dict(dim=3, H=48, M=4, sigma=0.1)), ("rwpo", "quadratic", dict(dim=2, H=32, sigma=0.1))]
 
 
 @pytest.mark.parametrize("typ,sub,kw", STEP_CASES)
@@ -232,3 +234,22 @@ def test_reference_api_on_a_wide_flow():
   loss, grads = applications.value_and_grad(loss_fn)(params, random.PRNGKey(1), 50.0, 1024)
   assert torch.isfinite(torch.as_tensor(float(loss)))
   assert float(grads.blob.abs().max()) > 0
+
+
+def test_host_entry_on_a_wide_flow():
+  """cnfot_mfc_step_host (host buffers in and out) on the wide engine: pinned rows are read in place, pageable ones
+  are staged; both agree with the device entry."""
+  cfg = make_cfg("ot", "free", dim=3, H=64, B=1024, lam=100.0)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, 0.05)
+  inputs = make_inputs(cfg)
+  dev = run_step(cfg, shape, params, inputs, 100.0)
+  b = 1024 // 32
+  W = pack(shape, params)
+  for pinned in (True, False):
+    mk = (lambda t: t.float().contiguous().pin_memory()) if pinned else (lambda t: t.float().contiguous().clone())
+    out = torch.empty(shape.blob_size + 8, dtype=torch.float32)
+    out = out.pin_memory() if pinned else out
+    ops.mfc_step_host(shape, ops.problem_desc(cfg), mk(W), None, mk(inputs["latent"][:b]), mk(inputs["src"]),
+                      mk(inputs["tgt"]), inputs["t_batch"].tolist(), 100.0, 1024, b, out)
+    assert float((out.double() - dev).abs().max() / dev.abs().max()) < 2e-6
