@@ -861,11 +861,10 @@ struct WideEngine {
     int64_t nb = (n + 127) / 128;   // 8 warps x 16 rows per block pass
     if (nb > 148 * 4) nb = 148 * 4;
     const size_t smem = (size_t)H * (Pp + 4) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(wide_out_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = true;
-    }
+    if (smem > 48 * 1024)   // per device and cheap: no cached flag (one process may drive several GPUs)
+      check(cudaFuncSetAttribute(wide_out_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            "cudaFuncSetAttribute");
+    if (!ok()) return;
     wide_out_fwd_kernel<16><<<(unsigned)nb, kThreads, smem, s>>>(a_last, w, bias, n, H, theta);
     check_launch("wide_out_fwd_kernel launch");
   }
@@ -902,11 +901,9 @@ struct WideEngine {
       int64_t ny = (n + 63) / 64;   // >= 64 rows per block, one block per SM (the ring takes 132 KB)
       if (ny * hb > 148) ny = 148 / hb;
       if (ny < 1) ny = 1;
-      static bool attr_done = false;
-      if (!attr_done) {
-        cudaFuncSetAttribute(wide_out_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out_bwd_smem<16>());
-        attr_done = true;
-      }
+      check(cudaFuncSetAttribute(wide_out_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out_bwd_smem<16>()),
+            "cudaFuncSetAttribute");
+      if (!ok()) return;
       wide_out_bwd_kernel<16><<<dim3((unsigned)hb, (unsigned)ny), kOutBwdThreads, out_bwd_smem<16>(), s>>>(
           a_last, GTheta, W + off_out, n, H, gc, grad + off_out, grad + off_out + (int64_t)H * Pp);
       check_launch("wide_out_bwd_kernel launch");
