@@ -151,6 +151,18 @@ def run_reference(args):
   if rank != 0:
     return
   torch.set_num_threads(os.cpu_count() or 1)
+  if args.workload == "cfg5":
+    # BASELINE configs[4] on the CPU restatement: one bounded sample per step (128 rows of the same flow and loss)
+    cb = cpu_baseline_cfg5(args.layers)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 1, "ms_per_step": 128 / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic scale-out, ot/free structure (BASELINE configs[4])", "dim": 32,
+                       "flow_num_layers": args.layers, "mlp": "2x512", "rows_per_step_cpu": 128},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return
   # bounded sample per step so K + W steps end within minutes
   probe = oracle_step_timer(1 << 12)
   probe()
