@@ -73,10 +73,12 @@ __device__ __forceinline__ void commit_to(uint32_t bar) {
 
 // 3xTF32 split with round-to-nearest parts (zero-mean errors; a truncating split is biased and the bias adds
 // up over the contraction): hi = rn_tf32(v), lo = rn_tf32(v - hi); v - hi is exact in fp32.
+// (cvt.rna.tf32.f32 leaves the low 13 bits of its result zero -- tools/cvt_probe.cu, 4M bit patterns -- so the result
+// is the tf32 value as a float and v - hi is the exact residual)
 __device__ __forceinline__ float tf32_rn(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r & 0xFFFFE000u);
+  return __uint_as_float(r);
 }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));

@@ -64,12 +64,12 @@ __device__ __forceinline__ void put_split(float* tile_base, int64_t n_cols, int 
   // round-to-nearest 3xTF32 split, as dense_prep_kernel
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  const float hi = __uint_as_float(r & 0xFFFFE000u);
+  const float hi = __uint_as_float(r);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - hi));
   float* t = tile_base + (int64_t)(k >> 4) * 2 * n_cols * 16;
   const int p = sw64_pos(n, k & 15);
   t[p] = hi;
-  t[n_cols * 16 + p] = __uint_as_float(r & 0xFFFFE000u);
+  t[n_cols * 16 + p] = __uint_as_float(r);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -303,10 +303,11 @@ wide_out_fwd_kernel(const float* __restrict__ A, const float* __restrict__ Wout,
 }
 
 // ---- bulk-copy ring shared by the two streaming kernels below ---------------------------------------------------
-// A CTA walks its row range in tiles of kRingRows rows; one thread fetches tile t + kRingStages - 1 with 1-D bulk
-// copies (cp.async.bulk -> mbarrier complete_tx) while everybody computes tile t, so ~100 KB per SM are in flight
-// without occupying registers (per-thread loads kept only ~8 KB per SM in flight: 194 us for 310 MB, r01 launch list).
-constexpr int kRingStages = 4;
+// A CTA walks its row range in tiles of kRingRows rows; one thread fetches the next tile with 1-D bulk copies
+// (cp.async.bulk -> mbarrier complete_tx) while everybody computes the current one: 33 KB per CTA in flight without
+// occupying registers.  Two stages, so that two CTAs (16 warps) fit an SM: ncu (profiles/r01_wide_out_bwd_ncu_full.txt)
+// showed the 4-stage / one-CTA version issue-bound at 8 warps per SM (issue slots 52 % busy, 2 warps per scheduler).
+constexpr int kRingStages = 2;
 constexpr int kRingRows = 16;
 __device__ __forceinline__ uint32_t ring_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ring_init(uint64_t* bar) {
@@ -898,8 +899,8 @@ struct WideEngine {
     float* gn = Gb;
     {
       const int hb = (H + kOutBwdCols - 1) / kOutBwdCols;
-      int64_t ny = (n + 63) / 64;   // >= 64 rows per block, one block per SM (the ring takes 132 KB)
-      if (ny * hb > 148) ny = 148 / hb;
+      int64_t ny = (n + 63) / 64;   // >= 64 rows per block, two blocks per SM (the ring takes 66 KB)
+      if (ny * hb > 296) ny = 296 / hb;
       if (ny < 1) ny = 1;
       check(cudaFuncSetAttribute(wide_out_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out_bwd_smem<16>()),
             "cudaFuncSetAttribute");
@@ -920,7 +921,7 @@ struct WideEngine {
     const int kv4 = (wd.D + 1 + 3) / 4;
     const int hb = (H + kInWgradCols - 1) / kInWgradCols;
     int64_t ny = (n + 63) / 64;
-    if (ny * hb > 148) ny = 148 / hb;
+    if (ny * hb > 296) ny = 296 / hb;
     if (ny < 1) ny = 1;
     dim3 grid((unsigned)hb, (unsigned)ny);
     const size_t ring_bytes = in_wgrad_smem(Kx);
