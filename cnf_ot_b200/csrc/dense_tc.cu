@@ -125,6 +125,7 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[NT];
   using S = DenseSmem<NT>;
   // acc2: the two small products (x_lo w_hi, x_hi w_lo) go to a second accumulator, NT columns further
   const int kTmemCols = acc2 ? tmem_cols(2 * NT) : tmem_cols(NT);
@@ -148,6 +149,10 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // the tile's bias values wait in shared memory for the epilogue (read there as broadcasts): loading them from
+  // global memory inside the epilogue loop exposed one L2 latency per 16-column step
+  if (EPI == 0 || EPI == 1)
+    for (int j = tid; j < NT; j += 128) bias_s[j] = __ldg(bias + n0 + j);
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
@@ -205,10 +210,26 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
   mbar_wait(s_u32(&bar_done), 0);
   asm volatile("tcgen05.fence::after_thread_sync;");
 
-  // epilogue: thread = row (TMEM lane), 16 columns per tcgen05.ld
+  // epilogue: thread = row (TMEM lane), 16 columns per tcgen05.ld.  The global-memory operands of a step (the ReLU
+  // mask source, EPI 2; the old output, EPI 4) are fetched one step ahead.
   const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cur[4] = {z4, z4, z4, z4}, nxt[4] = {z4, z4, z4, z4};
+  auto prefetch = [&](int c0, float4 (&dst)[4]) {
+    if (EPI == 2) {
+      const float4* m4 = reinterpret_cast<const float4*>(mask_src + r * ldm + n0 + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = __ldg(m4 + q);
+    } else if (EPI == 4) {
+      const float4* y4 = reinterpret_cast<const float4*>(Y + r * ldy + n0 + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = y4[q];
+    }
+  };
+  if (live && (EPI == 2 || EPI == 4)) prefetch(0, cur);
 #pragma unroll 1
   for (int c0 = 0; c0 < NT; c0 += 16) {
+    if (live && (EPI == 2 || EPI == 4) && c0 + 16 < NT) prefetch(c0 + 16, nxt);
     uint32_t v[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -230,17 +251,22 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
     if (live) {
       float o[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(v[j]);
-        if (EPI == 0 || EPI == 1) a += __ldg(bias + n0 + c0 + j);
-        if (EPI == 1) a = fmaxf(a, 0.f);
-        o[j] = a;
+      for (int q = 0; q < 4; ++q) {
+        float4 bq = z4;
+        if (EPI == 0 || EPI == 1) bq = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);
+        o[4 * q] = __uint_as_float(v[4 * q]) + bq.x;
+        o[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bq.y;
+        o[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bq.z;
+        o[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bq.w;
+      }
+      if (EPI == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
       }
       if (EPI == 2) {
-        const float4* m4 = reinterpret_cast<const float4*>(mask_src + r * ldm + n0 + c0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 m = __ldg(m4 + q);
+          const float4 m = cur[q];
           o[4 * q] = m.x > 0.f ? o[4 * q] : 0.f;
           o[4 * q + 1] = m.y > 0.f ? o[4 * q + 1] : 0.f;
           o[4 * q + 2] = m.z > 0.f ? o[4 * q + 2] : 0.f;
@@ -252,12 +278,14 @@ dense_tc_kernel(const float* __restrict__ X, int64_t rows, int K, int ldx, const
       for (int q = 0; q < 4; ++q) {
         float4 w = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         if (EPI == 4) {
-          const float4 old = y4[q];
+          const float4 old = cur[q];
           w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
         }
         y4[q] = w;
       }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
