@@ -97,7 +97,13 @@ static int check_fused(const cnfot_flow_desc* f, const FlowLayout& lay) {
 
 // shapes the fused per-row kernels cover (no error message: callers fall through to the wide engine)
 static bool fused_ok(const cnfot_flow_desc* f, const FlowLayout& lay) {
-  return f->dim <= kMaxDim && (f->num_layers + 1) * f->dim <= kMaxStateFloats && find_flow_eval_kernel(lay) != nullptr;
+  if (!(f->dim <= kMaxDim && (f->num_layers + 1) * f->dim <= kMaxStateFloats && find_flow_eval_kernel(lay) != nullptr))
+    return false;
+  if (tc_available(lay)) return true;   // 16-wide networks: the warp-MMA plans stream what does not fit
+  // CUDA-core engine: even the staged plan (one conditioner at a time in shared memory) must fit a CTA
+  DeviceInfo di;
+  if (device_info(&di)) return true;    // no device: let the launch path report it
+  return (int64_t)plan_smem(lay, true, false).floats * 4 <= di.max_smem_optin;
 }
 // the wide-conditioner engine (wide.cu) takes every shape the fused kernels do not, when it can
 // (CNFOT_ENGINE=wide forces it for shapes both cover: used by the cross-engine parity tests)

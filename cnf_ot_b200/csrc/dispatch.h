@@ -24,6 +24,8 @@ inline bool tc_available(const FlowLayout& f) { return f.H == 16 && f.K == 5 && 
   X(16, 5, 1)             \
   X(16, 5, 3)             \
   X(32, 8, 2)             \
+  X(32, 5, 2)             \
+  X(64, 5, 2)             \
   X(8, 3, 1)
 
 }  // namespace cnfot

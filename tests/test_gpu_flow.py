@@ -17,7 +17,7 @@ TOL, TOL_MAX = 2e-5, 2e-4
 
 # (D, L, M, H, K, sigma): sigma keeps the flows well conditioned (|log-det| <~ 6)
 SHAPES = [(2, 2, 2, 16, 5, 0.3), (3, 3, 1, 8, 3, 0.1), (10, 2, 2, 16, 5, 0.05),
-          (4, 3, 2, 32, 8, 0.05), (2, 2, 3, 16, 5, 0.2), (2, 4, 1, 16, 5, 0.05)]
+          (4, 3, 2, 32, 8, 0.05), (2, 2, 3, 16, 5, 0.2), (2, 4, 1, 16, 5, 0.05), (3, 2, 2, 32, 5, 0.1)]
 
 
 def close(a, b, tol=TOL, tol_max=TOL_MAX):

@@ -21,6 +21,8 @@ CASES = [
   ("fp", "nongradient", dict(dim=10, sigma=0.05, B=320)),
   ("rwpo", "double_well", dict(dim=4, H=32, K=8, sigma=0.1, B=320)),
   ("ot", "obstacle", dict(M=1)), ("rwpo", "quadratic", dict(M=3)),
+  ("ot", "obstacle", dict(dim=3, H=32, sigma=0.1, B=320)), ("fp", "lorenz", dict(dim=3, H=32, sigma=0.1, B=320)),
+  ("ot", "free", dict(dim=2, H=64, sigma=0.1, B=320)),   # hidden 64 fits the fused kernels at small dim
 ]
 
 

@@ -11,6 +11,14 @@ from oracle import losses as olosses
 from util import make_cfg, make_inputs, make_params, shape_of
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _force_wide_engine(monkeypatch):
+  """Shapes both engines cover (hidden 16 / 32 with 5 bins) must run on the wide engine here."""
+  monkeypatch.setenv("CNFOT_ENGINE", "wide")
+
+
 # same float32 tolerances as the fused kernels (tests/test_gpu_flow.py, tests/test_gpu_step.py)
 TOL, TOL_MAX = 2e-5, 2e-4
 TOL_LOSS, TOL_GRAD = 2e-5, 5e-5
