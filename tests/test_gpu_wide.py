@@ -136,7 +136,9 @@ STEP_CASES = [("ot", "free", dict(dim=4, H=64, sigma=0.05)), ("ot", "obstacle", 
               ("rwpo", "quadratic", dict(dim=2, H=64, sigma=0.1)), ("rwpo", "double_well", dict(dim=3, H=64, M=1, sigma=0.03)),
               ("fp", "gradient", dict(dim=2, H=64, sigma=0.1)), ("fp", "nongradient", dict(dim=4, H=64, sigma=0.05)),
               ("fp", "lorenz", dict(dim=3, H=128, L=3, sigma=0.02)),
-              ("ot", "obstacle", dict(dim=3, H=48, M=4, sigma=0.1)), ("rwpo", "quadratic", dict(dim=2, H=32, sigma=0.1))]
+              ("ot", "obstacle", dict(dim=3, H=48, M=4, sigma=0.1)), ("rwpo", "quadratic", dict(dim=2, H=32, sigma=0.1)),
+              # two layers of BASELINE configs[4] itself: dim 32, 2 x 512 (17.4 M parameters)
+              ("ot", "free", dict(dim=32, H=512, B=256, sigma=0.005))]
 
 
 @pytest.mark.parametrize("typ,sub,kw", STEP_CASES)
@@ -160,7 +162,8 @@ def test_loss_and_gradient(typ, sub, kw):
   # pre-activations, so a few such rows are expected: 99.9 % of the gradient entries are held to TOL_GRAD, every
   # entry to 3e-4 of the largest one.
   err = (G - Gor).abs() / Gor.abs().max()
-  assert float(err.quantile(0.999)) <= TOL_GRAD, float(err.quantile(0.999))
+  q999 = float(err.kthvalue(max(1, int(0.999 * err.numel()))).values)   # (torch.quantile stops at 16 M entries)
+  assert q999 <= TOL_GRAD, q999
   assert float(err.max()) <= 3e-4, float(err.max())
 
 
