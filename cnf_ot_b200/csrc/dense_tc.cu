@@ -463,11 +463,24 @@ dense_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
+// cudaFuncSetAttribute once per (kernel instantiation, device): it costs microseconds per call, which adds up over
+// the hundreds of launches of a wide-engine step on small batches
+static cudaError_t set_smem_once(const void* kern, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
 template <int NT>
 static cudaError_t launch_wgrad(cudaStream_t s, const float* A, int lda, const float* G, int ldg, int64_t rows, int Ka,
                                 int Nb, float* dW, int ldw, const WgradMap& map, float* db) {
   auto kern = dense_wgrad_kernel<NT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
+  static bool done[64] = {};
+  cudaError_t e = set_smem_once((const void*)kern, DenseSmem<NT>::kBytes, done);
   if (e != cudaSuccess) return e;
   const int mt = (Ka + 127) / 128, nt = (Nb + NT - 1) / NT;
   const int64_t chunks = (rows + 15) / 16;
@@ -496,7 +509,8 @@ template <int NT, int EPI>
 static cudaError_t launch_dense(cudaStream_t s, const float* X, int64_t rows, int K, int ldx, const float* Bt,
                                 int N, const float* bias, const float* mask_src, int ldm, float* Y, int ldy) {
   auto kern = dense_tc_kernel<NT, EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseSmem<NT>::kBytes);
+  static bool done[64] = {};
+  cudaError_t e = set_smem_once((const void*)kern, DenseSmem<NT>::kBytes, done);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)(((rows + 127) / 128) * (N / NT)));
   // CNFOT_DENSE_ACC2=1: separate accumulator for the small 3xTF32 terms (needs 2 NT <= 512 TMEM columns)

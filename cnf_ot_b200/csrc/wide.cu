@@ -726,6 +726,109 @@ __global__ void wide_energy_out_kernel(const double* __restrict__ slots, double*
   if (threadIdx.x == 0) out[0] = slots[kSlotKinetic];
 }
 
+// ---- batched passes: several flow passes that start from the same rows share ONE chunk ---------------------------
+// (rows [j n, (j + 1) n) of the chunk = pass j).  Fewer, larger launches: a small-batch step is launch-bound.
+struct MultiSrc {
+  const float* src[3];
+  float t[3];
+};
+// state 0 = [src_j rows | t_j | 0] for j < reps, states 1..L = [0 | t_j | 0]
+__global__ void __launch_bounds__(kThreads)
+wide_init_multi_kernel(MultiSrc ms, int64_t n, int reps, int D, int Kx, int L, int64_t state_stride, float* __restrict__ S) {
+  const int64_t per = n * reps * Kx;
+  const int64_t total = per * (L + 1);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e / per);
+    const int64_t q = e - (int64_t)s * per;
+    const int64_t row = q / Kx;
+    const int c = (int)(q - row * Kx);
+    const int j = (int)(row / n);
+    const int64_t r = row - (int64_t)j * n;
+    float v = 0.f;
+    if (c < D) v = s == 0 ? ms.src[j][r * D + c] : 0.f;
+    else if (c == D) v = ms.t[j];
+    S[(int64_t)s * state_stride + q] = v;
+  }
+}
+// the 2 D shifted copies of the rows R3 (n x Kx): copy j = 2 i + side is R3 + (side ? -shift : +shift) e_i, all at time t
+__global__ void __launch_bounds__(kThreads)
+wide_init_shift_kernel(const float* __restrict__ R3, int64_t n, int D, int Kx, int L, int64_t state_stride, float t, float shift,
+                       float* __restrict__ S) {
+  const int64_t per = n * 2 * D * Kx;
+  const int64_t total = per * (L + 1);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e / per);
+    const int64_t q = e - (int64_t)s * per;
+    const int64_t row = q / Kx;
+    const int c = (int)(q - row * Kx);
+    const int j = (int)(row / n);
+    const int64_t r = row - (int64_t)j * n;
+    float v = 0.f;
+    if (c < D) v = s == 0 ? R3[r * Kx + c] + (c == (j >> 1) ? ((j & 1) ? -shift : shift) : 0.f) : 0.f;
+    else if (c == D) v = t;
+    S[(int64_t)s * state_stride + q] = v;
+  }
+}
+// All coordinates of the score-kinetic term at once (wide_score_head_kernel for every i): Z / LD hold the 2 D n
+// latent outputs / log-dets of the shifted log-prob passes; seeds Gs (2 D n rows), GLs, the adjoints of r1, r2
+// (G1, G2; every column written), zeroes G3 and fills GRES.
+__global__ void __launch_bounds__(kThreads)
+wide_score_head_all_kernel(const float* __restrict__ R1, const float* __restrict__ R2, const float* __restrict__ R3,
+                           const float* __restrict__ Z, const float* __restrict__ LDs, int64_t n, int D, int Kx,
+                           StepConsts<float> pc, float* __restrict__ G1, float* __restrict__ G2, float* __restrict__ G3,
+                           float* __restrict__ Gs, float* __restrict__ GLs, float* __restrict__ GRES,
+                           double* __restrict__ slot_kin) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double lk = 0.0;
+  if (r < n) {
+    float truth[kMaxWideDim];
+    for (int c = 0; c < D; ++c) truth[c] = 0.f;
+    if (pc.type == kFP) {
+      float r3[kMaxWideDim];
+      for (int c = 0; c < D; ++c) r3[c] = R3[r * Kx + c];
+      drift_value<float>(pc.drift, pc.a, r3, D, truth);
+    }
+    for (int c = D; c < Kx; ++c) { G1[r * Kx + c] = 0.f; G2[r * Kx + c] = 0.f; GRES[r * Kx + c] = 0.f; }
+    for (int c = 0; c < Kx; ++c) G3[r * Kx + c] = 0.f;
+    for (int i = 0; i < D; ++i) {
+      const int64_t rp = (int64_t)(2 * i) * n + r, rm = rp + n;
+      float zp2 = 0.f, zm2 = 0.f;
+      for (int c = 0; c < D; ++c) {
+        zp2 += Z[rp * Kx + c] * Z[rp * Kx + c];
+        zm2 += Z[rm * Kx + c] * Z[rm * Kx + c];
+      }
+      const float score = ((-0.5f * zp2 + LDs[rp]) - (-0.5f * zm2 + LDs[rm])) / pc.dx;
+      const float resid = (R2[r * Kx + i] - R1[r * Kx + i]) / pc.dt + pc.kappa * score - truth[i];
+      lk += (double)pc.w_kin * (double)resid * (double)resid;
+      const float gres = 2.f * pc.w_kin * resid;
+      GRES[r * Kx + i] = gres;
+      G2[r * Kx + i] = gres / pc.dt;
+      G1[r * Kx + i] = -gres / pc.dt;
+      const float glp = gres * pc.kappa / pc.dx;
+      for (int c = 0; c < Kx; ++c) {
+        Gs[rp * Kx + c] = c < D ? -glp * Z[rp * Kx + c] : 0.f;
+        Gs[rm * Kx + c] = c < D ? glp * Z[rm * Kx + c] : 0.f;
+      }
+      GLs[rp] = glp;
+      GLs[rm] = -glp;
+    }
+  }
+  block_add(lk, slot_kin);
+}
+// G3[r][c] += sum_j Gs[j n + r][c], j < reps (the input adjoints of the shifted passes are adjoints of r3)
+__global__ void __launch_bounds__(kThreads)
+wide_fold_kernel(float* __restrict__ G3, const float* __restrict__ Gs, int64_t n, int reps, int Kx) {
+  const int64_t count = n * Kx;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    float acc = G3[e];
+    for (int j = 0; j < reps; ++j) acc += Gs[(int64_t)j * count + e];
+    G3[e] = acc;
+  }
+}
+__global__ void __launch_bounds__(kThreads) wide_fill_kernel(float* __restrict__ p, int64_t count, float v) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+
 // out slots: 0 total, 1 fit(0), 2 fit(T), 3 potential, 4 kinetic, 5-7 zero
 __global__ void wide_finalize_kernel(const double* __restrict__ slots, float* __restrict__ out_slots) {
   if (threadIdx.x == 0) {
@@ -791,6 +894,18 @@ wide_vjp_out_kernel(const float* __restrict__ G, const float* __restrict__ g_log
     if (add_base && dir == 0) g -= gl * Zin[r * Kx + c];
     g_in[r * D + c] = g;
   }
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a (kernel, device) needs more than it was given before:
+// the call costs microseconds, a small-batch step makes hundreds of launches
+cudaError_t set_smem_max(const void* kern, size_t bytes, int (&cur)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && (int)bytes <= cur[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) cur[dev] = (int)bytes;
+  return e;
 }
 
 // ---- the engine --------------------------------------------------------------------------------------------
@@ -862,9 +977,10 @@ struct WideEngine {
     int64_t nb = (n + 127) / 128;   // 8 warps x 16 rows per block pass
     if (nb > 148 * 4) nb = 148 * 4;
     const size_t smem = (size_t)H * (Pp + 4) * sizeof(float);
-    if (smem > 48 * 1024)   // per device and cheap: no cached flag (one process may drive several GPUs)
-      check(cudaFuncSetAttribute(wide_out_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "cudaFuncSetAttribute");
+    if (smem > 48 * 1024) {
+      static int cur[64] = {};
+      check(set_smem_max((const void*)wide_out_fwd_kernel<16>, smem, cur), "cudaFuncSetAttribute");
+    }
     if (!ok()) return;
     wide_out_fwd_kernel<16><<<(unsigned)nb, kThreads, smem, s>>>(a_last, w, bias, n, H, theta);
     check_launch("wide_out_fwd_kernel launch");
@@ -902,8 +1018,8 @@ struct WideEngine {
       int64_t ny = (n + 63) / 64;   // >= 64 rows per block, two blocks per SM (the ring takes 66 KB)
       if (ny * hb > 296) ny = 296 / hb;
       if (ny < 1) ny = 1;
-      check(cudaFuncSetAttribute(wide_out_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out_bwd_smem<16>()),
-            "cudaFuncSetAttribute");
+      static int cur[64] = {};
+      check(set_smem_max((const void*)wide_out_bwd_kernel<16>, out_bwd_smem<16>(), cur), "cudaFuncSetAttribute");
       if (!ok()) return;
       wide_out_bwd_kernel<16><<<dim3((unsigned)hb, (unsigned)ny), kOutBwdThreads, out_bwd_smem<16>(), s>>>(
           a_last, GTheta, W + off_out, n, H, gc, grad + off_out, grad + off_out + (int64_t)H * Pp);
@@ -927,11 +1043,14 @@ struct WideEngine {
     const size_t ring_bytes = in_wgrad_smem(Kx);
     switch (kv4) {
 #define CNFOT_IN_WGRAD(Q)                                                                                              \
-  case Q:                                                                                                              \
-    cudaFuncSetAttribute(wide_in_wgrad_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);       \
+  case Q: {                                                                                                            \
+    static int cur[64] = {};                                                                                           \
+    check(set_smem_max((const void*)wide_in_wgrad_kernel<Q>, ring_bytes, cur), "cudaFuncSetAttribute");                \
+    if (!ok()) return;                                                                                                 \
     wide_in_wgrad_kernel<Q><<<grid, kThreads, ring_bytes, s>>>(cst, Kx, gc, n, H, wd.D, d, layer & 1, grad + off_w0,   \
                                                                grad + off_b0);                                         \
-    break;
+    break;                                                                                                             \
+  }
       CNFOT_IN_WGRAD(1) CNFOT_IN_WGRAD(2) CNFOT_IN_WGRAD(3) CNFOT_IN_WGRAD(4) CNFOT_IN_WGRAD(5) CNFOT_IN_WGRAD(6)
       CNFOT_IN_WGRAD(7) CNFOT_IN_WGRAD(8) CNFOT_IN_WGRAD(9) CNFOT_IN_WGRAD(10) CNFOT_IN_WGRAD(11) CNFOT_IN_WGRAD(12)
       CNFOT_IN_WGRAD(13) CNFOT_IN_WGRAD(14) CNFOT_IN_WGRAD(15) CNFOT_IN_WGRAD(16)
@@ -974,6 +1093,29 @@ struct WideEngine {
     wide_init_kernel<<<(unsigned)b, kThreads, 0, s>>>(rows, ld_rows ? ld_rows : wd.D, n, wd.D, wd.Kx, wd.L, state_stride(), t, cond,
                                                       cond_stride, shift_col, shift, S[p]);
     check_launch("wide_init_kernel launch");
+  }
+
+  static unsigned grid_for(int64_t count) {
+    int64_t b = (count + kThreads - 1) / kThreads;
+    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+  }
+  // pass p = `reps` passes over the same n rows (sources / times per pass in ms), stacked in one chunk
+  void init_multi(int p, const MultiSrc& ms, int64_t n, int reps) {
+    if (!ok()) return;
+    wide_init_multi_kernel<<<grid_for(n * reps * wd.Kx * (wd.L + 1)), kThreads, 0, s>>>(ms, n, reps, wd.D, wd.Kx, wd.L,
+                                                                                        state_stride(), S[p]);
+    check_launch("wide_init_multi_kernel launch");
+  }
+  void init_shift(int p, const float* R3, int64_t n, float t, float shift) {
+    if (!ok()) return;
+    wide_init_shift_kernel<<<grid_for(n * 2 * wd.D * wd.Kx * (wd.L + 1)), kThreads, 0, s>>>(R3, n, wd.D, wd.Kx, wd.L,
+                                                                                            state_stride(), t, shift, S[p]);
+    check_launch("wide_init_shift_kernel launch");
+  }
+  void fill(float* p, int64_t count, float v) {
+    if (!ok()) return;
+    wide_fill_kernel<<<grid_for(count), kThreads, 0, s>>>(p, count, v);
+    check_launch("wide_fill_kernel launch");
   }
 
   bool stashing(int p) const { return p == 0 && stashA != nullptr; }
@@ -1155,16 +1297,96 @@ void kinetic_chunk(WideEngine& e, const StepConsts<float>& pc, const float* rows
   if (obstacle || with_score) e.flow_bwd<K>(0, 2, n, 0.f, nullptr);
 }
 
+// CNFOT_WIDE_BATCH=0 keeps one flow pass per chunk (the path large batches take anyway)
+bool batching_enabled() {
+  const char* ev = getenv("CNFOT_WIDE_BATCH");
+  return !(ev && ev[0] == '0');
+}
+
+// kinetic_chunk with the passes of a row stacked in shared chunks: [r(t-dt/2); r(t+dt/2); r(t)] is ONE sample-
+// direction pass of 2-3 n rows and the 2 D shifted log-prob passes of the score are ONE pass of 2 D n rows.
+// Requires 3 n <= R and (score) 2 D n <= R.
+template <int K>
+void kinetic_chunk_batched(WideEngine& e, const StepConsts<float>& pc, const float* rows, int64_t n, float t) {
+  const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  const bool with_score = pc.type != kOT;
+  const bool obstacle = pc.potential == kPotObstacle && !with_score;
+  const int reps = (obstacle || with_score) ? 3 : 2;
+  MultiSrc ms;
+  for (int j = 0; j < 3; ++j) ms.src[j] = rows;
+  ms.t[0] = t - pc.dt / 2.f; ms.t[1] = t + pc.dt / 2.f; ms.t[2] = t;
+  e.init_multi(0, ms, n, reps);
+  e.flow_pass<K>(0, 0, n * reps);
+  if (!e.ok()) return;
+  const int64_t blk = n * Kx;
+  float* r1 = e.state(0, L);
+  float* g1 = e.G[0];
+  if (!with_score) {
+    wide_kinetic_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+        r1, r1 + blk, obstacle ? r1 + 2 * blk : nullptr, n, D, Kx, pc.dt, pc.w_kin, pc.w_pot, g1, g1 + blk, g1 + 2 * blk,
+        e.slots + kSlotKinetic, e.slots + kSlotPotential);
+    e.check_launch("wide_kinetic_head_kernel launch");
+  } else {
+    e.init_shift(1, r1 + 2 * blk, n, t, pc.dx / 2.f);
+    e.flow_pass<K>(1, 1, n * 2 * D);
+    if (!e.ok()) return;
+    wide_score_head_all_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+        r1, r1 + blk, r1 + 2 * blk, e.state(1, L), e.LD[1], n, D, Kx, pc, g1, g1 + blk, g1 + 2 * blk, e.G[1], e.GL, e.GRES,
+        e.slots + kSlotKinetic);
+    e.check_launch("wide_score_head_all_kernel launch");
+    e.flow_bwd<K>(1, 1, n * 2 * D, 0.f, e.GL);
+    if (!e.ok()) return;
+    wide_fold_kernel<<<WideEngine::grid_for(blk), kThreads, 0, e.s>>>(g1 + 2 * blk, e.G[1], n, 2 * D, Kx);
+    e.check_launch("wide_fold_kernel launch");
+    if (pc.type == kFP) {
+      wide_drift_pullback_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(r1 + 2 * blk, e.GRES, n, D, Kx, pc, g1 + 2 * blk);
+      e.check_launch("wide_drift_pullback_kernel launch");
+    }
+  }
+  e.flow_bwd<K>(0, 0, n * reps, 0.f, nullptr);
+}
+
 template <int K>
 void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent, const float* latent_sub, const float* src,
               const float* tgt, const float* t_batch_host, int n_t, int64_t rows_B, int64_t rows_b) {
   const int D = e.wd.D, Kx = e.wd.Kx, L = e.wd.L;
+  const bool batch = batching_enabled();
   // kinetic terms: the b-row sub-batch at every sampled time
-  for (int it = 0; it < n_t && e.ok(); ++it)
-    for (int64_t r0 = 0; r0 < rows_b && e.ok(); r0 += e.R)
-      kinetic_chunk<K>(e, pc, latent_sub + r0 * D, rows_b - r0 < e.R ? rows_b - r0 : e.R, t_batch_host[it]);
+  const bool with_score = pc.type != kOT;
+  for (int it = 0; it < n_t && e.ok(); ++it) {
+    // rows per chunk such that the stacked passes fit: 3 n <= R and, with the score, 2 D n <= R
+    int64_t cap = e.R / (with_score && 2 * D > 3 ? 2 * D : 3);
+    const bool stacked = batch && cap >= 1 && rows_b <= cap * 4;   // large sub-batches: plain chunks fill the GPU anyway
+    if (!stacked) cap = e.R;
+    for (int64_t r0 = 0; r0 < rows_b && e.ok(); r0 += cap) {
+      const int64_t n = rows_b - r0 < cap ? rows_b - r0 : cap;
+      if (stacked) kinetic_chunk_batched<K>(e, pc, latent_sub + r0 * D, n, t_batch_host[it]);
+      else kinetic_chunk<K>(e, pc, latent_sub + r0 * D, n, t_batch_host[it]);
+    }
+  }
+  const int64_t half = e.R / 2;
   if (pc.type == kOT) {
     // density-fit terms: -lambda mean log p(data | t) at t = 0 (source) and t = T (target)
+    if (batch && half >= 1) {
+      // source rows at t = 0 and the same number of target rows at t = T share a chunk
+      for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += half) {
+        const int64_t n = rows_B - r0 < half ? rows_B - r0 : half;
+        MultiSrc ms;
+        ms.src[0] = src + r0 * D; ms.src[1] = tgt + r0 * D; ms.src[2] = nullptr;
+        ms.t[0] = 0.f; ms.t[1] = pc.horizon; ms.t[2] = 0.f;
+        e.init_multi(0, ms, n, 2);
+        e.flow_pass<K>(1, 0, 2 * n, true);
+        if (!e.ok()) break;
+        for (int side = 0; side < 2; ++side) {
+          wide_nll_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+              e.state(0, L) + side * n * Kx, e.LD[0] + side * n, n, D, Kx, pc.w_fit, e.G[0] + side * n * Kx,
+              e.slots + (side == 0 ? kSlotFit0 : kSlotFitT));
+          e.check_launch("wide_nll_head_kernel launch");
+        }
+        e.flow_bwd<K>(1, 0, 2 * n, -pc.w_fit, nullptr, true);
+      }
+      return;
+    }
     for (int side = 0; side < 2 && e.ok(); ++side) {
       const float* data = side == 0 ? src : tgt;
       const float t = side == 0 ? 0.f : pc.horizon;
@@ -1184,6 +1406,29 @@ void run_step(WideEngine& e, const StepConsts<float>& pc, const float* latent, c
   }
   // rwpo / fp: reverse-KL fit at t = 0 on the B latent rows; rwpo adds the terminal potential at t = T
   const int n_seg = pc.type == kRWPO ? 2 : 1;
+  if (batch && n_seg == 2 && half >= 1) {
+    // the fit rows at t = 0 and the same latent rows at t = T (potential) share a chunk; the log-det adjoint is
+    // -w_fit on the first half and 0 on the second: per-row
+    for (int64_t r0 = 0; r0 < rows_B && e.ok(); r0 += half) {
+      const int64_t n = rows_B - r0 < half ? rows_B - r0 : half;
+      MultiSrc ms;
+      ms.src[0] = latent + r0 * D; ms.src[1] = latent + r0 * D; ms.src[2] = nullptr;
+      ms.t[0] = 0.f; ms.t[1] = pc.horizon; ms.t[2] = 0.f;
+      e.init_multi(0, ms, n, 2);
+      e.flow_pass<K>(0, 0, 2 * n, true);
+      if (!e.ok()) break;
+      for (int seg = 0; seg < 2; ++seg) {
+        wide_sample_head_kernel<<<WideEngine::blocks_for(n), kThreads, 0, e.s>>>(
+            e.state(0, 0) + seg * n * Kx, e.state(0, L) + seg * n * Kx, e.LD[0] + seg * n, n, D, Kx, ms.t[seg], seg == 0,
+            seg == 1, pc, e.G[0] + seg * n * Kx, e.slots + kSlotFit0, e.slots + kSlotPotential);
+        e.check_launch("wide_sample_head_kernel launch");
+      }
+      e.fill(e.GL, n, -pc.w_fit);
+      e.fill(e.GL + n, n, 0.f);
+      e.flow_bwd<K>(0, 0, 2 * n, 0.f, e.GL, true);
+    }
+    return;
+  }
   for (int seg = 0; seg < n_seg && e.ok(); ++seg) {
     const int do_fit = seg == 0, do_pot = seg == 1;
     const float t = seg == 0 ? 0.f : pc.horizon;

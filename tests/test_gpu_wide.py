@@ -264,3 +264,18 @@ def test_host_entry_on_a_wide_flow():
     ops.mfc_step_host(shape, ops.problem_desc(cfg), mk(W), None, mk(inputs["latent"][:b]), mk(inputs["src"]),
                       mk(inputs["tgt"]), inputs["t_batch"].tolist(), 100.0, 1024, b, out)
     assert float((out.double() - dev).abs().max() / dev.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("typ,sub,kw", [("ot", "obstacle", dict(dim=3, H=64)), ("rwpo", "double_well", dict(dim=3, H=64)),
+                                        ("fp", "nongradient", dict(dim=4, H=64))])
+def test_stacked_passes_match_one_pass_per_chunk(typ, sub, kw, monkeypatch):
+  """Small batches stack the passes that share rows into one chunk (fewer launches); CNFOT_WIDE_BATCH=0 runs one
+  pass per chunk (what large batches do).  Both orders of the same arithmetic agree to float32 rounding."""
+  cfg = make_cfg(typ, sub, Tn=2, lam=100.0, B=1024, **kw)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, 0.05)
+  inputs = make_inputs(cfg)
+  stacked = run_step(cfg, shape, params, inputs, 100.0)
+  monkeypatch.setenv("CNFOT_WIDE_BATCH", "0")
+  plain = run_step(cfg, shape, params, inputs, 100.0)
+  assert float((stacked - plain).abs().max() / plain.abs().max()) < 5e-6
