@@ -1,0 +1,163 @@
+"""Generate tests/golden/ref_*.npz by running the REFERENCE'S OWN SOURCE FILES from /root/reference.
+
+  python tests/golden/make_reference_golden.py        (needs /root/reference; run in the build container only)
+
+PROVENANCE: `cnf_ot/models/{flows,autoregressive,conditional}.py` and `cnf_ot/mfc/applications.py` are imported
+unmodified from /root/reference and executed on the torch-float64 stand-ins of `tests/golden/refshim.py` (JAX, haiku and
+distrax cannot be installed here).  The model is built exactly as `cnf_ot/mfc/solvers.py:41-54,58-88` builds it
+(`hk.without_apply_rng(hk.multi_transform(RQSFlow(...)))`, `partial(applications.<type>_loss_fn, model, ...)`), the
+loss is the reference's loss function called with `(params, rng, _lambda, batch_size)` as `update` calls it
+(`solvers.py:94`) and the gradient is autograd through the reference's own code.  The only restated piece on that
+path is `distrax.RationalQuadraticSpline` (third-party, not vendored: delegates to oracle/rqs.py).
+These fixtures pin oracle/flow.py and oracle/losses.py (tests/test_reference_golden.py, CPU, 1e-10) and the CUDA path
+(same file, -m gpu, float32 tolerances) to the reference's code, not to a restatement of it.
+"""
+import os
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+import refshim  # noqa: E402
+
+refshim.install()
+sys.path.insert(0, "/root/reference")
+
+import haiku as hk  # noqa: E402  (stand-in)
+import jax  # noqa: E402  (stand-in)
+import jax.numpy as jnp  # noqa: E402
+from cnf_ot.mfc import applications  # noqa: E402  (the reference)
+from cnf_ot.models.flows import RQSFlow  # noqa: E402  (the reference)
+
+from cnf_ot_b200.layout import pack  # noqa: E402
+from util import make_cfg, make_params, shape_of  # noqa: E402
+
+f32 = lambda t: t.to(torch.float32).to(torch.float64)
+CENTRES = torch.tensor([[0.0, 5.0], [5.0, 0.0], [0.0, -5.0], [-5.0, 0.0], [3.0, 4.0], [3.0, -4.0], [-3.0, -4.0],
+                        [-3.0, 4.0]], dtype=torch.float64)
+
+
+def build_model(cfg):
+  """solvers.py:41-48."""
+  c = cfg["cnf"]
+  model = RQSFlow(event_shape=(cfg["general"]["dim"], ), num_layers=c["flow_num_layers"],
+                  hidden_sizes=[c["hidden_size"]] * c["mlp_num_layers"], num_bins=c["num_bins"], periodized=False)
+  return hk.without_apply_rng(hk.multi_transform(model))
+
+
+def check_tree(model, cfg, params):
+  """model.init (solvers.py:54) creates exactly the leaves (names, shapes) of our parameter tree."""
+  dim = cfg["general"]["dim"]
+  init = model.init(jax.random.PRNGKey(0), jnp.zeros((1, dim)), jnp.zeros((1, )))
+  assert set(init) == set(params), set(init) ^ set(params)
+  for mod in init:
+    assert set(init[mod]) == set(params[mod]), mod
+    for k in init[mod]:
+      assert tuple(init[mod][k].shape) == tuple(params[mod][k].shape), (mod, k)
+  assert init["~"]["first"].dtype == torch.float32 and float(init["~"]["first"].abs().max()) == 0.0
+  return sum(v.numel() for lv in init.values() for v in lv.values())
+
+
+def loss_fn_of(cfg, model):
+  """solvers.py:58-88."""
+  g = cfg["general"]
+  dim, dt, dx, tbs = g["dim"], g["dt"], g["dx"], g["t_batch_size"]
+  if g["type"] == "rwpo":
+    r = cfg["rwpo"]
+    return partial(applications.rwpo_loss_fn, model, dim, r["T"], r["beta"], dt, dx, tbs, r["pot_type"], r["a"]), r["T"]
+  if g["type"] == "fp":
+    f = cfg["fp"]
+    return partial(applications.fp_loss_fn, model, dim, f["T"], f["a"], f["sigma"], dt, dx, tbs,
+                   f["velocity_field_type"]), f["T"]
+  return partial(applications.ot_loss_fn, model, dim, 1, dt, tbs, cfg["ot"]["subtype"]), 1
+
+
+def grad_tree(params):
+  return {m: {k: v.clone().requires_grad_(True) for k, v in lv.items()} for m, lv in params.items()}
+
+
+def step_case(typ, sub, B, lam, Tn, seed, sigma=0.3, **kw):
+  cfg = make_cfg(typ, sub, Tn=Tn, lam=lam, B=B, **kw)
+  shape = shape_of(cfg)
+  D = cfg["general"]["dim"]
+  _, params = make_params(cfg, sigma)
+  model = build_model(cfg)
+  n_params = check_tree(model, cfg, params)
+  g = torch.Generator().manual_seed(seed)
+  z = f32(torch.randn(B, D, generator=g, dtype=torch.float64))
+  u = f32(torch.rand(Tn, generator=g, dtype=torch.float64))
+  idx = torch.randint(0, 8, (B, ), generator=g)
+  refshim.Draws.set(normal=z, uniform=u, choice=idx)
+  loss_fn, T = loss_fn_of(cfg, model)
+  p = grad_tree(params)
+  loss = loss_fn(p, jax.random.PRNGKey(cfg["general"]["seed"]), lam, B)
+  loss.backward()
+  grads = {m: {k: (v.grad if v.grad is not None else torch.zeros_like(v)).double() for k, v in lv.items()}
+           for m, lv in p.items()}
+  out = {"shape": np.array([D, shape.num_layers, shape.mlp_layers, shape.hidden, shape.num_bins]),
+         "blob": pack(shape, params, torch.float64), "latent": z, "t_batch": u * T, "lam": np.array(lam),
+         "loss": loss.detach(), "grad": pack(shape, grads, torch.float64), "n_params": np.array(n_params)}
+  if typ == "ot":   # kl_loss_fn's draws (applications.py:34-82): the mixture noise and the target share the key
+    out["src"], out["tgt"] = z + CENTRES[idx], z.clone()
+  else:
+    out["src"], out["tgt"] = torch.zeros(0, D, dtype=torch.float64), torch.zeros(0, D, dtype=torch.float64)
+  print("  draws:", sorted(set(refshim.Draws.log)))
+  return out
+
+
+def flow_case(D, L, M, H, K, sigma, n, seed):
+  """model.apply.{sample_and_log_prob, log_prob, forward, inverse} (flows.py:213-224)."""
+  cfg = make_cfg(dim=D, L=L, M=M, H=H, K=K)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, sigma)
+  model = build_model(cfg)
+  check_tree(model, cfg, params)
+  g = torch.Generator().manual_seed(seed)
+  z = f32(torch.randn(n, D, generator=g, dtype=torch.float64))
+  t = f32(torch.rand(n, generator=g, dtype=torch.float64))
+  t0 = float(t[0])
+  refshim.Draws.set(normal=z)
+  key = jax.random.PRNGKey(0)
+  with torch.no_grad():
+    y, lp = model.apply.sample_and_log_prob(params, cond=t.reshape(-1, 1), seed=key, sample_shape=(n, ))
+    ys = model.apply.sample(params, cond=t.reshape(-1, 1), seed=key, sample_shape=(n, ))
+    x = f32(z * 1.5)
+    c0 = jnp.ones((1, )) * t0
+    out = {"shape": np.array([D, L, M, H, K]), "blob": pack(shape, params, torch.float64), "latent": z, "t": t,
+           "sample_y": y, "sample_log_prob": lp, "x": x, "t0": np.array(t0),
+           "log_prob_x": model.apply.log_prob(params, x, cond=c0), "forward_x": model.apply.forward(params, x, c0),
+           "inverse_x": model.apply.inverse(params, x, c0)}
+  assert torch.equal(y, ys)
+  return out
+
+
+def save(name, d):
+  out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+  print(name, "loss" in out and float(out["loss"]), {k: v.shape for k, v in out.items()})
+
+
+# name -> (type, subtype, B, lambda, t_batch_size, seed, overrides); the reference's mixture source and its
+# nongradient / gradient drifts exist for dim 2 only, lorenz for dim 3
+STEP_CASES = {
+  "ref_step_ot_free_d2": ("ot", "free", 256, 500.0, 2, 101, {}),
+  "ref_step_ot_obstacle_d2": ("ot", "obstacle", 256, 500.0, 2, 102, {}),
+  "ref_step_rwpo_double_well_d2": ("rwpo", "double_well", 256, 500.0, 2, 103, {}),
+  "ref_step_rwpo_quadratic_d3": ("rwpo", "quadratic", 128, 100.0, 1, 104, dict(dim=3, sigma=0.1)),
+  "ref_step_fp_gradient_d2": ("fp", "gradient", 256, 500.0, 2, 105, {}),
+  "ref_step_fp_nongradient_d2": ("fp", "nongradient", 256, 100.0, 1, 106, {}),
+  "ref_step_fp_lorenz_d3": ("fp", "lorenz", 128, 100.0, 1, 107, dict(dim=3, sigma=0.1)),
+}
+
+if __name__ == "__main__":
+  save("ref_flow_d2", flow_case(2, 2, 2, 16, 5, 0.3, 256, 21))
+  save("ref_flow_d3_h8", flow_case(3, 3, 1, 8, 3, 0.1, 128, 22))
+  for name, (typ, sub, B, lam, Tn, seed, kw) in STEP_CASES.items():
+    save(name, step_case(typ, sub, B, lam, Tn, seed, **dict(kw)))
