@@ -138,6 +138,27 @@ def flow_case(D, L, M, H, K, sigma, n, seed):
   return out
 
 
+def energy_case(D, sigma, n, t_size, beta, T, seed):
+  """utils.calc_kinetic_energy / calc_score_kinetic_energy (cnf_ot/utils.py:311-389) as solvers.py:138-160 calls them."""
+  refshim.stub_plotting()
+  from cnf_ot import utils as ref_utils  # the reference
+  cfg = make_cfg(dim=D)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, sigma)
+  model = build_model(cfg)
+  g = torch.Generator().manual_seed(seed)
+  z = f32(torch.randn(n, D, generator=g, dtype=torch.float64))
+  refshim.Draws.set(normal=z)
+  with torch.no_grad():
+    e_kin = ref_utils.calc_kinetic_energy(model.apply.sample, params, jax.random.PRNGKey(1), batch_size=n, t_size=t_size,
+                                          dim=D)
+    e_score = ref_utils.calc_score_kinetic_energy(model.apply.sample, model.apply.log_prob, params, T=T, beta=beta, dim=D,
+                                                  rng=jax.random.PRNGKey(1), batch_size=n, t_size=t_size)
+  return {"shape": np.array([D, shape.num_layers, shape.mlp_layers, shape.hidden, shape.num_bins]),
+          "blob": pack(shape, params, torch.float64), "latent": z, "t_size": np.array(t_size), "T": np.array(T),
+          "beta": np.array(beta), "e_kin": e_kin, "e_score": e_score}
+
+
 def save(name, d):
   out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
@@ -159,5 +180,7 @@ STEP_CASES = {
 if __name__ == "__main__":
   save("ref_flow_d2", flow_case(2, 2, 2, 16, 5, 0.3, 256, 21))
   save("ref_flow_d3_h8", flow_case(3, 3, 1, 8, 3, 0.1, 128, 22))
+  save("ref_energy_d2", energy_case(2, 0.3, 64, 4, 2.0, 2.0, 23))
+  save("ref_energy_d3", energy_case(3, 0.1, 32, 3, 4.0, 1.0, 24))
   for name, (typ, sub, B, lam, Tn, seed, kw) in STEP_CASES.items():
     save(name, step_case(typ, sub, B, lam, Tn, seed, **dict(kw)))

@@ -35,9 +35,10 @@ F64 = torch.float64
 def _as(v, dtype=None):
   if isinstance(v, torch.Tensor):
     return v if dtype is None else v.to(dtype)
-  if isinstance(v, np.ndarray):
-    v = np.ascontiguousarray(v)
-  t = torch.as_tensor(v)
+  if isinstance(v, (list, tuple)) and any(isinstance(e, torch.Tensor) for e in v):
+    t = torch.stack([_as(e) for e in v])
+  else:   # through numpy: python floats become float64 (torch.as_tensor(0.005) would round to float32 first)
+    t = torch.from_numpy(np.ascontiguousarray(np.asarray(v)))
   if dtype is not None:
     return t.to(dtype)
   return t.to(F64) if t.is_floating_point() else t
@@ -124,7 +125,8 @@ def _build_jax():
   jnp.exp, jnp.log, jnp.sin, jnp.cos = torch.exp, torch.log, torch.sin, torch.cos
   jnp.subtract = lambda a, b: a - b
   jnp.dot = lambda a, b: _as(a).to(F64) @ _as(b).to(F64)
-  jnp.linspace = lambda a, b, n: torch.linspace(a, b, n, dtype=F64)
+  # numpy, so that `np.ones(...) * (t - dt / 2)` (cnf_ot/utils.py:329) works as it does with a jax scalar
+  jnp.linspace = lambda a, b, n: np.linspace(a, b, n)
   jnp.broadcast_to = lambda x, shape: torch.broadcast_to(_as(x), _shape(shape))
   jnp.concatenate = lambda xs, axis=0: torch.cat([_as(x).to(F64) for x in xs], dim=axis)
   jnp.concat = jnp.concatenate
@@ -491,3 +493,15 @@ def install():
     def __class_getitem__(cls, item):
       return torch.Tensor
   jt.Float = jt.Int = jt.Bool = _Sub
+
+
+def stub_plotting():
+  """`cnf_ot/utils.py` imports matplotlib at module level for its plotting helpers (not installed here, not needed by
+  the two energy functions)."""
+  if "matplotlib" in sys.modules:
+    return
+  mpl = _mod("matplotlib")
+  for sub in ("colors", "cm", "pyplot"):
+    _mod("matplotlib." + sub)
+  mpl.colors.LinearSegmentedColormap = object
+  mpl.pyplot.quiver = None   # a bare `plt.quiver` expression statement sits in calc_score_kinetic_energy (utils.py:386)

@@ -6,7 +6,7 @@ executed on torch-float64 stand-ins for jax / haiku / distrax, tests/golden/refs
 `solvers.py:41-54`, loss functions as `solvers.py:58-88`, called as `update` calls them (`solvers.py:94`).
 
 CPU: the oracle (oracle/flow.py, oracle/losses.py) reproduces the reference's samples, log-probs, losses and
-gradients to float64 rounding (values 1e-10, loss 1e-9, gradient 1e-8; the float32 `first` leaf 2e-6) -- this pins the restatement to the reference's code.
+gradients to float64 rounding (values 1e-10, losses / gradients / energies 1e-12; the float32 `first` leaf 2e-6) -- this pins the restatement to the reference's code.
 GPU (-m gpu): the CUDA path through the C ABI matches them at the float32 tolerances of the other parity tests
 (values: 99 % within 2e-5, all within 2e-4; loss 2e-5 relative; gradient 5e-5 of the largest entry)."""
 import os
@@ -32,6 +32,7 @@ STEPS = {
   "ref_step_fp_lorenz_d3": ("fp", "lorenz", dict(dim=3)),
 }
 FLOWS = ["ref_flow_d2", "ref_flow_d3_h8"]
+ENERGIES = ["ref_energy_d2", "ref_energy_d3"]
 
 
 def load(name):
@@ -93,11 +94,26 @@ def test_oracle_step_matches_reference(name):
   cfg = step_cfg(name, g)
   inputs = {k: g[k] for k in ("latent", "src", "tgt", "t_batch")}
   loss, grads = olosses.value_and_grad(cfg, spec, params, inputs)
-  # the finite differences (1 / dt, 1 / dx = 100) amplify the float64 rounding of two different operation orders
-  assert abs(float(loss) - float(g["loss"])) <= 1e-9 * abs(float(g["loss"]))
+  assert abs(float(loss) - float(g["loss"])) <= 1e-12 * abs(float(g["loss"]))
   err = (pack(shape, grads, torch.float64) - g["grad"]).abs() / float(g["grad"].abs().max())
   # `first` is a float32 leaf in the reference (flows.py:47-55): its gradient is accumulated in float32 on both sides
-  assert float(err[:shape.Pp].max()) <= 2e-6 and float(err[shape.Pp:].max()) <= 1e-8
+  assert float(err[:shape.Pp].max()) <= 2e-6 and float(err[shape.Pp:].max()) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ENERGIES)
+def test_oracle_energies_match_reference(name):
+  """utils.calc_kinetic_energy / calc_score_kinetic_energy (cnf_ot/utils.py:311-389) run from the reference."""
+  from oracle import energies as oen
+  g = load(name)
+  shape, spec, params = parts(g)
+  n_t = int(g["t_size"])
+  ts = np.linspace(0.0, 1.0, n_t).tolist()
+  lat = g["latent"].unsqueeze(0).expand(n_t, *g["latent"].shape)
+  e = oen.kinetic_energy(spec, params, lat, ts)
+  assert abs(float(e) - float(g["e_kin"])) <= 1e-12 * abs(float(g["e_kin"]))
+  ts = np.linspace(0.0, float(g["T"]), n_t).tolist()
+  es = oen.score_kinetic_energy(spec, params, lat, ts, beta=float(g["beta"]))
+  assert abs(float(es) - float(g["e_score"])) <= 1e-12 * abs(float(g["e_score"]))
 
 
 # ------------------------------------------------------------------ GPU: kernels vs the reference's outputs
@@ -148,3 +164,19 @@ def test_gpu_step_matches_reference(name, engine):
   G, loss = out[:shape.blob_size], float(out[shape.blob_size])
   assert abs(loss - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
   assert float((G - g["grad"]).abs().max() / g["grad"].abs().max()) <= 5e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ENERGIES)
+def test_gpu_energies_match_reference(name, engine):
+  from cnf_ot_b200 import ops
+  g = load(name)
+  shape, _, _ = parts(g)
+  n_t = int(g["t_size"])
+  W, lat = g["blob"].float().cuda(), g["latent"].float().cuda()
+  e = ops.kinetic_energy(shape, W, lat, np.linspace(0.0, 1.0, n_t).tolist(), latent_blocks=1)
+  # finite differences with 1/dt = 1/dx = 100 amplify float32 rounding: stated tolerance 2e-4 relative
+  assert abs(float(e) - float(g["e_kin"])) <= 2e-4 * abs(float(g["e_kin"]))
+  es = ops.kinetic_energy(shape, W, lat, np.linspace(0.0, float(g["T"]), n_t).tolist(), with_score=True,
+                          kappa=1.0 / float(g["beta"]), latent_blocks=1)
+  assert abs(float(es) - float(g["e_score"])) <= 2e-4 * abs(float(g["e_score"]))
