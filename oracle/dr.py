@@ -7,8 +7,10 @@ tests/ and nothing else; the product path never touches it).
   dec_only:  y = decoder.inverse(x); y[:, sub_dim:] = 0; x' = decoder.forward(y)
   loss = mean_rows( sum_dims (x - x')^2 )
 
-Parity unpinned in absolute value, like the rest of oracle/ (no JAX here, no golden vectors in the reference);
-pinned by autograd-vs-finite-differences and the identity-flow closed form (tests/test_oracle_dr.py).
+Parity pinned to the reference's own `train()` run for one epoch in this container (its `loss_fn` and
+`jax.value_and_grad(loss_fn)`, on torch-f64 stand-ins for jax / haiku / distrax / optax:
+tests/golden/ref_dr_*.npz, tests/test_reference_golden.py, 1e-12), plus autograd-vs-finite-differences and the
+identity-flow closed form (tests/test_oracle_dr.py).
 """
 from __future__ import annotations
 

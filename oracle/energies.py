@@ -1,6 +1,7 @@
 """CPU oracle: the evaluation energies, torch f64.
 
-TEST INFRASTRUCTURE ONLY (see `oracle/rqs.py` header).  PARITY UNPINNED in absolute value.
+TEST INFRASTRUCTURE ONLY (see `oracle/rqs.py` header).  PARITY PINNED to the reference's
+own `cnf_ot/utils.py` run unmodified here (`tests/golden/ref_energy_*.npz`, 1e-12; see `oracle/flow.py`).
 
 Restates `calc_kinetic_energy` / `calc_score_kinetic_energy` of
 `/root/reference/cnf_ot/utils.py:311-389` with the per-time latent batches made an explicit input

@@ -1,8 +1,11 @@
 """CPU oracle: the reference's time-conditioned autoregressive RQS flow, torch f64.
 
 TEST INFRASTRUCTURE ONLY (see `oracle/rqs.py` header for who may import it).
-PARITY UNPINNED in absolute value (no JAX/haiku/distrax here, no golden vectors
-in the reference); pinned by the invariants in `tests/test_oracle_*.py`.
+PARITY PINNED to outputs of the reference's own source files run in this container
+(`tests/golden/ref_flow_*.npz`: flows.py / autoregressive.py / conditional.py imported unmodified from
+/root/reference on torch-f64 stand-ins for jax / haiku / distrax, `tests/golden/make_reference_golden.py`;
+agreement 1e-10, `tests/test_reference_golden.py`), plus the invariants in `tests/test_oracle_*.py`.
+The spline underneath is third-party (distrax) and stays a restatement: see `oracle/rqs.py`.
 
 Restates, with explicit arrays instead of haiku/JAX tracing:
   * conditioner: `/root/reference/cnf_ot/models/flows.py:46-86`

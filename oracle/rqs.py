@@ -20,8 +20,9 @@ omits it).  This file restates the published algorithm of
 Durkan et al. 2019 neural-spline-flow formulas, the same rational-quadratic
 form the reference's own `cnf_ot/models/nsf_symbol.py:6-10` writes down).
 
-PARITY UNPINNED (absolute values): neither JAX nor distrax can be installed
-in this environment, and the reference's only test of this path
+PARITY OF THIS FILE UNPINNED in absolute value (the rest of oracle/ is pinned to the reference's own
+code, which calls this file where it would call distrax: `tests/golden/refshim.py`): neither JAX nor
+distrax can be installed in this environment, and the reference's only test of this path
 (`/root/reference/tests/test_rqs_accuracy.py`) holds no golden vectors, only
 invariants (round trips, log-det vs autodiff Jacobian, boundary round trips,
 all < 1e-12 in float64).  `tests/test_oracle_rqs.py` re-runs exactly those

@@ -159,6 +159,63 @@ def energy_case(D, sigma, n, t_size, beta, T, seed):
           "beta": np.array(beta), "e_kin": e_kin, "e_score": e_score}
 
 
+def dr_case(model, D, L, H, sub_dim, sigma, n, seed):
+  """cnf_ot/dr/trainers.py:train run for ONE epoch with a no-op optimiser: its own `loss_fn` (:91-111) and
+  `jax.value_and_grad(loss_fn)(params, data)` (:117) on the two unconditional flows it builds (:41-73)."""
+  refshim.stub_trainer()
+  from cnf_ot.dr import trainers as ref_trainers  # the reference
+  from cnf_ot_b200.layout import FlowShape
+  from oracle import flow as oflow
+  spec = oflow.FlowSpec(D, L, [H, H], 5, conditional=False)
+  shape = FlowShape(D, L, 2, H, 5, conditional=False)
+
+  def mk(s):
+    p = oflow.perturb_params(oflow.init_params(spec, s), sigma, seed=s + 10)
+    return {m: {k: v.to(torch.float32).to(v.dtype) for k, v in lv.items()} for m, lv in p.items()}
+  g = torch.Generator().manual_seed(seed)
+  x = f32(torch.randn(n, D, generator=g, dtype=torch.float64) * 1.5)
+  enc, dec = mk(1), mk(2)
+  refshim.Trainer.init_queue = [enc, dec] if model == "enc_dec" else [dec]
+  refshim.Trainer.captured = []
+  cfg = {"cnf": {"flow_num_layers": L, "hidden_size": H, "mlp_num_layers": 2, "num_bins": 5}, "train": {"lr": 1e-3}}
+  ret = ref_trainers.train(jax.random.PRNGKey(0), x, D, sub_dim, model, 1, cfg)
+  (loss, grads), = refshim.Trainer.captured
+  assert float(ret[-1][0]) == float(loss) and not refshim.Trainer.init_queue
+  out = {"shape": np.array([D, L, 2, H, 5]), "sub_dim": np.array(sub_dim), "x": x, "loss": loss,
+         "blob_decoder": pack(shape, dec, torch.float64),
+         "grad_decoder": pack(shape, grads["decoder"] if model == "enc_dec" else grads, torch.float64)}
+  if model == "enc_dec":
+    out["blob_encoder"] = pack(shape, enc, torch.float64)
+    out["grad_encoder"] = pack(shape, grads["encoder"], torch.float64)
+  return out
+
+
+def symbolic_spline_case(K, n, seed):
+  """The reference's own symbolic statement of the rational-quadratic map (cnf_ot/models/nsf_symbol.py:3-10:
+  f = yk + alpha / beta), lambdified with sympy and evaluated at the knots oracle/rqs.py derives from raw parameters
+  drawn as the reference test draws them (tests/test_rqs_accuracy.py:60-69).  Pins the in-bin formula and its
+  derivative (the log-det) of the restated spline to a file of the reference; the knot parametrisation (softmax
+  widths / heights, softplus slopes) remains distrax's published one."""
+  import contextlib
+  import io
+  import sympy
+  with contextlib.redirect_stdout(io.StringIO()):   # the module prints a simplified derivative on import
+    from cnf_ot.models import nsf_symbol as ns
+  args = (ns.x, ns.xk, ns.xk1, ns.yk, ns.yk1, ns.deltak, ns.deltak1)
+  f = sympy.lambdify(args, ns.f, "numpy")
+  df = sympy.lambdify(args, sympy.diff(ns.f, ns.x), "numpy")
+  from oracle import rqs as orqs
+  g = torch.Generator().manual_seed(seed)
+  theta = f32(torch.randn(n, 3 * K + 1, generator=g, dtype=torch.float64) * 0.5)
+  x = f32((torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * 19.9)   # inside the knot range
+  xp, yp, sl = (a.numpy() for a in orqs.normalize_knots(theta))
+  xn = x.numpy()
+  k = np.clip((xn[:, None] >= xp).sum(-1) - 1, 0, K - 1)
+  r = np.arange(n)
+  a = (xn, xp[r, k], xp[r, k + 1], yp[r, k], yp[r, k + 1], sl[r, k], sl[r, k + 1])
+  return {"theta": theta, "x": x, "bin": k, "y": f(*a), "logdet": np.log(df(*a))}
+
+
 def save(name, d):
   out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
@@ -180,6 +237,10 @@ STEP_CASES = {
 if __name__ == "__main__":
   save("ref_flow_d2", flow_case(2, 2, 2, 16, 5, 0.3, 256, 21))
   save("ref_flow_d3_h8", flow_case(3, 3, 1, 8, 3, 0.1, 128, 22))
+  save("ref_rqs_symbolic_k5", symbolic_spline_case(5, 512, 27))
+  save("ref_rqs_symbolic_k8", symbolic_spline_case(8, 256, 28))
+  save("ref_dr_enc_dec_d4", dr_case("enc_dec", 4, 2, 16, 2, 0.08, 192, 25))
+  save("ref_dr_dec_only_d4", dr_case("dec_only", 4, 2, 16, 2, 0.08, 192, 26))
   save("ref_energy_d2", energy_case(2, 0.3, 64, 4, 2.0, 2.0, 23))
   save("ref_energy_d3", energy_case(3, 0.1, 32, 3, 4.0, 1.0, 24))
   for name, (typ, sub, B, lam, Tn, seed, kw) in STEP_CASES.items():

@@ -120,7 +120,7 @@ def _build_jax():
   jnp.zeros_like = lambda x: torch.zeros_like(x)
   jnp.array = lambda v, dtype=None: _as(v, dtype)
   jnp.asarray = jnp.array
-  jnp.arange = lambda *a: torch.arange(*a)
+  jnp.arange = lambda *a: torch.from_numpy(np.arange(*a))   # numpy semantics: an empty range is allowed
   jnp.eye = lambda n: torch.eye(int(n), dtype=F64)
   jnp.exp, jnp.log, jnp.sin, jnp.cos = torch.exp, torch.log, torch.sin, torch.cos
   jnp.subtract = lambda a, b: a - b
@@ -338,6 +338,11 @@ def _build_haiku():
     def init(rng, *args, **kwargs):
       params = {}
       run(lambda template, fns: template, params, True, args, kwargs)
+      if Trainer.init_queue:   # same leaves (names, shapes), caller-chosen values
+        preset = Trainer.init_queue.pop(0)
+        assert {m: {k: tuple(v.shape) for k, v in lv.items()} for m, lv in preset.items()} == \
+               {m: {k: tuple(v.shape) for k, v in lv.items()} for m, lv in params.items()}
+        return preset
       return params
 
     _Frame.params, _Frame.init, _Frame.scope = {}, True, []
@@ -505,3 +510,57 @@ def stub_plotting():
     _mod("matplotlib." + sub)
   mpl.colors.LinearSegmentedColormap = object
   mpl.pyplot.quiver = None   # a bare `plt.quiver` expression statement sits in calc_score_kinetic_energy (utils.py:386)
+
+
+# ---------------------------------------------------------------------------------------------- dr/trainers.py
+class Trainer:
+  """State shared with the stand-ins that `cnf_ot/dr/trainers.py:train` needs beyond the model code."""
+  init_queue = []     # parameter trees handed out by successive `model.init` calls (instead of random draws)
+  captured = []       # (loss, grads) of every jax.value_and_grad(loss_fn)(...) call
+
+
+def stub_trainer():
+  """optax / box / ml_collections / flax stand-ins + `jax.value_and_grad`, `jax.tree.leaves`, so that
+  `cnf_ot.dr.trainers.train(..., epochs=1)` runs its own `loss_fn` once on parameters we choose: the optimiser
+  stand-in applies no update, `model.init` pops the trees queued in `Trainer.init_queue`."""
+  stub_plotting()
+  import jax
+  plt = sys.modules["matplotlib.pyplot"]
+  for name in ("plot", "yscale", "savefig", "clf"):
+    setattr(plt, name, lambda *a, **k: None)
+  _mod("ml_collections").ConfigDict = dict
+
+  class Box(dict):
+    def __getattr__(self, k):
+      v = self[k]
+      return Box(v) if isinstance(v, dict) else v
+  _mod("box").Box = Box
+  _mod("flax")
+  tr = _mod("flax.traverse_util")
+
+  def flatten_dict(d, prefix=()):
+    out = {}
+    for k, v in d.items():
+      out.update(flatten_dict(v, prefix + (k, )) if isinstance(v, dict) else {prefix + (k, ): v})
+    return out
+  tr.flatten_dict = flatten_dict
+
+  optax = _mod("optax")
+  optax.piecewise_constant_schedule = lambda init_value, boundaries_and_scales=None: (lambda step: init_value)
+  Opt = namedtuple("GradientTransformation", ["init", "update"])
+  optax.adam = lambda lr: Opt(lambda params: None, lambda grads, state, params=None: (None, state))
+  optax.apply_updates = lambda params, updates: params
+
+  def value_and_grad(fn):
+    def run(params, *args):
+      p = jax.tree_util.tree_map(lambda v: v.detach().clone().requires_grad_(True), params)
+      loss = fn(p, *args)
+      loss.backward()
+      grads = jax.tree_util.tree_map(lambda v: v.grad if v.grad is not None else torch.zeros_like(v), p)
+      Trainer.captured.append((loss.detach(), grads))
+      return loss.detach(), grads
+    return run
+  jax.value_and_grad = value_and_grad
+  tree = _mod("jax.tree")
+  Leaf = namedtuple("Leaf", ["size"])
+  tree.leaves = lambda t: [Leaf(v.numel()) for v in flatten_dict(t).values()]

@@ -33,6 +33,7 @@ STEPS = {
 }
 FLOWS = ["ref_flow_d2", "ref_flow_d3_h8"]
 ENERGIES = ["ref_energy_d2", "ref_energy_d3"]
+DR = {"ref_dr_enc_dec_d4": "enc_dec", "ref_dr_dec_only_d4": "dec_only"}
 
 
 def load(name):
@@ -116,6 +117,50 @@ def test_oracle_energies_match_reference(name):
   assert abs(float(es) - float(g["e_score"])) <= 1e-12 * abs(float(g["e_score"]))
 
 
+@pytest.mark.parametrize("name", ["ref_rqs_symbolic_k5", "ref_rqs_symbolic_k8"])
+def test_oracle_spline_matches_reference_symbolic_form(name):
+  """In-bin map and derivative of the restated spline vs the reference's own symbolic statement
+  (cnf_ot/models/nsf_symbol.py:3-10, lambdified with sympy by the generator)."""
+  from oracle import rqs as orqs
+  g = load(name)
+  y, ld, b = orqs.rqs_forward(g["x"], g["theta"])
+  assert torch.equal(b, g["bin"])
+  assert float((y - g["y"]).abs().max()) < 1e-12 and float((ld - g["logdet"]).abs().max()) < 1e-11
+  xi, ldi, _ = orqs.rqs_inverse(g["y"], g["theta"])
+  assert float((xi - g["x"]).abs().max()) < 1e-11 and float((ldi + g["logdet"]).abs().max()) < 1e-10
+
+
+def _dr_parts(g):
+  D, L, M, H, K = (int(v) for v in g["shape"])
+  shape = FlowShape(D, L, M, H, K, conditional=False)
+  spec = oflow.FlowSpec(D, L, [H] * M, K, conditional=False)
+
+  def tree(blob):
+    p = unpack(shape, blob)
+    p["~"]["first"] = p["~"]["first"].float()
+    return p
+  return shape, spec, tree
+
+
+@pytest.mark.parametrize("name", list(DR))
+def test_oracle_dr_matches_reference(name):
+  """cnf_ot/dr/trainers.py:train's own loss_fn and value_and_grad (:91-117), run for one epoch from the reference."""
+  from oracle import dr as odr
+  g = load(name)
+  shape, spec, tree = _dr_parts(g)
+  model = DR[name]
+  dec = tree(g["blob_decoder"])
+  params = {"encoder": tree(g["blob_encoder"]), "decoder": dec} if model == "enc_dec" else dec
+  loss, grads = odr.value_and_grad(model, spec, params, g["x"], int(g["sub_dim"]))
+  assert abs(float(loss) - float(g["loss"])) <= 1e-12 * abs(float(g["loss"]))
+  for key, gr in (("decoder", grads["decoder"] if model == "enc_dec" else grads),
+                  ("encoder", grads.get("encoder") if model == "enc_dec" else None)):
+    if gr is None:
+      continue
+    err = (pack(shape, gr, torch.float64) - g["grad_" + key]).abs() / float(g["grad_" + key].abs().max())
+    assert float(err[:shape.Pp].max()) <= 2e-6 and float(err[shape.Pp:].max()) <= 1e-12, key
+
+
 # ------------------------------------------------------------------ GPU: kernels vs the reference's outputs
 @pytest.fixture(params=["mma", "cuda", "wide"])
 def engine(request, monkeypatch):
@@ -163,7 +208,9 @@ def test_gpu_step_matches_reference(name, engine):
   out = out.cpu().double()
   G, loss = out[:shape.blob_size], float(out[shape.blob_size])
   assert abs(loss - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
-  assert float((G - g["grad"]).abs().max() / g["grad"].abs().max()) <= 5e-5
+  # score terms: the finite difference (1 / dx = 100) amplifies the float32 rounding of the log-prob and only b = 4-8
+  # rows share a term here, so nothing averages out: 1e-4 for rwpo / fp, 5e-5 for ot
+  assert float((G - g["grad"]).abs().max() / g["grad"].abs().max()) <= (5e-5 if typ == "ot" else 1e-4)
 
 
 @pytest.mark.gpu
@@ -180,3 +227,23 @@ def test_gpu_energies_match_reference(name, engine):
   es = ops.kinetic_energy(shape, W, lat, np.linspace(0.0, float(g["T"]), n_t).tolist(), with_score=True,
                           kappa=1.0 / float(g["beta"]), latent_blocks=1)
   assert abs(float(es) - float(g["e_score"])) <= 2e-4 * abs(float(g["e_score"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(DR))
+def test_gpu_dr_matches_reference(name):
+  from cnf_ot_b200 import dr
+  from cnf_ot_b200.flows import ParamTree
+  g = load(name)
+  shape, _, _ = _dr_parts(g)
+  model = DR[name]
+  cfg = {"cnf": {"flow_num_layers": shape.num_layers, "mlp_num_layers": shape.mlp_layers, "hidden_size": shape.hidden,
+                 "num_bins": shape.num_bins}}
+  enc, dec = dr.build(shape.dim, cfg, model)
+  td = ParamTree(shape, g["blob_decoder"].float().cuda())
+  params = {"encoder": ParamTree(shape, g["blob_encoder"].float().cuda()), "decoder": td} if model == "enc_dec" else td
+  loss, grads = dr.value_and_grad(model, enc, dec, int(g["sub_dim"]))(params, g["x"].float().cuda())
+  assert abs(float(loss) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+  G = (grads["decoder"] if model == "enc_dec" else grads).blob.cpu().double()
+  err = (G - g["grad_decoder"]).abs() / g["grad_decoder"].abs().max()
+  assert float(err.quantile(0.99)) <= 5e-5 and float(err.max()) <= 1e-3   # tie rows: see tests/test_gpu_dr.py
