@@ -35,6 +35,19 @@ __device__ __forceinline__ void tile_load(float* s, const float* __restrict__ g,
   if (TL::kVec) {
     constexpr int C = P / 4;  // 16-byte chunks per row
     const float4* src = reinterpret_cast<const float4*>(g);
+    if (nrows == kTile && (kTile % C) == 0) {
+      // full tile: chunk q = tid + j kTile sits in row (tid / C) + j (kTile / C), column tid % C -- one base address
+      // on each side, the C copies are immediate offsets from it and all C loads are in flight together
+      const int r = threadIdx.x / C, c = threadIdx.x - r * C;
+      const float4* sp = src + threadIdx.x;
+      float* dp = s + r * TL::kStride + c * 4;
+      float4 v[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) v[j] = __ldcs(sp + j * kTile);  // streamed once: evict-first
+#pragma unroll
+      for (int j = 0; j < C; ++j) *reinterpret_cast<float4*>(dp + j * (kTile / C) * TL::kStride) = v[j];
+      return;
+    }
     const int n = nrows * C;
 #pragma unroll 4
     for (int q = threadIdx.x; q < n; q += kTile) {
@@ -58,6 +71,14 @@ __device__ __forceinline__ void tile_store(float* __restrict__ g, const float* s
   if (TL::kVec) {
     constexpr int C = P / 4;
     float4* dst = reinterpret_cast<float4*>(g);
+    if (nrows == kTile && (kTile % C) == 0) {   // full tile: see tile_load
+      const int r = threadIdx.x / C, c = threadIdx.x - r * C;
+      float4* gp = dst + threadIdx.x;
+      const float* sp = s + r * TL::kStride + c * 4;
+#pragma unroll
+      for (int j = 0; j < C; ++j) __stcs(gp + j * kTile, *reinterpret_cast<const float4*>(sp + j * (kTile / C) * TL::kStride));
+      return;
+    }
     const int n = nrows * C;
 #pragma unroll 4
     for (int q = threadIdx.x; q < n; q += kTile) {

@@ -65,21 +65,49 @@ inline SplineConsts<T> make_spline_consts(int K, double lo, double hi, double mi
 // ~250 to ~120 instructions; the parity tests bound the effect (it is below the float32
 // rounding already present in the knot positions).  -DCNFOT_PRECISE_MATH restores libm paths.
 #if defined(__CUDA_ARCH__) && !defined(CNFOT_PRECISE_MATH)
-CNFOT_HD float m_exp(float v) { return __expf(v); }
-CNFOT_HD float m_log(float v) { return __logf(v); }
-CNFOT_HD float m_div(float a, float b) { return __fdividef(a, b); }
-CNFOT_HD float m_rcp(float a) { return __fdividef(1.f, a); }
+#define CNFOT_FAST_MATH 1
+// One SFU instruction each (the __expf / __logf / __fdividef intrinsics wrap the same instructions in denormal
+// scaling and range checks: 5 instructions per call, 25 % of the stand-alone spline kernel in ncu's source view).
+// Arguments here are normal numbers: bin sizes >= 1e-4, softmax sums >= 1, slopes >= 1e-4; results below 2^-126
+// flush to zero, where the exact value changes nothing at float32 precision.
+CNFOT_HD float m_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+CNFOT_HD float m_lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+CNFOT_HD float m_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+CNFOT_HD float m_exp(float v) { return m_ex2(v * 1.4426950408889634f); }
+CNFOT_HD float m_log(float v) { return m_lg2(v) * 0.6931471805599453f; }
+CNFOT_HD float m_div(float a, float b) { return a * m_rcp(b); }
+// exp(u - m) as one FFMA + one SFU instruction: nm = -m log2(e) is computed once per softmax
+CNFOT_HD float m_exp_shift_prep(float m) { return -m * 1.4426950408889634f; }
+CNFOT_HD float m_exp_shifted(float u, float nm) { return m_ex2(fmaf(u, 1.4426950408889634f, nm)); }
+// log(1 + e) for e in [0, 1] (the only use: softplus): e + e^2 Q(e), Q from a degree-8 least-squares fit of log1p(e) / e
+// on Chebyshev nodes (fit error 3e-8); the last FFMA rounds the result once: 1.4e-7 maximum, 4e-8 mean relative error
+// in float32 (log1pf: ~32 instructions, this: 9)
+CNFOT_HD float m_log1p(float e) {
+  float q = 0.005253457929939032f;
+  q = fmaf(q, e, -0.02958850748836994f);
+  q = fmaf(q, e, 0.07836166769266129f);
+  q = fmaf(q, e, -0.13674770295619965f);
+  q = fmaf(q, e, 0.19111430644989014f);
+  q = fmaf(q, e, -0.24844369292259216f);
+  q = fmaf(q, e, 0.33319270610809326f);
+  q = fmaf(q, e, -0.49999502301216125f);
+  return fmaf(q * e, e, e);
+}
 #else
 CNFOT_HD float m_exp(float v) { return expf(v); }
 CNFOT_HD float m_log(float v) { return logf(v); }
 CNFOT_HD float m_div(float a, float b) { return a / b; }
 CNFOT_HD float m_rcp(float a) { return 1.f / a; }
+CNFOT_HD float m_exp_shift_prep(float m) { return m; }
+CNFOT_HD float m_exp_shifted(float u, float m) { return expf(u - m); }
+CNFOT_HD float m_log1p(float v) { return log1pf(v); }
 #endif
 CNFOT_HD double m_exp(double v) { return exp(v); }
 CNFOT_HD double m_log(double v) { return log(v); }
 CNFOT_HD double m_div(double a, double b) { return a / b; }
 CNFOT_HD double m_rcp(double a) { return 1.0 / a; }
-CNFOT_HD float m_log1p(float v) { return log1pf(v); }
+CNFOT_HD double m_exp_shift_prep(double m) { return m; }
+CNFOT_HD double m_exp_shifted(double u, double m) { return exp(u - m); }
 CNFOT_HD double m_log1p(double v) { return log1p(v); }
 CNFOT_HD float m_sqrt(float v) { return sqrtf(v); }
 CNFOT_HD double m_sqrt(double v) { return sqrt(v); }
@@ -122,17 +150,19 @@ CNFOT_HD void softmax_bins(const T* u, const SplineConsts<T>& c, T* prob, T* siz
   T m = u[0];
 #pragma unroll
   for (int k = 1; k < K; ++k) m = m_max(m, u[k]);
+  const T sh = m_exp_shift_prep(m);
   T sum = (T)0;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    prob[k] = m_exp(u[k] - m);
+    prob[k] = m_exp_shifted(u[k], sh);
     sum += prob[k];
   }
-  T inv = m_rcp(sum);
+  const T inv = m_rcp(sum);
+  const T scale = inv * c.bin_scale;   // one FFMA per bin; prob is only read by the backward pass
 #pragma unroll
   for (int k = 0; k < K; ++k) {
+    size[k] = prob[k] * scale + c.min_bin;
     prob[k] *= inv;
-    size[k] = prob[k] * c.bin_scale + c.min_bin;
   }
 }
 
@@ -167,9 +197,12 @@ CNFOT_HD void locate(T v, const T* search, const T* other, const T* us,
   s0 = search[0]; s1 = search[1];
   o0 = other[0]; o1 = other[1];
   T u0 = us[0], u1 = us[1];
+  // the knots ascend, so "v >= search[k]" is monotone in k: overwriting in ascending order leaves the last bin whose
+  // left knot is <= v (outside the range the gathered bin is only read by the lower tail, where no test passes)
+  const bool inside = v < search[K];
 #pragma unroll
   for (int k = 1; k < K; ++k) {
-    bool hit = (idx == k);
+    const bool hit = inside && (v >= search[k]);
     s0 = hit ? search[k] : s0;
     s1 = hit ? search[k + 1] : s1;
     o0 = hit ? other[k] : o0;
