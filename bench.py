@@ -35,6 +35,17 @@ B_PER_GPU = 1 << 18
 SIGMA = 0.3  # parameter perturbation
 
 
+# stdout carries exactly ONE line (the JSON): everything a library writes to file descriptor 1 (NCCL prints its
+# version banner there) is sent to stderr, the JSON goes to a private copy of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+  _JSON_OUT.write(json.dumps(line) + "\n")
+  _JSON_OUT.flush()
+
+
 def workload_cfg(batch):
   return {
     "general": {"type": "ot", "dim": 2, "dx": 0.01, "dt": 0.01, "t_batch_size": 1, "seed": 42},
@@ -161,7 +172,7 @@ def run_reference(args):
                        "flow_num_layers": args.layers, "mlp": "2x512", "rows_per_step_cpu": 128},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return
   # bounded sample per step so K + W steps end within minutes
   probe = oracle_step_timer(1 << 12)
@@ -192,7 +203,7 @@ def run_reference(args):
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 # ---------------------------------------------------------------- our arm
@@ -419,7 +430,7 @@ def run_ours(args):
     if world == 1:
       line["roofline_spline"] = spline_rooflines(hbm)
       line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     td.barrier()
     td.destroy_process_group()
@@ -540,7 +551,7 @@ def run_cfg5(args):
     }
     if world == 1 and not args.no_cpu_baseline:
       line["cpu_baseline"] = cpu_baseline_cfg5(L)
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     td.barrier()
     td.destroy_process_group()
