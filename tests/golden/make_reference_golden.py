@@ -232,6 +232,11 @@ STEP_CASES = {
   "ref_step_fp_gradient_d2": ("fp", "gradient", 256, 500.0, 2, 105, {}),
   "ref_step_fp_nongradient_d2": ("fp", "nongradient", 256, 100.0, 1, 106, {}),
   "ref_step_fp_lorenz_d3": ("fp", "lorenz", 128, 100.0, 1, 107, dict(dim=3, sigma=0.1)),
+  # other network shapes: hidden 64 (wide-conditioner engine on the GPU), 3 hidden layers, 3 flow layers, 8 bins
+  "ref_step_ot_obstacle_d2_h64": ("ot", "obstacle", 256, 500.0, 1, 108, dict(H=64, sigma=0.05)),
+  "ref_step_rwpo_double_well_d2_m3": ("rwpo", "double_well", 256, 500.0, 1, 109, dict(M=3, sigma=0.2)),
+  "ref_step_fp_nongradient_d2_l3": ("fp", "nongradient", 256, 100.0, 1, 110, dict(L=3, sigma=0.2)),
+  "ref_step_ot_free_d2_k8_h32": ("ot", "free", 256, 500.0, 2, 111, dict(K=8, H=32, sigma=0.1)),
 }
 
 if __name__ == "__main__":

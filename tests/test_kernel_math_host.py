@@ -106,3 +106,27 @@ def test_step_value_and_grad(typ, sub, kw, dtype, tol_loss, tol_grad):
   assert abs(tot - float(loss)) <= tol_loss * abs(float(loss)), (tot, float(loss))
   gerr = float((G - Gor).abs().max() / Gor.abs().max())
   assert gerr <= tol_grad, gerr
+
+
+def test_device_log1p_polynomial_accuracy():
+  """softplus on the device uses log(1 + e) = e + e^2 Q(e) on [0, 1] (csrc/rqs_math.cuh:m_log1p, float32 FFMA chain).
+  Re-evaluate the same chain here with the coefficients read from the header, rounding every step to float32:
+  maximum relative error below 2e-7 (log1pf is ~1e-7), which is what DESIGN.md section 4.1 states."""
+  import os
+  import re
+  import numpy as np
+  src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "cnf_ot_b200", "csrc", "rqs_math.cuh")).read()
+  body = src[src.index("CNFOT_HD float m_log1p(float e) {"):]
+  body = body[:body.index("}")]
+  first = float(re.search(r"float q = (-?[0-9.eE+-]+)f;", body).group(1))
+  rest = [float(m) for m in re.findall(r"q = fmaf\(q, e, (-?[0-9.eE+-]+)f\);", body)]
+  assert len(rest) == 7 and "return fmaf(q * e, e, e);" in body
+  e = np.linspace(0.0, 1.0, 200001)[1:].astype(np.float32)
+  fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + np.asarray(c, dtype=np.float64)).astype(np.float32)
+  q = np.full_like(e, np.float32(first))
+  for c in rest:
+    q = fma(q, e, np.float32(c))
+  r = fma((q * e).astype(np.float32), e, e)
+  ref = np.log1p(e.astype(np.float64))
+  rel = np.abs(r.astype(np.float64) - ref) / ref
+  assert float(rel.max()) < 2e-7 and float(rel.mean()) < 6e-8

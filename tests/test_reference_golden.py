@@ -30,6 +30,11 @@ STEPS = {
   "ref_step_fp_gradient_d2": ("fp", "gradient", {}),
   "ref_step_fp_nongradient_d2": ("fp", "nongradient", {}),
   "ref_step_fp_lorenz_d3": ("fp", "lorenz", dict(dim=3)),
+  # other network shapes (taken from the fixture): hidden 64, 3 hidden layers, 3 flow layers, 8 bins x hidden 32
+  "ref_step_ot_obstacle_d2_h64": ("ot", "obstacle", {}),
+  "ref_step_rwpo_double_well_d2_m3": ("rwpo", "double_well", {}),
+  "ref_step_fp_nongradient_d2_l3": ("fp", "nongradient", {}),
+  "ref_step_ot_free_d2_k8_h32": ("ot", "free", {}),
 }
 FLOWS = ["ref_flow_d2", "ref_flow_d3_h8"]
 ENERGIES = ["ref_energy_d2", "ref_energy_d3"]
