@@ -2,10 +2,10 @@
 
   python tests/golden/make_golden.py
 
-PROVENANCE: these vectors are outputs of oracle/ (the restatement of the reference), NOT of the
-reference itself -- JAX / haiku / distrax cannot be installed in this image, and
-the reference's own test of this path (tests/test_rqs_accuracy.py) holds invariants, not values.
-They pin the oracle against silent change (tests/test_golden.py, CPU) and give the GPU parity
+PROVENANCE: these vectors are outputs of oracle/ (the restatement of the reference), NOT of the reference itself; the
+fixtures produced by the reference's own code are tests/golden/ref_*.npz (make_reference_golden.py), which also pin
+oracle/.  The files made here cover shapes the reference's code does not run (3- and 4-dimensional mixtures, the hidden-64
+flow of the wide engine), pin the oracle against silent change (tests/test_golden.py, CPU) and give the GPU parity
 tests fixed vectors that do not depend on torch's RNG stream (tests/test_golden.py, -m gpu).
 Every input is float32-representable so the kernels see exactly the same numbers.
 """
