@@ -85,6 +85,18 @@ def reverse_kl_loss_fn(model, dim, T, beta, params, cond, rng, batch_size):
   return (lp.double() - logq).mean()
 
 
+def ot_reverse_kl_loss_fn(model, dim, T, params, rng, batch_size):
+  """applications.py:91-126: reverse KL against N(3, I) at t = 0 plus N(0, I) at t = 1 (the reference keeps it beside
+  `density_fit_kl_loss_fn`; its only call site, :390, is commented out)."""
+  loss = 0.0
+  for cond, mean in ((0.0, 3.0), (1.0, 0.0)):
+    samples, lp = model.apply.sample_and_log_prob(
+      params, cond=_cond_rows(batch_size, cond, model.device), seed=rng, sample_shape=(batch_size, ))
+    d2 = ((samples.double() - mean)**2).sum(-1)
+    loss = loss + (lp.double() - (-0.5 * d2 - 0.5 * dim * math.log(2 * math.pi))).mean()
+  return loss
+
+
 def potential_loss_fn(model, dim, a, subtype, params, cond, rng, batch_size):
   """applications.py:176-205."""
   r = model.apply.sample(params, cond=_cond_rows(batch_size, cond, model.device), seed=rng,

@@ -135,6 +135,8 @@ def flow_case(D, L, M, H, K, sigma, n, seed):
            "log_prob_x": model.apply.log_prob(params, x, cond=c0), "forward_x": model.apply.forward(params, x, c0),
            "inverse_x": model.apply.inverse(params, x, c0)}
   assert torch.equal(y, ys)
+  with torch.no_grad():   # applications.py:91-126 on the same latent rows
+    out["ot_reverse_kl"] = applications.ot_reverse_kl_loss_fn(model, D, 1, params, key, n)
   return out
 
 

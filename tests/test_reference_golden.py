@@ -92,6 +92,54 @@ def test_oracle_flow_matches_reference(name):
   assert float((lat - g["inverse_x"]).abs().max()) < 1e-10
 
 
+def _ot_reverse_kl_oracle(spec, params, latent):
+  """applications.py:91-126 restated on the oracle flow (targets N(3, I) at t = 0 and N(0, I) at t = 1)."""
+  n, d = latent.shape
+  tot = 0.0
+  for cond, mean in ((0.0, 3.0), (1.0, 0.0)):
+    y, lp = oflow.sample_and_log_prob(spec, params, latent, torch.full((n, 1), cond, dtype=torch.float64))
+    tot = tot + (lp - (-0.5 * ((y - mean)**2).sum(-1) - 0.5 * d * np.log(2 * np.pi))).mean()
+  return tot
+
+
+@pytest.mark.parametrize("name", FLOWS)
+def test_oracle_ot_reverse_kl_matches_reference(name):
+  g = load(name)
+  shape, spec, params = parts(g)
+  got = _ot_reverse_kl_oracle(spec, params, g["latent"])
+  assert abs(float(got) - float(g["ot_reverse_kl"])) <= 1e-12 * abs(float(g["ot_reverse_kl"]))
+
+
+REF = "/root/reference/cnf_ot"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_mirror_signatures_match_the_reference():
+  """Every function of the reference's applications.py, the two energies of utils.py, RQSFlow and solvers.main exist in
+  the mirror with the same parameter names in the same order (extra trailing optional parameters allowed)."""
+  import ast
+  import inspect
+  import cnf_ot_b200.applications as A
+  import cnf_ot_b200.flows as F
+  import cnf_ot_b200.solvers as S
+  import cnf_ot_b200.utils as U
+
+  def ref_sigs(path):
+    tree = ast.parse(open(path).read())
+    return {n.name: [a.arg for a in n.args.args + n.args.kwonlyargs] for n in tree.body if isinstance(n, ast.FunctionDef)}
+  checks = [(A, ref_sigs(REF + "/mfc/applications.py"), None),
+            (U, ref_sigs(REF + "/utils.py"), {"calc_kinetic_energy", "calc_score_kinetic_energy"}),
+            (F, ref_sigs(REF + "/models/flows.py"), {"RQSFlow"}), (S, ref_sigs(REF + "/mfc/solvers.py"), {"main"})]
+  for mod, sigs, only in checks:
+    for name, args in sigs.items():
+      if only is not None and name not in only:
+        continue
+      mine = list(inspect.signature(getattr(mod, name)).parameters)
+      assert mine[:len(args)] == args, (mod.__name__, name, args, mine)
+      extra = list(inspect.signature(getattr(mod, name)).parameters.values())[len(args):]
+      assert all(p.default is not inspect.Parameter.empty for p in extra), (name, extra)
+
+
 @pytest.mark.parametrize("name", list(STEPS))
 def test_oracle_step_matches_reference(name):
   g = load(name)
@@ -252,3 +300,20 @@ def test_gpu_dr_matches_reference(name):
   G = (grads["decoder"] if model == "enc_dec" else grads).blob.cpu().double()
   err = (G - g["grad_decoder"]).abs() / g["grad_decoder"].abs().max()
   assert float(err.quantile(0.99)) <= 5e-5 and float(err.max()) <= 1e-3   # tie rows: see tests/test_gpu_dr.py
+
+
+@pytest.mark.gpu
+def test_gpu_ot_reverse_kl_mirror():
+  """applications.ot_reverse_kl_loss_fn of the mirror vs the restatement pinned above, on the mirror's own draws."""
+  from cnf_ot_b200 import applications, random
+  from cnf_ot_b200.flows import ParamTree, RQSFlow
+  g = load("ref_flow_d2")
+  shape, spec, params = parts(g)
+  model = RQSFlow((shape.dim, ), shape.num_layers, [shape.hidden] * shape.mlp_layers, shape.num_bins)
+  tree = ParamTree(model.shape, g["blob"].float().cuda())
+  rng = random.PRNGKey(3)
+  n = 1024
+  got = applications.ot_reverse_kl_loss_fn(model, shape.dim, 1, tree, rng, n)
+  latent = random.normal(rng, (n, shape.dim)).double().cpu()
+  want = _ot_reverse_kl_oracle(spec, params, latent)
+  assert abs(float(got) - float(want)) <= 2e-5 * abs(float(want))
