@@ -25,8 +25,10 @@ code, which calls this file where it would call distrax: `tests/golden/refshim.p
 distrax can be installed in this environment, and the reference's only test of this path
 (`/root/reference/tests/test_rqs_accuracy.py`) holds no golden vectors, only
 invariants (round trips, log-det vs autodiff Jacobian, boundary round trips,
-all < 1e-12 in float64).  `tests/test_oracle_rqs.py` re-runs exactly those
-invariants on this restatement, on that test's own configurations.
+all < 1e-12 in float64).  That test file is executed UNMODIFIED against this restatement
+(`tests/golden/run_reference_tests.py`, on stand-ins for jax / distrax) and passes; `tests/test_oracle_rqs.py` re-runs
+the same invariants, and `tests/golden/ref_rqs_symbolic_k*.npz` pin the in-bin map and its derivative to the
+reference's own symbolic statement (`cnf_ot/models/nsf_symbol.py:3-10`).
 """
 from __future__ import annotations
 

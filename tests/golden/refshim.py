@@ -124,6 +124,9 @@ def _build_jax():
   jnp.eye = lambda n: torch.eye(int(n), dtype=F64)
   jnp.exp, jnp.log, jnp.sin, jnp.cos = torch.exp, torch.log, torch.sin, torch.cos
   jnp.subtract = lambda a, b: a - b
+  jnp.abs = torch.abs
+  jnp.max = lambda x, axis=None: torch.max(x) if axis is None else torch.max(x, dim=axis).values
+  jnp.tile = lambda x, reps: x.repeat(*reps)
   jnp.dot = lambda a, b: _as(a).to(F64) @ _as(b).to(F64)
   # numpy, so that `np.ones(...) * (t - dt / 2)` (cnf_ot/utils.py:329) works as it does with a jax scalar
   jnp.linspace = lambda a, b, n: np.linspace(a, b, n)
@@ -139,6 +142,7 @@ def _build_jax():
   linalg = _mod("jax.numpy.linalg")
   linalg.norm = lambda x, axis=None: torch.linalg.norm(x) if axis is None else torch.linalg.norm(x, dim=axis)
   linalg.cholesky = torch.linalg.cholesky
+  linalg.det = torch.linalg.det
 
   nn = _mod("jax.nn")
   nn.relu, nn.tanh = torch.relu, torch.tanh
@@ -157,9 +161,12 @@ def _build_jax():
     Draws.log.append(("normal", shape))
     return src[:shape[0]].clone()
 
-  def uniform(key, shape=(), dtype=None):
+  def uniform(key, shape=(), dtype=None, minval=0.0, maxval=1.0):
     shape = _shape(shape)
-    assert len(shape) == 1 and shape[0] <= Draws.uniform.shape[0]
+    if Draws.uniform is None:   # not programmed (the reference's own unit tests): a seeded stream per key
+      g = torch.Generator().manual_seed(int(key) % (2**63 - 1))
+      return minval + (maxval - minval) * torch.rand(shape, generator=g, dtype=F64)
+    assert len(shape) == 1 and shape[0] <= Draws.uniform.shape[0] and minval == 0.0 and maxval == 1.0
     Draws.log.append(("uniform", shape))
     return Draws.uniform[:shape[0]].clone()
 
@@ -197,7 +204,7 @@ def _build_jax():
 
   def _not_needed(*a, **k):
     raise NotImplementedError("not on the train-step path")
-  jax.jacfwd = lambda fn: _not_needed
+  jax.jacfwd = lambda fn: (lambda x: torch.autograd.functional.jacobian(fn, x))
   jax.eval_shape = _not_needed
 
   cfg = types.SimpleNamespace(update=lambda *a, **k: None)
@@ -389,6 +396,12 @@ def _build_distrax(jax):
     is_constant_jacobian = property(lambda self: self._is_constant_jacobian)
     is_constant_log_det = property(lambda self: self._is_constant_log_det)
     name = property(lambda self: type(self).__name__)
+
+    def forward(self, x):
+      return self.forward_and_log_det(x)[0]
+
+    def inverse(self, y):
+      return self.inverse_and_log_det(y)[0]
 
     def _check_forward_input_shape(self, x):
       assert x.ndim >= self._event_ndims_in

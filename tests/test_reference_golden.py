@@ -140,6 +140,20 @@ def test_mirror_signatures_match_the_reference():
       assert all(p.default is not inspect.Parameter.empty for p in extra), (name, extra)
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_reference_own_spline_test_passes_on_the_restated_spline():
+  """/root/reference/tests/test_rqs_accuracy.py, executed UNMODIFIED against oracle/rqs.py behind the
+  `distrax.RationalQuadraticSpline` interface (tests/golden/run_reference_tests.py; own process because the stand-ins
+  register fake jax / distrax modules): round trips, log-det vs autodiff Jacobian, boundaries, all < 1e-12."""
+  import subprocess
+  import sys
+  here = os.path.dirname(os.path.abspath(__file__))
+  r = subprocess.run([sys.executable, os.path.join(here, "golden", "run_reference_tests.py")], capture_output=True,
+                     text=True, timeout=600)
+  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+  assert "PASSED /root/reference/tests/test_rqs_accuracy.py::TestRQSAccuracy::test_rqs_comprehensive" in r.stdout
+
+
 @pytest.mark.parametrize("name", list(STEPS))
 def test_oracle_step_matches_reference(name):
   g = load(name)
