@@ -56,6 +56,35 @@ class ParamTree(dict):
   def clone(self) -> "ParamTree":
     return ParamTree(self.shape, self.blob.clone())
 
+  # -- parameter I/O (the reference itself never saves its parameters): one array per
+  # haiku leaf under the key "<module>/<leaf>" (e.g. "mlp_layer0_d1/~/linear_0/w", "~/first"), float32, plus the
+  # flow shape -- the file a `np.savez(path, **flatten(params))` of the reference's pytree would give.
+  def save(self, path: str) -> None:
+    import numpy as np
+    out = {f"{mod}/{leaf}": view.detach().cpu().numpy() for mod, leaves in self.items() for leaf, view in leaves.items()}
+    sh = self.shape
+    out["__flow_shape__"] = np.array([sh.dim, sh.num_layers, sh.mlp_layers, sh.hidden, sh.num_bins, int(sh.conditional)])
+    np.savez(path, **out)
+
+  @staticmethod
+  def load(path: str, device=None) -> "ParamTree":
+    import numpy as np
+    z = np.load(path)
+    d, n_layers, m, h, k, cond = (int(v) for v in z["__flow_shape__"])
+    shape = FlowShape(d, n_layers, m, h, k, conditional=bool(cond))
+    tree = ParamTree(shape, torch.zeros(shape.blob_size, dtype=torch.float32))
+    want = {f"{mod}/{leaf}" for mod, leaves in tree.items() for leaf in leaves}
+    have = set(z.files) - {"__flow_shape__"}
+    if want != have:
+      raise ValueError(f"parameter file does not match the flow shape: {sorted(want ^ have)[:4]} ...")
+    for mod, leaves in tree.items():
+      for leaf, view in leaves.items():
+        arr = torch.from_numpy(np.asarray(z[f"{mod}/{leaf}"], dtype=np.float32))
+        if tuple(arr.shape) != tuple(view.shape):
+          raise ValueError(f"{mod}/{leaf}: shape {tuple(arr.shape)} != {tuple(view.shape)}")
+        view.copy_(arr)
+    return tree if device is None else ParamTree(shape, tree.blob.to(device))
+
 
 def _blob_of(shape: FlowShape, params, device) -> torch.Tensor:
   if isinstance(params, ParamTree):

@@ -85,6 +85,13 @@ def main(config_dict: Dict, progress: bool = False):
   dim = config["general"]["dim"]
   model_rng, rng = random.split(rng)
   params = model.init(model_rng, torch.zeros(1, dim), torch.zeros(1))
+  # optional keys beyond the reference's mfc.yaml (it has no checkpointing at all): train.params_in / train.params_out
+  # name .npz files of the haiku-shaped pytree (ParamTree.save / load)
+  if tr.get("params_in"):
+    loaded = ParamTree.load(tr["params_in"], device=params.blob.device)
+    if loaded.shape != params.shape:
+      raise ValueError("train.params_in holds a different flow shape than the config")
+    params = loaded
   opt_state = AdamState(params)
   update = make_update(loss_fn, tr["lr"], batch_size)
   loss_hist = []
@@ -99,6 +106,8 @@ def main(config_dict: Dict, progress: bool = False):
         KL = applications.density_fit_kl_loss_fn(model, dim, T, params, eval_rng, batch_size)
         desc += f" KL={float(KL):.4f}"
       print(desc, flush=True)
+  if tr.get("params_out"):
+    params.save(tr["params_out"])
   return params, loss_hist
 
 

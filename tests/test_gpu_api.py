@@ -97,3 +97,20 @@ def test_training_reduces_loss():
   h = torch.stack([l.detach() for l in hist]).cpu()
   assert bool(torch.isfinite(h).all())
   assert float(h[-10:].mean()) < 0.7 * float(h[:5].mean())
+
+
+def test_params_out_and_params_in(tmp_path):
+  """train.params_out writes the haiku-shaped pytree as .npz after training; train.params_in resumes from it
+  (the reference has no parameter I/O)."""
+  path = str(tmp_path / "params.npz")
+  cfg = make_cfg("ot", "free", B=1024, lam=50.0)
+  cfg["train"].update(epochs=3, lr=5e-3, params_out=path)
+  params, _ = solvers.main(cfg)
+  back = ParamTree.load(path)
+  for mod in params:
+    for leaf in params[mod]:
+      assert torch.equal(back[mod][leaf], params[mod][leaf].cpu()), (mod, leaf)
+  cfg2 = make_cfg("ot", "free", B=1024, lam=50.0)
+  cfg2["train"].update(epochs=0, params_in=path)
+  resumed, hist = solvers.main(cfg2)
+  assert hist == [] and torch.equal(resumed.blob.cpu(), back.blob)

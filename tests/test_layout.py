@@ -76,3 +76,31 @@ def test_unsupported_shapes_fail_loudly():
   assert b"no fused kernel" in lib.cnfot_last_error()
   assert lib.cnfot_flow_supported(_lib.flow_desc(FlowShape(2, 2, 2, 16, 5))) == 0
   assert lib.cnfot_param_count(_lib.flow_desc(FlowShape(2, 2, 2, 18, 5))) == -1
+
+
+def test_param_tree_npz_round_trip(tmp_path):
+  """ParamTree.save / load: one array per haiku leaf ("<module>/<leaf>"), same values back, shape mismatches refused."""
+  import numpy as np
+  import pytest
+  import torch
+  from cnf_ot_b200.flows import ParamTree
+  from cnf_ot_b200.layout import FlowShape
+  for shape in (FlowShape(3, 2, 2, 16, 5), FlowShape(4, 2, 1, 8, 3, conditional=False)):
+    g = torch.Generator().manual_seed(5)
+    tree = ParamTree(shape, torch.randn(shape.blob_size, generator=g))
+    # the padding slots of the blob are not parameters: compare leaves
+    path = str(tmp_path / "params.npz")
+    tree.save(path)
+    z = np.load(path)
+    assert "~/first" in z.files and z["~/first"].shape == (1, 3 * shape.num_bins + 1)
+    assert sum(z[k].size for k in z.files if k != "__flow_shape__") == shape.param_count()
+    back = ParamTree.load(path)
+    assert back.shape == shape
+    for mod in tree:
+      for leaf in tree[mod]:
+        assert torch.equal(back[mod][leaf], tree[mod][leaf]), (mod, leaf)
+  bad = dict(np.load(path))
+  bad.pop("~/first")
+  np.savez(str(tmp_path / "bad.npz"), **bad)
+  with pytest.raises(ValueError):
+    ParamTree.load(str(tmp_path / "bad.npz"))
