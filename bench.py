@@ -1,23 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the cnf_ot flow train step (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reps R] [--impl ours|reference]
 
 A "step" = one evaluation of the configured MFC loss and its parameter gradient
 (all flow passes forward + inverse + log-det + loss terms + backward; optimiser
-excluded) over one synthetic batch.  Workload = BASELINE.json
+excluded) over one synthetic batch.  Headline workload = BASELINE.json
 configs[1]: mfc.yaml type=ot subtype=obstacle, 2-D, RQS flow (2 layers, 2x16
 conditioner, 5 bins), batch 2^18 per GPU (weak scaling), lambda=5000, dt=0.01.
 
-  value  samples/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e    the same through the C-ABI call with HOST (pinned) buffers: H2D of the batch
-         and the weights, the step, D2H of [gradient | loss] inside the timed region
+  value       samples/s with the batch already resident in HBM (CUDA events, max over ranks;
+              median of --reps repetitions of the K-step block, min / max in `spread`)
+  e2e         the same through the C-ABI call with HOST (pinned) buffers: H2D of the inputs
+              and the weights, the step, D2H of [gradient | loss] inside the timed region
+  parity      the SAME parameter blob and the SAME 2^18-row input set evaluated by the CPU
+              oracle (oracle/, torch f64): relative loss / gradient error of the timed path
+  dp_check    N > 1: the fused step + all-reduce (cnfot_mfc_step_dp) against step + NCCL
+              all-reduce on the same inputs, and whether every rank holds identical bytes
+  per_config  the other BASELINE configs (cfg 1 B=4096; cfg 3 rwpo/double_well 2^20; cfg 4
+              fp/nongradient d=10, 2^22 rows over the GPUs; cfg 5 d=32 16x(2x512), reduced
+              rows), each with ms/step, samples/s, a roofline object and a small-batch
+              oracle check
   --impl reference : the CPU restatement of the reference step (oracle/, torch f64,
-         all host threads) on a bounded sample of the same workload.
+              all host threads) on a bounded sample of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
+import statistics
 import sys
 import threading
 import time
@@ -46,29 +57,66 @@ def emit(line):
   _JSON_OUT.flush()
 
 
-def workload_cfg(batch):
-  return {
-    "general": {"type": "ot", "dim": 2, "dx": 0.01, "dt": 0.01, "t_batch_size": 1, "seed": 42},
+def log(msg):
+  print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------- workloads (BASELINE.json configs)
+def mfc_cfg(typ, sub, dim, batch, H=16, L=2, M=2, K=5, lam=5000.0):
+  """mfc.yaml-shaped dict (config/mfc.yaml:6-40) of one BASELINE config."""
+  cfg = {
+    "general": {"type": typ, "dim": dim, "dx": 0.01, "dt": 0.01, "t_batch_size": 1, "seed": 42},
     "ot": {"subtype": "obstacle"},
     "rwpo": {"T": 1, "beta": 1, "a": 1, "pot_type": "double_well"},
     "fp": {"T": 1, "a": 1, "sigma": 0.5, "velocity_field_type": "nongradient"},
-    "cnf": {"flow_num_layers": 2, "mlp_num_layers": 2, "hidden_size": 16, "num_bins": 5},
-    "train": {"epochs": 1, "lr": 1e-3, "_lambda": 5000.0, "batch_size": batch, "eval_frequency": 100},
+    "cnf": {"flow_num_layers": L, "mlp_num_layers": M, "hidden_size": H, "num_bins": K},
+    "train": {"epochs": 1, "lr": 1e-3, "_lambda": lam, "batch_size": batch, "eval_frequency": 100},
   }
+  cfg[typ][{"ot": "subtype", "rwpo": "pot_type", "fp": "velocity_field_type"}[typ]] = sub
+  return cfg
 
 
-def config_block(n_gpus, extra=None):
-  c = {
-    "workload": "mfc.yaml type=ot subtype=obstacle (BASELINE configs[1])",
+# name -> (BASELINE label, type, subtype, dim, (H, L, M, K), rows rule, param sigma)
+#   rows rule: ("weak", rows per GPU) or ("strong", global rows shared by the GPUs)
+WORKLOADS = {
+  "cfg1": ("mfc.yaml type=ot subtype=free, 2-D Gaussian->Gaussian, batch 4096 (BASELINE configs[0])",
+           "ot", "free", 2, (16, 2, 2, 5), ("strong", 4096), 0.3),
+  "cfg2": ("mfc.yaml type=ot subtype=obstacle (BASELINE configs[1])",
+           "ot", "obstacle", 2, (16, 2, 2, 5), ("weak", B_PER_GPU), 0.3),
+  "cfg3": ("mfc.yaml type=rwpo pot_type=double_well T=1 beta=1 a=1, batch 2^20 per GPU (BASELINE configs[2])",
+           "rwpo", "double_well", 2, (16, 2, 2, 5), ("weak", 1 << 20), 0.3),
+  "cfg4": ("mfc.yaml type=fp velocity_field_type=nongradient sigma=0.5, d=10, batch 2^22 over the GPUs (BASELINE configs[3])",
+           "fp", "nongradient", 10, (16, 2, 2, 5), ("strong", 1 << 22), 0.05),
+  "cfg5": ("synthetic scale-out, ot/free structure, d=32, 16 layers, conditioner 2x512 (BASELINE configs[4], reduced rows)",
+           "ot", "free", 32, (512, 16, 2, 5), ("weak", 1 << 15), 0.0),
+}
+
+
+def mlp_flops_per_row_eval(D, L, M, H, Pp=16):
+  """2 L sum_{d=1}^{D-1} [(d+1) H + (M-1) H^2 + H P]."""
+  return 2 * L * sum((d + 1) * H + (M - 1) * H * H + H * Pp for d in range(1, D))
+
+
+def flow_evals_per_step(typ, sub, D, B, b):
+  """Rows pushed through the flow per step."""
+  if typ == "ot":
+    return 2 * B + (3 if sub == "obstacle" else 2) * b
+  if typ == "rwpo":
+    return 2 * B + (3 + 2 * D) * b
+  return B + (3 + 2 * D) * b
+
+
+def config_block(n_gpus):
+  """`config` of the JSON line: identical in both arms (our arm's run details go to `run`)."""
+  return {
+    "workload": WORKLOADS["cfg2"][0],
     "dim": 2, "flow_num_layers": 2, "mlp": "2x16", "num_bins": 5, "params": 1200,
     "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "sub_batch": "batch//32",
     "t_batch_size": 1, "lambda": 5000.0, "param_sigma": SIGMA,
     "rows_through_flow_per_step": "2B log-prob dir + 3(B/32) sample dir",
     "parallelism": f"dp{n_gpus} (rows sharded, one all-reduce of [grad|loss])",
+    "l2_policy": "rotating input sets, > 2x L2 in aggregate (every step streams its batch from HBM)",
   }
-  if extra:
-    c.update(extra)
-  return c
 
 
 # ---------------------------------------------------------------- clocks (NVML, in-process)
@@ -122,36 +170,69 @@ class ClockSampler:
             "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ---------------------------------------------------------------- CPU reference arm
-def oracle_step_timer(rows):
-  """One reference train step on the host: value_and_grad of the CPU restatement."""
+# ---------------------------------------------------------------- CPU oracle legs (checker / baseline only)
+def oracle_params_from_blob(shape, blob):
+  """The haiku-shaped float64 parameter dict the oracle takes, from the blob the GPU arm runs."""
+  from cnf_ot_b200.layout import unpack
+  p = unpack(shape, blob.detach().cpu())
+  return {mod: {k: v.double() for k, v in leaves.items()} for mod, leaves in p.items()}
+
+
+def oracle_value_and_grad(cfg, shape, blob, inputs):
+  """loss (float), gradient (float64 blob) of the CPU restatement on explicit inputs."""
+  from cnf_ot_b200.layout import pack
   from oracle import losses as olosses
-  from util import make_inputs, make_params
-  cfg = workload_cfg(rows)
-  spec, params = make_params(cfg, SIGMA)
-  inputs = make_inputs(cfg)
+  spec = olosses.spec_from_config(cfg)
+  params = oracle_params_from_blob(shape, blob)
+  t0 = time.perf_counter()
+  loss, grads = olosses.value_and_grad(cfg, spec, params, inputs)
+  dt = time.perf_counter() - t0
+  return float(loss), pack(shape, grads, torch.float64), dt
 
-  def step():
-    t0 = time.perf_counter()
-    loss, _ = olosses.value_and_grad(cfg, spec, params, inputs)
-    return time.perf_counter() - t0, float(loss)
 
-  return step
+def parity_against_oracle(cfg, shape, blob, inputs_dev, t_batch, lam, out_dev):
+  """Relative loss / gradient error of a device result against the oracle on the same blob and inputs."""
+  dbl = lambda x: None if x is None else x.detach().cpu().double()
+  inputs = {"t_batch": torch.tensor(list(t_batch), dtype=torch.float64)}
+  for k in ("latent", "latent_sub", "src", "tgt"):
+    if inputs_dev.get(k) is not None:
+      inputs[k] = dbl(inputs_dev[k])
+  if "latent" not in inputs:          # ot: the oracle's sub-batch rows
+    inputs["latent"] = inputs["latent_sub"]
+  loss, G, dt = oracle_value_and_grad(cfg, shape, blob, inputs)
+  out = out_dev.detach().cpu().double()
+  n = shape.blob_size
+  return {"loss_rel": abs(float(out[n]) - loss) / abs(loss),
+          "grad_rel": float((out[:n] - G).abs().max() / G.abs().max()),
+          "loss": float(out[n]), "oracle_loss": loss, "oracle_seconds": dt}
 
 
 def cpu_baseline(budget_s=15.0):
+  """The oracle (port of the reference step) timed on the host cores on a bounded sample."""
+  from oracle import losses as olosses
+  from util import make_inputs, make_params
   torch.set_num_threads(os.cpu_count() or 1)
-  probe = oracle_step_timer(1 << 13)
+
+  def timer(rows):
+    cfg = mfc_cfg("ot", "obstacle", 2, rows)
+    spec, params = make_params(cfg, SIGMA)
+    inputs = make_inputs(cfg)
+
+    def step():
+      t0 = time.perf_counter()
+      olosses.value_and_grad(cfg, spec, params, inputs)
+      return time.perf_counter() - t0
+    return step
+
+  probe = timer(1 << 13)
   probe()
-  dt, _ = probe()
-  rate = (1 << 13) / dt
+  rate = (1 << 13) / probe()
   rows = 1 << 13
   while rows < B_PER_GPU and (rows * 2) / rate * 3 < budget_s:
     rows *= 2
-  step = oracle_step_timer(rows)
+  step = timer(rows)
   step()
-  ts = [step()[0] for _ in range(2)]
-  best = min(ts)
+  best = min(step() for _ in range(2))
   return {"value": rows / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
           "sample": f"oracle (torch f64 restatement of the reference step) on {rows} rows of the "
                     f"same workload, best of 2 after 1 warm-up"}
@@ -161,29 +242,27 @@ def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  from oracle import losses as olosses
+  from util import make_inputs, make_params
   torch.set_num_threads(os.cpu_count() or 1)
-  if args.workload == "cfg5":
-    # BASELINE configs[4] on the CPU restatement: one bounded sample per step (128 rows of the same flow and loss)
-    cb = cpu_baseline_cfg5(args.layers)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
-            "warmup": 1, "ms_per_step": 128 / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic scale-out, ot/free structure (BASELINE configs[4])", "dim": 32,
-                       "flow_num_layers": args.layers, "mlp": "2x512", "rows_per_step_cpu": 128},
-            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
-    return
+
+  def timer(rows):
+    cfg = mfc_cfg("ot", "obstacle", 2, rows)
+    spec, params = make_params(cfg, SIGMA)
+    inputs = make_inputs(cfg)
+    return lambda: olosses.value_and_grad(cfg, spec, params, inputs)
+
   # bounded sample per step so K + W steps end within minutes
-  probe = oracle_step_timer(1 << 12)
+  probe = timer(1 << 12)
   probe()
-  dt, _ = probe()
-  rate = (1 << 12) / dt
+  t0 = time.perf_counter()
+  probe()
+  rate = (1 << 12) / (time.perf_counter() - t0)
   total = args.steps + args.warmup
   rows = 1 << 12
   while rows < B_PER_GPU and (rows * 2) / rate * total < 120.0:
     rows *= 2
-  step = oracle_step_timer(rows)
+  step = timer(rows)
   for _ in range(args.warmup):
     step()
   t0 = time.perf_counter()
@@ -193,32 +272,32 @@ def run_reference(args):
   value = rows * args.steps / el
   sample = (f"reference step restated on CPU (oracle/, torch f64, autograd), {rows} rows per step "
             f"(bounded sample of the 2^18-row workload), {torch.get_num_threads()} threads")
-  line = {
+  emit({
     "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-    "data": "synthetic", "config": config_block(args.gpus, {"rows_per_step_cpu": rows}),
+    "data": "synthetic", "config": config_block(args.gpus),
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                      "sample": sample},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    "gpu_launches": 0,
-  }
-  emit(line)
+    "gpu_launches": 0, "run": {"rows_per_step_cpu": rows},
+  })
 
 
 # ---------------------------------------------------------------- our arm
-def make_blob(shape, device):
-  """Reference init + N(0, sigma^2) on biases, output layers and `first` (seed 43)."""
+def make_blob(shape, device, sigma, seed=43):
+  """Reference init (FlowModel.init) + N(0, sigma^2) on biases, output layers and `first`."""
   from cnf_ot_b200 import random as crandom
   from cnf_ot_b200.flows import FlowModel
   model = FlowModel(shape, device)
   params = model.init(crandom.PRNGKey(3))
-  g = torch.Generator(device="cpu").manual_seed(43)
-  for mod, leaves in params.items():
-    for name, v in leaves.items():
-      if name == "w" and mod.startswith("mlp_"):
-        continue
-      v.add_((torch.randn(v.shape, generator=g) * SIGMA).to(device))
+  g = torch.Generator(device="cpu").manual_seed(seed)
+  if sigma > 0:
+    for mod, leaves in params.items():
+      for name, v in leaves.items():
+        if name == "w" and mod.startswith("mlp_"):
+          continue
+        v.add_((torch.randn(v.shape, generator=g) * sigma).to(device))
   return params.blob
 
 
@@ -227,23 +306,243 @@ def peaks():
   if os.path.exists(path):
     with open(path) as f:
       return json.load(f), "measured (MEASURED_PEAKS.json)"
-  return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+  return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "bf16_tflops_sustained": 1392.5}, "fallback (B200_PROFILING.md)"
 
 
-def time_region(fn, n, stream_sync):
+def time_region(fn, n, stream_sync, first=0):
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   stream_sync()
   e0.record()
-  for i in range(n):
+  for i in range(first, first + n):
     fn(i)
   e1.record()
   stream_sync()
   return e0.elapsed_time(e1) / 1e3  # seconds
 
 
+class Dist:
+  """Rank plumbing of one bench process."""
+
+  def __init__(self):
+    import torch.distributed as td
+    self.td = td
+    self.world = int(os.environ.get("WORLD_SIZE", "1"))
+    self.rank = int(os.environ.get("RANK", "0"))
+    self.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+      raise SystemExit("bench.py needs a CUDA device: cnf_ot_b200 has no CPU path")
+    torch.cuda.set_device(self.local)
+    self.dev = torch.device("cuda", self.local)
+    if self.world > 1:
+      os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the ONE JSON line
+      td.init_process_group("nccl", device_id=self.dev)
+
+  def sync(self):
+    if self.world > 1:
+      self.td.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(self, seconds):
+    t = torch.tensor(list(seconds), dtype=torch.float64, device=self.dev)
+    if self.world > 1:
+      self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+    return t.tolist()
+
+  def close(self):
+    if self.world > 1:
+      self.td.barrier()
+      self.td.destroy_process_group()
+
+
+def timed_reps(dist, step, steps, reps):
+  """`reps` repetitions of a `steps`-step block; per-step seconds of each block, max over ranks."""
+  per = []
+  for r in range(reps):
+    per.append(time_region(step, steps, dist.sync, first=r * steps) / steps)
+  return dist.max_over_ranks(per)
+
+
+def spread(per_step_s):
+  return {"median_ms": statistics.median(per_step_s) * 1e3, "min_ms": min(per_step_s) * 1e3,
+          "max_ms": max(per_step_s) * 1e3, "reps": len(per_step_s)}
+
+
+class Workload:
+  """One BASELINE config on this rank: shapes, parameter blob, rotating synthetic input sets, the step closure."""
+
+  def __init__(self, name, dist, max_sets_bytes=2 * 126 * 2**20 + 2**20, oracle_rows=None, rows_override=None):
+    from cnf_ot_b200 import ops
+    from cnf_ot_b200.layout import FlowShape
+    label, typ, sub, D, (H, L, M, K), (rule, rows), sigma = WORKLOADS[name]
+    self.name, self.label, self.typ, self.sub, self.D, self.rule, self.sigma = name, label, typ, sub, D, rule, sigma
+    self.dist = dist
+    dev, world, rank = dist.dev, dist.world, dist.rank
+    if oracle_rows is not None:     # the small-batch oracle check: one GPU's worth, whole batch on this rank
+      self.gB, self.B = oracle_rows, oracle_rows
+    elif rows_override:             # --only cfgN --rows-per-gpu R (e.g. cfg 5 at its BASELINE size, 2^21 rows per GPU)
+      self.gB, self.B, self.rule = rows_override * world, rows_override, "weak"
+    elif rule == "weak":
+      self.gB, self.B = rows * world, rows
+    else:
+      self.gB, self.B = rows, rows // world
+    self.gb, self.b = self.gB // 32, self.B // 32
+    self.lam = 5000.0
+    self.cfg = mfc_cfg(typ, sub, D, self.gB, H, L, M, K, self.lam)
+    self.shape = FlowShape(D, L, M, H, K)
+    self.problem = ops.problem_desc(self.cfg)
+    if name == "cfg5":
+      # haiku-like scale for the hidden matrices (1/sqrt(fan_in) ~ 0.04 at 512), small output layers: a well-conditioned flow
+      g = torch.Generator(device=dev).manual_seed(43)
+      self.W = torch.randn(self.shape.blob_size, device=dev, generator=g) * 0.02
+    else:
+      self.W = make_blob(self.shape, dev, sigma)
+    if world > 1:
+      dist.td.broadcast(self.W, 0)
+    row_bytes = D * 4
+    per_set = ((2 if typ == "ot" else 1) * self.B + self.b) * row_bytes
+    self.bytes_per_set = per_set
+    self.n_sets = 1 if oracle_rows is not None else max(2, min(64, max_sets_bytes // max(per_set, 1) + 1))
+    if per_set > 126 * 2**20:
+      self.n_sets = 2
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    centres = torch.tensor([[0., 5.], [5., 0.], [0., -5.], [-5., 0.], [3., 4.], [3., -4.], [-3., -4.], [-3., 4.]], device=dev)
+    self.sets = []
+    for _ in range(self.n_sets):
+      s = {"latent_sub": torch.randn(self.b, D, device=dev, generator=g)}
+      if typ == "ot":
+        z = torch.randn(self.B, D, device=dev, generator=g)
+        if sub == "obstacle" and D == 2:   # the live 8-mode mixture source (applications.py:34-71)
+          s["src"] = z + centres[torch.randint(0, 8, (self.B, ), device=dev, generator=g)]
+        else:                               # Gaussian -> Gaussian (applications.py:28-32, ot.py:72-80)
+          s["src"] = z - 3.0
+        s["tgt"] = z
+      else:
+        s["latent"] = torch.randn(self.B, D, device=dev, generator=g)
+      self.sets.append(s)
+    horizon = 1.0 if typ == "ot" else float(self.cfg[typ]["T"])
+    self.t_vals = (torch.rand(4096, generator=torch.Generator().manual_seed(42)) * horizon).tolist()
+    self.out = torch.empty(self.shape.blob_size + 8, dtype=torch.float32, device=dev)
+    self.px, self.transport = None, "none"
+    self.wide = H > 64
+
+  def attach_peer_exchange(self):
+    """N > 1: fused all-reduce over peer-mapped memory where the library supports it, else NCCL."""
+    if self.dist.world == 1:
+      return
+    if self.wide:
+      self.transport = f"NCCL all-reduce ({self.shape.blob_size * 4 >> 20} MiB)"
+      return
+    if self.shape.blob_size + 8 > 9000:
+      # the exchange kernel needs all its blocks co-resident (ADVICE r1): larger buffers go through NCCL
+      self.transport = "NCCL all-reduce"
+      return
+    try:
+      from cnf_ot_b200 import dist as cdist
+      self.px = cdist.PeerExchange(self.shape, self.dist.dev)
+      self.transport = "fused in the step's reduction over peer-mapped memory (NVLink/NVSwitch)"
+    except Exception as exc:  # symmetric memory unavailable
+      log(f"PeerExchange unavailable ({exc!r}); using NCCL all-reduce")
+      self.transport = "NCCL all-reduce"
+
+  def args_of(self, s, i):
+    return (s.get("latent"), s["latent_sub"], s.get("src"), s.get("tgt"), [self.t_vals[i % 4096]])
+
+  def step(self, i, peers="default", out=None):
+    from cnf_ot_b200 import ops
+    s = self.sets[i % self.n_sets]
+    lat, sub, src, tgt, tb = self.args_of(s, i)
+    px = self.px if peers == "default" else peers
+    out = self.out if out is None else out
+    ops.mfc_step(self.shape, self.problem, self.W, lat, sub, src, tgt, tb, self.lam, self.gB, self.gb, out=out, peers=px)
+    if self.dist.world > 1 and px is None:
+      self.dist.td.all_reduce(out)
+    return out
+
+  def flops_per_step(self):
+    H, L, M = self.shape.hidden, self.shape.num_layers, self.shape.mlp_layers
+    evals = flow_evals_per_step(self.typ, self.sub, self.D, self.B, self.b)
+    return evals * 3.0 * mlp_flops_per_row_eval(self.D, L, M, H), evals
+
+
+def oracle_check_small(name, dist, rows):
+  """Small-batch parity of one config against the CPU oracle (rank 0, its own GPU only)."""
+  from cnf_ot_b200 import ops
+  w = Workload(name, dist_single(dist), oracle_rows=rows)
+  s = w.sets[0]
+  lat, sub, src, tgt, tb = w.args_of(s, 0)
+  out = ops.mfc_step(w.shape, w.problem, w.W, lat, sub, src, tgt, tb, w.lam, w.gB, w.gb)
+  torch.cuda.synchronize()
+  r = parity_against_oracle(w.cfg, w.shape, w.W, s, tb, w.lam, out)
+  return {"rows": rows, "loss_rel": r["loss_rel"], "grad_rel": r["grad_rel"], "oracle_seconds": r["oracle_seconds"]}
+
+
+class _Single:
+  """A world-size-1 view of a Dist (rank 0's own GPU)."""
+
+  def __init__(self, dist):
+    self.dev, self.world, self.rank, self.local, self.td = dist.dev, 1, 0, dist.local, dist.td
+
+  def sync(self):
+    torch.cuda.synchronize()
+
+  def max_over_ranks(self, seconds):
+    return list(seconds)
+
+
+def dist_single(dist):
+  return _Single(dist)
+
+
+def fused_rooflines(w, t_step, pk, pk_src):
+  """The three views of the fused step kernel: HBM (contract), fp32 CUDA-core peak on algorithmic FLOPs."""
+  hbm = float(pk["hbm_gbs"])
+  clk = float(pk.get("sm_max_mhz", 1965.0)) * 1e6
+  n = w.shape.blob_size
+  alg_bytes = w.bytes_per_set + n * 4 + (n + 8) * 4
+  flops, evals = w.flops_per_step()
+  fp32_peak = 148 * 128 * 2 * clk / 1e12
+  ach = alg_bytes / t_step / 1e9
+  return {
+    "roofline": {"bound": "hbm", "kernel": "mfc_step_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                 "frac": ach / hbm, "traffic": None, "peak_source": pk_src, "algorithmic_bytes_per_launch": alg_bytes},
+    "roofline_fp32": {"bound": "fp32", "kernel": "mfc_step_kernel", "achieved": flops / t_step / 1e12, "peak": fp32_peak,
+                      "unit": "TFLOP/s", "frac": flops / t_step / 1e12 / fp32_peak, "flops_per_launch": flops,
+                      "rows_through_flow_per_launch": evals},
+  }
+
+
+def kernel_fingerprint():
+  """Identity of the loaded library: the profile-derived constants in profiles/traffic.json are only
+  trusted when they were captured from the same kernels (tools/ncu_summary.py records the same hash)."""
+  from cnf_ot_b200 import _lib
+  h = hashlib.sha256()
+  csrc = os.path.join(ROOT, "cnf_ot_b200", "csrc")
+  for fn in sorted(os.listdir(csrc)):
+    if fn.endswith((".cu", ".cuh", ".h")):
+      with open(os.path.join(csrc, fn), "rb") as f:
+        h.update(fn.encode())
+        h.update(f.read())
+  return h.hexdigest()[:16]
+
+
+def profile_constants():
+  """(dram bytes per launch, warp instructions per launch, note) of mfc_step_kernel from profiles/traffic.json, or
+  Nones when the file was captured from other kernel sources than the ones built here."""
+  tpath = os.path.join(ROOT, "profiles", "traffic.json")
+  if not os.path.exists(tpath):
+    return None, None, "no profiles/traffic.json"
+  with open(tpath) as f:
+    tj = json.load(f)
+  fp = kernel_fingerprint()
+  if tj.get("csrc_sha16") != fp:
+    return None, None, f"profiles/traffic.json was captured from other kernel sources ({tj.get('csrc_sha16')} != {fp}): not used"
+  return (tj.get("mfc_step_kernel_dram_bytes_per_launch"), tj.get("mfc_step_kernel_warp_insts_per_launch"),
+          tj.get("source"))
+
+
 def spline_rooflines(peak_gbs):
   """Stand-alone spline kernels (seam 2), HBM-bound: algorithmic bytes 4P+12 / 8P+16 per row."""
-  from cnf_ot_b200 import _lib, ops
+  from cnf_ot_b200 import _lib
   lib = _lib.load()
   n, K, P = 1 << 24, 5, 16
   theta = torch.randn(n, P, device="cuda") * SIGMA
@@ -269,328 +568,239 @@ def spline_rooflines(peak_gbs):
   return out
 
 
-def run_ours(args):
-  import torch.distributed as td
-  from cnf_ot_b200 import _lib, ops
-  from cnf_ot_b200.layout import FlowShape
+def dense_roofline(dev, pk, pk_src):
+  """cfg 5's dominant kernel (hidden-layer GEMM rows x 512 x 512, 3xTF32 on tcgen05), timed alone on one row chunk."""
+  from cnf_ot_b200 import ops
+  H, rows = 512, 4 * 148 * 128
+  X = torch.randn(rows, H, device=dev)
+  P = ops.PreparedDense(torch.randn(H, H, device=dev) / H**0.5)
+  bias = torch.zeros(H, device=dev)
+  Y = torch.empty(rows, H, device=dev)
+  fn = lambda i: ops.dense_forward(X, P, bias=bias, epilogue="bias_relu", out=Y)
+  for i in range(3):
+    fn(i)
+  tk = time_region(fn, 20, torch.cuda.synchronize) / 20
+  tf32_peak = float(pk.get("bf16_tflops_sustained", 1392.5)) / 2.0
+  pipe = 3 * 2.0 * rows * H * H / tk / 1e12   # tf32 MMA flops issued (3 per fp32-fidelity product)
+  return {"bound": "tensor", "kernel": "dense_tc_kernel<256,1> (hidden layer, rows x 512 x 512, timed alone)",
+          "achieved": pipe, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pipe / tf32_peak, "traffic": None,
+          "peak_source": pk_src + ": bf16_tflops_sustained / 2 (tf32)", "fp32_fidelity_tflops": pipe / 3,
+          "us_per_launch": tk * 1e6}
 
-  world = int(os.environ.get("WORLD_SIZE", "1"))
-  rank = int(os.environ.get("RANK", "0"))
-  local = int(os.environ.get("LOCAL_RANK", "0"))
-  if not torch.cuda.is_available():
-    raise SystemExit("bench.py needs a CUDA device: cnf_ot_b200 has no CPU path")
-  torch.cuda.set_device(local)
-  dev = torch.device("cuda", local)
-  if world > 1:
-    # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    td.init_process_group("nccl", device_id=dev)
-  _lib.load()
 
-  n_gpus = world
-  B, b = B_PER_GPU, B_PER_GPU // 32
-  gB, gb = B * n_gpus, b * n_gpus
-  cfg = workload_cfg(gB)
-  shape = FlowShape(2, 2, 2, 16, 5)
-  problem = ops.problem_desc(cfg)
-  lam = 5000.0
-  W = make_blob(shape, dev)
-  if world > 1:
-    td.broadcast(W, 0)
-
-  # rotating input sets, > 2x L2 in aggregate, so every step streams its batch from HBM
-  bytes_per_set = (2 * B + b) * 2 * 4
-  n_sets = max(4, (2 * 126 * 2**20) // bytes_per_set + 1)
-  g = torch.Generator(device=dev).manual_seed(42 + rank)
-  centres = torch.tensor([[0., 5.], [5., 0.], [0., -5.], [-5., 0.], [3., 4.], [3., -4.], [-3., -4.], [-3., 4.]], device=dev)
-  sets = []
-  for _ in range(n_sets):
-    z = torch.randn(B, 2, device=dev, generator=g)
-    src = z + centres[torch.randint(0, 8, (B, ), device=dev, generator=g)]
-    sets.append((src, z, torch.randn(b, 2, device=dev, generator=g)))
-  tgen = torch.Generator().manual_seed(42)
-  t_vals = torch.rand(4096, generator=tgen).tolist()
-  out = torch.empty(shape.blob_size + 8, dtype=torch.float32, device=dev)
-
-  # N > 1: the step's final reduction kernel also does the all-reduce of [gradient | loss] over
-  # peer-mapped memory (NVLink / NVSwitch; cnfot_mfc_step_dp).  NCCL is the fallback transport.
-  px, transport = None, "none"
-  if world > 1:
+def per_config_entry(name, dist, args, pk, pk_src):
+  """Timing + roofline + small-batch oracle check of one BASELINE config other than the headline one."""
+  steps = {"cfg1": 50, "cfg2": 20, "cfg3": 10, "cfg4": 3, "cfg5": 2}[name]
+  reps = {"cfg1": 5, "cfg2": 5, "cfg3": 5, "cfg4": 3, "cfg5": 1}[name]
+  if args.only:
+    steps, reps = args.steps, args.reps
+  w = Workload(name, dist, rows_override=args.rows_per_gpu if args.only else None)
+  w.attach_peer_exchange()
+  for i in range(3 if name != "cfg5" else 1):
+    w.step(i)
+  per = timed_reps(dist, w.step, steps, reps)
+  t_step = statistics.median(per)
+  entry = {
+    "workload": w.label, "dim": w.D, "params": w.shape.blob_size, "batch_per_gpu": w.B, "global_batch": w.gB,
+    "scaling": w.rule, "steps": steps, "ms_per_step": t_step * 1e3, "spread": spread(per),
+    "value": w.gB / t_step, "unit": UNIT, "all_reduce": w.transport, "param_sigma": w.sigma,
+    "input_sets": w.n_sets, "input_set_bytes": w.bytes_per_set,
+    "loss_last_step": float(w.out[w.shape.blob_size]),
+  }
+  if dist.rank == 0:
+    if w.wide:
+      entry["roofline"] = dense_roofline(dist.dev, pk, pk_src)
+      flops, evals = w.flops_per_step()
+      entry["roofline"]["step_algorithmic_tflops"] = flops / t_step / 1e12
+    else:
+      entry.update(fused_rooflines(w, t_step, pk, pk_src))
+  del w
+  torch.cuda.empty_cache()
+  if dist.rank == 0 and not args.no_oracle:
+    rows = {"cfg1": 4096, "cfg3": 4096, "cfg4": 512, "cfg5": 64}[name]
     try:
-      from cnf_ot_b200 import dist
-      px = dist.PeerExchange(shape, dev)
-      transport = "fused in the step's reduction kernel over peer-mapped memory (NVLink/NVSwitch)"
-    except Exception as exc:  # symmetric memory unavailable
-      print(f"[bench] PeerExchange unavailable ({exc!r}); using NCCL all-reduce", file=sys.stderr)
-      transport = "NCCL all-reduce"
+      entry["oracle_check"] = oracle_check_small(name, dist, rows)
+    except Exception as exc:   # keep the line: a failed check is reported, not hidden
+      entry["oracle_check"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+  return entry
 
-  def step(i):
-    src, tgt, sub = sets[i % n_sets]
-    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out, peers=px)
-    if world > 1 and px is None:
-      td.all_reduce(out)
 
-  def sync():
-    if world > 1:
-      td.barrier()
+def run_ours(args):
+  from cnf_ot_b200 import _lib, ops
+  dist = Dist()
+  td, world, rank, dev = dist.td, dist.world, dist.rank, dist.dev
+  _lib.load()
+  pk, pk_src = peaks()
+
+  w = Workload("cfg2", dist)
+  w.attach_peer_exchange()
+  shape, n = w.shape, w.shape.blob_size
+  warm = max(args.warmup, 3)
+  for i in range(warm):
+    w.step(i)
+  with ClockSampler(dist.local) as clk:
+    per = timed_reps(dist, w.step, args.steps, args.reps)
+  t_step = statistics.median(per)
+  value = w.gB / t_step
+  loss_dev = float(w.out[n])
+  launch = _lib.last_launch_info()
+
+  # ---- parity at the FULL batch: same blob, same input set, CPU oracle (rank 0's shard as a whole batch)
+  parity = None
+  if rank == 0 and not args.no_oracle:
+    s = w.sets[0]
+    lat, sub, src, tgt, tb = w.args_of(s, 0)
+    o = ops.mfc_step(shape, w.problem, w.W, lat, sub, src, tgt, tb, w.lam, w.B, w.b)
     torch.cuda.synchronize()
+    pcfg = mfc_cfg(w.typ, w.sub, w.D, w.B)
+    parity = parity_against_oracle(pcfg, shape, w.W, s, tb, w.lam, o)
+    parity["rows"] = w.B
+    parity["note"] = ("the timed kernel on input set 0 of this run (this rank's 2^18 rows as one batch) against "
+                      "oracle/ (torch f64) on the same parameter blob and rows; tolerance 2e-5 / 5e-5 (tests/test_gpu_step.py)")
 
-  for i in range(max(args.warmup, 3)):
-    step(i)
-  with ClockSampler(local) as clk:
-    el = time_region(step, args.steps, sync)
-  t = torch.tensor([el], dtype=torch.float64, device=dev)
+  # ---- N > 1: the fused step + all-reduce against step + NCCL all-reduce, same inputs
+  dp_check = None
   if world > 1:
-    td.all_reduce(t, op=td.ReduceOp.MAX)
-  el = float(t)
-  value = gB * args.steps / el
-  loss_dev = float(out[shape.blob_size])
+    a = torch.empty_like(w.out)
+    w.step(0, peers=None, out=a)            # plain step, then NCCL all-reduce
+    ref = a.clone()
+    if w.px is not None:
+      w.step(0, out=a)                      # fused
+    torch.cuda.synchronize()
+    err = float((a.double() - ref.double()).abs().max() / ref.double().abs().max())
+    digest = torch.tensor(list(hashlib.sha256(a.cpu().numpy().tobytes()).digest()[:8]), dtype=torch.int64, device=dev)
+    alld = [torch.empty_like(digest) for _ in range(world)]
+    td.all_gather(alld, digest)
+    dp_check = {"dp_check_rel_err": err, "identical_on_all_ranks": all(bool((d == alld[0]).all()) for d in alld),
+                "fused": w.px is not None,
+                "note": "cnfot_mfc_step_dp (all-reduce inside the step's reduction kernel) vs cnfot_mfc_step + NCCL all_reduce"}
 
-  # ---- e2e: host buffers through the C ABI (N=1) / pinned copies + all-reduce (N>1)
+  # ---- e2e: host buffers through the C ABI (N=1) / pinned rows read in place + all-reduce (N>1)
   n_host = 8
-  pin = lambda x: x.cpu().contiguous().pin_memory()
-  hsets = [(pin(s[0]), pin(s[1]), pin(s[2])) for s in sets[:n_host]]
-  hW = pin(W)
-  hout = torch.empty(shape.blob_size + 8, dtype=torch.float32).pin_memory()
-  dW2 = torch.empty_like(W)
+  pin = lambda x: None if x is None else x.cpu().contiguous().pin_memory()
+  hsets = [{k: pin(v) for k, v in s.items()} for s in w.sets[:n_host]]
+  hW = pin(w.W)
+  hout = torch.empty(n + 8, dtype=torch.float32).pin_memory()
+  dW2 = torch.empty_like(w.W)
 
   def step_e2e(i):
-    src, tgt, sub = hsets[i % n_host]
+    s = hsets[i % n_host]
+    lat, sub, src, tgt, tb = w.args_of(s, i)
     if world == 1:
-      ops.mfc_step_host(shape, problem, hW, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, hout, device=dev)
+      ops.mfc_step_host(shape, w.problem, hW, lat, sub, src, tgt, tb, w.lam, w.gB, w.gb, hout, device=dev)
     else:
-      # weights H2D; the pinned row buffers are read in place by the kernel (zero-copy over PCIe)
       dW2.copy_(hW, non_blocking=True)
-      ops.mfc_step(shape, problem, dW2, None, sub, src, tgt, [t_vals[i % 4096]], lam, gB, gb, out=out, peers=px)
-      if px is None:
-        td.all_reduce(out)
-      hout.copy_(out, non_blocking=True)
+      ops.mfc_step(shape, w.problem, dW2, lat, sub, src, tgt, tb, w.lam, w.gB, w.gb, out=w.out, peers=w.px)
+      if w.px is None:
+        td.all_reduce(w.out)
+      hout.copy_(w.out, non_blocking=True)
       torch.cuda.synchronize()
 
   for i in range(3):
     step_e2e(i)
-  el_e = time_region(step_e2e, args.steps, sync)
-  t = torch.tensor([el_e], dtype=torch.float64, device=dev)
-  if world > 1:
-    td.all_reduce(t, op=td.ReduceOp.MAX)
-  el_e = float(t)
-  h2d = (2 * B + b) * 2 * 4 + shape.blob_size * 4
-  d2h = (shape.blob_size + 8) * 4
+  per_e = timed_reps(dist, step_e2e, args.steps, args.reps)
+  t_e2e = statistics.median(per_e)
+  h2d = w.bytes_per_set + n * 4
+  d2h = (n + 8) * 4
 
+  line = None
   if rank == 0:
-    pk, pk_src = peaks()
-    hbm = float(pk["hbm_gbs"])
-    # dominant kernel: mfc_step_kernel (one launch per step; finalize + an 8-byte memset ride along)
-    alg_bytes = (2 * B + b) * 2 * 4 + shape.blob_size * 4 + (shape.blob_size + 8) * 4
-    t_launch = el / args.steps
-    ach = alg_bytes / t_launch / 1e9
-    # fp32 view of the same kernel: algorithmic FLOPs = conditioner fwd+dgrad+wgrad (3 x 2176/row/pass)
-    rows_evals = 2 * B + 3 * b
-    flops = rows_evals * 3 * 2176.0
-    fp32_peak = 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-    traffic, insts = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-      with open(tpath) as f:
-        tj = json.load(f)
-      traffic = tj.get("mfc_step_kernel_dram_bytes_per_launch")
-      insts = tj.get("mfc_step_kernel_warp_insts_per_launch")
+    rf = fused_rooflines(w, t_step, pk, pk_src)
+    traffic, insts, tsrc = profile_constants()
+    rf["roofline"]["traffic"] = traffic
+    rf["roofline"]["traffic_source"] = tsrc
+    rf["roofline"]["note"] = ("the fused step kernel is bound by instruction issue, not by HBM or the tensor pipe "
+                              "(SURVEY.md §8d; ncu: profiles/): see roofline_issue / roofline_fp32; the HBM-bound kernels "
+                              "of the path are the stand-alone spline kernels in roofline_spline")
     issue_peak = 148 * 4 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6  # warp instructions / s
     line = {
-      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-      "warmup": max(args.warmup, 3), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+      "warmup": warm, "ms_per_step": t_step * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": config_block(n_gpus, {"all_reduce": transport, "l2_policy": f"{n_sets} rotating input sets ({n_sets * bytes_per_set >> 20} MiB > 2x L2)",
-                                      "loss_last_step": loss_dev}),
-      "e2e": {"value": gB * args.steps / el_e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-              "d2h_bytes_per_step": d2h, "ms_per_step": el_e / args.steps * 1e3,
+      "config": config_block(world),
+      "spread": spread(per),
+      "run": {"all_reduce": w.transport, "input_sets": w.n_sets, "input_sets_mib": w.n_sets * w.bytes_per_set >> 20,
+              "loss_last_step": loss_dev, "launch": launch},
+      "e2e": {"value": w.gB / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+              "ms_per_step": t_e2e * 1e3, "spread": spread(per_e),
               "api": "cnfot_mfc_step_host (C ABI; pinned host rows read in place by the kernel over PCIe, "
                      "weights H2D, [grad|loss] D2H)" if world == 1 else
                      "weights H2D + cnfot_mfc_step[_dp] on pinned host rows (zero-copy) + all-reduce + D2H"},
-      "gpu_launches": 2 * args.steps,  # mfc_step_kernel + finalize[_allreduce]_kernel per step
+      "gpu_launches": 2 * args.steps * args.reps,  # mfc_step_kernel + finalize[_allreduce]_kernel per step
       "clocks": clk.summary(),
-      "roofline": {"bound": "hbm", "kernel": "mfc_step_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                   "frac": ach / hbm, "traffic": traffic, "peak_source": pk_src,
-                   "note": "the fused step kernel is bound by instruction issue, not by HBM or the tensor pipe "
-                           "(SURVEY.md §8d; ncu: profiles/): see roofline_issue / roofline_fp32; the HBM-bound kernels "
-                           "of the path are the stand-alone spline kernels in roofline_spline"},
+      "parity": parity, "dp_check": dp_check,
+      "roofline": rf["roofline"],
       "roofline_issue": {"bound": "issue", "kernel": "mfc_step_kernel",
-                         "achieved": (insts / t_launch / 1e9) if insts else None, "peak": issue_peak / 1e9,
-                         "unit": "G warp-inst/s", "frac": (insts / t_launch / issue_peak) if insts else None,
+                         "achieved": (insts / t_step / 1e9) if insts else None, "peak": issue_peak / 1e9,
+                         "unit": "G warp-inst/s", "frac": (insts / t_step / issue_peak) if insts else None,
                          "warp_insts_per_launch": insts,
                          "note": "executed warp instructions per launch (ncu smsp__inst_executed.sum, profiles/) / "
                                  "live launch time, against 148 SM x 4 schedulers x max clock"},
-      "roofline_fp32": {"bound": "fp32", "kernel": "mfc_step_kernel", "achieved": flops / t_launch / 1e12,
-                        "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / fp32_peak,
-                        "flops_per_launch": flops,
-                        "note": "algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only, against the CUDA-core fp32 peak "
-                                "148 SM x 128 FMA x 2 x max clock; the 16x16 layers run on the tensor pipe (mma.sync "
-                                "tf32, 3 MMAs per product for fp32 fidelity), the input layers and splines on CUDA cores"},
+      "roofline_fp32": rf["roofline_fp32"],
     }
-    if world == 1:
-      line["roofline_spline"] = spline_rooflines(hbm)
-      line["cpu_baseline"] = cpu_baseline()
-    emit(line)
-  if world > 1:
-    td.barrier()
-    td.destroy_process_group()
+    line["roofline_fp32"]["note"] = ("algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only, against the CUDA-core fp32 peak "
+                                     "148 SM x 128 FMA x 2 x max clock; the 16x16 layers run on the tensor pipe (3 MMAs per "
+                                     "product for fp32 fidelity), the input layers and splines on CUDA cores")
+  del hsets, w
+  torch.cuda.empty_cache()
 
-
-# ---------------------------------------------------------------- BASELINE configs[4] on the wide-conditioner engine
-def run_cfg5(args):
-  """Synthetic scale-out workload (BASELINE configs[4]): d = 32, 16 layers, conditioner 2 x 512, ot/free structure,
-  Gaussian source N(-3, I) -> target N(0, I), rows sharded over the GPUs, ONE NCCL all-reduce of the 556 MB
-  [gradient | loss] buffer per step.  Not the driver's default line (that is configs[1]); run with
-  --workload cfg5 [--rows-per-gpu R] (BASELINE: 2^24 / 8 = 2^21 rows per GPU)."""
-  import torch.distributed as td
-  from cnf_ot_b200 import _lib, ops
-  from cnf_ot_b200.layout import FlowShape
-  world = int(os.environ.get("WORLD_SIZE", "1"))
-  rank = int(os.environ.get("RANK", "0"))
-  local = int(os.environ.get("LOCAL_RANK", "0"))
-  torch.cuda.set_device(local)
-  dev = torch.device("cuda", local)
-  if world > 1:
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    td.init_process_group("nccl", device_id=dev)
-  D, L, H = 32, args.layers, 512
-  shape = FlowShape(D, L, 2, H, 5)
-  B = args.rows_per_gpu
-  b = B // 32
-  gB, gb = B * world, b * world
-  cfg = {"general": {"type": "ot", "dim": D, "dx": 0.01, "dt": 0.01}, "ot": {"subtype": "free"}}
-  problem = ops.problem_desc(cfg)
-  g = torch.Generator(device=dev).manual_seed(43)
-  # haiku-like scale for the hidden matrices (1/sqrt(fan_in) ~ 0.04 at 512), small output layers: a well-conditioned flow
-  W = torch.randn(shape.blob_size, device=dev, generator=g) * 0.02
-  if world > 1:
-    td.broadcast(W, 0)
-  g = torch.Generator(device=dev).manual_seed(42 + rank)
-  n_sets = 2
-  sets = [(torch.randn(B, D, device=dev, generator=g) - 3.0, torch.randn(B, D, device=dev, generator=g),
-           torch.randn(b, D, device=dev, generator=g)) for _ in range(n_sets)]
-  out = torch.empty(shape.blob_size + 8, dtype=torch.float32, device=dev)
-  t_vals = torch.rand(64, generator=torch.Generator().manual_seed(42)).tolist()
-
-  def step(i):
-    src, tgt, sub = sets[i % n_sets]
-    ops.mfc_step(shape, problem, W, None, sub, src, tgt, [t_vals[i % 64]], 5000.0, gB, gb, out=out)
-    if world > 1:
-      td.all_reduce(out)
-
-  def sync():
-    if world > 1:
-      td.barrier()
-    torch.cuda.synchronize()
-
-  for i in range(max(args.warmup, 1)):
-    step(i)
-  with ClockSampler(local) as clk:
-    el = time_region(step, args.steps, sync)
-  t = torch.tensor([el], dtype=torch.float64, device=dev)
-  if world > 1:
-    td.all_reduce(t, op=td.ReduceOp.MAX)
-  el = float(t)
-  # e2e: pinned host rows read in place, weights H2D, [gradient | loss] D2H
-  pin = lambda x: x.cpu().contiguous().pin_memory()
-  hsrc, htgt, hsub = (pin(x) for x in sets[0])
-  hW, hout = pin(W), torch.empty(shape.blob_size + 8, dtype=torch.float32).pin_memory()
-  dW2 = torch.empty_like(W)
-
-  def step_e2e(i):
-    dW2.copy_(hW, non_blocking=True)
-    ops.mfc_step(shape, problem, dW2, None, hsub, hsrc, htgt, [t_vals[i % 64]], 5000.0, gB, gb, out=out)
-    if world > 1:
-      td.all_reduce(out)
-    hout.copy_(out, non_blocking=True)
-    torch.cuda.synchronize()
-
-  if args.no_e2e:   # BASELINE-size multi-GPU runs: one 42 s step per timed region is expensive; e2e measured at N = 1
-    el_e = float("nan")
-  else:
-    step_e2e(0)
-    el_e = time_region(step_e2e, max(1, args.steps // 2), sync) / max(1, args.steps // 2) * args.steps
-  t = torch.tensor([el_e], dtype=torch.float64, device=dev)
-  if world > 1:
-    td.all_reduce(t, op=td.ReduceOp.MAX)
-  el_e = float(t)
+  if not args.no_per_config:
+    pc = {}
+    for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
+      t0 = time.time()
+      try:
+        pc[name] = per_config_entry(name, dist, args, pk, pk_src)
+      except Exception as exc:
+        if world > 1:
+          raise           # ranks must stay in lock step
+        pc[name] = {"error": repr(exc)}
+      log(f"per_config {name}: {time.time() - t0:.1f} s")
+    if rank == 0:
+      line["per_config"] = pc
   if rank == 0:
-    pk, pk_src = peaks()
-    # dominant kernel: the hidden-layer GEMM (rows x 512 x 512, 3xTF32), timed alone on one chunk of rows
-    rows = 4 * 148 * 128
-    X = torch.randn(rows, H, device=dev)
-    P = ops.PreparedDense(torch.randn(H, H, device=dev) / H**0.5)
-    bias = torch.zeros(H, device=dev)
-    Y = torch.empty(rows, H, device=dev)
-    fn = lambda i: ops.dense_forward(X, P, bias=bias, epilogue="bias_relu", out=Y)
-    for i in range(3):
-      fn(i)
-    tk = time_region(fn, 20, torch.cuda.synchronize) / 20
-    tf32_peak = float(pk.get("bf16_tflops_sustained", 1392.5)) / 2.0
-    pipe = 3 * 2.0 * rows * H * H / tk / 1e12   # tf32 MMA flops issued (3 per fp32-fidelity product)
-    per_pass = 2 * L * sum((d + 1) * H + H * H + 16 * H for d in range(1, D))
-    line = {
-      "metric": METRIC, "value": gB * args.steps / el, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-      "warmup": max(args.warmup, 1), "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
-      "config": {"workload": "synthetic scale-out, ot/free structure (BASELINE configs[4])", "dim": D, "flow_num_layers": L,
-                 "mlp": "2x512", "num_bins": 5, "params": shape.blob_size, "batch_per_gpu": B, "global_batch": gB,
-                 "sub_batch": "batch//32", "engine": _lib.last_launch_info()["engine"],
-                 "parallelism": f"dp{world} (rows sharded, one NCCL all-reduce of [grad|loss], {shape.blob_size * 4 >> 20} MiB)",
-                 "l2_policy": "inputs and activations far larger than L2", "loss_last_step": float(out[shape.blob_size])},
-      "e2e": {"value": None if args.no_e2e else gB * args.steps / el_e, "unit": UNIT,
-              "h2d_bytes_per_step": (2 * B + b) * D * 4 + shape.blob_size * 4,
-              "d2h_bytes_per_step": (shape.blob_size + 8) * 4,
-              "api": "weights H2D + cnfot_mfc_step on pinned host rows (read in place) + all-reduce + D2H"},
-      "gpu_launches": None, "clocks": clk.summary(),
-      "roofline": {"bound": "tensor", "kernel": "dense_tc_kernel<256,1> (hidden layer, rows x 512 x 512, timed alone)",
-                   "achieved": pipe, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pipe / tf32_peak, "traffic": None,
-                   "peak_source": pk_src + ": bf16_tflops_sustained / 2 (tf32)",
-                   "fp32_fidelity_tflops": pipe / 3, "us_per_launch": tk * 1e6,
-                   "step_algorithmic_tflops": 3 * per_pass * (2 * B + 2 * b) / (el / args.steps) / 1e12},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-      line["cpu_baseline"] = cpu_baseline_cfg5(L)
+    if world == 1:
+      line["roofline_spline"] = spline_rooflines(float(pk["hbm_gbs"]))
+      if not args.no_oracle:
+        line["cpu_baseline"] = cpu_baseline()
     emit(line)
-  if world > 1:
-    td.barrier()
-    td.destroy_process_group()
+  dist.close()
 
 
-def cpu_baseline_cfg5(L, rows=128):
-  """The CPU restatement (oracle/, torch f64, autograd) on a bounded sample of the configs[4] workload."""
-  from oracle import losses as olosses
-  from util import make_cfg, make_inputs, make_params
-  torch.set_num_threads(os.cpu_count() or 1)
-  cfg = make_cfg("ot", "free", dim=32, L=L, M=2, H=512, K=5, B=rows, Tn=1, lam=5000.0)
-  spec, params = make_params(cfg, 0.01)
-  inputs = make_inputs(cfg)
-  olosses.value_and_grad(cfg, spec, params, inputs)
-  t0 = time.perf_counter()
-  olosses.value_and_grad(cfg, spec, params, inputs)
-  dt = time.perf_counter() - t0
-  return {"value": rows / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-          "sample": f"oracle (torch f64 restatement of the reference step) on {rows} rows of the same workload "
-                    f"(dim 32, {L} layers, 2x512), 1 timed step after 1 warm-up"}
+def run_only(args):
+  """One BASELINE config alone (--only cfgN [--rows-per-gpu R]): its per_config entry as the JSON line."""
+  from cnf_ot_b200 import _lib
+  dist = Dist()
+  _lib.load()
+  pk, pk_src = peaks()
+  with ClockSampler(dist.local) as clk:
+    e = per_config_entry(args.only, dist, args, pk, pk_src)
+  if dist.rank == 0:
+    line = {"metric": METRIC, "value": e["value"], "unit": UNIT, "n_gpus": dist.world, "steps": e["steps"], "warmup": 3,
+            "ms_per_step": e["ms_per_step"], "higher_is_better": True, "scaling": e["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": e["workload"], "batch_per_gpu": e["batch_per_gpu"],
+                                                            "global_batch": e["global_batch"]},
+            "clocks": clk.summary(), "entry": e}
+    emit(line)
+  dist.close()
 
 
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=50)
+  ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--reps", type=int, default=5, help="repetitions of the K-step timed block (median reported)")
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
-                  help="cfg2 = BASELINE configs[1] (the driver's line); cfg5 = configs[4] on the wide-conditioner engine")
-  ap.add_argument("--rows-per-gpu", type=int, default=1 << 17, help="cfg5 only (BASELINE: 2^21)")
-  ap.add_argument("--layers", type=int, default=16, help="cfg5 only: flow layers (BASELINE: 16)")
-  ap.add_argument("--no-cpu-baseline", action="store_true", help="cfg5 only: skip the CPU oracle timing")
-  ap.add_argument("--no-e2e", action="store_true", help="cfg5 only: skip the host-buffer end-to-end timing")
+  ap.add_argument("--no-per-config", action="store_true", help="skip the per_config block (configs 1, 3, 4, 5)")
+  ap.add_argument("--no-oracle", action="store_true", help="skip every CPU-oracle leg (parity, cpu_baseline)")
+  ap.add_argument("--only", default=None, choices=sorted(WORKLOADS), help="time ONE config alone (builder tool)")
+  ap.add_argument("--rows-per-gpu", type=int, default=None, help="--only: rows per GPU (weak scaling)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
-  elif args.workload == "cfg5":
-    run_cfg5(args)
+  elif args.only:
+    run_only(args)
   else:
     run_ours(args)
 
