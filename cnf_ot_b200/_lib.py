@@ -11,9 +11,9 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcnfot.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("CNFOT_LIB", "libcnfot.so"))   # CNFOT_LIB: an alternative build (A/B timing)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NUM_LOSS_SLOTS = 8
 
 OT, RWPO, FP = 0, 1, 2
@@ -49,6 +49,15 @@ class PeerDesc(Structure):
   _fields_ = [("rank", c_int32), ("world", c_int32), ("epoch", ctypes.c_uint32),
               ("xbuf", c_void_p * 8), ("flags", c_void_p * 8)]
 
+
+class AdamDesc(Structure):
+  """cnfot_adam_desc: optax.adam hyper-parameters (solvers.py:55)."""
+  _fields_ = [("lr", c_float), ("b1", c_float), ("b2", c_float), ("eps", c_float)]
+
+
+# cnfot_philox_rows sources (include/cnfot.h)
+ROWS_NORMAL, ROWS_OT_SOURCE = 1, 3
+STATUS_WORD = 4
 
 _F = POINTER(FlowDesc)
 _P = POINTER(ProblemDesc)
@@ -95,6 +104,20 @@ SIGNATURES = {
   "cnfot_dp_exchange_floats": (c_int64, [_F, c_int32]),
   "cnfot_dp_flag_count": (c_int64, [_F, c_int32]),
   "cnfot_mfc_step_dp": (c_int32, _STEP + [POINTER(PeerDesc)]),
+  "cnfot_philox_rows": (c_int32, [c_void_p, ctypes.c_uint64, ctypes.c_uint32, c_int32, c_int64, c_int64, c_int64, c_int32,
+                                  c_void_p]),
+  "cnfot_philox_times_host": (c_int32, [ctypes.c_uint64, ctypes.c_uint32, c_int32, c_float, c_void_p]),
+  "cnfot_mfc_step_rng": (c_int32, [c_void_p, _F, _P, c_void_p, ctypes.c_uint64, ctypes.c_uint32, c_int32, c_int64, c_int64,
+                                   c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_int64,
+                                   POINTER(PeerDesc)]),
+  "cnfot_mfc_step_rng_host_workspace_bytes": (c_int64, [_F]),
+  "cnfot_mfc_step_rng_host": (c_int32, [c_void_p, _F, _P, c_void_p, ctypes.c_uint64, ctypes.c_uint32, c_int32, c_int64,
+                                        c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_int64]),
+  "cnfot_train_state_bytes": (c_int64, [_F]),
+  "cnfot_train_state_init": (c_int32, [c_void_p, _F, c_void_p, c_int64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),
+  "cnfot_mfc_update": (c_int32, [c_void_p, _F, _P, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(AdamDesc),
+                                 c_int32, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
+                                 c_void_p, c_int64, POINTER(PeerDesc)]),
   "cnfot_dense_prepared_floats": (c_int64, [c_int32, c_int32]),
   "cnfot_dense_prepare": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
   "cnfot_dense_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p,

@@ -30,16 +30,9 @@ from .flows import ParamTree
 # ------------------------------------------------------------------ data draws
 def sample_source_fn(seed, sample_shape: int, dim: int, device):
   """8-mode Gaussian mixture of kl_loss_fn (applications.py:34-71), dim == 2;
-  for other dims the Gaussian variant the reference keeps commented (:28-32, ot.py:72-80)."""
-  z = random.normal(seed, (sample_shape, dim), device=device)
-  if dim != 2:
-    return z - 3.0
-  R = 5.0
-  centres = torch.tensor(
-    [[0.0, R], [R, 0.0], [0.0, -R], [-R, 0.0], [0.6 * R, 0.8 * R], [0.6 * R, -0.8 * R],
-     [-0.6 * R, -0.8 * R], [-0.6 * R, 0.8 * R]], dtype=torch.float32, device=device)
-  idx = random.randint(seed, (sample_shape, ), 8, device=device)
-  return z + centres[idx]
+  for other dims the Gaussian variant the reference keeps commented (:28-32, ot.py:72-80).
+  The component noise is the SAME z `sample_target_fn` returns for this key (:81-82)."""
+  return random.ot_source(seed, (sample_shape, dim), device=device)
 
 
 def sample_target_fn(seed, sample_shape: int, dim: int, device):
@@ -244,38 +237,77 @@ def _step_config(loss_fn) -> Dict:
   return {"model": model, "cfg": cfg, "horizon": horizon, "problem": ops.problem_desc(cfg)}
 
 
-def draw_step_inputs(model, cfg, horizon, rng, batch_size):
-  """The draws one loss call makes, all from the same key (applications.py:81-82,392,416)."""
+def draw_step_inputs(model, cfg, horizon, rng, batch_size, shard=None):
+  """The draws one loss call makes, all from the same key (applications.py:81-82,392,416) -- the arrays the
+  step kernel generates on chip for this key.  shard = (rows of the B-row terms, rows of the b-row terms) as
+  slices: only that part is materialised (data-parallel ranks never draw the whole batch)."""
+  from . import _lib
   dim, dev = model.shape.dim, model.device
   b = batch_size // 32
+  rs, ss = (slice(0, batch_size), slice(0, b)) if shard is None else shard
   typ = cfg["general"]["type"]
+  key = random.as_key(rng).value
   inputs = {"t_batch": _t_batch(rng, cfg["general"]["t_batch_size"], horizon),
-            "latent_sub": random.normal(rng, (b, dim), device=dev)}
+            "latent_sub": ops.philox_rows(key, 0, _lib.ROWS_NORMAL, b, dim, dev, rows=ss)}
   if typ == "ot":
-    inputs["src"] = sample_source_fn(rng, batch_size, dim, dev)
-    inputs["tgt"] = sample_target_fn(rng, batch_size, dim, dev)
+    inputs["src"] = ops.philox_rows(key, 0, _lib.ROWS_OT_SOURCE, batch_size, dim, dev, rows=rs)
+    inputs["tgt"] = ops.philox_rows(key, 0, _lib.ROWS_NORMAL, batch_size, dim, dev, rows=rs)
   else:
-    inputs["latent"] = random.normal(rng, (batch_size, dim), device=dev)
+    inputs["latent"] = ops.philox_rows(key, 0, _lib.ROWS_NORMAL, batch_size, dim, dev, rows=rs)
   return inputs
+
+
+_peer_exchanges = {}
+
+
+def peer_exchange(shape, device):
+  """The exchange buffers of the fused step + all-reduce for this flow shape (one per process and shape), or
+  None when the all-reduce has to go through torch.distributed: a single process, the gloo backend of the CPU
+  tests, the wide-conditioner engine, symmetric memory unavailable, or CNFOT_DP_TRANSPORT=nccl."""
+  import os
+  import torch.distributed as td
+  rank, world = _dist.rank_world()
+  if world == 1 or world > 8 or torch.device(device).type != "cuda" or os.environ.get("CNFOT_DP_TRANSPORT") == "nccl":
+    return None
+  if td.get_backend() != "nccl" or not ops.fused_update_supported(shape):
+    return None
+  k = (shape, torch.device(device).index)
+  if k not in _peer_exchanges:
+    try:
+      _peer_exchanges[k] = _dist.PeerExchange(shape, torch.device(device))
+    except Exception:   # symmetric memory unavailable: NCCL all-reduce
+      _peer_exchanges[k] = None
+  return _peer_exchanges[k]
 
 
 def value_and_grad(loss_fn: Callable):
   """jax.value_and_grad(loss_fn) of solvers.py:94 for the three MFC losses.
 
-  Returns f(params, rng, _lambda, batch_size) -> (loss, grads) with grads a ParamTree.
-  With torch.distributed initialised the batch rows are sharded over the ranks and the
-  [gradient | loss] buffer is summed with ONE all-reduce."""
+  Returns f(params, rng, _lambda, batch_size) -> (loss, grads) with grads a ParamTree.  The draws of the call are
+  made inside the step kernel from `rng` (the same numbers `draw_step_inputs` returns).  With torch.distributed
+  initialised every rank evaluates ITS rows only and the [gradient | loss] buffer is summed with ONE all-reduce
+  (SURVEY.md §8e): inside the step kernel over peer-mapped memory when the GPUs share a node, else by
+  torch.distributed."""
   sc = _step_config(loss_fn)
   model, cfg, problem = sc["model"], sc["cfg"], sc["problem"]
 
   def fn(params, rng, _lambda, batch_size, inputs: Optional[Dict] = None):
     if not isinstance(params, ParamTree):
       raise TypeError("params must be the ParamTree returned by model.init / update")
-    if inputs is None:
-      inputs = draw_step_inputs(model, cfg, sc["horizon"], rng, batch_size)
     rank, world = _dist.rank_world()
     B, b = batch_size, batch_size // 32
     rs, ss = _dist.shard(B, rank, world), _dist.shard(b, rank, world)
+    n = model.shape.blob_size
+    if inputs is None and ops.fused_update_supported(model.shape):
+      px = peer_exchange(model.shape, model.device)
+      out = ops.mfc_step_rng(model.shape, problem, params.blob, random.as_key(rng).value, 0,
+                             cfg["general"]["t_batch_size"], float(_lambda), B, b, rows_B=rs, rows_b=ss, peers=px)
+      if px is None:
+        _dist.all_reduce_sum(out)
+      return out[n], ParamTree(model.shape, out[:n])
+    if inputs is None:   # the wide-conditioner engine takes arrays: this rank's shard of the same draws
+      inputs = draw_step_inputs(model, cfg, sc["horizon"], rng, batch_size, shard=(rs, ss))
+      rs, ss = slice(None), slice(None)
     g = lambda k: None if inputs.get(k) is None else inputs[k]
     out = ops.mfc_step(model.shape, problem, params.blob,
                        None if g("latent") is None else g("latent")[rs],
@@ -284,7 +316,6 @@ def value_and_grad(loss_fn: Callable):
                        None if g("tgt") is None else g("tgt")[rs],
                        inputs["t_batch"], float(_lambda), B, b)
     _dist.all_reduce_sum(out)
-    n = model.shape.blob_size
     return out[n], ParamTree(model.shape, out[:n])
 
   fn.step_config = sc

@@ -82,7 +82,18 @@ static int check_flow(const cnfot_flow_desc* f, FlowLayout* lay) {
   return 0;
 }
 
+// The fused kernels hold the reference's spline constants (flows.py:124-132) as immediates.
+static bool reference_spline_consts(const cnfot_flow_desc* f) {
+  const SplineConsts<float> c = make_spline_consts<float>(f->num_bins, f->range_min, f->range_max, f->min_bin_size,
+                                                          f->min_knot_slope);
+  return c.lo == -10.f && c.hi == 10.f && c.min_bin == 1e-4f && c.min_slope == 1e-4f &&
+         fabsf(c.slope_offset - 0.5411666523385311f) <= 1e-7f;
+}
+
 static int check_fused(const cnfot_flow_desc* f, const FlowLayout& lay) {
+  if (!reference_spline_consts(f))
+    return fail(CNFOT_ERR_ARG, "the fused flow kernels are compiled for the reference's spline constants (range -10..10, "
+                               "min_bin_size = min_knot_slope = 1e-4; cnf_ot/models/flows.py:124-132)");
   if (f->dim > kMaxDim) return fail(CNFOT_ERR_ARG, "fused kernels support dim <= %d (got %d)", kMaxDim, f->dim);
   if ((f->num_layers + 1) * f->dim > kMaxStateFloats)
     return fail(CNFOT_ERR_ARG, "fused kernels need (num_layers+1)*dim <= %d (got %d)", kMaxStateFloats,
@@ -99,6 +110,7 @@ static int check_fused(const cnfot_flow_desc* f, const FlowLayout& lay) {
 static bool fused_ok(const cnfot_flow_desc* f, const FlowLayout& lay) {
   if (!(f->dim <= kMaxDim && (f->num_layers + 1) * f->dim <= kMaxStateFloats && find_flow_eval_kernel(lay) != nullptr))
     return false;
+  if (!reference_spline_consts(f)) return false;
   if (tc_available(lay)) return true;   // 16-wide networks: the warp-MMA plans stream what does not fit
   // CUDA-core engine: even the staged plan (one conditioner at a time in shared memory) must fit a CTA
   DeviceInfo di;
@@ -338,87 +350,6 @@ static int launch_finalize(cudaStream_t s, const PartialBuf& pb, int n_cta, int 
   return 0;
 }
 
-// ---- finalize fused with the data-parallel all-reduce ---------------------
-// One kernel per rank does: (1) the rank's own reduction of its CTAs' partials (as finalize_kernel),
-// (2) pushes the result into every peer's exchange buffer with peer-to-peer stores over
-// NVLink / NVSwitch, (3) raises a per-block flag on every peer, (4) waits for the same block of
-// every peer, (5) sums the W contributions in rank order (bit-identical on all ranks) into `out`.
-// Block b of every rank owns outputs [32 b, 32 b + 32): no grid-wide synchronisation, and the
-// <= 38 + ... blocks of a launch are always co-resident.  Exchange buffers are double-buffered by
-// the parity of `epoch` (a rank cannot run two steps ahead of a peer: it needs the peer's flag of
-// the step in between); flags carry the epoch and never need resetting.
-struct PeerArgs {
-  int rank, world;
-  uint32_t epoch;
-  int stride;          // floats per rank slot in an exchange buffer (>= total + kNumSlots)
-  int nblk;            // blocks per launch = flags per rank
-  float* xbuf[8];
-  uint32_t* flags[8];
-};
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(32 * kFinWarps)
-finalize_allreduce_kernel(const float* __restrict__ pgrad, const double* __restrict__ ploss, int n_cta,
-                          int total, float* __restrict__ out, const PeerArgs pa) {
-  __shared__ double part[kFinWarps][32];
-  __shared__ int timed_out;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  const int n_out = total + kNumSlots;
-  double acc = 0.0;
-  if (i < total) {
-    acc = column_partial(pgrad, n_cta, total, i, warp);
-  } else if (i < n_out) {
-    // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
-    const int sl = i - total;
-    for (int c = warp; c < n_cta; c += kFinWarps) {
-      const double* q = ploss + (int64_t)c * kNumSlots;
-      if (sl == 0) acc += q[0] + q[1] + q[2] + q[3];
-      else if (sl <= 4) acc += q[sl - 1];
-    }
-  }
-  part[warp][lane] = acc;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  if (warp != 0) return;
-  double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < kFinWarps; ++w) t += part[w][lane];
-  const float mine = (float)t;
-  const int par = pa.epoch & 1u;
-  if (i < n_out)
-    for (int p = 0; p < pa.world; ++p) pa.xbuf[p][((int64_t)par * pa.world + pa.rank) * pa.stride + i] = mine;
-  __threadfence_system();
-  __syncwarp();
-  if (lane < pa.world) st_release_sys(pa.flags[lane] + pa.rank * pa.nblk + blockIdx.x, pa.epoch);
-  if (lane < pa.world) {
-    const uint32_t* f = pa.flags[pa.rank] + lane * pa.nblk + blockIdx.x;
-    const long long t0 = clock64();
-    // epochs are compared modulo 2^32 (a peer is never more than one step ahead)
-    while ((int32_t)(ld_acquire_sys(f) - pa.epoch) < 0) {
-      if (clock64() - t0 > (4LL << 30)) {  // ~2 s: a peer never arrived; poison the result instead of hanging
-        timed_out = 1;
-        break;
-      }
-    }
-  }
-  __syncwarp();
-  if (i < n_out) {
-    const float* mybuf = pa.xbuf[pa.rank] + (int64_t)par * pa.world * pa.stride + i;
-    float sum = 0.f;
-    for (int q = 0; q < pa.world; ++q) sum += __ldcg(mybuf + (int64_t)q * pa.stride);
-    out[i] = *(volatile int*)&timed_out ? __int_as_float(0x7fc00000) : sum;
-  }
-}
-
 // ---- energy finalize: sum the CTAs' kinetic partials into one double ----------------------
 __global__ void energy_finalize_kernel(const double* __restrict__ ploss, int n_cta, double* __restrict__ out) {
   double v = 0.0;
@@ -630,7 +561,6 @@ static int flow_eval_call(int dir, void* stream, const cnfot_flow_desc* flow, co
   a.W = weights; a.frags = nullptr; a.in = in; a.cond = cond; a.cond_stride = cond_stride; a.rows = rows;
   a.out = out; a.logdet = logdet; a.dir = dir; a.add_base = add_base;
   a.D = lay.D; a.L = lay.L; a.plan = sp;
-  a.sc = spline_consts(flow);
   void* args[] = {&a};
   cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "flow_eval_kernel launch");
@@ -723,7 +653,6 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
   }
   a.g_out = g_out; a.g_logdet = g_logdet; a.g_in = g_in; a.dir = dir; a.add_base = add_base;
   a.D = lay.D; a.L = lay.L; a.plan = sp;
-  a.sc = spline_consts(flow);
   a.pb = carve_partials(workspace, &counter);
   void* args[] = {&a};
   cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
@@ -795,27 +724,69 @@ static int mfc_step_wide(void* stream, const cnfot_flow_desc* flow, const FlowLa
   return 0;
 }
 
+// Everything a step call can vary: where the rows come from, what the kernel's tail does with the result.
+struct StepIo {
+  // explicit inputs (rng == false)
+  const float* latent = nullptr;
+  const float* latent_sub = nullptr;
+  const float* src = nullptr;
+  const float* tgt = nullptr;
+  const float* t_batch_host = nullptr;
+  // on-chip draws (rng == true): philox.cuh streams of (key, step); row0_* = global index of the shard's first row
+  bool rng = false;
+  uint64_t key = 0;
+  uint32_t step = 0;
+  int64_t row0_B = 0, row0_b = 0;
+  // result
+  float* out = nullptr;
+  bool accumulate = false;
+  const cnfot_peer_desc* peers = nullptr;
+  // device-resident update (state != nullptr): `workspace` is the train state, Adam runs in the kernel's tail
+  bool stateful = false;
+  float* weights_rw = nullptr;
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  float lr = 0.f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  float* loss_hist = nullptr;
+  int64_t loss_hist_len = 0;
+};
+
+static unsigned long long dp_timeout_ns() {
+  unsigned long long ms = 20000ULL;   // a rank that is this late is gone (CNFOT_DP_TIMEOUT_MS overrides)
+  if (const char* e = getenv("CNFOT_DP_TIMEOUT_MS")) {
+    const long long v = atoll(e);
+    if (v > 0) ms = (unsigned long long)v;
+  }
+  return ms * 1000000ULL;
+}
+
 static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
-                         const float* weights, const float* latent, const float* latent_sub,
-                         const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
+                         const float* weights, const StepIo& io, int32_t n_t,
                          int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b, float lambda,
-                         float* out, void* workspace, int64_t workspace_bytes, bool accumulate,
-                         const cnfot_peer_desc* peers = nullptr) {
+                         void* workspace, int64_t workspace_bytes) {
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
-  if (use_wide(flow, lay))
-    return mfc_step_wide(stream, flow, lay, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t, rows_B, rows_b,
-                         global_B, global_b, lambda, out, workspace, workspace_bytes, accumulate, peers);
+  if (use_wide(flow, lay)) {
+    if (io.rng || io.stateful)
+      return fail(CNFOT_ERR_ARG, "the wide-conditioner engine takes explicit row arrays: fill them with cnfot_philox_rows "
+                                 "and call cnfot_mfc_step (+ cnfot_adam_update)");
+    return mfc_step_wide(stream, flow, lay, problem, weights, io.latent, io.latent_sub, io.src, io.tgt, io.t_batch_host, n_t,
+                         rows_B, rows_b, global_B, global_b, lambda, io.out, workspace, workspace_bytes, io.accumulate, io.peers);
+  }
   if (int rc = check_fused(flow, lay)) return rc;
   if (!problem) return fail(CNFOT_ERR_ARG, "problem descriptor is NULL");
-  PeerArgs pa;
+  StepArgs a;
+  memset(&a.tail, 0, sizeof(a.tail));
+  PeerArgs& pa = a.tail.pa;
+  const cnfot_peer_desc* peers = io.peers;
   if (peers) {
     if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world)
       return fail(CNFOT_ERR_ARG, "peer descriptor: need 1 <= world <= 8 and 0 <= rank < world");
-    if (peers->epoch == 0) return fail(CNFOT_ERR_ARG, "peer descriptor: epoch starts at 1");
+    if (peers->epoch == 0 && !io.stateful) return fail(CNFOT_ERR_ARG, "peer descriptor: epoch starts at 1");
     pa.rank = peers->rank; pa.world = peers->world; pa.epoch = peers->epoch;
     pa.stride = (int)cnfot_dp_exchange_stride(flow);
-    pa.nblk = (lay.total + kNumSlots + 31) / 32;
+    pa.n_slices = (lay.total + kNumSlots + 7) / 8;
+    pa.timeout_ns = dp_timeout_ns();
     for (int k = 0; k < peers->world; ++k) {
       if (!peers->xbuf[k] || !peers->flags[k]) return fail(CNFOT_ERR_ARG, "peer descriptor: NULL peer buffer");
       pa.xbuf[k] = peers->xbuf[k]; pa.flags[k] = peers->flags[k];
@@ -824,61 +795,75 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   if (rows_B < 0 || rows_b < 0 || global_B < 1 || global_b < 1 || rows_B > global_B || rows_b > global_b)
     return fail(CNFOT_ERR_ARG, "bad row counts");
   if (n_t < 1 || n_t > kMaxSegments - 4) return fail(CNFOT_ERR_ARG, "t_batch_size must be in [1, %d]", kMaxSegments - 4);
-  if (!weights || !out || !workspace || !t_batch_host) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (!weights || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (!io.out && !io.stateful) return fail(CNFOT_ERR_ARG, "out is NULL");
+  if (!io.rng && !io.t_batch_host) return fail(CNFOT_ERR_ARG, "t_batch is NULL");
   if (workspace_bytes < partial_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
                                                         (long long)workspace_bytes, (long long)partial_bytes(lay));
-  StepArgs a;
   const char* err = nullptr;
   if (make_step_consts<float>(*problem, lay.D, (double)lambda, global_B, global_b, n_t, &a.pc, &err))
     return fail(CNFOT_ERR_ARG, "%s", err);
-  if (problem->type == CNFOT_OT) {
-    if (rows_B > 0 && (!src || !tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
-  } else {
-    if (rows_B > 0 && !latent) return fail(CNFOT_ERR_ARG, "latent is NULL");
+  if (!io.rng) {
+    if (problem->type == CNFOT_OT) {
+      if (rows_B > 0 && (!io.src || !io.tgt)) return fail(CNFOT_ERR_ARG, "ot needs src and tgt batches");
+    } else {
+      if (rows_B > 0 && !io.latent) return fail(CNFOT_ERR_ARG, "latent is NULL");
+    }
+    if (rows_b > 0 && !io.latent_sub) return fail(CNFOT_ERR_ARG, "latent_sub is NULL");
+  } else if (io.row0_B < 0 || io.row0_b < 0 || io.row0_B + rows_B > global_B || io.row0_b + rows_b > global_b) {
+    return fail(CNFOT_ERR_ARG, "shard [row0, row0 + rows) outside the global batch");
   }
-  if (rows_b > 0 && !latent_sub) return fail(CNFOT_ERR_ARG, "latent_sub is NULL");
-
-  // segments, most expensive first (kinetic rows run 3..3+4D passes each)
-  int ns = 0;
-  int64_t tiles = 0;
-  auto add = [&](int kind, int slot, int do_fit, int do_pot, float t, const float* rows, int64_t n) {
-    if (n <= 0) return;
-    Segment& sg = a.seg[ns++];
-    sg.kind = kind; sg.slot = slot; sg.do_fit = do_fit; sg.do_pot = do_pot; sg.t = t; sg.rows = rows;
-    sg.n = n; sg.first_tile = tiles;
-    tiles += (n + kTile - 1) / kTile;
-  };
-  for (int i = 0; i < n_t; ++i) add(kSegKinetic, kSlotKinetic, 0, 0, t_batch_host[i], latent_sub, rows_b);
-  if (problem->type == CNFOT_OT) {
-    add(kSegNll, kSlotFit0, 1, 0, 0.f, src, rows_B);
-    add(kSegNll, kSlotFitT, 1, 0, (float)a.pc.horizon, tgt, rows_B);
-  } else {
-    add(kSegSample, kSlotFit0, 1, 0, 0.f, latent, rows_B);
-    if (problem->type == CNFOT_RWPO) add(kSegSample, kSlotFit0, 0, 1, (float)a.pc.horizon, latent, rows_B);
-  }
-  a.n_seg = ns;
-  a.n_tiles = tiles;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tiles == 0 && !peers) {
-    if (accumulate) return 0;
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), s);
+  if (rows_B == 0 && rows_b == 0 && !peers && !io.stateful) {
+    if (io.accumulate) return 0;
+    cudaError_t e = cudaMemsetAsync(io.out, 0, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    return 0;
-  }
-  if (tiles == 0) {  // an empty shard still takes part in the all-reduce
-    PartialBuf none;
-    none.grad = nullptr; none.loss = nullptr;
-    finalize_allreduce_kernel<<<pa.nblk, 32 * kFinWarps, 0, s>>>(none.grad, none.loss, 0, lay.total, out, pa);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "finalize_allreduce_kernel launch");
     return 0;
   }
   SmemPlan sp;
   int engine;
   if (int rc = make_plan(lay, true, &sp, &engine)) return rc;
   const void* kernel = find_mfc_step_kernel(lay, engine);
+  // Row units: the CTA claims 128-row tiles.  The warp-level engines can also claim 32 rows per WARP (no CTA barrier
+  // in the loop, CNFOT_STEP_UNIT=32); measured on B200 that is SLOWER (0.196 vs 0.184 ms on cfg 2): warps that
+  // drift out of phase spread over the whole 125 KB kernel and miss the 32 KB instruction cache.
+  int unit = kTile;
+  if (const char* e = getenv("CNFOT_STEP_UNIT")) {
+    if (atoi(e) == 32 && (engine == kEngMma || engine == kEngMmaStream)) unit = 32;
+  }
+
+  // segments, most expensive first (kinetic rows run 3..3+4D passes each)
+  int ns = 0;
+  int64_t tiles = 0;
+  auto add = [&](int kind, int slot, int do_fit, int do_pot, float t, int t_index, const float* rows, int source,
+                 int64_t row0, int64_t n) {
+    if (n <= 0) return;
+    Segment& sg = a.seg[ns++];
+    sg.kind = kind; sg.slot = slot; sg.do_fit = do_fit; sg.do_pot = do_pot; sg.t = t; sg.t_index = t_index;
+    sg.rows = rows; sg.source = io.rng ? source : (int)kRowsMemory; sg.row0 = row0;
+    sg.n = n; sg.first_tile = tiles;
+    tiles += (n + unit - 1) / unit;
+  };
+  for (int i = 0; i < n_t; ++i)
+    add(kSegKinetic, kSlotKinetic, 0, 0, io.rng ? 0.f : io.t_batch_host[i], io.rng ? i : -1, io.latent_sub, kRowsNormal, io.row0_b, rows_b);
+  if (problem->type == CNFOT_OT) {
+    add(kSegNll, kSlotFit0, 1, 0, 0.f, -1, io.src, kRowsOtSource, io.row0_B, rows_B);
+    add(kSegNll, kSlotFitT, 1, 0, (float)a.pc.horizon, -1, io.tgt, kRowsNormal, io.row0_B, rows_B);
+  } else {
+    add(kSegSample, kSlotFit0, 1, 0, 0.f, -1, io.latent, kRowsNormal, io.row0_B, rows_B);
+    if (problem->type == CNFOT_RWPO) add(kSegSample, kSlotFit0, 0, 1, (float)a.pc.horizon, -1, io.latent, kRowsNormal, io.row0_B, rows_B);
+  }
+  a.n_seg = ns;
+  a.n_tiles = tiles;
+  a.unit_rows = unit;
+  a.key = io.key;
+  a.step = io.step;
+  a.salt_B = philox_salt(kDrawNormal, (uint64_t)global_B);
+  a.salt_Bc = philox_salt(kDrawCategorical, (uint64_t)global_B);
+  a.salt_b = philox_salt(kDrawNormal, (uint64_t)global_b);
+  a.salt_t = philox_salt(kDrawUniform, (uint64_t)n_t);
   LaunchCfg cfg;
-  if (int rc = configure(kernel, sp, tiles, &cfg)) return rc;
+  if (int rc = configure(kernel, sp, (tiles * unit + kTile - 1) / kTile, &cfg)) return rc;
   a.W = weights;
   a.frags = nullptr;
   if (engine == kEngMmaStream) {
@@ -887,20 +872,39 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     a.frags = fr;
   }
   a.D = lay.D; a.L = lay.L; a.plan = sp;
-  a.sc = spline_consts(flow);
-  a.pb = carve_partials(workspace, &a.tile_counter);
-  cudaError_t e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned long long), s);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-  void* args[] = {&a};
-  e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
-  if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
-  if (peers) {
-    finalize_allreduce_kernel<<<pa.nblk, 32 * kFinWarps, 0, s>>>(a.pb.grad, a.pb.loss, cfg.grid, lay.total, out, pa);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "finalize_allreduce_kernel launch");
-    return 0;
+  // workspace / train state: [header: sync words, state words, loss row | partial gradient rows]
+  TailArgs& t = a.tail;
+  char* wsb = (char*)workspace;
+  t.sync = (uint32_t*)wsb;
+  t.loss_row = (double*)(wsb) + kLossRowOffset;
+  t.grad_rows = (float*)(wsb + kCounterBytes);
+  t.n_rows = cfg.grid < kStepRows ? cfg.grid : kStepRows;
+  if (const char* e = getenv("CNFOT_STEP_ROWS")) {   // tuning knob: partial gradient rows (<= 1184)
+    const int v = atoi(e);
+    if (v >= 1 && v <= (io.stateful ? kStepRows : kMaxGrid)) t.n_rows = v < cfg.grid ? v : cfg.grid;
   }
-  return launch_finalize(s, a.pb, cfg.grid, lay.total, out, out + lay.total, accumulate);
+  const int n_slices = (lay.total + kNumSlots + 7) / 8;
+  int n_tail = cfg.grid / 4;
+  if (n_tail < 1) n_tail = 1;
+  if (n_tail > n_slices) n_tail = n_slices;
+  t.n_tail = n_tail;
+  t.total = lay.total;
+  t.accumulate = io.accumulate ? 1 : 0;
+  t.out = io.out;
+  if (io.stateful) {
+    t.self_clean = 1;
+    t.state = (unsigned long long*)wsb + kStateWordOffset;
+    t.weights = io.weights_rw; t.adam_m = io.adam_m; t.adam_v = io.adam_v;
+    t.lr = io.lr; t.b1 = io.b1; t.b2 = io.b2; t.eps = io.eps;
+    t.loss_hist = io.loss_hist; t.loss_hist_len = io.loss_hist_len;
+  } else {
+    cudaError_t e = cudaMemsetAsync(wsb, 0, (size_t)kCounterBytes + (size_t)t.n_rows * lay.total * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  }
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
+  return 0;
 }
 
 int64_t cnfot_dp_exchange_stride(const cnfot_flow_desc* flow) {
@@ -913,8 +917,10 @@ int64_t cnfot_dp_exchange_floats(const cnfot_flow_desc* flow, int32_t world) {
   return st < 0 ? -1 : 2 * (int64_t)world * st;
 }
 int64_t cnfot_dp_flag_count(const cnfot_flow_desc* flow, int32_t world) {
-  const int64_t st = cnfot_dp_exchange_stride(flow);
-  return st < 0 ? -1 : (int64_t)world * (st / 32);
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  // one flag per (source rank, 8-column slice) + the abort word, rounded up
+  return ((int64_t)world * ((lay.total + kNumSlots + 7) / 8) + 1 + 31) / 32 * 32;
 }
 
 int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
@@ -923,8 +929,11 @@ int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const cnfot_pro
                       int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
                       void* workspace, int64_t workspace_bytes, const cnfot_peer_desc* peers) {
   if (!peers) return fail(CNFOT_ERR_ARG, "peer descriptor is NULL");
-  return mfc_step_impl(stream, flow, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t,
-                       rows_B, rows_b, global_B, global_b, lambda, out, workspace, workspace_bytes, false, peers);
+  StepIo io;
+  io.latent = latent; io.latent_sub = latent_sub; io.src = src; io.tgt = tgt; io.t_batch_host = t_batch_host;
+  io.out = out; io.peers = peers;
+  return mfc_step_impl(stream, flow, problem, weights, io, n_t, rows_B, rows_b, global_B, global_b, lambda, workspace,
+                       workspace_bytes);
 }
 
 int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
@@ -932,8 +941,102 @@ int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_proble
                    const float* tgt, const float* t_batch_host, int32_t n_t, int64_t rows_B,
                    int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
                    void* workspace, int64_t workspace_bytes) {
-  return mfc_step_impl(stream, flow, problem, weights, latent, latent_sub, src, tgt, t_batch_host, n_t,
-                       rows_B, rows_b, global_B, global_b, lambda, out, workspace, workspace_bytes, false);
+  StepIo io;
+  io.latent = latent; io.latent_sub = latent_sub; io.src = src; io.tgt = tgt; io.t_batch_host = t_batch_host;
+  io.out = out;
+  return mfc_step_impl(stream, flow, problem, weights, io, n_t, rows_B, rows_b, global_B, global_b, lambda, workspace,
+                       workspace_bytes);
+}
+
+// ---- on-chip draws: the same numbers as arrays (explicit-input entries, the CPU oracle) ------------------
+__global__ void __launch_bounds__(256)
+philox_rows_kernel(unsigned long long key_n, unsigned long long key_c, uint32_t step, int source, int64_t row0, int64_t rows,
+                   int dim, float* __restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float row[kMaxDim];
+    philox_row(key_n, key_c, step, source, (uint64_t)(row0 + r), dim, row);
+    for (int i = 0; i < dim; ++i) out[r * dim + i] = row[i];
+  }
+}
+
+int cnfot_philox_rows(void* stream, uint64_t key, uint32_t step, int32_t source, int64_t global_rows, int64_t row0,
+                      int64_t rows, int32_t dim, float* out) {
+  if (rows < 0 || row0 < 0 || row0 + rows > global_rows || dim < 1 || dim > kMaxDim)
+    return fail(CNFOT_ERR_ARG, "philox_rows: need 0 <= row0, row0 + rows <= global_rows, 1 <= dim <= %d", kMaxDim);
+  if (source != CNFOT_ROWS_NORMAL && source != CNFOT_ROWS_OT_SOURCE) return fail(CNFOT_ERR_ARG, "philox_rows: unknown row source");
+  if (rows == 0) return 0;
+  if (!out) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  int64_t blocks = (rows + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  philox_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      key ^ philox_salt(kDrawNormal, (uint64_t)global_rows), key ^ philox_salt(kDrawCategorical, (uint64_t)global_rows), step,
+      source, row0, rows, dim, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "philox_rows_kernel launch");
+  return 0;
+}
+
+int cnfot_philox_times_host(uint64_t key, uint32_t step, int32_t n_t, float horizon, float* t_host) {
+  if (n_t < 0 || (n_t > 0 && !t_host)) return fail(CNFOT_ERR_ARG, "philox_times: bad arguments");
+  const uint64_t kt = key ^ philox_salt(kDrawUniform, (uint64_t)n_t);
+  for (int i = 0; i < n_t; ++i) t_host[i] = philox_time(kt, step, i, horizon);
+  return 0;
+}
+
+int cnfot_mfc_step_rng(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem, const float* weights,
+                       uint64_t key, uint32_t step, int32_t n_t, int64_t row0_B, int64_t rows_B, int64_t row0_b,
+                       int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out, void* workspace,
+                       int64_t workspace_bytes, const cnfot_peer_desc* peers) {
+  StepIo io;
+  io.rng = true; io.key = key; io.step = step; io.row0_B = row0_B; io.row0_b = row0_b;
+  io.out = out; io.peers = peers;
+  return mfc_step_impl(stream, flow, problem, weights, io, n_t, rows_B, rows_b, global_B, global_b, lambda, workspace,
+                       workspace_bytes);
+}
+
+// ---- device-resident update (solvers.py:90-97 as ONE kernel launch, CUDA-graph replayable) --------------------
+int64_t cnfot_train_state_bytes(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  if (use_wide(flow, lay)) { fail(CNFOT_ERR_ARG, "no device-resident update for the wide-conditioner engine"); return -1; }
+  return partial_bytes(lay);
+}
+
+int cnfot_train_state_init(void* stream, const cnfot_flow_desc* flow, void* state, int64_t state_bytes, uint64_t key,
+                           uint64_t step, uint32_t epoch) {
+  const int64_t need = cnfot_train_state_bytes(flow);
+  if (need < 0) return CNFOT_ERR_ARG;
+  if (!state) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (state_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "train state too small: %lld < %lld", (long long)state_bytes, (long long)need);
+  FlowLayout lay;
+  check_flow(flow, &lay);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(state, 0, (size_t)kCounterBytes + (size_t)kStepRows * lay.total * sizeof(float), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  const unsigned long long words[3] = {key, step, (unsigned long long)epoch};
+  e = cudaMemcpyAsync((unsigned long long*)state + kStateWordOffset, words, sizeof(words), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D train state");
+  e = cudaStreamSynchronize(s);   // `words` lives on this stack frame
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int cnfot_mfc_update(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem, void* state,
+                     int64_t state_bytes, float* weights, float* adam_m, float* adam_v, const cnfot_adam_desc* adam,
+                     int32_t n_t, int64_t row0_B, int64_t rows_B, int64_t row0_b, int64_t rows_b, int64_t global_B,
+                     int64_t global_b, float lambda, float* out, float* loss_hist, int64_t loss_hist_len,
+                     const cnfot_peer_desc* peers) {
+  if (!state || !weights || !adam_m || !adam_v || !adam) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (loss_hist_len < 0 || (loss_hist_len > 0 && !loss_hist)) return fail(CNFOT_ERR_ARG, "bad loss history buffer");
+  StepIo io;
+  io.rng = true; io.row0_B = row0_B; io.row0_b = row0_b;
+  io.out = out; io.peers = peers;
+  io.stateful = true;
+  io.weights_rw = weights; io.adam_m = adam_m; io.adam_v = adam_v;
+  io.lr = adam->lr; io.b1 = adam->b1; io.b2 = adam->b2; io.eps = adam->eps;
+  io.loss_hist = loss_hist; io.loss_hist_len = loss_hist_len;
+  return mfc_step_impl(stream, flow, problem, weights, io, n_t, rows_B, rows_b, global_B, global_b, lambda, state,
+                       state_bytes);
 }
 
 static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
@@ -1022,9 +1125,10 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
   if ((e = cudaMemcpyAsync(dW, weights_host, (size_t)lay.total * sizeof(float), cudaMemcpyHostToDevice, s)) != cudaSuccess)
     return cuda_fail(e, "H2D weights");
   if (zero_copy) {
-    int rc = mfc_step_impl(stream, flow, problem, dW, mapped[0], mapped[1], mapped[2], mapped[3], t_batch_host,
-                           n_t, rows_B, rows_b, global_B, global_b, lambda, dOut, ws,
-                           ws_bytes, false);
+    StepIo io;
+    io.latent = mapped[0]; io.latent_sub = mapped[1]; io.src = mapped[2]; io.tgt = mapped[3]; io.t_batch_host = t_batch_host;
+    io.out = dOut;
+    int rc = mfc_step_impl(stream, flow, problem, dW, io, n_t, rows_B, rows_b, global_B, global_b, lambda, ws, ws_bytes);
     if (rc) return rc;
   } else {
     // Staged path.  Row chunks: the H2D copy of chunk k+1 (internal copy stream) overlaps the kernels
@@ -1055,16 +1159,60 @@ int cnfot_mfc_step_host(void* stream, const cnfot_flow_desc* flow, const cnfot_p
     for (int k = 0; k < nchunk; ++k) {
       const int64_t lo = rows_B * k / nchunk, hi = rows_B * (k + 1) / nchunk;
       if ((e = cudaStreamWaitEvent(s, hp->ready[k], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-      int rc = mfc_step_impl(stream, flow, problem, dW, latent_host ? dLat + lo * lay.D : nullptr,
-                             latent_sub_host ? dSub : nullptr, src_host ? dSrc + lo * lay.D : nullptr,
-                             tgt_host ? dTgt + lo * lay.D : nullptr, t_batch_host, n_t, hi - lo,
-                             k == 0 ? rows_b : 0, global_B, global_b, lambda, dOut, ws,
-                             ws_bytes, k > 0);
+      StepIo io;
+      io.latent = latent_host ? dLat + lo * lay.D : nullptr;
+      io.latent_sub = latent_sub_host ? dSub : nullptr;
+      io.src = src_host ? dSrc + lo * lay.D : nullptr;
+      io.tgt = tgt_host ? dTgt + lo * lay.D : nullptr;
+      io.t_batch_host = t_batch_host;
+      io.out = dOut;
+      io.accumulate = k > 0;
+      int rc = mfc_step_impl(stream, flow, problem, dW, io, n_t, hi - lo, k == 0 ? rows_b : 0, global_B, global_b, lambda, ws,
+                             ws_bytes);
       if (rc) return rc;
     }
   }
   e = cudaMemcpyAsync(out_host, dOut, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float),
                       cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_fail(e, "D2H out");
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
+
+int64_t cnfot_mfc_step_rng_host_workspace_bytes(const cnfot_flow_desc* flow) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  if (use_wide(flow, lay)) { fail(CNFOT_ERR_ARG, "on-chip draws are not available on the wide-conditioner engine"); return -1; }
+  return align256(partial_bytes(lay)) + align256((int64_t)lay.total * sizeof(float)) +
+         align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
+}
+
+int cnfot_mfc_step_rng_host(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                            const float* weights_host, uint64_t key, uint32_t step, int32_t n_t, int64_t row0_B,
+                            int64_t rows_B, int64_t row0_b, int64_t rows_b, int64_t global_B, int64_t global_b,
+                            float lambda, float* out_host, void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (!weights_host || !out_host || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  const int64_t need = cnfot_mfc_step_rng_host_workspace_bytes(flow);
+  if (need < 0) return CNFOT_ERR_ARG;
+  if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                          (long long)workspace_bytes, (long long)need);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* p = (char*)workspace;
+  const int64_t ws_bytes = align256(partial_bytes(lay));
+  void* ws = p; p += ws_bytes;
+  float* dW = (float*)p; p += align256((int64_t)lay.total * sizeof(float));
+  float* dOut = (float*)p;
+  cudaError_t e = cudaMemcpyAsync(dW, weights_host, (size_t)lay.total * sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D weights");
+  StepIo io;
+  io.rng = true; io.key = key; io.step = step; io.row0_B = row0_B; io.row0_b = row0_b;
+  io.out = dOut;
+  if (int rc = mfc_step_impl(stream, flow, problem, dW, io, n_t, rows_B, rows_b, global_B, global_b, lambda, ws, ws_bytes))
+    return rc;
+  e = cudaMemcpyAsync(out_host, dOut, (size_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float), cudaMemcpyDeviceToHost, s);
   if (e != cudaSuccess) return cuda_fail(e, "D2H out");
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
@@ -1122,7 +1270,6 @@ int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float*
     a.frags = fr;
   }
   a.D = lay.D; a.L = lay.L; a.plan = sp;
-  a.sc = spline_consts(flow);
   a.latent = latent; a.batch = batch; a.latent_blocks = latent_blocks;
   a.t_dev = t_dev; a.n_t = n_t; a.with_score = with_score;
   a.dt = dt; a.dx = dx; a.kappa = kappa;

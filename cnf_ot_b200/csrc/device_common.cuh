@@ -136,7 +136,7 @@ struct DeviceCtx {
   using NetT = Net;
   static constexpr bool kWarpMlp = false;
   static constexpr bool kAccInGlobal = false;
-  __device__ __forceinline__ void bind_partials(float*) {}
+  __device__ __forceinline__ void bind_partials(float*, bool = true) {}
   __device__ __forceinline__ void bind_frags(const float*) {}
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
   float* smem;

@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "device_common.cuh"
+#include "philox.cuh"
 #include "step_math.cuh"
 #include "tc_engine.cuh"
 #include "warp_mlp.cuh"
@@ -49,7 +50,6 @@ struct EvalArgs {
   int add_base;
   int D, L;
   SmemPlan plan;
-  SplineConsts<float> sc;
 };
 
 template <class Net, class DimsT, int ENG>
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
     float st[kMaxStateFloats];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    float ld = a.dir == 0 ? flow_pass<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx)
-                          : flow_pass<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
+    float ld = a.dir == 0 ? flow_pass<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx)
+                          : flow_pass<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx);
     if (!live) continue;
     for (int i = 0; i < D; ++i) a.out[r * D + i] = st[L * D + i];
     if (a.logdet) {
@@ -122,7 +122,6 @@ struct VjpArgs {
   int add_base;
   int D, L;
   SmemPlan plan;
-  SplineConsts<float> sc;
   PartialBuf pb;
 };
 
@@ -151,8 +150,8 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
     float st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    if (a.dir == 0) flow_pass<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
-    else flow_pass<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, tl, ctx);
+    if (a.dir == 0) flow_pass<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx);
+    else flow_pass<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx);
     const float gl = (live && a.g_logdet) ? a.g_logdet[r] : 0.f;
     for (int i = 0; i < D; ++i) g[i] = live ? a.g_out[r * D + i] : 0.f;
     float gl_pass = gl;
@@ -162,9 +161,9 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
         for (int i = 0; i < D; ++i) g[i] -= gl * st[L * D + i];
     }
     if (a.dir == 0)
-      flow_pass_bwd<0, float, Net, DimsT, Ctx>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx);
     else
-      flow_pass_bwd<1, float, Net, DimsT, Ctx>(dm, a.sc, t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx);
     if (a.add_base && a.dir == 0)
       for (int i = 0; i < D; ++i) g[i] -= gl * st[i];
     if (live && a.g_in)
@@ -184,7 +183,6 @@ struct EnergyArgs {
   const float* frags;
   int D, L;
   SmemPlan plan;
-  SplineConsts<float> sc;
   const float* latent;     // (latent_blocks * batch, D)
   int64_t batch;
   int latent_blocks;
@@ -229,7 +227,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) energ
     const float* src = a.latent + ((int64_t)(ti % a.latent_blocks) * a.batch + r) * D;
     float row[kMaxDim];
     for (int i = 0; i < D; ++i) row[i] = live ? src[i] : 0.f;
-    const float v2 = row_kinetic_value<float, Net, DimsT, Ctx>(dm, a.sc, a.t_dev[ti], row, a.dt, a.with_score != 0,
+    const float v2 = row_kinetic_value<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), a.t_dev[ti], row, a.dt, a.with_score != 0,
                                                                a.kappa, a.dx, tl, ctx);
     if (live) loss[kSlotKinetic] += (double)v2 * a.weight;
   }
@@ -238,36 +236,272 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) energ
 }
 
 // ---- the fused train step ---------------------------------------------------------------
-// One persistent kernel evaluates every term of the configured loss: the work is a list
-// of segments (one per loss term and time), cut into 128-row tiles handed out by an
-// atomic counter, most expensive segments first.
+// One persistent kernel does the WHOLE step: every term of the configured loss and
+// its backward pass, the reduction of the CTAs' partial results, (multi-GPU) the all-reduce of
+// [gradient | loss slots] over peer-mapped memory, and (device-resident update) Adam.
+//   * work = a list of segments (one per loss term and time) cut into row units handed out by an atomic
+//     counter, most expensive segments first.  The warp-level engines claim 32-row units per WARP (a warp
+//     owns its rows end to end, no CTA barrier in the loop); the CTA-wide engines claim 128-row tiles.
+//   * rows come from the caller's arrays or are generated on chip (philox.cuh) -- the reference makes
+//     every draw inside the jitted step from one key (applications.py:81-82,392).
+//   * weight gradients are added (red.global) into one of `n_rows` partial rows (row = CTA index mod
+//     n_rows), loss sums into one row of doubles; both are zero on entry (memset by the stateless entry,
+//     self-cleaned by the previous launch in the device-resident one).
+//   * tail: the last `n_tail` CTAs to finish stay, wait until every CTA has arrived, and each reduces
+//     8-column slices of the partial rows in double; with peers the slice is pushed into every peer's
+//     exchange buffer (NVLink / NVSwitch stores), flagged, and summed in rank order once every peer's
+//     slice has arrived (bit-identical on all ranks); the owner of a column then writes the output and
+//     applies the Adam update of that parameter.
 enum SegmentKind { kSegNll = 0, kSegSample = 1, kSegKinetic = 2 };
 
 struct Segment {
   int kind;
   int slot;          // loss slot of the fit term (kSegNll / kSegSample)
   int do_fit, do_pot;
+  int source;        // RowSource: kRowsMemory reads `rows`, the others draw the rows on chip
+  int t_index;       // >= 0: t = horizon * U[0,1) drawn from (key, step, t_index); < 0: use `t`
   float t;
-  const float* rows; // (n, D) data or latent rows
+  const float* rows; // (n, D) data or latent rows (kRowsMemory)
+  int64_t row0;      // global index of this shard's first row (on-chip draws)
   int64_t n;
-  int64_t first_tile;
+  int64_t first_tile;  // in row units (32 or 128 rows)
 };
 
-constexpr int kMaxSegments = 40;
+constexpr int kMaxSegments = 36;
+
+// header words (uint32) of the step workspace / train state
+enum SyncWord { kSyncTile = 0 /* 64-bit: words 0, 1 */, kSyncDone = 2, kSyncTailDone = 3, kSyncStatus = 4 };
+constexpr int kStateWordOffset = 16;   // 64-bit words [key, step, epoch] start at byte 128 of the header
+constexpr int kLossRowOffset = 24;     // 8 doubles at byte 192 of the header
+constexpr int kStepRows = 148;         // partial gradient rows of the step kernel (one per SM's worth of CTAs)
+
+struct PeerArgs {
+  int rank, world;     // world <= 1: no exchange
+  uint32_t epoch;      // device-resident update: read from the train state instead
+  int stride;          // floats per rank slot in an exchange buffer (>= total + kNumSlots)
+  int n_slices;        // 8-column slices = flags per source rank; flag index world * n_slices is the abort word
+  unsigned long long timeout_ns;
+  float* xbuf[8];
+  uint32_t* flags[8];
+};
+
+struct TailArgs {
+  int n_rows;          // partial gradient rows
+  int n_tail;          // CTAs that stay for the reduction
+  int total;           // gradient floats
+  int accumulate;      // out += result (chunked host entry)
+  int self_clean;      // zero what was read (device-resident update: the next launch needs no memset)
+  uint32_t* sync;      // header words
+  double* loss_row;    // [kNumSlots], atomically accumulated
+  float* grad_rows;    // [n_rows][total]
+  float* out;          // [total + kNumSlots] or nullptr
+  float* weights;      // Adam (nullptr: none): parameters, first and second moments
+  float* adam_m;
+  float* adam_v;
+  float lr, b1, b2, eps;
+  unsigned long long* state;   // device train state [key, step, epoch] or nullptr
+  float* loss_hist;    // loss_hist[step] = total loss (device-resident update), or nullptr
+  long long loss_hist_len;
+  PeerArgs pa;
+};
 
 struct StepArgs {
   const float* W;
   const float* frags;
   int D, L;
   SmemPlan plan;
-  SplineConsts<float> sc;
   StepConsts<float> pc;
   int n_seg;
-  int64_t n_tiles;
+  int unit_rows;       // 32 (warp-level engines) or 128
+  int64_t n_tiles;     // in row units
+  unsigned long long key;       // on-chip draws (philox.cuh): key and step, or read from the train state
+  unsigned long long salt_B, salt_Bc, salt_b, salt_t;   // key modifiers: normal (B, D), categorical (B,), normal (b, D), uniform (n_t,)
+  uint32_t step;
   Segment seg[kMaxSegments];
-  unsigned long long* tile_counter;
-  PartialBuf pb;
+  TailArgs tail;
 };
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+  return v;
+}
+
+// optax.adam (scale_by_adam + scale(-lr); cnf_ot/mfc/solvers.py:55,95-96) of one parameter
+__device__ __forceinline__ void adam_one(const TailArgs& t, int i, float g, float c1, float c2) {
+  const float mi = t.b1 * t.adam_m[i] + (1.f - t.b1) * g;
+  const float vi = t.b2 * t.adam_v[i] + (1.f - t.b2) * g * g;
+  t.adam_m[i] = mi;
+  t.adam_v[i] = vi;
+  t.weights[i] -= t.lr * (mi / c1) / (sqrtf(vi / c2) + t.eps);
+}
+
+// The kernel's tail (see above).  Called by every thread of every CTA after its partial results are written.
+static __device__ __noinline__ void step_tail(const TailArgs& t) {
+  __shared__ double sh[16][8];
+  __shared__ unsigned s_ticket;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(t.sync + kSyncDone, 1u);
+  __syncthreads();
+  const unsigned grid = gridDim.x, S = (unsigned)t.n_tail, ticket = s_ticket;
+  if (ticket + S < grid) return;
+  const int k = (int)(ticket - (grid - S));
+  if (tid == 0) {
+    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(32);
+    s_bad = 0;
+  }
+  __syncthreads();
+  const int total = t.total, n_out = total + kNumSlots, n_slices = (n_out + 7) >> 3;
+  const int j = tid & 7, g = tid >> 3;
+  const bool dp = t.pa.world > 1;
+  uint32_t epoch = t.pa.epoch, stepno = 0;
+  if (t.state) {
+    stepno = (uint32_t)__ldcg(t.state + 1);
+    if (dp) epoch = (uint32_t)__ldcg(t.state + 2);
+  }
+  float c1 = 1.f, c2 = 1.f;
+  if (t.weights && tid < 8) {
+    c1 = (float)(1.0 - pow((double)t.b1, (double)stepno + 1.0));
+    c2 = (float)(1.0 - pow((double)t.b2, (double)stepno + 1.0));
+  }
+  const int par = epoch & 1u;
+  uint32_t* my_flags = dp ? t.pa.flags[t.pa.rank] : nullptr;
+  const int abort_idx = t.pa.world * t.pa.n_slices;
+  if (dp && tid == 0 && ld_acquire_sys(my_flags + abort_idx) != 0u) s_bad = 1;   // a peer gave up earlier: stay poisoned
+  __syncthreads();
+
+  auto finish = [&](int col, float v) {   // the owner of an output column
+    if (col < total) {
+      if (t.out) t.out[col] = t.accumulate ? t.out[col] + v : v;
+      if (t.weights && v == v) adam_one(t, col, v, c1, c2);   // a poisoned (NaN) gradient leaves the parameters alone
+    } else if (col < n_out) {
+      const int sl = col - total;
+      if (t.out) t.out[col] = sl <= 4 ? (t.accumulate ? t.out[col] + v : v) : 0.f;
+      if (sl == 0 && t.loss_hist && (long long)stepno < t.loss_hist_len) t.loss_hist[stepno] = v;
+    }
+  };
+
+  // phase A: this CTA's slices of the partial rows -> one float per column (pushed to the peers, or final)
+  for (int s = k; s < n_slices; s += (int)S) {
+    const int col = 8 * s + j;
+    double acc = 0.0;
+    if (col < total) {
+      // 16 loads in flight per thread (the reduction is latency-bound: every load is an L2 round trip)
+      float* p = t.grad_rows + col;
+      for (int r0 = g; r0 < t.n_rows; r0 += 16 * 16) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int r = r0 + 16 * q;
+          v[q] = r < t.n_rows ? __ldcg(p + (size_t)r * total) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc += (double)v[q];
+        if (t.self_clean) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int r = r0 + 16 * q;
+            if (r < t.n_rows) __stcg(p + (size_t)r * total, 0.f);
+          }
+        }
+      }
+    } else if (col < n_out && g == 0) {
+      // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
+      const int sl = col - total;
+      if (sl == 0) acc = __ldcg(t.loss_row) + __ldcg(t.loss_row + 1) + __ldcg(t.loss_row + 2) + __ldcg(t.loss_row + 3);
+      else if (sl <= 4) acc = __ldcg(t.loss_row + sl - 1);
+    }
+    sh[g][j] = acc;
+    __syncthreads();
+    if (tid < 32) {
+      float mine = 0.f;
+      if (tid < 8) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tot += sh[q][tid];
+        mine = (float)tot;
+      }
+      if (!dp) {
+        if (tid < 8) finish(col, mine);
+      } else {
+        if (tid < 8 && col < n_out)
+          for (int p = 0; p < t.pa.world; ++p)
+            t.pa.xbuf[p][((size_t)par * t.pa.world + t.pa.rank) * t.pa.stride + col] = mine;
+        __threadfence_system();
+        __syncwarp();
+        if (tid < t.pa.world) st_release_sys(t.pa.flags[tid] + t.pa.rank * t.pa.n_slices + s, epoch);
+      }
+    }
+    __syncthreads();
+  }
+  // phase B: wait for every peer's slice, sum in rank order
+  if (dp && tid < 32) {
+    for (int s = k; s < n_slices; s += (int)S) {
+      const int col = 8 * s + tid;
+      bool bad = *(volatile int*)&s_bad != 0;
+      if (!bad && tid < t.pa.world) {
+        const uint32_t* f = my_flags + tid * t.pa.n_slices + s;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        // epochs are compared modulo 2^32 (a peer is never more than one step ahead)
+        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+          if ((++spins & 1023u) == 0u) {
+            if (ld_acquire_sys(my_flags + abort_idx) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns) {
+              bad = true;
+              break;
+            }
+          }
+        }
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (bad) {
+        // a peer never arrived (or gave up): poison this rank's result AND tell every peer, so no rank
+        // continues with a sum the others do not have; the status word is read by the host
+        if (tid < t.pa.world) st_release_sys(t.pa.flags[tid] + abort_idx, 1u);
+        if (tid == 0) { s_bad = 1; t.sync[kSyncStatus] = 1u; }
+        if (tid < 8) finish(col, __int_as_float(0x7fc00000));
+        continue;
+      }
+      if (tid < 8 && col < n_out) {
+        const float* mybuf = t.pa.xbuf[t.pa.rank] + (size_t)par * t.pa.world * t.pa.stride + col;
+        float sum = 0.f;
+        for (int q = 0; q < t.pa.world; ++q) sum += __ldcg(mybuf + (size_t)q * t.pa.stride);
+        finish(col, sum);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(t.sync + kSyncTailDone, 1u) == S - 1) {
+      // the last CTA of the launch: leave the header ready for the next one
+      t.sync[kSyncTile] = 0u; t.sync[kSyncTile + 1] = 0u; t.sync[kSyncDone] = 0u; t.sync[kSyncTailDone] = 0u;
+      if (t.self_clean)
+        for (int q = 0; q < kNumSlots; ++q) t.loss_row[q] = 0.0;
+      if (t.state) {
+        t.state[1] += 1ULL;
+        t.state[2] += 1ULL;
+      }
+      __threadfence();
+    }
+  }
+}
 
 template <class Net, class DimsT, int ENG>
 __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
@@ -278,14 +512,22 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
   __shared__ uint32_t tc_slot;
   using Ctx = typename CtxSelect<Net, ENG>::type;
   float* sAcc = Ctx::kAccInGlobal ? nullptr : smem + a.plan.off_acc;
+  float* my_row = a.tail.grad_rows + (int64_t)(blockIdx.x % a.tail.n_rows) * a.plan.total;
   Ctx ctx;
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
-  ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
+  ctx.bind_partials(my_row, false);   // shared, pre-zeroed partial rows: the context must not clear them
   ctx.bind_frags(a.frags);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D();
+  unsigned long long key = a.key;
+  uint32_t step = a.step;
+  if (a.tail.state) {
+    key = __ldcg(a.tail.state);
+    step = (uint32_t)__ldcg(a.tail.state + 1);
+  }
+  unsigned long long* tile_counter = reinterpret_cast<unsigned long long*>(a.tail.sync + kSyncTile);
   float gfirst[Net::kPp];
 #pragma unroll
   for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
@@ -293,28 +535,54 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
 #pragma unroll
   for (int s = 0; s < kNumSlots; ++s) loss[s] = 0.0;
 
+  bool first = true;
   while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(a.tile_counter, 1ULL);
-    __syncthreads();
-    const long long tile = s_tile;
+    long long tile;
+    int row_in_unit;
+    if (Ctx::kWarpMlp && a.unit_rows == 32) {
+      // a warp owns its 32 rows end to end: claim per warp, no CTA barrier.  The first unit of every warp is
+      // its global warp index (2368 simultaneous atomics on one address would stagger the start by microseconds)
+      const int lane = threadIdx.x & 31;
+      if (first) {
+        tile = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+        first = false;
+      } else {
+        if (lane == 0) tile = (long long)atomicAdd(tile_counter, 1ULL) + (long long)gridDim.x * kWarps;
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      }
+      row_in_unit = 8 * (lane & 3) + (lane >> 2);
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1ULL);
+      __syncthreads();
+      tile = s_tile;
+      row_in_unit = ctx.row_in_tile();
+    }
     if (tile >= a.n_tiles) break;
     int si = 0;
     while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
     const Segment& sg = a.seg[si];
-    const int64_t r = (tile - sg.first_tile) * kTile + ctx.row_in_tile();
+    const int64_t r = (tile - sg.first_tile) * a.unit_rows + row_in_unit;
     const bool live = r < sg.n;
     float row[kMaxDim];
-    for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;
+    if (sg.source == kRowsMemory) {
+      for (int i = 0; i < D; ++i) row[i] = live ? sg.rows[r * D + i] : 0.f;
+    } else {
+      for (int i = 0; i < D; ++i) row[i] = 0.f;
+      if (live)
+        philox_row(key ^ (sg.kind == kSegKinetic ? a.salt_b : a.salt_B), key ^ a.salt_Bc, step, sg.source,
+                   (uint64_t)(sg.row0 + r), D, row);
+    }
+    const float tval = sg.t_index >= 0 ? philox_time(key ^ a.salt_t, step, sg.t_index, a.pc.horizon) : sg.t;
     if (sg.kind == kSegNll) {
-      float v = row_nll<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row,
+      float v = row_nll<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row,
                                                            live ? a.pc.w_fit : 0.f, gfirst, tl, ctx);
       loss[sg.slot] += (double)v;
     } else if (sg.kind == kSegSample) {
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_fit = 0.f; pc.w_pot = 0.f; }
       float lf = 0.f, lp = 0.f;
-      row_sample_terms<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row, sg.do_fit != 0,
+      row_sample_terms<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, sg.do_fit != 0,
                                                           sg.do_pot != 0, pc, &lf, &lp, gfirst, tl, ctx);
       loss[sg.slot] += (double)lf;
       loss[kSlotPotential] += (double)lp;
@@ -322,15 +590,27 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
       float lk = 0.f, lp = 0.f;
-      row_kinetic<float, Net, DimsT, Ctx>(dm, a.sc, sg.t, row, pc, &lk, &lp, gfirst,
+      row_kinetic<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, &lk, &lp, gfirst,
                                                      tl, ctx);
       loss[kSlotKinetic] += (double)lk;
       loss[kSlotPotential] += (double)lp;
     }
   }
   ctx.flush_first(gfirst, tl);
-  flush_partials(a.pb, sAcc, a.plan.total, loss, scratch);
+  // partial results -> the shared rows
+  __syncthreads();
+  if (sAcc)
+    for (int i = threadIdx.x; i < a.plan.total; i += blockDim.x) {
+      const float v = sAcc[i];
+      if (v != 0.f) atomicAdd(my_row + i, v);
+    }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {   // the four live slots (fit0, fitT, potential, kinetic)
+    const double v = block_sum(loss[s], scratch);
+    if (threadIdx.x == 0 && v != 0.0) atomicAdd(a.tail.loss_row + s, v);
+  }
   ctx_teardown(ctx);
+  step_tail(a.tail);
 }
 
 }  // namespace cnfot

@@ -288,9 +288,10 @@ CNFOT_HD void fill_mlp_input(const RowTiles<T, Net>& tl, T t, const T* cvec, int
 //        Autoregressive.forward_and_log_det (conditioners read the OUTPUT being
 //        built, sequential in d, spline forward formula).
 // states[0..D) is the input; states[(s+1)*D ..] the result of step s.
+//
 // Returns the summed log-det of the pass.
-template <int DIR, typename T, class Net, class DimsT, class Ctx>
-CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* states,
+template <int DIR, typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
                        const RowTiles<T, Net>& tl, Ctx& ctx) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
@@ -340,8 +341,8 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SplineConsts<T>& sc, T t, T* state
 // the adjoint of the pass input.  gfirst[Pp] accumulates the adjoint of the
 // shared `first` parameter (flushed to the sink once per kernel).  Conditioner
 // activations are re-computed, not stored.
-template <int DIR, typename T, class Net, class DimsT, class Ctx>
-CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* states,
+template <int DIR, typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* states,
                               T* g, T gld, T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
@@ -408,7 +409,6 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SplineConsts<T>& sc, T t, c
     }
   }
 }
-
 // log N(x; 0, I)
 template <typename T>
 CNFOT_HD T base_log_prob(const T* x, int D) {

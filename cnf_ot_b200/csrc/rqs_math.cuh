@@ -59,6 +59,19 @@ inline SplineConsts<T> make_spline_consts(int K, double lo, double hi, double mi
   return c;
 }
 
+// The constants the reference hard-codes at /root/reference/cnf_ot/models/flows.py:124-132 (range -10 .. 10,
+// min_knot_slope 1e-4; min_bin_size 1e-4 is the distrax default) as COMPILE-TIME values: every use becomes an
+// immediate operand.  The fused flow kernels use this type (a SplineConsts passed by reference to their
+// non-inlined per-pass routines costs a generic load plus descriptor moves per use: 2.7 % of the step kernel's
+// instructions, profiles/r02_*); the stand-alone spline kernels and the host harness keep the run-time struct.
+template <typename T, int K>
+struct FixedSplineConsts {
+  static constexpr T lo = (T)-10, hi = (T)10;
+  static constexpr T min_bin = (T)1e-4;
+  static constexpr T bin_scale = (T)(20.0 - K * 1e-4);
+  static constexpr T min_slope = (T)1e-4;
+  static constexpr T slope_offset = (T)0.5411666523385311;   // log(exp(1 - 1e-4) - 1)
+};
 // ---- scalar helpers (overloaded so float uses the f-suffixed device paths) --
 // On the device the float versions of exp / log / divide / reciprocal map to the SFU
 // approximations (ex2.approx, lg2.approx, rcp.approx: <= 2-3 ulp), which cuts the spline from
@@ -145,8 +158,8 @@ struct SplineState {
   T u_tail;   // its logit (+offset)
 };
 
-template <typename T, int K>
-CNFOT_HD void softmax_bins(const T* u, const SplineConsts<T>& c, T* prob, T* size) {
+template <typename T, int K, class SC>
+CNFOT_HD void softmax_bins(const T* u, const SC& c, T* prob, T* size) {
   T m = u[0];
 #pragma unroll
   for (int k = 1; k < K; ++k) m = m_max(m, u[k]);
@@ -168,8 +181,8 @@ CNFOT_HD void softmax_bins(const T* u, const SplineConsts<T>& c, T* prob, T* siz
 
 // Knot positions from bin sizes: pos[0] = lo, pos[K] = hi exactly (the last
 // knot is the constant range end, not a cumulative sum).
-template <typename T, int K>
-CNFOT_HD void knot_positions(const T* size, const SplineConsts<T>& c, T* pos) {
+template <typename T, int K, class SC>
+CNFOT_HD void knot_positions(const T* size, const SC& c, T* pos) {
   pos[0] = c.lo;
   T acc = (T)0;
 #pragma unroll
@@ -183,9 +196,9 @@ CNFOT_HD void knot_positions(const T* size, const SplineConsts<T>& c, T* pos) {
 // Bin search + gather.  `search` are the knot positions on the axis the input
 // lives on, `other` the positions on the opposite axis.  Half-open bins
 // [pos[k], pos[k+1]); outside the range the reference falls back to bin 0.
-template <typename T, int K>
+template <typename T, int K, class SC>
 CNFOT_HD void locate(T v, const T* search, const T* other, const T* us,
-                     const SplineConsts<T>& c, SplineState<T, K>& st, T& s0, T& s1,
+                     const SC& c, SplineState<T, K>& st, T& s0, T& s1,
                      T& o0, T& o1) {
   int tail = 0;
   if (v <= search[0]) tail = 1;
@@ -225,8 +238,8 @@ CNFOT_HD void locate(T v, const T* search, const T* other, const T* us,
 }
 
 // y = S(x), log|S'(x)|.  theta: raw params [K widths | K heights | K+1 slopes].
-template <typename T, int K>
-CNFOT_HD void rqs_forward(T x, const T* theta, const SplineConsts<T>& c,
+template <typename T, int K, class SC>
+CNFOT_HD void rqs_forward(T x, const T* theta, const SC& c,
                           SplineState<T, K>& st, T& y, T& logdet) {
   T w[K], h[K], xp[K + 1], yp[K + 1];
   softmax_bins<T, K>(theta, c, st.pw, w);
@@ -257,8 +270,8 @@ CNFOT_HD void rqs_forward(T x, const T* theta, const SplineConsts<T>& c,
 }
 
 // x = S^{-1}(y), log|dS^{-1}/dy|.
-template <typename T, int K>
-CNFOT_HD void rqs_inverse(T y, const T* theta, const SplineConsts<T>& c,
+template <typename T, int K, class SC>
+CNFOT_HD void rqs_inverse(T y, const T* theta, const SC& c,
                           SplineState<T, K>& st, T& x, T& logdet) {
   T w[K], h[K], xp[K + 1], yp[K + 1];
   softmax_bins<T, K>(theta, c, st.pw, w);
@@ -297,8 +310,8 @@ CNFOT_HD void rqs_inverse(T y, const T* theta, const SplineConsts<T>& c,
 // Knot positions: pos[j] = lo + sum_{i<j} size[i] for 1 <= j <= K-1; pos[0]
 // and pos[K] are constants, so the last bin's size only gets gradient through
 // earlier cumulative sums.  Slopes: softplus'(u) = sigmoid(u).
-template <typename T, int K>
-CNFOT_HD void scatter_to_raw(const SplineState<T, K>& st, const SplineConsts<T>& c,
+template <typename T, int K, class SC>
+CNFOT_HD void scatter_to_raw(const SplineState<T, K>& st, const SC& c,
                              T gx0, T gx1, T gy0, T gy1, T gd0, T gd1, T gs_tail,
                              T* gtheta) {
   T gsx[K], gsy[K];  // adjoints of the bin sizes
@@ -340,8 +353,8 @@ CNFOT_HD void scatter_to_raw(const SplineState<T, K>& st, const SplineConsts<T>&
 
 // Reverse mode of rqs_forward: given (gy, gl) = adjoints of (y, logdet),
 // returns gx and writes gtheta[3K+1] (overwrites).
-template <typename T, int K>
-CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<T>& c,
+template <typename T, int K, class SC>
+CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SC& c,
                            T gy, T gl, T* gtheta) {
   T gx;
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
@@ -398,8 +411,8 @@ CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SplineConsts<
 
 // Reverse mode of rqs_inverse: (gx_out, gl) = adjoints of (x, logdet);
 // returns the adjoint of the input y and writes gtheta.
-template <typename T, int K>
-CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SplineConsts<T>& c,
+template <typename T, int K, class SC>
+CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SC& c,
                            T gxo, T gl, T* gtheta) {
   T gyin;
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;

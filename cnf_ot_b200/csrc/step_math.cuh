@@ -116,8 +116,8 @@ CNFOT_HD void drift_pullback(int kind, T a, const T* r, int D, const T* gres, T*
 }
 
 // ---- KL row: -w log p(data | t) --------------------------------------------------
-template <typename T, class Net, class DimsT, class Ctx>
-CNFOT_HD T row_nll(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* data, T weight,
+template <typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_HD T row_nll(const DimsT& dm, const SC& sc, T t, const T* data, T weight,
                    T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
@@ -133,8 +133,8 @@ CNFOT_HD T row_nll(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* dat
 
 // ---- rows pushed through the sample direction at one time t ----------------------
 // do_fit: reverse-KL term  w_fit (log p(y) - log q_t(y));  do_pot: w_pot V(y).
-template <typename T, class Net, class DimsT, class Ctx>
-CNFOT_HD void row_sample_terms(const DimsT& dm, const SplineConsts<T>& sc, T t,
+template <typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_HD void row_sample_terms(const DimsT& dm, const SC& sc, T t,
                                const T* latent, bool do_fit, bool do_pot,
                                const StepConsts<T>& pc, T* loss_fit, T* loss_pot, T* gfirst,
                                const RowTiles<T, Net>& tl, Ctx& ctx) {
@@ -187,8 +187,8 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const SplineConsts<T>& sc, T t,
 // rwpo/fp:  v += kappa * score,  score_i = (log p(r3 + e_i dx/2) - log p(r3 - e_i dx/2)) / dx
 //           fp additionally subtracts the drift target.
 // Every pass starts from the SAME latent row (the reference reuses one PRNG key).
-template <typename T, class Net, class DimsT, class Ctx>
-CNFOT_HD void row_kinetic(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* latent,
+template <typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_HD void row_kinetic(const DimsT& dm, const SC& sc, T t, const T* latent,
                           const StepConsts<T>& pc, T* loss_kin, T* loss_pot, T* gfirst,
                           const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
@@ -264,8 +264,8 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const SplineConsts<T>& sc, T t, const
 // /root/reference/cnf_ot/utils.py:311-340: v = (r(t+dt/2) - r(t-dt/2)) / dt) or of
 // utils.calc_score_kinetic_energy (with_score, utils.py:343-389: v += kappa * score, the score by
 // central differences of log_prob with step dx).  All passes start from the same latent row.
-template <typename T, class Net, class DimsT, class Ctx>
-CNFOT_HD T row_kinetic_value(const DimsT& dm, const SplineConsts<T>& sc, T t, const T* latent, T dt,
+template <typename T, class Net, class DimsT, class Ctx, class SC>
+CNFOT_HD T row_kinetic_value(const DimsT& dm, const SC& sc, T t, const T* latent, T dt,
                              bool with_score, T kappa, T dx, const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T s1[kMaxStateFloats], s2[kMaxStateFloats];

@@ -12,7 +12,7 @@
 //     k = t+4 <-> feature 2t+1 inside each 8-wide k-step); the weight fragments are built with
 //     the same re-labelling, so chaining layers costs no shuffles and no shared memory.
 //   * fp32 fidelity: every product is split  x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo  with
-//     x_hi = x truncated to tf32 and x_lo = x - x_hi (exact); the weights' hi/lo fragments are
+//     x_hi = x rounded to tf32 and x_lo = x - x_hi (exact); the weights' hi/lo fragments are
 //     built once per CTA.  24 MMAs replace the 256 FMAs per row of a 16x16 layer.
 //   * row <-> C-layout changes (the spline needs all 16 parameters of its row in one thread) and
 //     the transposed operands of the weight gradient  dW = A^T G  go through per-warp
@@ -45,14 +45,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 3xTF32 split  v = hi + lo  with hi = v ROUNDED to tf32 (nearest, ties away: two integer instructions) and
+// lo = v - hi (exact, |lo| <= 2^-12 |v|).  The tensor core truncates an operand register to its tf32 bits, so hi is
+// passed explicitly; what the truncation then loses of lo is <= 2^-23 |v|.  Round 1 split by truncation
+// (hi = the register itself, one instruction less per element): |lo| <= 2^-10 |v|, the truncated lo loses up to
+// 2^-21 |v| and always towards zero -- a bias that does not average out over 10^5 rows and that the finite
+// differences of the score terms (1 / dx = 100) amplify: 4.8e-5 of the largest gradient entry at 2^18 rows.
+#if defined(CNFOT_TF32_TRUNC)   // the round-1 split, kept for A/B measurements (tools/diag_parity.py)
+__device__ __forceinline__ uint32_t tf32_round(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
+#else
+__device__ __forceinline__ uint32_t tf32_round(float v) { return (__float_as_uint(v) + 0x00001000u) & 0xFFFFE000u; }
+#endif
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xFFFFE000u;
+  hi = tf32_round(v);
   lo = __float_as_uint(v - __uint_as_float(hi));
-}
-// the tensor core reads only the tf32 bits of an operand register, so the "hi" operand of the split
-// is the fp32 value itself (ptxas drops an explicit mask for the same reason); this is the "lo" one
-__device__ __forceinline__ uint32_t tf32_residual(float v) {
-  return __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
 }
 
 // Shared-memory plan of the warp-MMA kernels (same struct as the CUDA-core plan; the row tiles
@@ -230,7 +236,8 @@ struct DeviceCtxMma {
   Ref w_ref, frag_ref;  // blob and fragments (shared-window address or global pointer)
   uint32_t s_wt;        // shared-window address of this warp's tiles
 
-  __device__ __forceinline__ void bind_partials(float* q) { gacc = q; }
+  bool clear_acc;       // setup() zeroes the partial row (false: rows shared between CTAs, cleared by the caller)
+  __device__ __forceinline__ void bind_partials(float* q, bool clear = true) { gacc = q; clear_acc = clear; }
   __device__ __forceinline__ void bind_frags(const float* q) { gfrag = q; }
 
   // row of the CTA tile owned by the calling thread
@@ -243,7 +250,7 @@ struct DeviceCtxMma {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
     load_weights(smem + p.off_w, gW, RES ? p.total : Pp);
-    if (gacc)
+    if (gacc && clear_acc)
       for (int i = threadIdx.x; i < p.total; i += blockDim.x) gacc[i] = 0.f;
     if constexpr (RES) {
       w_ref = Ref{s0 + (uint32_t)p.off_w * 4u};
@@ -332,10 +339,7 @@ struct DeviceCtxMma {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ahi[mt][e] = __float_as_uint(a[mt][ks][e]);
-          alo[mt][e] = tf32_residual(a[mt][ks][e]);
-        }
+        for (int e = 0; e < 4; ++e) split_tf32(a[mt][ks][e], ahi[mt][e], alo[mt][e]);
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         const float4 f = (fr + (ks * 2 + nt) * 128).ld4();
@@ -463,18 +467,17 @@ struct DeviceCtxMma {
       av[3] = lds32(ta + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ 3));    // (m = g+8, k = t+4)
       uint32_t ahi[4], alo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        ahi[e] = __float_as_uint(av[e]);
-        alo[e] = tf32_residual(av[e]);
-      }
+      for (int e = 0; e < 4; ++e) split_tf32(av[e], ahi[e], alo[e]);
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         const float b0 = lds32(tg + ks * 512 + 16 * (ln.tu ^ ks ^ (2 * nt)));            // (k = t,   n = g)
         const float b1 = lds32(tg + ks * 512 + 256 + 16 * (ln.tu ^ ks ^ (2 * nt) ^ 1));  // (k = t+4, n = g)
-        const uint32_t bl0 = tf32_residual(b0), bl1 = tf32_residual(b1);
-        mma_tf32(dw[nt], alo, __float_as_uint(b0), __float_as_uint(b1));
+        uint32_t bh0, bh1, bl0, bl1;
+        split_tf32(b0, bh0, bl0);
+        split_tf32(b1, bh1, bl1);
+        mma_tf32(dw[nt], alo, bh0, bh1);
         mma_tf32(dw[nt], ahi, bl0, bl1);
-        mma_tf32(dw[nt], ahi, __float_as_uint(b0), __float_as_uint(b1));
+        mma_tf32(dw[nt], ahi, bh0, bh1);
       }
     }
 #pragma unroll

@@ -74,11 +74,16 @@ class PeerExchange:
     self.epoch = 0
 
   def next_desc(self, shape):
+    d = self.peek_desc(shape)
+    self.epoch += 1
+    return d
+
+  def peek_desc(self, shape):
+    """The descriptor of the NEXT exchange (epoch + 1) without consuming it."""
     if shape != self.shape:
       raise ValueError("PeerExchange was sized for another flow shape")
-    self.epoch += 1
     d = self._lib.PeerDesc()
-    d.rank, d.world, d.epoch = self.rank, self.world, self.epoch & 0xFFFFFFFF or 1
+    d.rank, d.world, d.epoch = self.rank, self.world, (self.epoch + 1) & 0xFFFFFFFF or 1
     for k in range(self.world):
       d.xbuf[k] = self._xptrs[k]
       d.flags[k] = self._fptrs[k]

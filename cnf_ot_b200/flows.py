@@ -57,24 +57,55 @@ class ParamTree(dict):
     return ParamTree(self.shape, self.blob.clone())
 
   # -- parameter I/O (the reference itself never saves its parameters): one array per
-  # haiku leaf under the key "<module>/<leaf>" (e.g. "mlp_layer0_d1/~/linear_0/w", "~/first"), float32, plus the
-  # flow shape -- the file a `np.savez(path, **flatten(params))` of the reference's pytree would give.
-  def save(self, path: str) -> None:
+  # haiku leaf under the key "<module>/<leaf>" (e.g. "mlp_layer0_d1/~/linear_0/w", "~/first"), float32 -- the file a
+  # `np.savez(path, **flatten(params))` of the reference's pytree would give -- plus optional extras: the flow shape
+  # ("__flow_shape__", inferred from the leaves when absent) and whatever the caller adds (solvers.main: "opt/mu",
+  # "opt/nu" in blob layout, "opt/count", "rng/train_key").
+  @staticmethod
+  def _npz_path(path: str) -> str:
+    return path if str(path).endswith(".npz") else str(path) + ".npz"   # np.savez appends the suffix itself
+
+  def save(self, path: str, extras: Optional[Dict] = None) -> None:
     import numpy as np
     out = {f"{mod}/{leaf}": view.detach().cpu().numpy() for mod, leaves in self.items() for leaf, view in leaves.items()}
     sh = self.shape
     out["__flow_shape__"] = np.array([sh.dim, sh.num_layers, sh.mlp_layers, sh.hidden, sh.num_bins, int(sh.conditional)])
-    np.savez(path, **out)
+    for k, v in (extras or {}).items():
+      out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.uint64 if k.startswith("rng/") else None)
+    np.savez(ParamTree._npz_path(path), **out)
 
   @staticmethod
-  def load(path: str, device=None) -> "ParamTree":
+  def _infer_shape(files, z) -> FlowShape:
+    """FlowShape from the leaf names and shapes of a plain `np.savez(path, **flatten(params))` file."""
+    import re
+    layers, dims, mlps = set(), set(), set()
+    for f in files:
+      m = re.match(r"mlp_layer(\d+)_d(\d+)/~/linear_(\d+)/w$", f)
+      if m:
+        layers.add(int(m.group(1))); dims.add(int(m.group(2))); mlps.add(int(m.group(3)))
+    if not layers:
+      raise ValueError("cannot infer the flow shape: no mlp_layer*_d*/~/linear_*/w leaves")
+    dim, L, M = max(dims) + 1, max(layers) + 1, max(mlps) + 1
+    w0 = z["mlp_layer0_d1/~/linear_0/w"]
+    hidden = int(w0.shape[1])
+    P = int(np_shape(z["~/first"])[-1])
+    if (P - 1) % 3:
+      raise ValueError("~/first has an unexpected size")
+    return FlowShape(dim, L, M, hidden, (P - 1) // 3, conditional=int(w0.shape[0]) == 2)
+
+  @staticmethod
+  def load(path: str, device=None, with_extras: bool = False):
     import numpy as np
-    z = np.load(path)
-    d, n_layers, m, h, k, cond = (int(v) for v in z["__flow_shape__"])
-    shape = FlowShape(d, n_layers, m, h, k, conditional=bool(cond))
+    z = np.load(ParamTree._npz_path(path) if not __import__("os").path.exists(path) else path)
+    extra_keys = {f for f in z.files if f == "__flow_shape__" or f.startswith(("opt/", "rng/"))}
+    if "__flow_shape__" in z.files:
+      d, n_layers, m, h, k, cond = (int(v) for v in z["__flow_shape__"])
+      shape = FlowShape(d, n_layers, m, h, k, conditional=bool(cond))
+    else:
+      shape = ParamTree._infer_shape(set(z.files) - extra_keys, z)
     tree = ParamTree(shape, torch.zeros(shape.blob_size, dtype=torch.float32))
     want = {f"{mod}/{leaf}" for mod, leaves in tree.items() for leaf in leaves}
-    have = set(z.files) - {"__flow_shape__"}
+    have = set(z.files) - extra_keys
     if want != have:
       raise ValueError(f"parameter file does not match the flow shape: {sorted(want ^ have)[:4]} ...")
     for mod, leaves in tree.items():
@@ -83,7 +114,18 @@ class ParamTree(dict):
         if tuple(arr.shape) != tuple(view.shape):
           raise ValueError(f"{mod}/{leaf}: shape {tuple(arr.shape)} != {tuple(view.shape)}")
         view.copy_(arr)
-    return tree if device is None else ParamTree(shape, tree.blob.to(device))
+    tree = tree if device is None else ParamTree(shape, tree.blob.to(device))
+    if not with_extras:
+      return tree
+    extras = {}
+    for k in extra_keys - {"__flow_shape__"}:
+      a = np.asarray(z[k])
+      extras[k] = int(a) if a.ndim == 0 else torch.from_numpy(a.astype(np.float32))
+    return tree, extras
+
+
+def np_shape(a):
+  return tuple(a.shape)
 
 
 def _blob_of(shape: FlowShape, params, device) -> torch.Tensor:

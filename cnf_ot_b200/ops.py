@@ -255,6 +255,135 @@ def mfc_step_host(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, 
   return out
 
 
+# ---------------------------------------------------------------- the step's draws, made on chip
+def philox_rows(key: int, step: int, source: int, global_rows: int, dim: int, device, rows=None) -> torch.Tensor:
+  """Rows `rows` (a slice of range(global_rows); default all) of the (global_rows, dim) array the step kernel draws
+  for (key, step): `source` is _lib.ROWS_NORMAL or _lib.ROWS_OT_SOURCE."""
+  lib = _lib.load()
+  rs = slice(0, global_rows) if rows is None else rows
+  out = torch.empty(rs.stop - rs.start, dim, dtype=torch.float32, device=device)
+  with torch.cuda.device(out.device):
+    _lib.check(lib.cnfot_philox_rows(_stream(), int(key) & (2**64 - 1), int(step) & 0xFFFFFFFF, int(source),
+                                     int(global_rows), rs.start, rs.stop - rs.start, int(dim), _ptr(out)))
+  return out
+
+
+def philox_times(key: int, step: int, n_t: int, horizon: float):
+  """The n_t uniform times horizon * U[0, 1) of step (key, step), as a list of floats (computed on the host)."""
+  lib = _lib.load()
+  tb = torch.empty(max(n_t, 1), dtype=torch.float32)
+  _lib.check(lib.cnfot_philox_times_host(int(key) & (2**64 - 1), int(step) & 0xFFFFFFFF, int(n_t), float(horizon),
+                                         tb.data_ptr()))
+  return tb[:n_t].tolist()
+
+
+def mfc_step_rng(shape: FlowShape, problem: _lib.ProblemDesc, weights, key: int, step: int, n_t: int, lam: float,
+                 global_B: int, global_b: int, rows_B=None, rows_b=None, out: Optional[torch.Tensor] = None,
+                 peers=None) -> torch.Tensor:
+  """cnfot_mfc_step with the draws made inside the kernel from (key, step).  rows_B / rows_b: this rank's shard as
+  slices of range(global_B) / range(global_b) (default: everything)."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  device = weights.device
+  rB = slice(0, global_B) if rows_B is None else rows_B
+  rb = slice(0, global_b) if rows_b is None else rows_b
+  if out is None:
+    out = torch.empty(shape.blob_size + _lib.NUM_LOSS_SLOTS, dtype=torch.float32, device=device)
+  desc = _lib.flow_desc(shape)
+  ws = _workspace(lib.cnfot_mfc_step_workspace_bytes(desc, rB.stop - rB.start, rb.stop - rb.start, n_t), device)
+  pd = None if peers is None else peers.next_desc(shape)
+  with torch.cuda.device(device):
+    _lib.check(lib.cnfot_mfc_step_rng(_stream(), desc, problem, _ptr(weights), int(key) & (2**64 - 1),
+                                      int(step) & 0xFFFFFFFF, int(n_t), rB.start, rB.stop - rB.start, rb.start,
+                                      rb.stop - rb.start, global_B, global_b, float(lam), _ptr(out), ws.data_ptr(),
+                                      ws.numel(), None if pd is None else ctypes.byref(pd)))
+  return out
+
+
+def mfc_step_rng_host(shape: FlowShape, problem: _lib.ProblemDesc, weights_host, key: int, step: int, n_t: int, lam: float,
+                      global_B: int, global_b: int, out_host: torch.Tensor, device=None) -> torch.Tensor:
+  """The same with HOST weights in and HOST [gradient | loss] out (transfers and a stream synchronisation inside)."""
+  lib = _lib.load()
+  device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+  for name, t in (("weights", weights_host), ("out", out_host)):
+    if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+      raise _lib.CnfotError(f"{name}: expected a contiguous float32 host tensor")
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_mfc_step_rng_host_workspace_bytes(desc)
+  if nbytes < 0:
+    _lib.check(1)
+  ws = _workspace(nbytes, device)
+  with torch.cuda.device(device):
+    _lib.check(lib.cnfot_mfc_step_rng_host(_stream(), desc, problem, _ptr(weights_host), int(key) & (2**64 - 1),
+                                           int(step) & 0xFFFFFFFF, int(n_t), 0, global_B, 0, global_b, global_B,
+                                           global_b, float(lam), _ptr(out_host), ws.data_ptr(), ws.numel()))
+  return out_host
+
+
+def fused_update_supported(shape: FlowShape) -> bool:
+  """True when the fused per-row step kernel (on-chip draws, device-resident update) covers this flow shape;
+  False for the wide-conditioner engine."""
+  return _lib.load().cnfot_train_state_bytes(_lib.flow_desc(shape)) >= 0
+
+
+class TrainState:
+  """Device-resident state of the fused update (cnfot_mfc_update): key, step count, all-reduce epoch and the step
+  kernel's self-cleaning reduction buffers, plus the optax.adam moments (solvers.py:55-56)."""
+
+  def __init__(self, shape: FlowShape, params_blob: torch.Tensor, key: int, step: int = 0, peers=None):
+    lib = _lib.load()
+    self.shape, self.device = shape, params_blob.device
+    self.desc = _lib.flow_desc(shape)
+    n = lib.cnfot_train_state_bytes(self.desc)
+    if n < 0:
+      _lib.check(1)
+    self.buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+    self.mu = torch.zeros_like(params_blob)
+    self.nu = torch.zeros_like(params_blob)
+    self.key = int(key) & (2**64 - 1)
+    self.peers = peers
+    self._peer_desc = None
+    epoch0 = 1
+    if peers is not None:
+      # the state's device-side epoch continues the exchange's host-side count (mfc_update keeps both in step)
+      self._peer_desc = peers.peek_desc(shape)
+      epoch0 = self._peer_desc.epoch
+    with torch.cuda.device(self.device):
+      _lib.check(lib.cnfot_train_state_init(_stream(), self.desc, self.buf.data_ptr(), self.buf.numel(), self.key,
+                                            int(step), epoch0))
+    self.steps_issued = int(step)
+
+  def step_count(self) -> int:
+    """Updates completed so far (reads the device counter: synchronises)."""
+    return int(self.buf[128 + 8:128 + 16].view(torch.int64)[0])
+
+  def status(self) -> int:
+    """0 ok; 1: a peer never arrived in the all-reduce (results are NaN from then on)."""
+    return int(self.buf[:64].view(torch.int32)[_lib.STATUS_WORD])
+
+
+def mfc_update(shape: FlowShape, problem: _lib.ProblemDesc, state: TrainState, weights: torch.Tensor, n_t: int, lam: float,
+               global_B: int, global_b: int, lr: float, rows_B=None, rows_b=None, out: Optional[torch.Tensor] = None,
+               loss_hist: Optional[torch.Tensor] = None, b1=0.9, b2=0.999, eps=1e-8) -> None:
+  """One `update` (solvers.py:90-97): value_and_grad on on-chip draws + all-reduce + Adam in ONE kernel launch.
+  Nothing host-side changes between calls, so a run of calls can be captured in a CUDA graph and replayed."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  rB = slice(0, global_B) if rows_B is None else rows_B
+  rb = slice(0, global_b) if rows_b is None else rows_b
+  adam = _lib.AdamDesc(float(lr), float(b1), float(b2), float(eps))
+  pd = state._peer_desc
+  with torch.cuda.device(weights.device):
+    _lib.check(lib.cnfot_mfc_update(_stream(), state.desc, problem, state.buf.data_ptr(), state.buf.numel(),
+                                    _ptr(weights), _ptr(state.mu), _ptr(state.nu), ctypes.byref(adam), int(n_t),
+                                    rB.start, rB.stop - rB.start, rb.start, rb.stop - rb.start, global_B, global_b,
+                                    float(lam), _ptr(out), _ptr(loss_hist), 0 if loss_hist is None else loss_hist.numel(),
+                                    None if pd is None else ctypes.byref(pd)))
+  state.steps_issued += 1
+  if state.peers is not None:
+    state.peers.epoch += 1   # keep the host-side epoch of the exchange in step with the device-side one
+
+
 def kinetic_energy(shape: FlowShape, weights, latent, t_values: Sequence[float], dt: float = 0.01,
                    with_score: bool = False, kappa: float = 0.0, dx: float = 0.01,
                    latent_blocks: int = 1) -> torch.Tensor:

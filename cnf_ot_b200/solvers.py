@@ -75,8 +75,14 @@ def make_update(loss_fn, lr: float, batch_size: int):
   return update
 
 
-def main(config_dict: Dict, progress: bool = False):
-  """Training loop of solvers.py:26-129; returns (params, loss_hist)."""
+def main(config_dict: Dict, progress: bool = False, graph_steps: int = None):
+  """Training loop of solvers.py:26-129; returns (params, loss_hist).
+
+  Flows the fused step kernel covers train DEVICE-RESIDENT: one kernel launch per `update` (on-chip draws,
+  value_and_grad, the data-parallel all-reduce, Adam: `cnfot_mfc_update`), `graph_steps` updates per CUDA graph
+  (default: eval_frequency, at most 100), the loss history written by the kernel -- the host only replays graphs.
+  The draws of update k are those of (train key, step k).  Wide-conditioner flows take the update() loop of
+  `make_update` (one key per step, split from the run's key as in solvers.py:104)."""
   config = config_dict
   rng = random.PRNGKey(config["general"]["seed"])
   tr = config["train"]
@@ -86,28 +92,93 @@ def main(config_dict: Dict, progress: bool = False):
   model_rng, rng = random.split(rng)
   params = model.init(model_rng, torch.zeros(1, dim), torch.zeros(1))
   # optional keys beyond the reference's mfc.yaml (it has no checkpointing at all): train.params_in / train.params_out
-  # name .npz files of the haiku-shaped pytree (ParamTree.save / load)
+  # name .npz files of the haiku-shaped pytree (ParamTree.save / load); the file also carries the optimiser state
+  # (Adam moments, update count) and the run's key, so a resumed run continues the same trajectory
+  resume = None
   if tr.get("params_in"):
-    loaded = ParamTree.load(tr["params_in"], device=params.blob.device)
+    loaded, resume = ParamTree.load(tr["params_in"], device=params.blob.device, with_extras=True)
     if loaded.shape != params.shape:
       raise ValueError("train.params_in holds a different flow shape than the config")
     params = loaded
-  opt_state = AdamState(params)
-  update = make_update(loss_fn, tr["lr"], batch_size)
-  loss_hist = []
-  for step in range(epochs):
-    update_rng, rng = random.split(rng)
-    loss, params, opt_state = update(params, update_rng, _lambda, opt_state)
-    loss_hist.append(loss)  # device scalar: no host sync in the hot loop (solvers.py:106)
-    if progress and step % eval_frequency == 0:
+  rank, world = applications._dist.rank_world()
+  step0 = int(resume["opt/count"]) if resume and "opt/count" in resume else 0
+
+  def show(step, loss, rng):
+    # solvers.py:108-127: the key is split at every evaluation point whether or not anything is printed
+    eval_rng, rng = random.split(rng)
+    if progress:
       desc = f"step {step} loss={float(loss):.4e}"
       if config["general"]["type"] == "ot":
-        eval_rng, rng = random.split(rng)
         KL = applications.density_fit_kl_loss_fn(model, dim, T, params, eval_rng, batch_size)
         desc += f" KL={float(KL):.4f}"
-      print(desc, flush=True)
-  if tr.get("params_out"):
-    params.save(tr["params_out"])
+      if rank == 0:
+        print(desc, flush=True)
+    return rng
+
+  if ops.fused_update_supported(model.shape) and params.blob.is_cuda:
+    sc = applications._step_config(loss_fn)
+    shape, problem, n_t = model.shape, sc["problem"], config["general"]["t_batch_size"]
+    B, b = batch_size, batch_size // 32
+    rs, ss = applications._dist.shard(B, rank, world), applications._dist.shard(b, rank, world)
+    train_key, rng = random.split(rng)
+    key = int(resume["rng/train_key"]) if resume and "rng/train_key" in resume else train_key.value
+    state = ops.TrainState(shape, params.blob, key, step=step0, peers=applications.peer_exchange(shape, model.device))
+    if resume and "opt/mu" in resume:
+      state.mu.copy_(resume["opt/mu"].to(state.mu.device))
+      state.nu.copy_(resume["opt/nu"].to(state.nu.device))
+    hist = torch.zeros(step0 + epochs, dtype=torch.float32, device=params.blob.device)
+
+    def one_update():
+      ops.mfc_update(shape, problem, state, params.blob, n_t, _lambda, B, b, tr["lr"], rows_B=rs, rows_b=ss, loss_hist=hist)
+
+    K = max(1, min(graph_steps or min(eval_frequency, 100), max(epochs, 1)))
+    n_eager = epochs % K or min(K, epochs)   # the first updates run eagerly (they also warm the launch path up)
+    done = 0
+    next_eval = 0
+    graph = None
+    while done < epochs:
+      if done < n_eager:
+        one_update()
+        done += 1
+      else:
+        if graph is None:
+          # capture K updates once (nothing runs during capture; the calls' host-side bookkeeping is that of the
+          # first replay), then replay: the device-side step counter selects draws, Adam's bias correction and
+          # the loss slot, so every replay is K NEW updates
+          graph = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(graph):
+            for _ in range(K):
+              one_update()
+        else:
+          state.steps_issued += K
+          if state.peers is not None:
+            state.peers.epoch += K
+        graph.replay()
+        done += K
+      while next_eval < done:   # the evaluation points step % eval_frequency == 0 (solvers.py:108) passed so far
+        rng = show(next_eval, hist[step0 + next_eval], rng)
+        next_eval += eval_frequency
+    loss_hist = list(hist[step0:].unbind()) if epochs > 0 else []
+    opt_extras = {"opt/mu": state.mu, "opt/nu": state.nu, "opt/count": step0 + epochs, "rng/train_key": key}
+    if epochs > 0 and state.status() != 0:
+      raise RuntimeError("a peer GPU never arrived in the step's all-reduce (see CNFOT_DP_TIMEOUT_MS): results are NaN")
+  else:
+    opt_state = AdamState(params)
+    opt_state.count = step0
+    if resume and "opt/mu" in resume:
+      opt_state.mu.copy_(resume["opt/mu"].to(opt_state.mu.device))
+      opt_state.nu.copy_(resume["opt/nu"].to(opt_state.nu.device))
+    update = make_update(loss_fn, tr["lr"], batch_size)
+    loss_hist = []
+    for step in range(epochs):
+      update_rng, rng = random.split(rng)
+      loss, params, opt_state = update(params, update_rng, _lambda, opt_state)
+      loss_hist.append(loss.clone())  # a detached device scalar: neither a host sync (solvers.py:106) nor a hold on the step's buffer
+      if step % eval_frequency == 0:
+        rng = show(step, loss, rng)
+    opt_extras = {"opt/mu": opt_state.mu, "opt/nu": opt_state.nu, "opt/count": opt_state.count}
+  if tr.get("params_out") and rank == 0:
+    params.save(tr["params_out"], extras=opt_extras)
   return params, loss_hist
 
 

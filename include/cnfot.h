@@ -42,7 +42,7 @@ extern "C" {
 #define CNFOT_API
 #endif
 
-#define CNFOT_ABI_VERSION 1
+#define CNFOT_ABI_VERSION 2
 
 enum {
   CNFOT_OK = 0,
@@ -194,23 +194,27 @@ CNFOT_API int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cn
                    int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
                    float lambda, float* out, void* workspace, int64_t workspace_bytes);
 /* ---- data-parallel step: the train step fused with its all-reduce -------
- * Same as cnfot_mfc_step on this rank's shard, but the final reduction kernel also exchanges the
+ * Same as cnfot_mfc_step on this rank's shard, but the step kernel's tail also exchanges the
  * [gradient | loss slots] buffer with the peer GPUs of the node through peer-mapped memory
- * (NVLink / NVSwitch, no NCCL call): on return (stream-ordered) `out` holds the SUM over all ranks,
- * bit-identical on every rank.  The caller owns the exchange memory and maps it across processes
- * (e.g. torch.distributed._symmetric_memory, CUDA IPC or VMM handles):
+ * (NVLink / NVSwitch, no NCCL call, no second launch): on return (stream-ordered) `out` holds the SUM
+ * over all ranks, bit-identical on every rank.  The caller owns the exchange memory and maps it across
+ * processes (e.g. torch.distributed._symmetric_memory, CUDA IPC or VMM handles):
  *   xbuf[k]   rank k's exchange buffer, cnfot_dp_exchange_floats() floats, as addressable from THIS
  *             process (k == rank: the local allocation)
  *   flags[k]  rank k's flag array, cnfot_dp_flag_count() uint32, zero-initialised once
  *   epoch     1, 2, 3, ... : must increase by one per call, identically on all ranks
- * Every rank must make the call (an empty shard passes rows_B = rows_b = 0).  A peer that never
- * arrives makes the wait time out after ~2 s and `out` is filled with NaN (no hang). */
+ * Every rank must make the call (an empty shard passes rows_B = rows_b = 0).  A peer that does not
+ * arrive within CNFOT_DP_TIMEOUT_MS (environment, default 20000) makes the waiting rank fill `out` with
+ * NaN, raise the abort word of EVERY rank's flag array (the late rank then reports NaN as well, and so
+ * does every later call on these buffers: no rank continues with a sum the others do not have) and set
+ * word CNFOT_STATUS_WORD of its workspace / train state to 1. */
 typedef struct cnfot_peer_desc {
   int32_t rank, world;   /* world <= 8 (one node) */
-  uint32_t epoch;
+  uint32_t epoch;        /* ignored by cnfot_mfc_update (the train state carries it) */
   float* xbuf[8];
   uint32_t* flags[8];
 } cnfot_peer_desc;
+#define CNFOT_STATUS_WORD 4   /* uint32 index into the workspace / train state: 0 ok, 1 a peer never arrived */
 CNFOT_API int64_t cnfot_dp_exchange_stride(const cnfot_flow_desc* flow);
 CNFOT_API int64_t cnfot_dp_exchange_floats(const cnfot_flow_desc* flow, int32_t world);
 CNFOT_API int64_t cnfot_dp_flag_count(const cnfot_flow_desc* flow, int32_t world);
@@ -220,6 +224,59 @@ CNFOT_API int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const
                       int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
                       float lambda, float* out, void* workspace, int64_t workspace_bytes,
                       const cnfot_peer_desc* peers);
+
+/* ---- the step's random draws, made on chip -----------------------------------------------------------
+ * The reference makes every draw of an `update` inside the jitted step from ONE key
+ * (cnf_ot/mfc/applications.py:81-82,233-239,392,416,435; solvers.py:104-105).  Here a draw is a pure
+ * function of (key, step, kind and leading size n of the drawn array, GLOBAL row, column) -- Philox4x32-10 keyed
+ * with key ^ salt(kind, n), Box-Muller; cnf_ot_b200/csrc/philox.cuh -- so, like jax.random, arrays of different
+ * shapes drawn from one key are unrelated and equal (key, shape) gives equal numbers; the step kernel
+ * generates its rows itself (nothing crosses PCIe or HBM) and any shard is generated independently of how
+ * the batch is split over GPUs.  jax.random's threefry streams are not reproduced.
+ *   cnfot_philox_rows        rows [row0, row0 + rows) of the (global_rows, dim) array of that draw, as an array:
+ *                            feed the explicit-input entries or a CPU check
+ *   cnfot_philox_times_host  the n_t uniform times horizon * U[0,1) of a step, computed on the host
+ *   cnfot_mfc_step_rng       cnfot_mfc_step[_dp] (peers may be NULL) with the draws made inside the kernel:
+ *                            latent / target rows = NORMAL (global_B, dim), source rows = OT_SOURCE (global_B, dim),
+ *                            sub-batch latent = NORMAL (global_b, dim), times = n_t uniforms; this rank's shard is
+ *                            rows [row0_B, row0_B + rows_B) of the B-row terms and [row0_b, row0_b + rows_b) of
+ *                            the b-row terms
+ *   cnfot_mfc_step_rng_host  the same with HOST weights in and HOST [gradient | loss] out (transfers inside,
+ *                            synchronises): the key is the only other input */
+enum { CNFOT_ROWS_NORMAL = 1,     /* N(0, I) rows: latent draws and the target of kl_loss_fn (applications.py:73-82) */
+       CNFOT_ROWS_OT_SOURCE = 3   /* kl_loss_fn source: z + 8-mode mixture centre (dim 2, applications.py:34-71), z - 3
+                                     otherwise; z = the NORMAL draw of the same shape (the reference reuses the key) */ };
+CNFOT_API int cnfot_philox_rows(void* stream, uint64_t key, uint32_t step, int32_t source, int64_t global_rows,
+                      int64_t row0, int64_t rows, int32_t dim, float* out);
+CNFOT_API int cnfot_philox_times_host(uint64_t key, uint32_t step, int32_t n_t, float horizon, float* t_host);
+CNFOT_API int cnfot_mfc_step_rng(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                       const float* weights, uint64_t key, uint32_t step, int32_t n_t, int64_t row0_B,
+                       int64_t rows_B, int64_t row0_b, int64_t rows_b, int64_t global_B, int64_t global_b,
+                       float lambda, float* out, void* workspace, int64_t workspace_bytes,
+                       const cnfot_peer_desc* peers);
+CNFOT_API int64_t cnfot_mfc_step_rng_host_workspace_bytes(const cnfot_flow_desc* flow);
+CNFOT_API int cnfot_mfc_step_rng_host(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                            const float* weights_host, uint64_t key, uint32_t step, int32_t n_t, int64_t row0_B,
+                            int64_t rows_B, int64_t row0_b, int64_t rows_b, int64_t global_B, int64_t global_b,
+                            float lambda, float* out_host, void* workspace, int64_t workspace_bytes);
+
+/* ---- device-resident update: `update` of cnf_ot/mfc/solvers.py:90-97 as ONE kernel launch -----------------
+ * value_and_grad with on-chip draws + (peers) the all-reduce + optax.adam, all inside the step kernel; no host
+ * data enters the call after cnfot_train_state_init, so a sequence of calls can be captured in a CUDA graph
+ * and replayed (the 30 000-step loop of solvers.py:99-106).  The train state (device memory owned by the caller,
+ * cnfot_train_state_bytes()) carries the key, the step count (starts at `step`, +1 per call: it selects the
+ * draws, Adam's bias correction and the slot of loss_hist) and the all-reduce epoch, plus the kernel's
+ * self-cleaning reduction buffers.  out (may be NULL): [gradient | loss slots] of the step; loss_hist (may be
+ * NULL): loss_hist[step] = total loss when step < loss_hist_len.  weights, adam_m, adam_v are updated in place. */
+typedef struct cnfot_adam_desc { float lr, b1, b2, eps; } cnfot_adam_desc;   /* optax.adam defaults: b1 .9 b2 .999 eps 1e-8 */
+CNFOT_API int64_t cnfot_train_state_bytes(const cnfot_flow_desc* flow);
+CNFOT_API int cnfot_train_state_init(void* stream, const cnfot_flow_desc* flow, void* state, int64_t state_bytes,
+                           uint64_t key, uint64_t step, uint32_t epoch);
+CNFOT_API int cnfot_mfc_update(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,
+                     void* state, int64_t state_bytes, float* weights, float* adam_m, float* adam_v,
+                     const cnfot_adam_desc* adam, int32_t n_t, int64_t row0_B, int64_t rows_B, int64_t row0_b,
+                     int64_t rows_b, int64_t global_B, int64_t global_b, float lambda, float* out,
+                     float* loss_hist, int64_t loss_hist_len, const cnfot_peer_desc* peers);
 
 /* Same step with HOST buffers in and out (weights, latent, latent_sub, src, tgt, out are host
  * pointers): copies inputs to the device workspace, runs the step, copies `out` back and

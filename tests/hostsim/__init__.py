@@ -18,10 +18,11 @@ def _build(name):
   out = os.path.join(HERE, f"libhostsim_{name}.so")
   deps = [src] + [
     os.path.join(ROOT, "cnf_ot_b200", "csrc", f)
-    for f in ("rqs_math.cuh", "flow_math.cuh", "step_math.cuh", "step_host.h")
+    for f in ("rqs_math.cuh", "flow_math.cuh", "step_math.cuh", "step_host.h", "philox.cuh")
   ] + [os.path.join(ROOT, "include", "cnfot.h")]
   if (not os.path.exists(out)) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", out])
+    extra = os.environ.get("CNFOT_HOSTSIM_FLAGS", "").split()   # e.g. -DCNFOT_MERGED_SWEEP: the alternative build of the flow sweep
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC"] + extra + ["-x", "c++", src, "-o", out])
   return ctypes.CDLL(out)
 
 
@@ -111,3 +112,27 @@ def step(shape, pd, W, latent, latent_sub, src, tgt, t_batch, gB, gb, lam, dtype
           ctypes.c_int64(gB), ctypes.c_int64(gb), ctypes.c_double(lam), _p(G), _p(slots))
   assert rc == 0, rc
   return G, slots
+
+
+def philox_words(ctr, key):
+  import numpy as np
+  c = np.asarray(ctr, dtype=np.uint32)
+  k = np.asarray(key, dtype=np.uint32)
+  out = np.zeros(4, dtype=np.uint32)
+  lib("philox").hs_philox4x32_10(c.ctypes.data_as(ctypes.c_void_p), k.ctypes.data_as(ctypes.c_void_p),
+                                 out.ctypes.data_as(ctypes.c_void_p))
+  return out
+
+
+def philox_rows(key, step, source, global_rows, dim, row0=0, rows=None):
+  rows = global_rows - row0 if rows is None else rows
+  out = torch.empty(rows, dim, dtype=torch.float32)
+  lib("philox").hs_philox_rows(ctypes.c_uint64(key), ctypes.c_uint32(step), source, ctypes.c_int64(global_rows),
+                               ctypes.c_int64(row0), ctypes.c_int64(rows), dim, _p(out))
+  return out
+
+
+def philox_times(key, step, n_t, horizon):
+  out = torch.empty(n_t, dtype=torch.float32)
+  lib("philox").hs_philox_times(ctypes.c_uint64(key), ctypes.c_uint32(step), n_t, ctypes.c_float(horizon), _p(out))
+  return out

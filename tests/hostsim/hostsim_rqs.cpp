@@ -48,3 +48,18 @@ extern "C" int hs_rqs_f32(int64_t n, int K, int dir, const float* v, const float
                           float* ld, int32_t* idx, float* gin, float* gtheta) {
   DISPATCH(float)
 }
+
+// the compile-time constants of the fused kernels next to the run-time ones (tests pin the literals)
+extern "C" void hs_spline_consts(int K, double* fixed6, double* runtime6) {
+  SplineConsts<double> c = make_spline_consts<double>(K, -10.0, 10.0, 1e-4, 1e-4);
+  double r[6] = {c.lo, c.hi, c.min_bin, c.bin_scale, c.min_slope, c.slope_offset};
+  for (int i = 0; i < 6; ++i) runtime6[i] = r[i];
+  auto put = [&](auto f) {
+    double v[6] = {f.lo, f.hi, f.min_bin, f.bin_scale, f.min_slope, f.slope_offset};
+    for (int i = 0; i < 6; ++i) fixed6[i] = v[i];
+  };
+  if (K == 3) put(FixedSplineConsts<double, 3>());
+  else if (K == 5) put(FixedSplineConsts<double, 5>());
+  else if (K == 8) put(FixedSplineConsts<double, 8>());
+  else for (int i = 0; i < 6; ++i) fixed6[i] = 0.0;
+}

@@ -85,7 +85,9 @@ def test_value_and_grad_equals_forward_losses_and_oracle(typ, sub):
   l_or, g_or = olosses.value_and_grad(cfg, spec, ref, o_in, 50.0)
   assert abs(float(loss) - float(l_or)) <= 2e-5 * abs(float(l_or))
   Gor = pack(model.shape, g_or, torch.float64)
-  assert float((grads.blob.cpu().double() - Gor).abs().max() / Gor.abs().max()) < 5e-5
+  # the score terms of rwpo / fp are finite differences of float32 log-densities (1 / dx = 100): stated tolerance 2e-4
+  tol = 5e-5 if typ == "ot" else 2e-4
+  assert float((grads.blob.cpu().double() - Gor).abs().max() / Gor.abs().max()) < tol
 
 
 def test_training_reduces_loss():

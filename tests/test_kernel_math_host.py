@@ -130,3 +130,14 @@ def test_device_log1p_polynomial_accuracy():
   ref = np.log1p(e.astype(np.float64))
   rel = np.abs(r.astype(np.float64) - ref) / ref
   assert float(rel.max()) < 2e-7 and float(rel.mean()) < 6e-8
+
+
+def test_compile_time_spline_constants_equal_the_runtime_ones():
+  """The fused kernels hold the reference's spline constants (flows.py:124-132) as immediates
+  (FixedSplineConsts, rqs_math.cuh): the literals equal what make_spline_consts computes."""
+  import ctypes
+  import numpy as np
+  for K in (3, 5, 8):
+    f, r = np.zeros(6), np.zeros(6)
+    hs.lib("rqs").hs_spline_consts(K, f.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p))
+    assert np.allclose(f, r, rtol=0, atol=1e-15), (K, f, r)

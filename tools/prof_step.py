@@ -1,31 +1,51 @@
-"""A few train steps of the benchmark workload (short, for ncu)."""
+"""A few train steps of a BASELINE config (short: for ncu, and for A/B timing of tuning knobs).
+
+  python tools/prof_step.py [cfg2|cfg1|cfg3|cfg4] [n] [explicit|rng|update] [--time]
+"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import bench
-from cnf_ot_b200 import ops
-from cnf_ot_b200.layout import FlowShape
+from cnf_ot_b200 import _lib, ops
 
-typ = sys.argv[1] if len(sys.argv) > 1 else "ot"
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-dev = torch.device("cuda", 0)
-if typ == "ot":
-  B = 1 << 18; shape = FlowShape(2, 2, 2, 16, 5); cfg = bench.workload_cfg(B)
-elif typ == "rwpo":
-  B = 1 << 20; shape = FlowShape(2, 2, 2, 16, 5); cfg = bench.workload_cfg(B); cfg["general"]["type"] = "rwpo"
-else:
-  B = 1 << 19; shape = FlowShape(10, 2, 2, 16, 5); cfg = bench.workload_cfg(B); cfg["general"].update(type="fp", dim=10)
-b = B // 32
-D = shape.dim
-W = bench.make_blob(shape, dev) if D == 2 else torch.randn(shape.blob_size, device=dev) * 0.05
-g = torch.Generator(device=dev).manual_seed(1)
-lat = torch.randn(B, D, device=dev, generator=g); sub = torch.randn(b, D, device=dev, generator=g)
-src = lat + 3.0; tgt = torch.randn(B, D, device=dev, generator=g)
-pd = ops.problem_desc(cfg)
-out = torch.empty(shape.blob_size + 8, device=dev)
-for i in range(n):
-  ops.mfc_step(shape, pd, W, None if typ == "ot" else lat, sub, src if typ == "ot" else None,
-               tgt if typ == "ot" else None, [0.37], 5000.0, B, b, out=out)
+mode = sys.argv[3] if len(sys.argv) > 3 else "explicit"
+timing = "--time" in sys.argv
+
+
+class _D:
+  world, rank, local = 1, 0, 0
+  dev = torch.device("cuda", 0)
+  td = None
+
+
+torch.cuda.set_device(0)
+w = bench.Workload(name, _D(), rows_override=(1 << 19) if name == "cfg4" else None)
+state = ops.TrainState(w.shape, w.W, 1234) if mode == "update" else None
+
+
+def step(i):
+  if mode == "explicit":
+    w.step(i)
+  elif mode == "rng":
+    ops.mfc_step_rng(w.shape, w.problem, w.W, 1234, i, 1, w.lam, w.gB, w.gb, out=w.out)
+  else:
+    ops.mfc_update(w.shape, w.problem, state, w.W, 1, w.lam, w.gB, w.gb, 1e-4, out=w.out)
+
+
+for i in range(3 if timing else 0):
+  step(i)
 torch.cuda.synchronize()
-print("loss", float(out[shape.blob_size]))
+if timing:
+  ts = []
+  for r in range(5):
+    ts.append(bench.time_region(step, n, torch.cuda.synchronize, first=r * n) / n * 1e3)
+  print(f"{name} {mode} env[{os.environ.get('CNFOT_STEP_UNIT', '-')},{os.environ.get('CNFOT_STEP_ROWS', '-')},{os.environ.get('CNFOT_ENGINE', '-')}]: "
+        f"{sorted(ts)[2]:.4f} ms/step (min {min(ts):.4f}, max {max(ts):.4f}); {_lib.last_launch_info()}; loss {float(w.out[w.shape.blob_size]):.6e}")
+else:
+  for i in range(n):
+    step(i)
+  torch.cuda.synchronize()
+  print("loss", float(w.out[w.shape.blob_size]))
