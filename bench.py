@@ -588,6 +588,73 @@ def dense_roofline(dev, pk, pk_src):
           "us_per_launch": tk * 1e6}
 
 
+def train_loop_block(dist, batch):
+  """The reference's training loop (solvers.py:99-106) at its own batch size: device-resident updates (draws +
+  value_and_grad + all-reduce + Adam in one kernel), 100 updates per CUDA graph.  Wall clock per update (host
+  timer around replay + synchronize) next to the device time of the same updates."""
+  from cnf_ot_b200 import ops
+  from cnf_ot_b200.layout import FlowShape
+  shape = FlowShape(2, 2, 2, 16, 5)
+  cfg = mfc_cfg("rwpo", "double_well", 2, batch)
+  cfg["rwpo"].update(T=2, beta=10)          # config/mfc.yaml as shipped
+  problem = ops.problem_desc(cfg)
+  W = make_blob(shape, dist.dev, 0.0)       # the reference's initialisation
+  rank, world = dist.rank, dist.world
+  B, b = batch, batch // 32
+  rs = slice(rank * B // world, (rank + 1) * B // world)
+  ss = slice(rank * b // world, (rank + 1) * b // world)
+  px = None
+  if world > 1:
+    from cnf_ot_b200 import applications
+    px = applications.peer_exchange(shape, dist.dev)
+  state = ops.TrainState(shape, W, 42, peers=px)
+  K = 100
+  hist = torch.zeros(K * 8, device=dist.dev)
+  one = lambda: ops.mfc_update(shape, problem, state, W, 1, 5000.0, B, b, 1e-3, rows_B=rs, rows_b=ss, loss_hist=hist)
+  for _ in range(5):
+    one()
+  dist.sync()
+  t0 = time.perf_counter()
+  for _ in range(K):
+    one()
+  dist.sync()
+  eager = (time.perf_counter() - t0) / K
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    for _ in range(K):
+      one()
+  state.steps_issued -= K
+  if px is not None:
+    px.epoch -= K
+
+  def replay():
+    g.replay()
+    state.steps_issued += K
+    if px is not None:
+      px.epoch += K
+
+  replay()
+  dist.sync()
+  walls, devs = [], []
+  for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.sync()
+    t0 = time.perf_counter()
+    e0.record()
+    replay()
+    e1.record()
+    torch.cuda.synchronize()
+    walls.append((time.perf_counter() - t0) / K)
+    devs.append(e0.elapsed_time(e1) / 1e3 / K)
+  wall, dev = dist.max_over_ranks([statistics.median(walls), statistics.median(devs)])
+  losses = hist[:state.step_count()].cpu()
+  return {"batch": batch, "updates_per_graph": K, "wall_us_per_update": wall * 1e6, "device_us_per_update": dev * 1e6,
+          "eager_wall_us_per_update": eager * 1e6, "wall_over_device": wall / dev, "samples_per_s": batch / wall,
+          "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "updates_run": int(losses.numel()),
+          "workload": "config/mfc.yaml (rwpo / double_well, T=2, beta=10), reference initialisation, lr 1e-3",
+          "api": "cnfot_mfc_update: draws + value_and_grad + all-reduce + Adam in ONE kernel launch per update"}
+
+
 def per_config_entry(name, dist, args, pk, pk_src):
   """Timing + roofline + small-batch oracle check of one BASELINE config other than the headline one."""
   steps = {"cfg1": 50, "cfg2": 20, "cfg3": 10, "cfg4": 3, "cfg5": 2}[name]
@@ -676,15 +743,37 @@ def run_ours(args):
                 "fused": w.px is not None,
                 "note": "cnfot_mfc_step_dp (all-reduce inside the step's reduction kernel) vs cnfot_mfc_step + NCCL all_reduce"}
 
-  # ---- e2e: host buffers through the C ABI (N=1) / pinned rows read in place + all-reduce (N>1)
+  # ---- e2e: the call a user of the reference makes -- update(params, key): host weights and the PRNG key in,
+  # [gradient | loss] out; the draws are made inside the kernel (the reference draws inside its jitted step too)
+  hW = w.W.cpu().contiguous().pin_memory()
+  hout = torch.empty(n + 8, dtype=torch.float32).pin_memory()
+  dW2 = torch.empty_like(w.W)
+  rs, ss = slice(rank * w.B, (rank + 1) * w.B), slice(rank * w.b, (rank + 1) * w.b)
+
+  def step_e2e(i):
+    if world == 1:
+      ops.mfc_step_rng_host(shape, w.problem, hW, 0x5EED, i, 1, w.lam, w.gB, w.gb, hout, device=dev)
+    else:
+      dW2.copy_(hW, non_blocking=True)
+      ops.mfc_step_rng(shape, w.problem, dW2, 0x5EED, i, 1, w.lam, w.gB, w.gb, rows_B=rs, rows_b=ss, out=w.out, peers=w.px)
+      if w.px is None:
+        td.all_reduce(w.out)
+      hout.copy_(w.out, non_blocking=True)
+      torch.cuda.synchronize()
+
+  for i in range(3):
+    step_e2e(i)
+  per_e = timed_reps(dist, step_e2e, args.steps, args.reps)
+  t_e2e = statistics.median(per_e)
+  h2d = n * 4 + 16          # weights + key / step
+  d2h = (n + 8) * 4
+
+  # the round-1 form of the same call: explicit HOST row arrays (pinned, read in place by the kernel over PCIe)
   n_host = 8
   pin = lambda x: None if x is None else x.cpu().contiguous().pin_memory()
   hsets = [{k: pin(v) for k, v in s.items()} for s in w.sets[:n_host]]
-  hW = pin(w.W)
-  hout = torch.empty(n + 8, dtype=torch.float32).pin_memory()
-  dW2 = torch.empty_like(w.W)
 
-  def step_e2e(i):
+  def step_e2e_rows(i):
     s = hsets[i % n_host]
     lat, sub, src, tgt, tb = w.args_of(s, i)
     if world == 1:
@@ -698,11 +787,20 @@ def run_ours(args):
       torch.cuda.synchronize()
 
   for i in range(3):
-    step_e2e(i)
-  per_e = timed_reps(dist, step_e2e, args.steps, args.reps)
-  t_e2e = statistics.median(per_e)
-  h2d = w.bytes_per_set + n * 4
-  d2h = (n + 8) * 4
+    step_e2e_rows(i)
+  per_er = timed_reps(dist, step_e2e_rows, args.steps, args.reps)
+  t_e2e_rows = statistics.median(per_er)
+  del hsets
+
+  # ---- the on-chip-draw step and the device-resident update on the same workload (device-timed)
+  def step_rng(i):
+    ops.mfc_step_rng(shape, w.problem, w.W, 0x5EED, i, 1, w.lam, w.gB, w.gb, rows_B=rs, rows_b=ss, out=w.out, peers=w.px)
+    if world > 1 and w.px is None:
+      td.all_reduce(w.out)
+
+  for i in range(3):
+    step_rng(i)
+  t_rng = statistics.median(timed_reps(dist, step_rng, args.steps, args.reps))
 
   line = None
   if rank == 0:
@@ -724,10 +822,15 @@ def run_ours(args):
               "loss_last_step": loss_dev, "launch": launch},
       "e2e": {"value": w.gB / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
               "ms_per_step": t_e2e * 1e3, "spread": spread(per_e),
-              "api": "cnfot_mfc_step_host (C ABI; pinned host rows read in place by the kernel over PCIe, "
-                     "weights H2D, [grad|loss] D2H)" if world == 1 else
-                     "weights H2D + cnfot_mfc_step[_dp] on pinned host rows (zero-copy) + all-reduce + D2H"},
-      "gpu_launches": 2 * args.steps * args.reps,  # mfc_step_kernel + finalize[_allreduce]_kernel per step
+              "api": "cnfot_mfc_step_rng_host (C ABI): host weights + PRNG key in, [grad|loss] out; the step's draws are "
+                     "made inside the kernel (Philox), like the reference draws inside its jitted update" if world == 1 else
+                     "weights H2D + cnfot_mfc_step_rng (draws on chip, all-reduce in the kernel tail) + [grad|loss] D2H",
+              "explicit_host_rows": {"value": w.gB / t_e2e_rows, "ms_per_step": t_e2e_rows * 1e3, "spread": spread(per_er),
+                                     "h2d_bytes_per_step": w.bytes_per_set + n * 4, "d2h_bytes_per_step": d2h,
+                                     "api": "cnfot_mfc_step_host: pinned host row arrays read in place over PCIe (round-1 form)"}},
+      "on_chip_draws": {"value": w.gB / t_rng, "ms_per_step": t_rng * 1e3,
+                        "note": "cnfot_mfc_step_rng, device-timed: same step, rows generated in the kernel instead of read from HBM"},
+      "gpu_launches": args.steps * args.reps,  # ONE kernel per step: mfc_step_kernel (reduction, all-reduce in its tail)
       "clocks": clk.summary(),
       "parity": parity, "dp_check": dp_check,
       "roofline": rf["roofline"],
@@ -742,9 +845,12 @@ def run_ours(args):
     line["roofline_fp32"]["note"] = ("algorithmic conditioner FLOPs (fwd+dgrad+wgrad) only, against the CUDA-core fp32 peak "
                                      "148 SM x 128 FMA x 2 x max clock; the 16x16 layers run on the tensor pipe (3 MMAs per "
                                      "product for fp32 fidelity), the input layers and splines on CUDA cores")
-  del hsets, w
+  del w
   torch.cuda.empty_cache()
 
+  tl = [train_loop_block(dist, bsz) for bsz in (2048, 4096)]
+  if rank == 0:
+    line["train_loop"] = tl
   if not args.no_per_config:
     pc = {}
     for name in ("cfg1", "cfg3", "cfg4", "cfg5"):

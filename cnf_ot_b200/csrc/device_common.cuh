@@ -52,9 +52,11 @@ struct SmemPlan {
   int off_wmma;         // tcgen05 engine: weights in MMA layout (4 tiles of 16x16 per dense layer)
   int off_frag;         // warp-MMA engine: hi/lo weight fragments (warp_mlp.cuh); -1 if unused
   int off_wt, wt_stride;  // warp-MMA engine: per-warp [32 x 16] tiles, floats per warp
+  int off_fk;             // normalised knots of the shared `first` spline (FirstKnots, kFirstKnotFloats floats)
   int floats;
 };
 
+constexpr int kFirstKnotFloats = 128;   // room for FirstKnots<float, K> up to K = 20
 constexpr int kTileAlign = 128;  // tiles start on 512-byte boundaries (hardware swizzle = address bits)
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -90,6 +92,8 @@ inline SmemPlan plan_smem(const FlowLayout& f, bool with_grad, bool w_in_smem = 
     p.off_lo = o; o += kTile * 16;
     p.off_wmma = o; o += f.L * (f.D - 1) * f.M * 4 * 256;
   }
+  o = align_up(o, 4);
+  p.off_fk = o; o += kFirstKnotFloats;
   p.floats = o;
   return p;
 }
@@ -101,6 +105,18 @@ __device__ inline void load_weights(float* sW, const float* __restrict__ gW, int
   float4* dst = reinterpret_cast<float4*>(sW);
   for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
   for (int i = (n4 << 2) + threadIdx.x; i < total; i += blockDim.x) sW[i] = __ldg(gW + i);
+}
+
+// once per CTA: the normalised knots of the shared `first` spline (one thread; ~300 instructions)
+template <class Net>
+__device__ inline void build_first_knots(const float* first_smem, float* fk_smem) {
+  static_assert(sizeof(FirstKnots<float, Net::kK>) <= kFirstKnotFloats * sizeof(float), "FirstKnots does not fit its slot");
+  if (threadIdx.x == 0) {
+    float theta[Net::kPp];
+    for (int j = 0; j < Net::kPp; ++j) theta[j] = first_smem[j];
+    first_knots_build<float, Net::kK>(theta, FixedSplineConsts<float, Net::kK>(),
+                                      *reinterpret_cast<FirstKnots<float, Net::kK>*>(fk_smem));
+  }
 }
 
 template <class Net>
@@ -154,9 +170,14 @@ struct DeviceCtx {
     if (p.off_acc >= 0)
       for (int i = threadIdx.x; i < p.total; i += blockDim.x) smem[p.off_acc + i] = 0.f;
     __syncthreads();
+    build_first_knots<Net>(smem + p.off_w, smem + p.off_fk);
+    __syncthreads();
   }
 
   __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
+  __device__ __forceinline__ const FirstKnots<float, Net::kK>& first_knots() const {
+    return *reinterpret_cast<const FirstKnots<float, Net::kK>*>(smem + p.off_fk);
+  }
 
   __device__ __forceinline__ const float* weights(int w_off, int count) {
     if (p.w_in_smem) return smem + p.off_w + w_off;

@@ -141,9 +141,9 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D(), L = dm.L();
-  float gfirst[Net::kPp];
+  FirstGrad<float, Net::kK> gfirst;   // knot adjoints of the shared `first` spline (pulled back once, below)
 #pragma unroll
-  for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
+  for (int j = 0; j <= Net::kK; ++j) { gfirst.gx[j] = 0.f; gfirst.gy[j] = 0.f; gfirst.gd[j] = 0.f; }
   for (int64_t tile = blockIdx.x; tile * kTile < a.rows; tile += gridDim.x) {
     const int64_t r = tile * kTile + ctx.row_in_tile();
     const bool live = r < a.rows;
@@ -169,7 +169,13 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
     if (live && a.g_in)
       for (int i = 0; i < D; ++i) a.g_in[r * D + i] = g[i];
   }
-  ctx.flush_first(gfirst, tl);
+  {
+    float graw[Net::kPp];
+#pragma unroll
+    for (int j = 0; j < Net::kPp; ++j) graw[j] = 0.f;
+    first_grad_to_raw<float, Net::kK>(gfirst, ctx.first_knots(), FixedSplineConsts<float, Net::kK>(), graw);
+    ctx.flush_first(graw, tl);
+  }
   double zero[kNumSlots];
   for (int s = 0; s < kNumSlots; ++s) zero[s] = 0.0;
   flush_partials(a.pb, sAcc, a.plan.total, zero, scratch);
@@ -239,9 +245,8 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) energ
 // One persistent kernel does the WHOLE step: every term of the configured loss and
 // its backward pass, the reduction of the CTAs' partial results, (multi-GPU) the all-reduce of
 // [gradient | loss slots] over peer-mapped memory, and (device-resident update) Adam.
-//   * work = a list of segments (one per loss term and time) cut into row units handed out by an atomic
-//     counter, most expensive segments first.  The warp-level engines claim 32-row units per WARP (a warp
-//     owns its rows end to end, no CTA barrier in the loop); the CTA-wide engines claim 128-row tiles.
+//   * work = a list of segments (one per loss term and time) cut into 128-row tiles handed out by an atomic
+//     counter, most expensive segments first.
 //   * rows come from the caller's arrays or are generated on chip (philox.cuh) -- the reference makes
 //     every draw inside the jitted step from one key (applications.py:81-82,392).
 //   * weight gradients are added (red.global) into one of `n_rows` partial rows (row = CTA index mod
@@ -264,7 +269,7 @@ struct Segment {
   const float* rows; // (n, D) data or latent rows (kRowsMemory)
   int64_t row0;      // global index of this shard's first row (on-chip draws)
   int64_t n;
-  int64_t first_tile;  // in row units (32 or 128 rows)
+  int64_t first_tile;  // in 128-row tiles
 };
 
 constexpr int kMaxSegments = 36;
@@ -273,16 +278,15 @@ constexpr int kMaxSegments = 36;
 enum SyncWord { kSyncTile = 0 /* 64-bit: words 0, 1 */, kSyncDone = 2, kSyncTailDone = 3, kSyncStatus = 4 };
 constexpr int kStateWordOffset = 16;   // 64-bit words [key, step, epoch] start at byte 128 of the header
 constexpr int kLossRowOffset = 24;     // 8 doubles at byte 192 of the header
-constexpr int kStepRows = 148;         // partial gradient rows of the step kernel (one per SM's worth of CTAs)
+constexpr int kStepRows = 32;          // partial gradient rows of the step kernel (CTA b adds into row b mod 32)
 
 struct PeerArgs {
   int rank, world;     // world <= 1: no exchange
   uint32_t epoch;      // device-resident update: read from the train state instead
-  int stride;          // floats per rank slot in an exchange buffer (>= total + kNumSlots)
-  int n_slices;        // 8-column slices = flags per source rank; flag index world * n_slices is the abort word
+  int stride;          // 64-bit slots per (parity, source rank) in an exchange buffer (>= total + kNumSlots)
   unsigned long long timeout_ns;
-  float* xbuf[8];
-  uint32_t* flags[8];
+  unsigned long long* xbuf[8];   // rank k's exchange buffer: [2 parities][world sources][stride] slots of {float bits, epoch}
+  uint32_t* flags[8];            // rank k's flag words: [0] = abort
 };
 
 struct TailArgs {
@@ -312,8 +316,7 @@ struct StepArgs {
   SmemPlan plan;
   StepConsts<float> pc;
   int n_seg;
-  int unit_rows;       // 32 (warp-level engines) or 128
-  int64_t n_tiles;     // in row units
+  int64_t n_tiles;     // 128-row tiles
   unsigned long long key;       // on-chip draws (philox.cuh): key and step, or read from the train state
   unsigned long long salt_B, salt_Bc, salt_b, salt_t;   // key modifiers: normal (B, D), categorical (B,), normal (b, D), uniform (n_t,)
   uint32_t step;
@@ -349,7 +352,24 @@ __device__ __forceinline__ void adam_one(const TailArgs& t, int i, float g, floa
   t.weights[i] -= t.lr * (mi / c1) / (sqrtf(vi / c2) + t.eps);
 }
 
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // The kernel's tail (see above).  Called by every thread of every CTA after its partial results are written.
+//
+// Reduction: an 8-column slice of the partial rows is summed by a group of 8 x G threads (G row groups; G = 16: the
+// whole CTA works on one slice, G = 4: every warp on its own slice -- small grids have few rows and few CTAs).
+// Exchange (world > 1): the slice's 8 sums are written into every peer's buffer as 64-bit {value, epoch} words
+// (one store each; an aligned 8-byte store arrives whole, so the data carries its own arrival flag: no fence, no
+// flag round trip -- the latency of ONE NVLink write), and the receiver spins on the epoch of each word it needs.
+// Buffers are double-buffered by the epoch's parity: a rank can be at most one step ahead of a peer, because
+// finishing a step needs every peer's words of that step.
 static __device__ __noinline__ void step_tail(const TailArgs& t) {
   __shared__ double sh[16][8];
   __shared__ unsigned s_ticket;
@@ -363,12 +383,17 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   if (ticket + S < grid) return;
   const int k = (int)(ticket - (grid - S));
   if (tid == 0) {
-    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(32);
+    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(20);
     s_bad = 0;
   }
   __syncthreads();
   const int total = t.total, n_out = total + kNumSlots, n_slices = (n_out + 7) >> 3;
-  const int j = tid & 7, g = tid >> 3;
+  const int G = t.n_rows > 64 ? 16 : 4;        // row groups per slice
+  const int per_pass = 16 / G;                 // slices the CTA works on at once
+  const int grp = tid >> 3, j = tid & 7;
+  const int sub = grp / G, g = grp - sub * G;  // which of the pass's slices, which row group
+  const bool owner = g == 0;                   // the 8 threads that finish a slice (the first 8 lanes of a warp)
+  const int lane = tid & 31;
   const bool dp = t.pa.world > 1;
   uint32_t epoch = t.pa.epoch, stepno = 0;
   if (t.state) {
@@ -376,14 +401,12 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
     if (dp) epoch = (uint32_t)__ldcg(t.state + 2);
   }
   float c1 = 1.f, c2 = 1.f;
-  if (t.weights && tid < 8) {
+  if (t.weights && owner) {
     c1 = (float)(1.0 - pow((double)t.b1, (double)stepno + 1.0));
     c2 = (float)(1.0 - pow((double)t.b2, (double)stepno + 1.0));
   }
-  const int par = epoch & 1u;
-  uint32_t* my_flags = dp ? t.pa.flags[t.pa.rank] : nullptr;
-  const int abort_idx = t.pa.world * t.pa.n_slices;
-  if (dp && tid == 0 && ld_acquire_sys(my_flags + abort_idx) != 0u) s_bad = 1;   // a peer gave up earlier: stay poisoned
+  const size_t par_off = (size_t)(epoch & 1u) * t.pa.world * t.pa.stride;
+  if (dp && tid == 0 && ld_acquire_sys(t.pa.flags[t.pa.rank]) != 0u) s_bad = 1;   // a peer gave up earlier: stay poisoned
   __syncthreads();
 
   auto finish = [&](int col, float v) {   // the owner of an output column
@@ -397,18 +420,20 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
     }
   };
 
-  // phase A: this CTA's slices of the partial rows -> one float per column (pushed to the peers, or final)
-  for (int s = k; s < n_slices; s += (int)S) {
+  // phase A: this CTA's slices of the partial rows -> one float per column (sent to the peers, or final)
+  const int n_pass = (n_slices + per_pass - 1) / per_pass;
+  for (int ps = k; ps < n_pass; ps += (int)S) {
+    const int s = ps * per_pass + sub;
     const int col = 8 * s + j;
     double acc = 0.0;
-    if (col < total) {
-      // 16 loads in flight per thread (the reduction is latency-bound: every load is an L2 round trip)
+    if (s < n_slices && col < total) {
+      // up to 16 loads in flight per thread (the reduction is latency-bound: every load is an L2 round trip)
       float* p = t.grad_rows + col;
-      for (int r0 = g; r0 < t.n_rows; r0 += 16 * 16) {
+      for (int r0 = g; r0 < t.n_rows; r0 += G * 16) {
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const int r = r0 + 16 * q;
+          const int r = r0 + G * q;
           v[q] = r < t.n_rows ? __ldcg(p + (size_t)r * total) : 0.f;
         }
 #pragma unroll
@@ -416,74 +441,68 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
         if (t.self_clean) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const int r = r0 + 16 * q;
+            const int r = r0 + G * q;
             if (r < t.n_rows) __stcg(p + (size_t)r * total, 0.f);
           }
         }
       }
-    } else if (col < n_out && g == 0) {
+    } else if (s < n_slices && col < n_out && owner) {
       // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
       const int sl = col - total;
       if (sl == 0) acc = __ldcg(t.loss_row) + __ldcg(t.loss_row + 1) + __ldcg(t.loss_row + 2) + __ldcg(t.loss_row + 3);
       else if (sl <= 4) acc = __ldcg(t.loss_row + sl - 1);
     }
-    sh[g][j] = acc;
+    sh[grp][j] = acc;
     __syncthreads();
-    if (tid < 32) {
-      float mine = 0.f;
-      if (tid < 8) {
-        double tot = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) tot += sh[q][tid];
-        mine = (float)tot;
-      }
+    if (owner && s < n_slices) {
+      double tot = 0.0;
+      for (int q = 0; q < G; ++q) tot += sh[grp + q][j];
+      const float mine = (float)tot;
       if (!dp) {
-        if (tid < 8) finish(col, mine);
-      } else {
-        if (tid < 8 && col < n_out)
-          for (int p = 0; p < t.pa.world; ++p)
-            t.pa.xbuf[p][((size_t)par * t.pa.world + t.pa.rank) * t.pa.stride + col] = mine;
-        __threadfence_system();
-        __syncwarp();
-        if (tid < t.pa.world) st_release_sys(t.pa.flags[tid] + t.pa.rank * t.pa.n_slices + s, epoch);
+        finish(col, mine);
+      } else if (col < n_out) {
+        const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
+        for (int p = 0; p < t.pa.world; ++p)
+          st_relaxed_sys_u64(t.pa.xbuf[p] + par_off + (size_t)t.pa.rank * t.pa.stride + col, word);
       }
     }
     __syncthreads();
   }
-  // phase B: wait for every peer's slice, sum in rank order
-  if (dp && tid < 32) {
-    for (int s = k; s < n_slices; s += (int)S) {
-      const int col = 8 * s + tid;
+  // phase B: every peer's words of this CTA's slices, summed in rank order
+  if (dp && owner) {
+    const unsigned long long* mybuf = t.pa.xbuf[t.pa.rank] + par_off;
+    const uint32_t* abort_word = t.pa.flags[t.pa.rank];
+    for (int ps = k; ps < n_pass; ps += (int)S) {
+      const int s = ps * per_pass + sub;
+      const int col = 8 * s + j;
+      if (s >= n_slices || col >= n_out) continue;
       bool bad = *(volatile int*)&s_bad != 0;
-      if (!bad && tid < t.pa.world) {
-        const uint32_t* f = my_flags + tid * t.pa.n_slices + s;
-        const unsigned long long t0 = global_timer_ns();
-        unsigned spins = 0;
-        // epochs are compared modulo 2^32 (a peer is never more than one step ahead)
-        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-          if ((++spins & 1023u) == 0u) {
-            if (ld_acquire_sys(my_flags + abort_idx) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns) {
+      float sum = 0.f;
+      for (int q = 0; q < t.pa.world && !bad; ++q) {
+        const unsigned long long* w = mybuf + (size_t)q * t.pa.stride + col;
+        unsigned long long v = ld_relaxed_sys_u64(w);
+        if ((uint32_t)(v >> 32) != epoch) {
+          const unsigned long long t0 = global_timer_ns();
+          unsigned spins = 0;
+          while ((uint32_t)((v = ld_relaxed_sys_u64(w)) >> 32) != epoch) {
+            if ((++spins & 255u) == 0u &&
+                (ld_acquire_sys(abort_word) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns)) {
               bad = true;
               break;
             }
           }
         }
+        sum += __uint_as_float((uint32_t)v);
       }
-      bad = __any_sync(0xffffffffu, bad);
       if (bad) {
         // a peer never arrived (or gave up): poison this rank's result AND tell every peer, so no rank
         // continues with a sum the others do not have; the status word is read by the host
-        if (tid < t.pa.world) st_release_sys(t.pa.flags[tid] + abort_idx, 1u);
-        if (tid == 0) { s_bad = 1; t.sync[kSyncStatus] = 1u; }
-        if (tid < 8) finish(col, __int_as_float(0x7fc00000));
-        continue;
+        for (int p = 0; p < t.pa.world; ++p) st_release_sys(t.pa.flags[p], 1u);
+        s_bad = 1;
+        t.sync[kSyncStatus] = 1u;
+        sum = __int_as_float(0x7fc00000);
       }
-      if (tid < 8 && col < n_out) {
-        const float* mybuf = t.pa.xbuf[t.pa.rank] + (size_t)par * t.pa.world * t.pa.stride + col;
-        float sum = 0.f;
-        for (int q = 0; q < t.pa.world; ++q) sum += __ldcg(mybuf + (size_t)q * t.pa.stride);
-        finish(col, sum);
-      }
+      finish(col, sum);
     }
   }
   __syncthreads();
@@ -501,6 +520,7 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
       __threadfence();
     }
   }
+  (void)lane;
 }
 
 template <class Net, class DimsT, int ENG>
@@ -528,41 +548,27 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
     step = (uint32_t)__ldcg(a.tail.state + 1);
   }
   unsigned long long* tile_counter = reinterpret_cast<unsigned long long*>(a.tail.sync + kSyncTile);
-  float gfirst[Net::kPp];
+  FirstGrad<float, Net::kK> gfirst;   // knot adjoints of the shared `first` spline (pulled back once, below)
 #pragma unroll
-  for (int j = 0; j < Net::kPp; ++j) gfirst[j] = 0.f;
+  for (int j = 0; j <= Net::kK; ++j) { gfirst.gx[j] = 0.f; gfirst.gy[j] = 0.f; gfirst.gd[j] = 0.f; }
   double loss[kNumSlots];
 #pragma unroll
   for (int s = 0; s < kNumSlots; ++s) loss[s] = 0.0;
 
-  bool first = true;
+  // Work distribution: 128-row tiles handed out by an atomic counter, most expensive segments first.  (Measured and
+  // rejected on B200, cfg 2: warps claiming 32-row units on their own, no CTA barrier: 0.196 vs 0.184 ms; tiles
+  // pre-assigned round-robin with the next tile's rows prefetched by cp.async: 0.184 vs 0.180 ms -- CTAs that share
+  // an SM run at different speeds, and only the counter evens that out.)
   while (true) {
-    long long tile;
-    int row_in_unit;
-    if (Ctx::kWarpMlp && a.unit_rows == 32) {
-      // a warp owns its 32 rows end to end: claim per warp, no CTA barrier.  The first unit of every warp is
-      // its global warp index (2368 simultaneous atomics on one address would stagger the start by microseconds)
-      const int lane = threadIdx.x & 31;
-      if (first) {
-        tile = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-        first = false;
-      } else {
-        if (lane == 0) tile = (long long)atomicAdd(tile_counter, 1ULL) + (long long)gridDim.x * kWarps;
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-      }
-      row_in_unit = 8 * (lane & 3) + (lane >> 2);
-    } else {
-      __syncthreads();
-      if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1ULL);
-      __syncthreads();
-      tile = s_tile;
-      row_in_unit = ctx.row_in_tile();
-    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1ULL);
+    __syncthreads();
+    const long long tile = s_tile;
     if (tile >= a.n_tiles) break;
     int si = 0;
     while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
     const Segment& sg = a.seg[si];
-    const int64_t r = (tile - sg.first_tile) * a.unit_rows + row_in_unit;
+    const int64_t r = (tile - sg.first_tile) * kTile + ctx.row_in_tile();
     const bool live = r < sg.n;
     float row[kMaxDim];
     if (sg.source == kRowsMemory) {
@@ -596,7 +602,13 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
       loss[kSlotPotential] += (double)lp;
     }
   }
-  ctx.flush_first(gfirst, tl);
+  {
+    float graw[Net::kPp];
+#pragma unroll
+    for (int j = 0; j < Net::kPp; ++j) graw[j] = 0.f;
+    first_grad_to_raw<float, Net::kK>(gfirst, ctx.first_knots(), FixedSplineConsts<float, Net::kK>(), graw);
+    ctx.flush_first(graw, tl);
+  }
   // partial results -> the shared rows
   __syncthreads();
   if (sAcc)

@@ -13,6 +13,7 @@
 //
 // Everything that is CTA-wide on the device is delegated to a context policy `Ctx`:
 //   first_params()               the shared `first` spline parameters (Pp floats)
+//   first_knots()                their normalised knots (FirstKnots, built once per kernel)
 //   weights(w_off, count)        the weights of the conditioner at blob offset w_off
 //                                (device: resident in, or staged into, shared memory)
 //   begin()                      the row tiles may be overwritten (device: barrier)
@@ -297,6 +298,9 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
   const int D = dm.D(), L = dm.L();
   if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, false);
   CNFOT_ASSUME_LOCAL(states);
+  CNFOT_ASSUME_LOCAL(&ctx);   // the callers' context, tiles and shape live in their local memory: LDL, not generic loads
+  CNFOT_ASSUME_LOCAL(&tl);
+  CNFOT_ASSUME_LOCAL(&dm);
   T ld_total = (T)0;
 #pragma unroll 1
   for (int s = 0; s < L; ++s) {
@@ -307,28 +311,25 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
       const int i = perm_at(layer, d, D);
-      T theta[Pp];
-      if (d == 0) {
-        const T* F = ctx.first_params();
-        CNFOT_ASSUME_SHARED(F);
-#pragma unroll
-        for (int j = 0; j < Pp; j += 4) {
-          T w[4];
-          load4<T>(F + j, w);
-          theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
-        }
-      } else if constexpr (Ctx::kWarpMlp) {
-        ctx.cond_forward(D, layer, d, t, cvec, theta, false);
-      } else {
-        const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
-        CNFOT_ASSUME_SHARED(W);
-        fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
-        mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
-      }
       SplineState<T, K> st;
+      if (d == 0) {
+        // the shared, unconditioned `first` spline: knots normalised once per kernel
+        rqs_locate_first<DIR == 0, T, K>(v[i], ctx.first_knots(), sc, st);
+      } else {
+        T theta[Pp];
+        if constexpr (Ctx::kWarpMlp) {
+          ctx.cond_forward(D, layer, d, t, cvec, theta, false);
+        } else {
+          const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
+          CNFOT_ASSUME_SHARED(W);
+          fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
+          mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
+        }
+        rqs_locate_raw<DIR == 0, T, K>(v[i], theta, sc, st);
+      }
       T out, ld;
-      if (DIR == 0) rqs_inverse<T, K>(v[i], theta, sc, st, out, ld);
-      else rqs_forward<T, K>(v[i], theta, sc, st, out, ld);
+      if (DIR == 0) rqs_inverse_map<T, K>(v[i], st, sc, out, ld);
+      else rqs_forward_map<T, K>(v[i], st, sc, out, ld);
       u[i] = out;
       ld_total += ld;
     }
@@ -338,18 +339,21 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
 
 // Reverse mode of flow_pass.  On entry g[0..D) is the adjoint of the pass
 // output (states[L*D..]), gld the adjoint of the summed log-det; on exit g is
-// the adjoint of the pass input.  gfirst[Pp] accumulates the adjoint of the
-// shared `first` parameter (flushed to the sink once per kernel).  Conditioner
-// activations are re-computed, not stored.
+// the adjoint of the pass input.  gfirst accumulates the knot adjoints of the
+// shared `first` spline (pulled back to its raw parameters and flushed to the sink
+// once per kernel).  Conditioner activations are re-computed, not stored.
 template <int DIR, typename T, class Net, class DimsT, class Ctx, class SC>
 CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* states,
-                              T* g, T gld, T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
+                              T* g, T gld, FirstGrad<T, Net::kK>& gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
   if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, true);
   CNFOT_ASSUME_LOCAL(states);
   CNFOT_ASSUME_LOCAL(g);
-  CNFOT_ASSUME_LOCAL(gfirst);
+  CNFOT_ASSUME_LOCAL(&gfirst);
+  CNFOT_ASSUME_LOCAL(&ctx);
+  CNFOT_ASSUME_LOCAL(&tl);
+  CNFOT_ASSUME_LOCAL(&dm);
 #pragma unroll 1
   for (int s = L - 1; s >= 0; --s) {
     const int layer = DIR == 0 ? s : L - 1 - s;
@@ -362,53 +366,48 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* state
     for (int dd = 0; dd < D; ++dd) {
       const int d = DIR == 0 ? dd : D - 1 - dd;
       const int i = perm_at(layer, d, D);
-      T theta[Pp], gtheta[Pp];
+      SplineState<T, K> st;
       int w_off = 0;
       const T* W = nullptr;
       if (d == 0) {
-        const T* F = ctx.first_params();
-        CNFOT_ASSUME_SHARED(F);
-#pragma unroll
-        for (int j = 0; j < Pp; j += 4) {
-          T w[4];
-          load4<T>(F + j, w);
-          theta[j] = w[0]; theta[j + 1] = w[1]; theta[j + 2] = w[2]; theta[j + 3] = w[3];
+        rqs_locate_first<DIR == 0, T, K>(v[i], ctx.first_knots(), sc, st);
+      } else {
+        T theta[Pp];
+        if constexpr (Ctx::kWarpMlp) {
+          ctx.cond_forward(D, layer, d, t, cvec, theta, true);
+        } else {
+          w_off = mlp_offset<Net>(D, layer, d);
+          ctx.begin();  // the tiles of the previous conditioner are free again
+          W = ctx.weights(w_off, (d + 1) * H + Net::kMlpConst);
+          CNFOT_ASSUME_SHARED(W);
+          fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
+          mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
         }
-      } else if constexpr (Ctx::kWarpMlp) {
-        ctx.cond_forward(D, layer, d, t, cvec, theta, true);
-      } else {
-        w_off = mlp_offset<Net>(D, layer, d);
-        ctx.begin();  // the tiles of the previous conditioner are free again
-        W = ctx.weights(w_off, (d + 1) * H + Net::kMlpConst);
-        CNFOT_ASSUME_SHARED(W);
-        fill_mlp_input<T, Net>(tl, t, cvec, layer, d, D);
-        mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
+        rqs_locate_raw<DIR == 0, T, K>(v[i], theta, sc, st);
       }
-      SplineState<T, K> st;
-      T out, ld;
-#pragma unroll
-      for (int j = 0; j < Pp; ++j) gtheta[j] = (T)0;
-      if (DIR == 0) {
-        rqs_inverse<T, K>(v[i], theta, sc, st, out, ld);
-        g[i] = rqs_inverse_bwd<T, K>(v[i], st, sc, g[i], gld, gtheta);
-      } else {
-        rqs_forward<T, K>(v[i], theta, sc, st, out, ld);
-        g[i] = rqs_forward_bwd<T, K>(v[i], st, sc, g[i], gld, gtheta);
-      }
+      KnotAdjoints<T> ka;
+      if (DIR == 0) g[i] = rqs_inverse_map_bwd<T, K>(v[i], st, sc, g[i], gld, ka);
+      else g[i] = rqs_forward_map_bwd<T, K>(v[i], st, sc, g[i], gld, ka);
       if (d == 0) {
-#pragma unroll
-        for (int j = 0; j < Pp; ++j) gfirst[j] += gtheta[j];
-      } else if constexpr (Ctx::kWarpMlp) {
-        ctx.cond_backward(D, layer, d, t, cvec, gtheta, g);
+        first_grad_add<T, K>(gfirst, st, ka.gx0, ka.gx1, ka.gy0, ka.gy1, ka.gd0, ka.gd1, ka.gst);
       } else {
-        T gin[kMaxDim + 1];
-        mlp_backward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, gtheta, gin, ctx);
-        for (int j = 0; j < d; ++j) g[perm_at(layer, j, D)] += gin[1 + j];
-        ctx.commit(w_off, d + 1, tl);
+        T gtheta[Pp];
+#pragma unroll
+        for (int j = 0; j < Pp; ++j) gtheta[j] = (T)0;
+        scatter_to_raw<T, K>(st, sc, ka.gx0, ka.gx1, ka.gy0, ka.gy1, ka.gd0, ka.gd1, ka.gst, gtheta);
+        if constexpr (Ctx::kWarpMlp) {
+          ctx.cond_backward(D, layer, d, t, cvec, gtheta, g);
+        } else {
+          T gin[kMaxDim + 1];
+          mlp_backward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, gtheta, gin, ctx);
+          for (int j = 0; j < d; ++j) g[perm_at(layer, j, D)] += gin[1 + j];
+          ctx.commit(w_off, d + 1, tl);
+        }
       }
     }
   }
 }
+
 // log N(x; 0, I)
 template <typename T>
 CNFOT_HD T base_log_prob(const T* x, int D) {

@@ -237,16 +237,120 @@ CNFOT_HD void locate(T v, const T* search, const T* other, const T* us,
   }
 }
 
-// y = S(x), log|S'(x)|.  theta: raw params [K widths | K heights | K+1 slopes].
-template <typename T, int K, class SC>
-CNFOT_HD void rqs_forward(T x, const T* theta, const SC& c,
-                          SplineState<T, K>& st, T& y, T& logdet) {
+// Knot normalisation + bin search of one spline evaluation: raw params -> the gathered knot data in `st`.
+// INV = false: the input lives on the x axis (forward map); true: on the y axis (inverse map).
+template <bool INV, typename T, int K, class SC>
+CNFOT_HD void rqs_locate_raw(T v, const T* theta, const SC& c, SplineState<T, K>& st) {
   T w[K], h[K], xp[K + 1], yp[K + 1];
   softmax_bins<T, K>(theta, c, st.pw, w);
   softmax_bins<T, K>(theta + K, c, st.ph, h);
   knot_positions<T, K>(w, c, xp);
   knot_positions<T, K>(h, c, yp);
-  locate<T, K>(x, xp, yp, theta + 2 * K, c, st, st.x0, st.x1, st.y0, st.y1);
+  if (INV) locate<T, K>(v, yp, xp, theta + 2 * K, c, st, st.y0, st.y1, st.x0, st.x1);
+  else locate<T, K>(v, xp, yp, theta + 2 * K, c, st, st.x0, st.x1, st.y0, st.y1);
+}
+
+// ---- the shared `first` spline ------------------------------------------------------------------
+// Position 0 of every flow layer uses the SAME unconditioned parameters (`~/first`, flows.py:47-55;
+// autoregressive.py:88-92): its knots depend on the weights only, not on the row.  They are normalised once per
+// kernel (FirstKnots, in shared memory); a row only searches its bin, and the adjoint is accumulated per KNOT
+// (FirstGrad) and pulled back through the softmax / cumulative-sum / softplus once per thread at the end.
+template <typename T, int K>
+struct FirstKnots {
+  T xp[K + 1], yp[K + 1];   // knot positions
+  T dk[K + 1];              // knot slopes  softplus(u + offset) + min_slope
+  T sg[K + 1];              // sigmoid(u + offset): d slope / d raw
+  T pw[K], ph[K];           // softmax probabilities of the bin widths / heights
+};
+template <typename T, int K>
+struct FirstGrad {
+  T gx[K + 1], gy[K + 1], gd[K + 1];   // adjoints of the knot positions and slopes (entries 0 and K of gx, gy stay unused)
+};
+
+template <typename T, int K, class SC>
+CNFOT_HD void first_knots_build(const T* theta, const SC& c, FirstKnots<T, K>& fk) {
+  T w[K], h[K];
+  softmax_bins<T, K>(theta, c, fk.pw, w);
+  softmax_bins<T, K>(theta + K, c, fk.ph, h);
+  knot_positions<T, K>(w, c, fk.xp);
+  knot_positions<T, K>(h, c, fk.yp);
+  for (int k = 0; k <= K; ++k) {
+    const T u = theta[2 * K + k] + c.slope_offset;
+    fk.dk[k] = softplus(u) + c.min_slope;
+    fk.sg[k] = sigmoid(u);
+  }
+}
+
+// Bin search in the precomputed knots (same bin / tail rules as `locate`).
+template <bool INV, typename T, int K, class SC>
+CNFOT_HD void rqs_locate_first(T v, const FirstKnots<T, K>& fk, const SC& c, SplineState<T, K>& st) {
+  CNFOT_ASSUME_SHARED(&fk);   // device: the contexts keep it in shared memory (LDS, not generic loads)
+  const T* search = INV ? fk.yp : fk.xp;
+  const T* other = INV ? fk.xp : fk.yp;
+  int tail = 0;
+  if (v <= search[0]) tail = 1;
+  if (v >= search[K]) tail = 2;
+  int idx = 0;
+#pragma unroll
+  for (int k = 1; k < K; ++k) idx += (v >= search[k]) ? 1 : 0;
+  if (v < search[0] || v >= search[K]) idx = 0;
+  T s0 = search[0], s1 = search[1], o0 = other[0], o1 = other[1], d0 = fk.dk[0], d1 = fk.dk[1];
+  const bool inside = v < search[K];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    const bool hit = inside && (v >= search[k]);
+    s0 = hit ? search[k] : s0;
+    s1 = hit ? search[k + 1] : s1;
+    o0 = hit ? other[k] : o0;
+    o1 = hit ? other[k + 1] : o1;
+    d0 = hit ? fk.dk[k] : d0;
+    d1 = hit ? fk.dk[k + 1] : d1;
+  }
+  st.idx = idx;
+  st.tail = tail;
+  st.d0 = d0;
+  st.d1 = d1;
+  st.s_tail = tail == 2 ? fk.dk[K] : d0;
+  if (INV) { st.y0 = s0; st.y1 = s1; st.x0 = o0; st.x1 = o1; }
+  else { st.x0 = s0; st.x1 = s1; st.y0 = o0; st.y1 = o1; }
+}
+
+// this row's knot adjoints -> the per-thread accumulators
+template <typename T, int K>
+CNFOT_HD void first_grad_add(FirstGrad<T, K>& a, const SplineState<T, K>& st, T gx0, T gx1, T gy0, T gy1, T gd0, T gd1,
+                             T gs_tail) {
+  if (st.tail == 0) {
+    const int i = st.idx;
+    a.gx[i] += gx0; a.gx[i + 1] += gx1;
+    a.gy[i] += gy0; a.gy[i + 1] += gy1;
+    a.gd[i] += gd0; a.gd[i + 1] += gd1;
+  } else {
+    a.gd[st.tail == 1 ? 0 : K] += gs_tail;
+  }
+}
+
+// accumulated knot adjoints -> adjoint of the raw `first` parameters (the pull-back `scatter_to_raw` does per row)
+template <typename T, int K, class SC>
+CNFOT_HD void first_grad_to_raw(const FirstGrad<T, K>& a, const FirstKnots<T, K>& fk, const SC& c, T* gtheta) {
+  T gsx[K], gsy[K];
+  T accx = (T)0, accy = (T)0;
+  for (int i = K - 1; i >= 0; --i) {
+    if (i + 1 <= K - 1) { accx += a.gx[i + 1]; accy += a.gy[i + 1]; }   // size[i] feeds every interior knot j >= i + 1
+    gsx[i] = accx;
+    gsy[i] = accy;
+  }
+  T dotx = (T)0, doty = (T)0;
+  for (int k = 0; k < K; ++k) { dotx += fk.pw[k] * gsx[k]; doty += fk.ph[k] * gsy[k]; }
+  for (int k = 0; k < K; ++k) {
+    gtheta[k] = c.bin_scale * fk.pw[k] * (gsx[k] - dotx);
+    gtheta[K + k] = c.bin_scale * fk.ph[k] * (gsy[k] - doty);
+  }
+  for (int k = 0; k <= K; ++k) gtheta[2 * K + k] = a.gd[k] * fk.sg[k];
+}
+
+// The forward map on located knot data: y = S(x), log|S'(x)|.
+template <typename T, int K, class SC>
+CNFOT_HD void rqs_forward_map(T x, const SplineState<T, K>& st, const SC& c, T& y, T& logdet) {
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
     T ibw = m_rcp(bw);
@@ -269,16 +373,9 @@ CNFOT_HD void rqs_forward(T x, const T* theta, const SC& c,
   }
 }
 
-// x = S^{-1}(y), log|dS^{-1}/dy|.
+// The inverse map on located knot data: x = S^{-1}(y), log|dS^{-1}/dy|.
 template <typename T, int K, class SC>
-CNFOT_HD void rqs_inverse(T y, const T* theta, const SC& c,
-                          SplineState<T, K>& st, T& x, T& logdet) {
-  T w[K], h[K], xp[K + 1], yp[K + 1];
-  softmax_bins<T, K>(theta, c, st.pw, w);
-  softmax_bins<T, K>(theta + K, c, st.ph, h);
-  knot_positions<T, K>(w, c, xp);
-  knot_positions<T, K>(h, c, yp);
-  locate<T, K>(y, yp, xp, theta + 2 * K, c, st, st.y0, st.y1, st.x0, st.x1);
+CNFOT_HD void rqs_inverse_map(T y, const SplineState<T, K>& st, const SC& c, T& x, T& logdet) {
   if (st.tail == 0) {
     T bw = st.x1 - st.x0, bh = st.y1 - st.y0;
     T sl = m_div(bh, bw);
@@ -304,6 +401,22 @@ CNFOT_HD void rqs_inverse(T y, const T* theta, const SC& c,
     x = m_div(y - px, st.s_tail) + px;
     logdet = -m_log(st.s_tail);
   }
+}
+
+// y = S(x), log|S'(x)|.  theta: raw params [K widths | K heights | K+1 slopes].
+template <typename T, int K, class SC>
+CNFOT_HD void rqs_forward(T x, const T* theta, const SC& c,
+                          SplineState<T, K>& st, T& y, T& logdet) {
+  rqs_locate_raw<false, T, K>(x, theta, c, st);
+  rqs_forward_map<T, K>(x, st, c, y, logdet);
+}
+
+// x = S^{-1}(y), log|dS^{-1}/dy|.
+template <typename T, int K, class SC>
+CNFOT_HD void rqs_inverse(T y, const T* theta, const SC& c,
+                          SplineState<T, K>& st, T& x, T& logdet) {
+  rqs_locate_raw<true, T, K>(y, theta, c, st);
+  rqs_inverse_map<T, K>(y, st, c, x, logdet);
 }
 
 // Adjoints of the six gathered knot scalars -> adjoints of the raw params.
@@ -351,11 +464,15 @@ CNFOT_HD void scatter_to_raw(const SplineState<T, K>& st, const SC& c,
   if (st.tail == 2) gtheta[3 * K] += gs_tail * sigmoid(st.u_tail);
 }
 
-// Reverse mode of rqs_forward: given (gy, gl) = adjoints of (y, logdet),
-// returns gx and writes gtheta[3K+1] (overwrites).
+// Adjoints of the gathered knot data of one evaluation.
+template <typename T>
+struct KnotAdjoints {
+  T gx0, gx1, gy0, gy1, gd0, gd1, gst;
+};
+
+// Reverse mode of rqs_forward_map: given (gy, gl) = adjoints of (y, logdet), returns gx and the knot adjoints.
 template <typename T, int K, class SC>
-CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SC& c,
-                           T gy, T gl, T* gtheta) {
+CNFOT_HD T rqs_forward_map_bwd(T x, const SplineState<T, K>& st, const SC& c, T gy, T gl, KnotAdjoints<T>& ka) {
   T gx;
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
   if (st.tail == 0) {
@@ -405,15 +522,25 @@ CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SC& c,
     gx = gy * st.s_tail;
     gst = gy * (x - px) + m_div(gl, st.s_tail);
   }
-  scatter_to_raw<T, K>(st, c, gx0, gx1, gy0, gy1, gd0, gd1, gst, gtheta);
+  ka.gx0 = gx0; ka.gx1 = gx1; ka.gy0 = gy0; ka.gy1 = gy1; ka.gd0 = gd0; ka.gd1 = gd1; ka.gst = gst;
   return gx;
 }
 
-// Reverse mode of rqs_inverse: (gx_out, gl) = adjoints of (x, logdet);
-// returns the adjoint of the input y and writes gtheta.
+// Reverse mode of rqs_forward: given (gy, gl) = adjoints of (y, logdet),
+// returns gx and writes gtheta[3K+1] (overwrites).
 template <typename T, int K, class SC>
-CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SC& c,
-                           T gxo, T gl, T* gtheta) {
+CNFOT_HD T rqs_forward_bwd(T x, const SplineState<T, K>& st, const SC& c,
+                           T gy, T gl, T* gtheta) {
+  KnotAdjoints<T> ka;
+  const T gx = rqs_forward_map_bwd<T, K>(x, st, c, gy, gl, ka);
+  scatter_to_raw<T, K>(st, c, ka.gx0, ka.gx1, ka.gy0, ka.gy1, ka.gd0, ka.gd1, ka.gst, gtheta);
+  return gx;
+}
+
+// Reverse mode of rqs_inverse_map: (gx_out, gl) = adjoints of (x, logdet); returns the adjoint of the input y
+// and the knot adjoints.
+template <typename T, int K, class SC>
+CNFOT_HD T rqs_inverse_map_bwd(T y, const SplineState<T, K>& st, const SC& c, T gxo, T gl, KnotAdjoints<T>& ka) {
   T gyin;
   T gx0 = 0, gx1 = 0, gy0 = 0, gy1 = 0, gd0 = 0, gd1 = 0, gst = 0;
   if (st.tail == 0) {
@@ -497,7 +624,18 @@ CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SC& c,
     gyin = gxo * is;
     gst = -gxo * (y - px) * is * is - gl * is;
   }
-  scatter_to_raw<T, K>(st, c, gx0, gx1, gy0, gy1, gd0, gd1, gst, gtheta);
+  ka.gx0 = gx0; ka.gx1 = gx1; ka.gy0 = gy0; ka.gy1 = gy1; ka.gd0 = gd0; ka.gd1 = gd1; ka.gst = gst;
+  return gyin;
+}
+
+// Reverse mode of rqs_inverse: (gx_out, gl) = adjoints of (x, logdet);
+// returns the adjoint of the input y and writes gtheta.
+template <typename T, int K, class SC>
+CNFOT_HD T rqs_inverse_bwd(T y, const SplineState<T, K>& st, const SC& c,
+                           T gxo, T gl, T* gtheta) {
+  KnotAdjoints<T> ka;
+  const T gyin = rqs_inverse_map_bwd<T, K>(y, st, c, gxo, gl, ka);
+  scatter_to_raw<T, K>(st, c, ka.gx0, ka.gx1, ka.gy0, ka.gy1, ka.gd0, ka.gd1, ka.gst, gtheta);
   return gyin;
 }
 

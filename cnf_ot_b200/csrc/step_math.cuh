@@ -116,9 +116,9 @@ CNFOT_HD void drift_pullback(int kind, T a, const T* r, int D, const T* gres, T*
 }
 
 // ---- KL row: -w log p(data | t) --------------------------------------------------
-template <typename T, class Net, class DimsT, class Ctx, class SC>
+template <typename T, class Net, class DimsT, class Ctx, class SC, class FG>
 CNFOT_HD T row_nll(const DimsT& dm, const SC& sc, T t, const T* data, T weight,
-                   T* gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
+                   FG& gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
   for (int i = 0; i < D; ++i) st[i] = data[i];
@@ -133,10 +133,10 @@ CNFOT_HD T row_nll(const DimsT& dm, const SC& sc, T t, const T* data, T weight,
 
 // ---- rows pushed through the sample direction at one time t ----------------------
 // do_fit: reverse-KL term  w_fit (log p(y) - log q_t(y));  do_pot: w_pot V(y).
-template <typename T, class Net, class DimsT, class Ctx, class SC>
+template <typename T, class Net, class DimsT, class Ctx, class SC, class FG>
 CNFOT_HD void row_sample_terms(const DimsT& dm, const SC& sc, T t,
                                const T* latent, bool do_fit, bool do_pot,
-                               const StepConsts<T>& pc, T* loss_fit, T* loss_pot, T* gfirst,
+                               const StepConsts<T>& pc, T* loss_fit, T* loss_pot, FG& gfirst,
                                const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
@@ -187,9 +187,9 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const SC& sc, T t,
 // rwpo/fp:  v += kappa * score,  score_i = (log p(r3 + e_i dx/2) - log p(r3 - e_i dx/2)) / dx
 //           fp additionally subtracts the drift target.
 // Every pass starts from the SAME latent row (the reference reuses one PRNG key).
-template <typename T, class Net, class DimsT, class Ctx, class SC>
+template <typename T, class Net, class DimsT, class Ctx, class SC, class FG>
 CNFOT_HD void row_kinetic(const DimsT& dm, const SC& sc, T t, const T* latent,
-                          const StepConsts<T>& pc, T* loss_kin, T* loss_pot, T* gfirst,
+                          const StepConsts<T>& pc, T* loss_kin, T* loss_pot, FG& gfirst,
                           const RowTiles<T, Net>& tl, Ctx& ctx) {
   const int D = dm.D(), L = dm.L();
   const bool with_score = pc.type != kOT;

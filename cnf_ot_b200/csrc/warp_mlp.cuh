@@ -86,6 +86,7 @@ inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad, bool resident
   p.off_wt = o;
   p.wt_stride = (with_grad ? f.M + 1 : 1) * kWtFloats;
   o += kWarps * p.wt_stride;
+  p.off_fk = o; o += kFirstKnotFloats;
   p.floats = o;
   return p;
 }
@@ -263,10 +264,15 @@ struct DeviceCtxMma {
       frag_ref = Ref{gfrag};
     }
     __syncthreads();
+    build_first_knots<Net>(smem + p.off_w, smem + p.off_fk);
+    __syncthreads();
   }
   __device__ __forceinline__ void teardown() {}
 
   __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
+  __device__ __forceinline__ const FirstKnots<float, Net::kK>& first_knots() const {
+    return *reinterpret_cast<const FirstKnots<float, Net::kK>*>(smem + p.off_fk);
+  }
 
   // ---- register layouts of a [32 x 16] matrix (thread (g, t); mt = m-tile, nt / ks = 8-column block)
   //   C order  c[mt][nt] = { (g, 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) }     MMA accumulator

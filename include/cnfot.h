@@ -199,9 +199,11 @@ CNFOT_API int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cn
  * (NVLink / NVSwitch, no NCCL call, no second launch): on return (stream-ordered) `out` holds the SUM
  * over all ranks, bit-identical on every rank.  The caller owns the exchange memory and maps it across
  * processes (e.g. torch.distributed._symmetric_memory, CUDA IPC or VMM handles):
- *   xbuf[k]   rank k's exchange buffer, cnfot_dp_exchange_floats() floats, as addressable from THIS
- *             process (k == rank: the local allocation)
- *   flags[k]  rank k's flag array, cnfot_dp_flag_count() uint32, zero-initialised once
+ *   xbuf[k]   rank k's exchange buffer, cnfot_dp_exchange_floats() floats (8-byte aligned), as addressable
+ *             from THIS process (k == rank: the local allocation), zero-initialised once.  Every value travels
+ *             as ONE 64-bit word {float bits, epoch}: an aligned 8-byte store arrives whole, so the data is its
+ *             own arrival flag (no fence, no flag round trip: the latency of one NVLink write)
+ *   flags[k]  rank k's flag words, cnfot_dp_flag_count() uint32, zero-initialised once (word 0: abort)
  *   epoch     1, 2, 3, ... : must increase by one per call, identically on all ranks
  * Every rank must make the call (an empty shard passes rows_B = rows_b = 0).  A peer that does not
  * arrive within CNFOT_DP_TIMEOUT_MS (environment, default 20000) makes the waiting rank fill `out` with

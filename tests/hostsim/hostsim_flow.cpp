@@ -32,7 +32,12 @@ struct HostSink {
   static constexpr bool kWarpMlp = false;
   double* G;     // gradient blob (double accumulation)
   const T* Wb;   // weight blob
+  FirstKnots<T, Net::kK> fk;   // normalised knots of the shared `first` spline (built once, like the device contexts)
+  HostSink(double* G_, const T* Wb_) : G(G_), Wb(Wb_) {
+    first_knots_build<T, Net::kK>(Wb, make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4), fk);
+  }
   const T* first_params() const { return Wb; }
+  const FirstKnots<T, Net::kK>& first_knots() const { return fk; }
   const T* weights(int w_off, int) const { return Wb + w_off; }
   void begin() {}
   template <int K, int N>
@@ -64,7 +69,7 @@ static int flow_eval(int D, int L, int dir, int64_t rows, const T* W, const T* i
   SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
   HostTiles<T, Net> ht;
   RowTiles<T, Net> tl = ht.view();
-  HostSink<T, Net> sink{nullptr, W};
+  HostSink<T, Net> sink(nullptr, W);
   for (int64_t r = 0; r < rows; ++r) {
     T st[kMaxStateFloats];
     for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
@@ -85,10 +90,10 @@ static int flow_vjp(int D, int L, int dir, int64_t rows, const T* W, const T* in
   if ((L + 1) * D > kMaxStateFloats || D > kMaxDim) return 1;
   Dims<0, 0> dm{D, L};
   SplineConsts<T> sc = make_spline_consts<T>(Net::kK, -10.0, 10.0, 1e-4, 1e-4);
-  HostSink<T, Net> sink{G, W};
+  HostSink<T, Net> sink(G, W);
   HostTiles<T, Net> ht;
   RowTiles<T, Net> tl = ht.view();
-  std::vector<T> gfirst(Net::kPp, (T)0);
+  FirstGrad<T, Net::kK> gfirst = {};
   for (int64_t r = 0; r < rows; ++r) {
     T st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = in[r * D + i];
@@ -103,14 +108,18 @@ static int flow_vjp(int D, int L, int dir, int64_t rows, const T* W, const T* in
     }
     if (dir == 0)
       flow_pass_bwd<0, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, g, gl_pass,
-                                                             gfirst.data(), tl, sink);
+                                                             gfirst, tl, sink);
     else
       flow_pass_bwd<1, T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, cond[r * cs], st, g, gl_pass,
-                                                             gfirst.data(), tl, sink);
+                                                             gfirst, tl, sink);
     if (add_base && dir == 0) for (int i = 0; i < D; ++i) g[i] += gl * (-st[i]);
     if (gin) for (int i = 0; i < D; ++i) gin[r * D + i] = g[i];
   }
-  for (int j = 0; j < Net::kPp; ++j) G[j] += (double)gfirst[j];
+  {
+    T graw[Net::kPp] = {};
+    first_grad_to_raw<T, Net::kK>(gfirst, sink.first_knots(), sc, graw);
+    for (int j = 0; j < Net::kPp; ++j) G[j] += (double)graw[j];
+  }
   return 0;
 }
 
@@ -125,27 +134,27 @@ static int step(int D, int L, const cnfot_problem_desc* pd, const T* W, const T*
   StepConsts<T> pc;
   const char* err = nullptr;
   if (make_step_consts<T>(*pd, D, lambda, gB, gb, n_t, &pc, &err)) return 2;
-  HostSink<T, Net> sink{G, W};
+  HostSink<T, Net> sink(G, W);
   HostTiles<T, Net> ht;
   RowTiles<T, Net> tl = ht.view();
-  std::vector<T> gfirst(Net::kPp, (T)0);
+  FirstGrad<T, Net::kK> gfirst = {};
   for (int s = 0; s < kNumSlots; ++s) slots[s] = 0.0;
   if (pd->type == CNFOT_OT) {
     for (int64_t r = 0; r < rows_B; ++r) {
       slots[kSlotFit0] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T, Net>>(
-          dm, sc, (T)0, src + r * D, pc.w_fit, gfirst.data(), tl, sink);
+          dm, sc, (T)0, src + r * D, pc.w_fit, gfirst, tl, sink);
       slots[kSlotFitT] += (double)row_nll<T, Net, Dims<0, 0>, HostSink<T, Net>>(
-          dm, sc, pc.horizon, tgt + r * D, pc.w_fit, gfirst.data(), tl, sink);
+          dm, sc, pc.horizon, tgt + r * D, pc.w_fit, gfirst, tl, sink);
     }
   } else {
     for (int64_t r = 0; r < rows_B; ++r) {
       T lf = 0, lp = 0;
       row_sample_terms<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, (T)0, latent + r * D, true,
-                                                             false, pc, &lf, &lp, gfirst.data(), tl, sink);
+                                                             false, pc, &lf, &lp, gfirst, tl, sink);
       if (pd->type == CNFOT_RWPO)
         row_sample_terms<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, pc.horizon, latent + r * D,
                                                                false, true, pc, &lf, &lp,
-                                                               gfirst.data(), tl, sink);
+                                                               gfirst, tl, sink);
       slots[kSlotFit0] += (double)lf;
       slots[kSlotPotential] += (double)lp;
     }
@@ -154,11 +163,15 @@ static int step(int D, int L, const cnfot_problem_desc* pd, const T* W, const T*
     for (int64_t r = 0; r < rows_b; ++r) {
       T lk = 0, lp = 0;
       row_kinetic<T, Net, Dims<0, 0>, HostSink<T, Net>>(dm, sc, (T)t_batch[it], latent_sub + r * D,
-                                                        pc, &lk, &lp, gfirst.data(), tl, sink);
+                                                        pc, &lk, &lp, gfirst, tl, sink);
       slots[kSlotKinetic] += (double)lk;
       slots[kSlotPotential] += (double)lp;
     }
-  for (int j = 0; j < Net::kPp; ++j) G[j] += (double)gfirst[j];
+  {
+    T graw[Net::kPp] = {};
+    first_grad_to_raw<T, Net::kK>(gfirst, sink.first_knots(), sc, graw);
+    for (int j = 0; j < Net::kPp; ++j) G[j] += (double)graw[j];
+  }
   return 0;
 }
 
