@@ -174,8 +174,10 @@ class ClockSampler:
 def oracle_params_from_blob(shape, blob):
   """The haiku-shaped float64 parameter dict the oracle takes, from the blob the GPU arm runs."""
   from cnf_ot_b200.layout import unpack
-  p = unpack(shape, blob.detach().cpu())
-  return {mod: {k: v.double() for k, v in leaves.items()} for mod, leaves in p.items()}
+  from oracle import flow as oflow
+  spec = oflow.FlowSpec(shape.dim, shape.num_layers, [shape.hidden] * shape.mlp_layers, shape.num_bins)
+  # the reference's dtypes: float64 everywhere, the shared `first` leaf float32 (flows.py:47-55)
+  return unpack(shape, blob.detach().cpu(), like=oflow.init_params(spec, seed=0))
 
 
 def oracle_value_and_grad(cfg, shape, blob, inputs):
@@ -655,6 +657,27 @@ def train_loop_block(dist, batch):
           "api": "cnfot_mfc_update: draws + value_and_grad + all-reduce + Adam in ONE kernel launch per update"}
 
 
+def density_block(dev):
+  """the density consumers after training, one launch each -- ten 500 x 500 grids of
+  exp(log_prob) (the reference: 100 x 100 snapshots, utils.py:572-595, and a 500 x 500 grid, solvers.py:282-301) and
+  the 10^6-sample Monte-Carlo L2 error (solvers.py:254-278)."""
+  from cnf_ot_b200 import ops
+  from cnf_ot_b200.layout import FlowShape
+  shape = FlowShape(2, 2, 2, 16, 5)
+  W = make_blob(shape, dev, SIGMA)
+  ts = torch.linspace(0, 1, 10).tolist()
+  grid = lambda i: ops.density_grid(shape, W, ts, [-6, 6, -6, 6], 500, 500)
+  mc = lambda i: ops.density_mc(shape, W, 1.0, 1234 + i, 1000000, ref=(1.0, 4.0, 0.6353352832366127))
+  out = {}
+  for name, fn, pts in (("grid_10x500x500", grid, 10 * 500 * 500), ("mc_rmse_1e6", mc, 1000000)):
+    for i in range(3):
+      fn(i)
+    el = time_region(fn, 10, torch.cuda.synchronize) / 10
+    out[name] = {"us": el * 1e6, "points_per_s": pts / el}
+  out["api"] = "cnfot_density_grid / cnfot_density_mc: one kernel launch, grid points and latent rows generated on chip"
+  return out
+
+
 def per_config_entry(name, dist, args, pk, pk_src):
   """Timing + roofline + small-batch oracle check of one BASELINE config other than the headline one."""
   steps = {"cfg1": 50, "cfg2": 20, "cfg3": 10, "cfg4": 3, "cfg5": 2}[name]
@@ -866,6 +889,7 @@ def run_ours(args):
       line["per_config"] = pc
   if rank == 0:
     if world == 1:
+      line["density_eval"] = density_block(dev)
       line["roofline_spline"] = spline_rooflines(float(pk["hbm_gbs"]))
       if not args.no_oracle:
         line["cpu_baseline"] = cpu_baseline()

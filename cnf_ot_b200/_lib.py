@@ -118,6 +118,12 @@ SIGNATURES = {
   "cnfot_mfc_update": (c_int32, [c_void_p, _F, _P, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(AdamDesc),
                                  c_int32, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
                                  c_void_p, c_int64, POINTER(PeerDesc)]),
+  "cnfot_density_workspace_bytes": (c_int64, [_F, c_int32]),
+  "cnfot_density_grid": (c_int32, [c_void_p, _F, c_void_p, c_void_p, c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, c_int32, c_int32, c_void_p, c_int32, c_float, c_float, c_float, c_void_p,
+                                   c_void_p, c_int64]),
+  "cnfot_density_mc": (c_int32, [c_void_p, _F, c_void_p, c_float, ctypes.c_uint64, ctypes.c_uint32, c_int64, c_void_p, c_void_p,
+                                 c_int32, c_float, c_float, c_float, c_void_p, c_void_p, c_int64]),
   "cnfot_dense_prepared_floats": (c_int64, [c_int32, c_int32]),
   "cnfot_dense_prepare": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
   "cnfot_dense_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p,

@@ -1283,6 +1283,96 @@ int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, const float*
   return 0;
 }
 
+// ---- densities on a grid / at Monte-Carlo samples ----------------------------
+int64_t cnfot_density_workspace_bytes(const cnfot_flow_desc* flow, int32_t n_t) {
+  FlowLayout lay;
+  if (check_flow(flow, &lay)) return -1;
+  if (use_wide(flow, lay)) { fail(CNFOT_ERR_ARG, "density evaluation runs on the fused kernels only"); return -1; }
+  return partial_bytes(lay) + ((int64_t)(n_t > 0 ? n_t : 0) * (int64_t)sizeof(float) + 255) / 256 * 256 + 256;
+}
+
+static int density_call(void* stream, const cnfot_flow_desc* flow, const float* weights, DensityArgs& a, const float* t_host,
+                        int32_t n_t, double* sq_err, void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay)) return fail(CNFOT_ERR_ARG, "density evaluation runs on the fused kernels only");
+  if (int rc = check_fused(flow, lay)) return rc;
+  if (!weights || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (a.with_ref && (!sq_err || !(a.var0 > 0.f) || !(a.var1 > 0.f))) return fail(CNFOT_ERR_ARG, "reference density: need sq_err and positive variances");
+  const int64_t need = cnfot_density_workspace_bytes(flow, n_t);
+  if (workspace_bytes < need) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a.n == 0) {
+    if (sq_err) { cudaError_t e = cudaMemsetAsync(sq_err, 0, sizeof(double), s); if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync"); }
+    return 0;
+  }
+  float* t_dev = (float*)((char*)workspace + partial_bytes(lay));
+  if (n_t > 0) {
+    cudaError_t e = cudaMemcpyAsync(t_dev, t_host, (size_t)n_t * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D times");
+  }
+  SmemPlan sp;
+  int engine;
+  if (int rc = make_plan(lay, false, &sp, &engine)) return rc;
+  const void* kernel = find_density_kernel(lay, engine);
+  if (!kernel) return fail(CNFOT_ERR_ARG, "no density kernel for this network shape");
+  LaunchCfg cfg;
+  if (int rc = configure(kernel, sp, (a.n + kTile - 1) / kTile, &cfg)) return rc;
+  a.W = weights;
+  a.frags = nullptr;
+  if (engine == kEngMmaStream) {
+    float* fr = carve_frags(workspace, lay);
+    if (int rc = launch_build_frags(s, lay, weights, fr)) return rc;
+    a.frags = fr;
+  }
+  a.D = lay.D; a.L = lay.L; a.plan = sp;
+  a.t_dev = t_dev;
+  unsigned long long* counter;
+  a.pb = carve_partials(workspace, &counter);
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  if (e != cudaSuccess) return cuda_fail(e, "density_kernel launch");
+  if (sq_err) {
+    energy_finalize_kernel<<<1, 32, 0, s>>>(a.pb.loss, cfg.grid, sq_err);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "energy_finalize_kernel launch");
+  }
+  return 0;
+}
+
+int cnfot_density_grid(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* t_host, int32_t n_t,
+                       double x_min, double x_max, double y_min, double y_max, int32_t nx, int32_t ny, float* density,
+                       int32_t with_ref, float mix, float var0, float var1, double* sq_err, void* workspace,
+                       int64_t workspace_bytes) {
+  if (!flow || flow->dim != 2) return fail(CNFOT_ERR_ARG, "density grids are two-dimensional (the reference's are): dim must be 2");
+  if (n_t < 1 || nx < 2 || ny < 2 || !t_host) return fail(CNFOT_ERR_ARG, "density_grid: need n_t >= 1, nx, ny >= 2");
+  if (!density && !with_ref) return fail(CNFOT_ERR_ARG, "density_grid: nothing to compute");
+  DensityArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 0; a.nx = nx; a.ny = ny; a.n_t = n_t;
+  a.x_min = x_min; a.x_step = (x_max - x_min) / (nx - 1);   // np.linspace(x_min, x_max, nx)
+  a.y_min = y_min; a.y_step = (y_max - y_min) / (ny - 1);
+  a.n = (int64_t)nx * ny * n_t;
+  a.density = density;
+  a.with_ref = with_ref; a.mix = mix; a.var0 = var0; a.var1 = var1;
+  return density_call(stream, flow, weights, a, t_host, n_t, with_ref ? sq_err : nullptr, workspace, workspace_bytes);
+}
+
+int cnfot_density_mc(void* stream, const cnfot_flow_desc* flow, const float* weights, float cond, uint64_t key, uint32_t step,
+                     int64_t n, float* samples, float* density, int32_t with_ref, float mix, float var0, float var1,
+                     double* sq_err, void* workspace, int64_t workspace_bytes) {
+  if (n < 0) return fail(CNFOT_ERR_ARG, "density_mc: n < 0");
+  if (!density && !with_ref && !samples) return fail(CNFOT_ERR_ARG, "density_mc: nothing to compute");
+  DensityArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 1; a.n = n; a.cond = cond;
+  a.key_n = key ^ philox_salt(kDrawNormal, (uint64_t)n);
+  a.step = step;
+  a.samples = samples; a.density = density;
+  a.with_ref = with_ref; a.mix = mix; a.var0 = var0; a.var1 = var1;
+  return density_call(stream, flow, weights, a, nullptr, 0, with_ref ? sq_err : nullptr, workspace, workspace_bytes);
+}
+
 // ---- wide conditioner layers on tcgen05 (dense_tc.cu) ----------------------------------------
 int64_t cnfot_dense_prepared_floats(int32_t K, int32_t N) {
   if (K < 16 || N < 16 || K % 16 || N % 16) return -1;

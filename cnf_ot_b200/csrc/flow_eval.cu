@@ -78,4 +78,25 @@ const void* find_energy_kernel(const FlowLayout& f, int engine) {
   return nullptr;
 }
 
+#define DENSITY_CASE(H_, K_, M_)                                                         \
+  if (f.H == H_ && f.K == K_ && f.M == M_)                                               \
+    return (const void*)&density_kernel<NetCfg<H_, K_, M_>, Dims<0, 0>, kEngCuda>;
+#define DENSITY_ENG_CASE(M_, E_)                                                         \
+  if (f.M == M_) return (const void*)&density_kernel<NetCfg<16, 5, M_>, Dims<0, 0>, E_>;
+
+const void* find_density_kernel(const FlowLayout& f, int engine) {
+  if (engine == kEngMma && tc_available(f)) {
+    if (f.M == 2 && f.D == 2 && f.L == 2)
+      return (const void*)&density_kernel<NetCfg<16, 5, 2>, Dims<2, 2>, kEngMma>;
+    DENSITY_ENG_CASE(1, kEngMma) DENSITY_ENG_CASE(2, kEngMma) DENSITY_ENG_CASE(3, kEngMma)
+    return nullptr;
+  }
+  if (engine == kEngMmaStream && tc_available(f)) {
+    DENSITY_ENG_CASE(1, kEngMmaStream) DENSITY_ENG_CASE(2, kEngMmaStream) DENSITY_ENG_CASE(3, kEngMmaStream)
+    return nullptr;
+  }
+  CNFOT_NET_LIST(DENSITY_CASE)
+  return nullptr;
+}
+
 }  // namespace cnfot

@@ -241,6 +241,99 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) energ
   ctx_teardown(ctx);
 }
 
+// ---- densities on a grid / at Monte-Carlo samples --------------------------
+// The consumers of `log_prob_fn` / `sample_and_log_prob` after training:
+//   grid mode  exp(log_prob(params, XY, cond = t)) on an nx x ny grid of [x_min, x_max] x [y_min, y_max] for n_t
+//              times in ONE launch -- utils.plot_density_snapshot / plot_density_and_trajectory
+//              (cnf_ot/utils.py:572-642: 100 x 100, ten times), solvers.py:184-222 (double-well density at T) and
+//              rmse_grid_loss_fn (solvers.py:282-301: 500 x 500).  The grid points are generated in the kernel
+//              (XY = hstack(meshgrid(linspace, linspace)) in float64, rounded to float32): no XY array in HBM.
+//   MC mode    samples, log_prob = sample_and_log_prob(cond, seed) with the latent drawn on chip --
+//              rmse_mc_loss_fn (solvers.py:254-278: 10^6 samples).
+// Optional epilogue of both: the squared error against the reference density
+// (1 - mix) N(0, var0 I) + mix N(0, var1 I) (solvers.py:238-252,270-276), summed in double.
+struct DensityArgs {
+  const float* W;
+  const float* frags;
+  int D, L;
+  SmemPlan plan;
+  int mode;                 // 0 grid, 1 Monte-Carlo
+  int nx, ny, n_t;          // grid
+  double x_min, x_step, y_min, y_step;
+  const float* t_dev;       // (n_t) times
+  unsigned long long key_n; // MC: Philox key of the (n, D) normal draw
+  uint32_t step;
+  float cond;               // MC: the time
+  int64_t n;                // points in total (nx * ny * n_t, or samples)
+  float* density;           // (n) exp(log_prob), or nullptr
+  float* samples;           // MC: (n, D) samples, or nullptr
+  int with_ref;
+  float mix, var0, var1;
+  PartialBuf pb;            // loss slot kSlotKinetic of each CTA receives its sum of squared errors
+};
+
+template <class Net, class DimsT, int ENG>
+__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) density_kernel(const __grid_constant__ DensityArgs a) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ double scratch[kWarps];
+  __shared__ __align__(8) uint64_t tc_mbar;
+  __shared__ uint32_t tc_slot;
+  using Ctx = typename CtxSelect<Net, ENG>::type;
+  Ctx ctx;
+  ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
+  ctx.bind_partials(nullptr);
+  ctx.bind_frags(a.frags);
+  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
+  const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
+  const DimsT dm{a.D, a.L};
+  const int D = dm.D(), L = dm.L();
+  const FixedSplineConsts<float, Net::kK> sc;
+  double loss[kNumSlots];
+#pragma unroll
+  for (int s = 0; s < kNumSlots; ++s) loss[s] = 0.0;
+  const float half_log_2pi = 0.91893853320467274178f;
+  for (int64_t tile = blockIdx.x; tile * kTile < a.n; tile += gridDim.x) {   // uniform cost per point: static tiles
+    const int64_t r = tile * kTile + ctx.row_in_tile();
+    const bool live = r < a.n;   // every thread runs the pass: the contexts have CTA / warp barriers
+    float st[kMaxStateFloats];
+    for (int i = 0; i < D; ++i) st[i] = 0.f;
+    float t = a.cond, lp;
+    const float* y;
+    if (a.mode == 0) {
+      const int64_t per_t = (int64_t)a.nx * a.ny;
+      const int ti = live ? (int)(r / per_t) : 0;
+      const int64_t q = live ? r - (int64_t)ti * per_t : 0;
+      const int iy = (int)(q / a.nx), ix = (int)(q - (int64_t)iy * a.nx);
+      st[0] = (float)(a.x_min + (double)ix * a.x_step);
+      st[1] = (float)(a.y_min + (double)iy * a.y_step);
+      t = a.t_dev[ti];
+      const float ld = flow_pass<1, float, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
+      lp = base_log_prob<float>(st + L * D, D) + ld;
+      y = st;
+    } else {
+      if (live) philox_row(a.key_n, a.key_n, a.step, kRowsNormal, (uint64_t)r, D, st);
+      const float fldj = flow_pass<0, float, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
+      lp = base_log_prob<float>(st, D) - fldj;
+      y = st + L * D;
+      if (live && a.samples)
+        for (int i = 0; i < D; ++i) a.samples[r * D + i] = y[i];
+    }
+    if (!live) continue;
+    const float p = m_exp(lp);
+    if (a.density) a.density[r] = p;
+    if (a.with_ref) {
+      float r2 = 0.f;
+      for (int i = 0; i < D; ++i) r2 += y[i] * y[i];
+      const float p0 = m_exp(-0.5f * r2 / a.var0 - (float)D * (half_log_2pi + 0.5f * m_log(a.var0)));
+      const float p1 = m_exp(-0.5f * r2 / a.var1 - (float)D * (half_log_2pi + 0.5f * m_log(a.var1)));
+      const float e = p - (p0 * (1.f - a.mix) + p1 * a.mix);
+      loss[kSlotKinetic] += (double)e * (double)e;
+    }
+  }
+  flush_partials(a.pb, nullptr, 0, loss, scratch);
+  ctx_teardown(ctx);
+}
+
 // ---- the fused train step ---------------------------------------------------------------
 // One persistent kernel does the WHOLE step: every term of the configured loss and
 // its backward pass, the reduction of the CTAs' partial results, (multi-GPU) the all-reduce of

@@ -408,6 +408,53 @@ def kinetic_energy(shape: FlowShape, weights, latent, t_values: Sequence[float],
   return out[0]
 
 
+def density_grid(shape: FlowShape, weights, t_values: Sequence[float], domain, nx: int, ny: int, ref=None,
+                 want_density: bool = True):
+  """exp(log_prob) on the grid hstack(meshgrid(linspace(x0, x1, nx), linspace(y0, y1, ny))) for every time of `t_values`
+  in ONE kernel launch (cnfot_density_grid).  domain = (x0, x1, y0, y1).  ref = (mix, var0, var1): also the sum of squared
+  errors against (1 - mix) N(0, var0 I) + mix N(0, var1 I).  Returns (density (n_t, ny, nx) or None, sq_err 0-d float64 or None)."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  tb = torch.as_tensor(list(t_values), dtype=torch.float32)
+  dens = torch.empty(tb.numel(), ny, nx, dtype=torch.float32, device=weights.device) if want_density else None
+  sq = torch.zeros(1, dtype=torch.float64, device=weights.device) if ref is not None else None
+  mix, v0, v1 = (0.0, 1.0, 1.0) if ref is None else ref
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_density_workspace_bytes(desc, tb.numel())
+  if nbytes < 0:
+    _lib.check(1)
+  ws = _workspace(nbytes, weights.device)
+  x0, x1, y0, y1 = (float(v) for v in domain)
+  with torch.cuda.device(weights.device):
+    _lib.check(lib.cnfot_density_grid(_stream(), desc, _ptr(weights), tb.data_ptr(), tb.numel(), x0, x1, y0, y1, int(nx), int(ny),
+                                      _ptr(dens), int(ref is not None), float(mix), float(v0), float(v1), _ptr(sq),
+                                      ws.data_ptr(), ws.numel()))
+  return dens, (None if sq is None else sq[0])
+
+
+def density_mc(shape: FlowShape, weights, cond: float, key: int, n: int, ref=None, want_samples: bool = False,
+               want_density: bool = False, step: int = 0):
+  """sample_and_log_prob at time `cond` for the NORMAL (n, dim) latent draw of (key, step), made on chip
+  (cnfot_density_mc).  Returns (samples or None, density = exp(log_prob) or None, sq_err or None); see density_grid."""
+  lib = _lib.load()
+  weights = _dev(weights, "weights")
+  dev = weights.device
+  smp = torch.empty(n, shape.dim, dtype=torch.float32, device=dev) if want_samples else None
+  dens = torch.empty(n, dtype=torch.float32, device=dev) if want_density else None
+  sq = torch.zeros(1, dtype=torch.float64, device=dev) if ref is not None else None
+  mix, v0, v1 = (0.0, 1.0, 1.0) if ref is None else ref
+  desc = _lib.flow_desc(shape)
+  nbytes = lib.cnfot_density_workspace_bytes(desc, 0)
+  if nbytes < 0:
+    _lib.check(1)
+  ws = _workspace(nbytes, dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.cnfot_density_mc(_stream(), desc, _ptr(weights), float(cond), int(key) & (2**64 - 1), int(step) & 0xFFFFFFFF,
+                                    int(n), _ptr(smp), _ptr(dens), int(ref is not None), float(mix), float(v0), float(v1),
+                                    _ptr(sq), ws.data_ptr(), ws.numel()))
+  return smp, dens, (None if sq is None else sq[0])
+
+
 class PreparedDense:
   """Weights of one dense layer in the tcgen05 kernels' tile order (hi / lo tf32 split)."""
 

@@ -187,7 +187,10 @@ def evaluate(config: Dict, model, params, rng, batch_size: int = 65536, t_size: 
   """Energy part of the evaluation tail, solvers.py:138-172.
   ot:   the kinetic energy with more / fewer samples (utils.calc_kinetic_energy)
   rwpo: T * score-corrected kinetic energy + potential energy at t = T; for the quadratic potential
-        the closed-form total dim (1 + log(T + 1)) / beta and the relative error in percent."""
+        the closed-form total dim (1 + log(T + 1)) / beta and the relative error in percent; for the 2-D double well
+        the density at T on the reference's grid (solvers.py:184-222)
+  fp:   the L2 errors of solvers.py:254-306 against the Ornstein-Uhlenbeck solution: Monte-Carlo (10^6 samples of
+        the flow) and, in 2-D, on the 500 x 500 grid."""
   import math
   g = config["general"]
   _type, dim = g["type"], g["dim"]
@@ -221,6 +224,22 @@ def evaluate(config: Dict, model, params, rng, batch_size: int = 65536, t_size: 
       if verbose:
         print("total energy: {:.3e}|relative err: {:.3e}".format(out["e_kin"] + out["e_pot"],
                                                                 out["relative_err_percent"]))
+    elif subtype == "double_well" and dim == 2:
+      # the flow's density at t = T on the 100 x 100 grid of [-2, 2]^2 (solvers.py:184-222; the reference compares it
+      # with an interpolated reference solution whose data file is not shipped)
+      out["density_T"] = utils.density_on_grid(log_prob_fn, params, [T], [-2, 2, -2, 2], 100)[0]
+  elif _type == "fp":
+    # solvers.py:238-306: L2 error against the Ornstein-Uhlenbeck solution (valid for the drift -a r), Monte-Carlo and,
+    # for dim 2, on a 500 x 500 grid
+    f = config["fp"]
+    T = f["T"] if T is None else T
+    out["rmse_mc"] = float(utils.rmse_mc_loss_fn(model, params, 1, eval_rng, 1000000, a=f["a"], T=T))
+    if verbose:
+      print("L2 error via Monte-Carlo: {:.3e}".format(out["rmse_mc"]))
+    if dim == 2:
+      out["rmse_grid"] = float(utils.rmse_grid_loss_fn(log_prob_fn, params, 1, 500, a=f["a"], T=T))
+      if verbose:
+        print("L2 error on grid: {:.3e}".format(out["rmse_grid"]))
   return out
 
 

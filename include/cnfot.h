@@ -311,6 +311,28 @@ CNFOT_API int cnfot_kinetic_energy(void* stream, const cnfot_flow_desc* flow, co
                          int32_t n_t, float dt, int32_t with_score, float kappa, float dx, double* out,
                          void* workspace, int64_t workspace_bytes);
 
+/* ---- densities on a grid / at Monte-Carlo samples: the consumers of log_prob_fn and
+ * sample_and_log_prob after training -------------------------------------------------------------------------
+ *   cnfot_density_grid  density[(ti, iy, ix)] = exp(log_prob(params, (x_ix, y_iy), cond = t_ti)) on the grid
+ *                       XY = hstack(meshgrid(linspace(x_min, x_max, nx), linspace(y_min, y_max, ny))) for n_t times in ONE
+ *                       launch, the grid generated in the kernel: utils.plot_density_snapshot / plot_density_and_trajectory
+ *                       (cnf_ot/utils.py:572-642), the double-well density at T (cnf_ot/mfc/solvers.py:184-222) and
+ *                       rmse_grid_loss_fn (solvers.py:282-301).  dim must be 2.  density: (n_t, ny, nx) floats or NULL.
+ *   cnfot_density_mc    samples, log_prob = sample_and_log_prob(cond, seed) for n rows whose latent is the NORMAL (n, dim)
+ *                       draw of (key, step) made on chip (cnfot_philox_rows gives the same rows): rmse_mc_loss_fn
+ *                       (solvers.py:254-278).  samples: (n, dim) or NULL; density: (n) exp(log_prob) or NULL.
+ * with_ref != 0: *sq_err (ONE double on the device) = sum over the points of
+ *   (density - ((1 - mix) N(y; 0, var0 I) + mix N(y; 0, var1 I)))^2       (solvers.py:238-252,270-276,296-299);
+ * the caller takes sqrt(sq_err / points). */
+CNFOT_API int64_t cnfot_density_workspace_bytes(const cnfot_flow_desc* flow, int32_t n_t);
+CNFOT_API int cnfot_density_grid(void* stream, const cnfot_flow_desc* flow, const float* weights, const float* t_host,
+                       int32_t n_t, double x_min, double x_max, double y_min, double y_max, int32_t nx, int32_t ny,
+                       float* density, int32_t with_ref, float mix, float var0, float var1, double* sq_err,
+                       void* workspace, int64_t workspace_bytes);
+CNFOT_API int cnfot_density_mc(void* stream, const cnfot_flow_desc* flow, const float* weights, float cond, uint64_t key,
+                     uint32_t step, int64_t n, float* samples, float* density, int32_t with_ref, float mix, float var0,
+                     float var1, double* sq_err, void* workspace, int64_t workspace_bytes);
+
 /* ---- wide conditioner layers on tcgen05 (BASELINE config 5: hidden = 512) -----------------------
  * Y (rows x N) = epilogue(X (rows x K) * W (K x N) [+ bias]), fp32 in / out with fp32 fidelity (3xTF32):
  * the dense layers of the conditioner MLP (cnf_ot/models/flows.py:65-81) and, with transpose != 0 at

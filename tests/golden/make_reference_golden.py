@@ -161,6 +161,59 @@ def energy_case(D, sigma, n, t_size, beta, T, seed):
           "beta": np.array(beta), "e_kin": e_kin, "e_score": e_score}
 
 
+def density_case(sigma, n_mc, grid_size, seed):
+  """SURVEY.md 8f row 3.  `utils.plot_density_snapshot` and `utils.plot_density_and_trajectory` (cnf_ot/utils.py:572-642)
+  run UNMODIFIED against a recording matplotlib stand-in: the fixture holds the arrays they hand to `imshow` (100 x 100
+  densities) and `scatter` (trajectories).  `rmse_mc_loss_fn` / `rmse_grid_loss_fn` are nested in `solvers.main`
+  (solvers.py:254-301) and cannot be imported: they are restated here line by line on the reference's model API."""
+  refshim.record_plots()
+  from cnf_ot import utils as ref_utils  # the reference
+  import math
+  cfg = make_cfg(dim=2)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, sigma)
+  model = build_model(cfg)
+  g = torch.Generator().manual_seed(seed)
+  r_ = f32(torch.randn(12, 2, generator=g, dtype=torch.float64) * 1.5)
+  t_traj = np.linspace(0, 1, 5)
+  dom = [-4.0, 5.0, -3.0, 6.0]
+  with torch.no_grad():
+    ref_utils.plot_density_snapshot(model.apply.log_prob, params)            # default t_array = linspace(0, 1, 10)
+    snap = torch.stack(refshim.Plots.images)
+    refshim.Plots.images, refshim.Plots.scatters = [], []
+    ref_utils.plot_density_and_trajectory(model.apply.forward, model.apply.inverse, model.apply.log_prob, params, r_,
+                                          t_traj, dom)
+    dens2 = torch.stack(refshim.Plots.images)
+    # every axes gets the same len(t) scatters: pixel coordinates of forward_fn(params, xi, t) (utils.py:626-633)
+    sc = refshim.Plots.scatters[:len(t_traj)]
+    traj = torch.stack([torch.stack([x * (dom[1] - dom[0]) / 100 + dom[0], y * (dom[3] - dom[2]) / 100 + dom[2]], dim=1)
+                        for x, y in sc])
+    # solvers.py:238-252 (dim = 2, a, T as in config/mfc.yaml fp block)
+    a, T, cond = 1.0, 1.0, 1.0
+    source_prob = lambda s: torch.exp(-0.5 * (s * s).sum(-1) / 4.0) / (2 * math.pi * 4.0)
+    vt = math.exp(-2 * a * T) * (4 - 1 / 2 / a) + 1 / 2 / a
+    target_prob = lambda s: torch.exp(-0.5 * (s * s).sum(-1) / vt) / (2 * math.pi * vt)
+    # solvers.py:254-278
+    z = f32(torch.randn(n_mc, 2, generator=g, dtype=torch.float64))
+    refshim.Draws.set(normal=z)
+    fake_cond_ = jnp.ones((n_mc, 1)) * cond
+    samples, log_prob = model.apply.sample_and_log_prob(params, cond=fake_cond_, seed=jax.random.PRNGKey(1),
+                                                        sample_shape=(n_mc, ))
+    rmse_mc = torch.sqrt(((torch.exp(log_prob) - (source_prob(samples) * (1 - cond) + target_prob(samples) * cond))**2).mean())
+    # solvers.py:282-301
+    x = np.linspace(-5, 5, grid_size)
+    X, Y = np.meshgrid(x, x)
+    XY = jnp.hstack([X.reshape(-1, 1), Y.reshape(-1, 1)])
+    rmse_grid = torch.sqrt(((torch.exp(model.apply.log_prob(params, XY, jnp.ones(1) * cond)) -
+                             (source_prob(XY) * (1 - cond) + target_prob(XY) * cond))**2).mean())
+  k = 3   # the fixture keeps every third grid point and the exact sums (the full arrays are 10 x 100 x 100 doubles)
+  return {"shape": np.array([2, shape.num_layers, shape.mlp_layers, shape.hidden, shape.num_bins]),
+          "blob": pack(shape, params, torch.float64), "snap_sub": snap[:, ::k, ::k], "snap_sum": snap.sum((1, 2)),
+          "stride": np.array(k), "domain2": np.array(dom), "t_traj": t_traj, "dens2_sub": dens2[:, ::k, ::k],
+          "dens2_sum": dens2.sum((1, 2)), "r": r_, "traj": traj, "latent_mc": z, "rmse_mc": rmse_mc,
+          "rmse_grid": rmse_grid, "grid_size": np.array(grid_size), "fp_a": np.array(a), "fp_T": np.array(T)}
+
+
 def dr_case(model, D, L, H, sub_dim, sigma, n, seed):
   """cnf_ot/dr/trainers.py:train run for ONE epoch with a no-op optimiser: its own `loss_fn` (:91-111) and
   `jax.value_and_grad(loss_fn)(params, data)` (:117) on the two unconditional flows it builds (:41-73)."""
@@ -248,6 +301,7 @@ if __name__ == "__main__":
   save("ref_rqs_symbolic_k8", symbolic_spline_case(8, 256, 28))
   save("ref_dr_enc_dec_d4", dr_case("enc_dec", 4, 2, 16, 2, 0.08, 192, 25))
   save("ref_dr_dec_only_d4", dr_case("dec_only", 4, 2, 16, 2, 0.08, 192, 26))
+  save("ref_density_d2", density_case(0.3, 2048, 60, 29))
   save("ref_energy_d2", energy_case(2, 0.3, 64, 4, 2.0, 2.0, 23))
   save("ref_energy_d3", energy_case(3, 0.1, 32, 3, 4.0, 1.0, 24))
   for name, (typ, sub, B, lam, Tn, seed, kw) in STEP_CASES.items():

@@ -133,6 +133,7 @@ def _build_jax():
   jnp.broadcast_to = lambda x, shape: torch.broadcast_to(_as(x), _shape(shape))
   jnp.concatenate = lambda xs, axis=0: torch.cat([_as(x).to(F64) for x in xs], dim=axis)
   jnp.concat = jnp.concatenate
+  jnp.hstack = lambda xs: torch.cat([_as(x).to(F64) for x in xs], dim=1)   # cnf_ot/utils.py:588,618: (n, 1) columns
 
   def _reduce(fn):
     def f(x, axis=None, keepdims=False):
@@ -523,6 +524,43 @@ def stub_plotting():
     _mod("matplotlib." + sub)
   mpl.colors.LinearSegmentedColormap = object
   mpl.pyplot.quiver = None   # a bare `plt.quiver` expression statement sits in calc_score_kinetic_energy (utils.py:386)
+
+
+class Plots:
+  """What the reference's plotting helpers hand to matplotlib (cnf_ot/utils.py:572-642), recorded instead of drawn."""
+  images = []     # every imshow(array)
+  scatters = []   # every scatter(x, y)
+
+
+def record_plots():
+  """A recording `matplotlib.pyplot`: `plot_density_snapshot` / `plot_density_and_trajectory` run unmodified and leave
+  the arrays they would draw in `Plots`."""
+  stub_plotting()
+  plt = sys.modules["matplotlib.pyplot"]
+  Plots.images, Plots.scatters = [], []
+
+  class Axes:
+    def imshow(self, a, **k):
+      Plots.images.append(torch.as_tensor(a).detach().clone())
+
+    def scatter(self, x, y, **k):
+      Plots.scatters.append((torch.as_tensor(x).detach().clone(), torch.as_tensor(y).detach().clone()))
+
+    def __getattr__(self, name):   # axis, set_xlabel, set_title, ...
+      return lambda *a, **k: None
+
+  class AxesArray(list):
+    def flatten(self):
+      return self
+
+  class Figure:
+    def __getattr__(self, name):
+      return lambda *a, **k: None
+  ax = Axes()
+  plt.imshow, plt.scatter = ax.imshow, ax.scatter
+  plt.subplots = lambda r, c, **k: (Figure(), AxesArray([Axes() for _ in range(int(r) * int(c))]))
+  for name in ("clf", "figure", "subplot", "axis", "title", "savefig", "legend", "colorbar", "tight_layout"):
+    setattr(plt, name, lambda *a, **k: None)
 
 
 # ---------------------------------------------------------------------------------------------- dr/trainers.py
