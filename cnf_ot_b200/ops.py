@@ -130,10 +130,15 @@ _workspaces = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-  key = (device.index if device.index is not None else torch.cuda.current_device())
+  """Scratch memory of the calling (device, stream): kernels of different streams never share partial-result rows or
+  tile counters, and a buffer is only ever used on the stream whose caching-allocator block it is."""
+  device = torch.device(device)
+  index = device.index if device.index is not None else torch.cuda.current_device()
+  key = (index, torch.cuda.current_stream(index).cuda_stream)
   ws = _workspaces.get(key)
   if ws is None or ws.numel() < nbytes:
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    with torch.cuda.device(index):
+      ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
     _workspaces[key] = ws
   return ws
 
