@@ -254,6 +254,20 @@ static int64_t partial_bytes(const FlowLayout& lay) {
   int64_t grad = ((int64_t)kMaxGrid * lay.total * sizeof(float) + 255) / 256 * 256;
   return kCounterBytes + loss + grad + frag_bytes(lay);
 }
+// Activation stash of the step kernel (warp-level engines, small flows): per CTA, per conditioner, 4 (M + 1) float4 per
+// thread.  Sized for the largest persistent grid; it is re-written tile after tile and lives in L2.
+static int64_t stash_cta_floats(const FlowLayout& lay) {
+  if (!tc_available(lay)) return 0;
+  const int64_t per_cta = (int64_t)lay.L * (lay.D - 1) * 4 * (lay.M + 1) * kTile * 4;
+  if (per_cta * (int64_t)sizeof(float) > 64 * 1024) return 0;   // larger flows: recompute (the buffer would not stay in L2)
+  if (const char* e = getenv("CNFOT_STEP_STASH")) {             // tuning knob: 0 = always recompute
+    if (e[0] == '0') return 0;
+  }
+  return per_cta;
+}
+static int64_t stash_bytes(const FlowLayout& lay) { return stash_cta_floats(lay) * (int64_t)sizeof(float) * 4 * 148; }
+// workspace of the step: [partials ... fragments | activation stash]
+static int64_t step_bytes(const FlowLayout& lay) { return partial_bytes(lay) + stash_bytes(lay); }
 static float* carve_frags(void* ws, const FlowLayout& lay) {
   return (float*)((char*)ws + partial_bytes(lay) - frag_bytes(lay));
 }
@@ -677,7 +691,7 @@ int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const floa
 
 // ---- seam 3 ---------------------------------------------------------------------------
 static int64_t step_ws_bytes(const cnfot_flow_desc* flow, const FlowLayout& lay, int64_t rows_B, int64_t rows_b) {
-  return use_wide(flow, lay) ? wide_step_workspace_bytes(lay, rows_B, rows_b) : partial_bytes(lay);
+  return use_wide(flow, lay) ? wide_step_workspace_bytes(lay, rows_B, rows_b) : step_bytes(lay);
 }
 
 int64_t cnfot_mfc_step_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows_B, int64_t rows_b,
@@ -798,8 +812,8 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   if (!weights || !workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
   if (!io.out && !io.stateful) return fail(CNFOT_ERR_ARG, "out is NULL");
   if (!io.rng && !io.t_batch_host) return fail(CNFOT_ERR_ARG, "t_batch is NULL");
-  if (workspace_bytes < partial_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
-                                                        (long long)workspace_bytes, (long long)partial_bytes(lay));
+  if (workspace_bytes < step_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                                     (long long)workspace_bytes, (long long)step_bytes(lay));
   const char* err = nullptr;
   if (make_step_consts<float>(*problem, lay.D, (double)lambda, global_B, global_b, n_t, &a.pc, &err))
     return fail(CNFOT_ERR_ARG, "%s", err);
@@ -865,6 +879,9 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     a.frags = fr;
   }
   a.D = lay.D; a.L = lay.L; a.plan = sp;
+  a.stash = nullptr;
+  a.stash_cta_floats = (engine == kEngMma || engine == kEngMmaStream) && cfg.grid <= 4 * 148 ? stash_cta_floats(lay) : 0;
+  if (a.stash_cta_floats > 0) a.stash = (float*)((char*)workspace + partial_bytes(lay));
   // workspace / train state: [header: sync words, state words, loss row | partial gradient rows]
   TailArgs& t = a.tail;
   char* wsb = (char*)workspace;
@@ -996,7 +1013,7 @@ int64_t cnfot_train_state_bytes(const cnfot_flow_desc* flow) {
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
   if (use_wide(flow, lay)) { fail(CNFOT_ERR_ARG, "no device-resident update for the wide-conditioner engine"); return -1; }
-  return partial_bytes(lay);
+  return step_bytes(lay);
 }
 
 int cnfot_train_state_init(void* stream, const cnfot_flow_desc* flow, void* state, int64_t state_bytes, uint64_t key,
@@ -1181,7 +1198,7 @@ int64_t cnfot_mfc_step_rng_host_workspace_bytes(const cnfot_flow_desc* flow) {
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
   if (use_wide(flow, lay)) { fail(CNFOT_ERR_ARG, "on-chip draws are not available on the wide-conditioner engine"); return -1; }
-  return align256(partial_bytes(lay)) + align256((int64_t)lay.total * sizeof(float)) +
+  return align256(step_bytes(lay)) + align256((int64_t)lay.total * sizeof(float)) +
          align256((int64_t)(lay.total + CNFOT_NUM_LOSS_SLOTS) * sizeof(float));
 }
 
@@ -1198,7 +1215,7 @@ int cnfot_mfc_step_rng_host(void* stream, const cnfot_flow_desc* flow, const cnf
                                           (long long)workspace_bytes, (long long)need);
   cudaStream_t s = (cudaStream_t)stream;
   char* p = (char*)workspace;
-  const int64_t ws_bytes = align256(partial_bytes(lay));
+  const int64_t ws_bytes = align256(step_bytes(lay));
   void* ws = p; p += ws_bytes;
   float* dW = (float*)p; p += align256((int64_t)lay.total * sizeof(float));
   float* dOut = (float*)p;

@@ -410,6 +410,8 @@ struct StepArgs {
   StepConsts<float> pc;
   int n_seg;
   int64_t n_tiles;     // 128-row tiles
+  float* stash;                 // activation stash of the warp-level engines (stash_cta_floats per CTA), or nullptr
+  long long stash_cta_floats;
   unsigned long long key;       // on-chip draws (philox.cuh): key and step, or read from the train state
   unsigned long long salt_B, salt_Bc, salt_b, salt_t;   // key modifiers: normal (B, D), categorical (B,), normal (b, D), uniform (n_t,)
   uint32_t step;
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx.bind_partials(my_row, false);   // shared, pre-zeroed partial rows: the context must not clear them
   ctx.bind_frags(a.frags);
+  ctx.bind_stash(a.stash ? a.stash + (size_t)blockIdx.x * a.stash_cta_floats : nullptr);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};

@@ -293,7 +293,7 @@ CNFOT_HD void fill_mlp_input(const RowTiles<T, Net>& tl, T t, const T* cvec, int
 // Returns the summed log-det of the pass.
 template <int DIR, typename T, class Net, class DimsT, class Ctx, class SC>
 CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
-                       const RowTiles<T, Net>& tl, Ctx& ctx) {
+                       const RowTiles<T, Net>& tl, Ctx& ctx, bool stash = false) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
   if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, false);
@@ -318,7 +318,7 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
       } else {
         T theta[Pp];
         if constexpr (Ctx::kWarpMlp) {
-          ctx.cond_forward(D, layer, d, t, cvec, theta, false);
+          ctx.cond_forward(D, layer, d, t, cvec, theta, false, stash);
         } else {
           const T* W = ctx.weights(mlp_offset<Net>(D, layer, d), (d + 1) * H + Net::kMlpConst);
           CNFOT_ASSUME_SHARED(W);
@@ -344,7 +344,8 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
 // once per kernel).  Conditioner activations are re-computed, not stored.
 template <int DIR, typename T, class Net, class DimsT, class Ctx, class SC>
 CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* states,
-                              T* g, T gld, FirstGrad<T, Net::kK>& gfirst, const RowTiles<T, Net>& tl, Ctx& ctx) {
+                              T* g, T gld, FirstGrad<T, Net::kK>& gfirst, const RowTiles<T, Net>& tl, Ctx& ctx,
+                              bool stash = false) {
   constexpr int K = Net::kK, Pp = Net::kPp, H = Net::kH;
   const int D = dm.D(), L = dm.L();
   if constexpr (!Ctx::kWarpMlp) assume_tiles_shared<T, Net>(tl, true);
@@ -374,7 +375,8 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* state
       } else {
         T theta[Pp];
         if constexpr (Ctx::kWarpMlp) {
-          ctx.cond_forward(D, layer, d, t, cvec, theta, true);
+          if (stash) ctx.cond_restore(D, layer, d, theta);
+          else ctx.cond_forward(D, layer, d, t, cvec, theta, true);
         } else {
           w_off = mlp_offset<Net>(D, layer, d);
           ctx.begin();  // the tiles of the previous conditioner are free again

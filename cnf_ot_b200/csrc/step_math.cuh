@@ -122,12 +122,13 @@ CNFOT_HD T row_nll(const DimsT& dm, const SC& sc, T t, const T* data, T weight,
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
   for (int i = 0; i < D; ++i) st[i] = data[i];
-  T ld = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
+  const bool stash = ctx.stash_on();   // forward and backward of the same rows, back to back: keep the activations
+  T ld = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx, stash);
   const T* x = st + L * D;
   T lp = base_log_prob<T>(x, D) + ld;
   T g[kMaxDim];
   for (int i = 0; i < D; ++i) g[i] = weight * x[i];  // d(-w lp)/dx = w x
-  flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, st, g, -weight, gfirst, tl, ctx);
+  flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, st, g, -weight, gfirst, tl, ctx, stash);
   return -weight * lp;
 }
 
@@ -141,7 +142,8 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const SC& sc, T t,
   const int D = dm.D(), L = dm.L();
   T st[kMaxStateFloats];
   for (int i = 0; i < D; ++i) st[i] = latent[i];
-  T fldj = flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx);
+  const bool stash = ctx.stash_on();
+  T fldj = flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, t, st, tl, ctx, stash);
   const T* y = st + L * D;
   T g[kMaxDim];
   for (int i = 0; i < D; ++i) g[i] = (T)0;
@@ -179,7 +181,7 @@ CNFOT_HD void row_sample_terms(const DimsT& dm, const SC& sc, T t,
     *loss_pot += pc.w_pot * v;
     for (int i = 0; i < D; ++i) g[i] += pc.w_pot * gp[i];
   }
-  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, st, g, gld, gfirst, tl, ctx);
+  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, st, g, gld, gfirst, tl, ctx, stash);
 }
 
 // ---- kinetic-energy rows ----------------------------------------------------------

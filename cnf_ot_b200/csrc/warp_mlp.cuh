@@ -236,6 +236,31 @@ struct DeviceCtxMma {
   const float* gfrag;   // streamed plan: the fragment buffer in global memory
   Ref w_ref, frag_ref;  // blob and fragments (shared-window address or global pointer)
   uint32_t s_wt;        // shared-window address of this warp's tiles
+  // Activation stash (this CTA's slice of a global buffer that stays in L2): the forward pass of a row that is
+  // differentiated right away (KL / reverse-KL / potential rows: 97 % of a step) leaves every conditioner's hidden
+  // activations and raw spline parameters here, exactly as the warp holds them (MMA fragments), and the backward
+  // pass reads them back instead of evaluating the conditioner a second time.  nullptr: recompute.
+  float* stash = nullptr;
+  static constexpr int kStashChunks = 4 * (M + 1);            // float4 per thread and conditioner: M hidden layers + theta
+  static constexpr int kStashCondFloats = kStashChunks * kTile * 4;
+  __device__ __forceinline__ void bind_stash(float* q) { stash = q; }
+  __device__ __forceinline__ bool stash_on() const { return stash != nullptr; }
+  __device__ __forceinline__ float* stash_of(int D, int layer, int d) const {
+    return stash + (size_t)(layer * (D - 1) + d - 1) * kStashCondFloats + threadIdx.x * 4;
+  }
+  __device__ __forceinline__ static void stash_put(float* q, int chunk0, const float (&v)[2][2][4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      __stcg(reinterpret_cast<float4*>(q + (chunk0 + c) * kTile * 4),
+             make_float4(v[c >> 1][c & 1][0], v[c >> 1][c & 1][1], v[c >> 1][c & 1][2], v[c >> 1][c & 1][3]));
+  }
+  __device__ __forceinline__ static void stash_get(const float* q, int chunk0, float (&v)[2][2][4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 f = __ldcg(reinterpret_cast<const float4*>(q + (chunk0 + c) * kTile * 4));
+      v[c >> 1][c & 1][0] = f.x; v[c >> 1][c & 1][1] = f.y; v[c >> 1][c & 1][2] = f.z; v[c >> 1][c & 1][3] = f.w;
+    }
+  }
 
   bool clear_acc;       // setup() zeroes the partial row (false: rows shared between CTAs, cleared by the caller)
   __device__ __forceinline__ void bind_partials(float* q, bool clear = true) { gacc = q; clear_acc = clear; }
@@ -376,8 +401,10 @@ struct DeviceCtxMma {
 
   // Conditioner forward for the warp's 32 rows: theta[0..16) of the calling thread's row.
   // keep: store the hidden activations in the warp's tiles for cond_backward.
+  // put: also leave them (and theta) in the activation stash for cond_restore.
   __device__ __forceinline__ void cond_forward(int D, int layer, int d, float tval, const float* cvec,
-                                               float* theta, bool keep) const {
+                                               float* theta, bool keep, bool put = false) const {
+    float* sq = put ? stash_of(D, layer, d) : nullptr;
     const MmaLane ln;
     const uint32_t wt = s_wt;
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
@@ -414,18 +441,43 @@ struct DeviceCtxMma {
       __syncwarp();   // the previous conditioner's readers are done with the tiles
       store_a(wt, ln, a);
     }
+    if (put) stash_put(sq, 0, a);
     Ref Wm = b0 + H;
 #pragma unroll
     for (int m = 1; m < M; ++m) {
       dense16(a, frag + (m - 1) * kFragFloats, Wm + H * H, ln, x);
       relu_to_a(x, a);
       if (keep) store_a(wt + m * kWtFloats * 4, ln, a);
+      if (put) stash_put(sq, 4 * m, a);
       Wm = Wm + (H * H + H);
     }
     dense16(a, frag + (M - 1) * kFragFloats, Wm + H * Pp, ln, x);
+    if (put) stash_put(sq, 4 * M, x);
     const uint32_t scratch = wt + (keep ? M : 0) * kWtFloats * 4;
     __syncwarp();
     store_c(scratch, ln, x);
+    __syncwarp();
+    load_row(scratch, ln, theta);
+  }
+
+  // What cond_forward(keep = true) leaves behind -- hidden activations in the warp's tiles, theta of the calling
+  // thread's row -- read back from the activation stash the forward pass of the same rows filled (put = true).
+  __device__ __forceinline__ void cond_restore(int D, int layer, int d, float* theta) const {
+    const MmaLane ln;
+    const uint32_t wt = s_wt;
+    const float* sq = stash_of(D, layer, d);
+    float a[2][2][4];
+    stash_get(sq, 0, a);
+    __syncwarp();   // the previous conditioner's readers are done with the tiles
+    store_a(wt, ln, a);
+#pragma unroll
+    for (int m = 1; m < M; ++m) {
+      stash_get(sq, 4 * m, a);
+      store_a(wt + m * kWtFloats * 4, ln, a);
+    }
+    stash_get(sq, 4 * M, a);
+    const uint32_t scratch = wt + M * kWtFloats * 4;
+    store_c(scratch, ln, a);
     __syncwarp();
     load_row(scratch, ln, theta);
   }

@@ -38,6 +38,7 @@ struct HostSink {
   }
   const T* first_params() const { return Wb; }
   const FirstKnots<T, Net::kK>& first_knots() const { return fk; }
+  bool stash_on() const { return false; }
   const T* weights(int w_off, int) const { return Wb + w_off; }
   void begin() {}
   template <int K, int N>
