@@ -76,6 +76,9 @@ SIGNATURES = {
   "cnfot_abi_version": (c_int32, []),
   "cnfot_last_error": (c_char_p, []),
   "cnfot_last_launch_info": (None, [POINTER(c_int32)] * 4),
+  "cnfot_debug_step_timeline": (None, [c_void_p]),
+  "cnfot_workspace_register": (c_int32, [c_void_p, _F, c_void_p, c_int64]),
+  "cnfot_workspace_release": (c_int32, [c_void_p]),
   "cnfot_param_count": (c_int64, [_F]),
   "cnfot_spline_param_stride": (c_int64, [_F]),
   "cnfot_offset_first": (c_int64, [_F]),

@@ -8,6 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/cnfot.h"
 #include "device_common.cuh"
 #include "dense_tc.h"
@@ -254,18 +257,19 @@ static int64_t partial_bytes(const FlowLayout& lay) {
   int64_t grad = ((int64_t)kMaxGrid * lay.total * sizeof(float) + 255) / 256 * 256;
   return kCounterBytes + loss + grad + frag_bytes(lay);
 }
-// Activation stash of the step kernel (warp-level engines, small flows): per CTA, per conditioner, 4 (M + 1) float4 per
-// thread.  Sized for the largest persistent grid; it is re-written tile after tile and lives in L2.
+// Activation stash of the step kernel (warp-level engines, small flows): per CTA, per conditioner, 4 M float4 of hidden
+// activations + ceil((2 K + 10) / 4) float4 of located-spline state per thread (DeviceCtxMma::kStashChunks).  Sized for the largest persistent grid; it is re-written tile after tile and lives in L2.
 static int64_t stash_cta_floats(const FlowLayout& lay) {
   if (!tc_available(lay)) return 0;
-  const int64_t per_cta = (int64_t)lay.L * (lay.D - 1) * 4 * (lay.M + 1) * kTile * 4;
+  const int64_t per_cta = (int64_t)lay.L * (lay.D - 1) * (4 * lay.M + (2 * lay.K + 10 + 3) / 4) * kTile * 4;
   if (per_cta * (int64_t)sizeof(float) > 64 * 1024) return 0;   // larger flows: recompute (the buffer would not stay in L2)
   if (const char* e = getenv("CNFOT_STEP_STASH")) {             // tuning knob: 0 = always recompute
     if (e[0] == '0') return 0;
   }
   return per_cta;
 }
-static int64_t stash_bytes(const FlowLayout& lay) { return stash_cta_floats(lay) * (int64_t)sizeof(float) * 4 * 148; }
+constexpr int kStashMaxGrid = 6 * 148;   // the stash is sized for this many persistent CTAs (larger grids recompute)
+static int64_t stash_bytes(const FlowLayout& lay) { return stash_cta_floats(lay) * (int64_t)sizeof(float) * kStashMaxGrid; }
 // workspace of the step: [partials ... fragments | activation stash]
 static int64_t step_bytes(const FlowLayout& lay) { return partial_bytes(lay) + stash_bytes(lay); }
 static float* carve_frags(void* ws, const FlowLayout& lay) {
@@ -419,6 +423,9 @@ using namespace cnfot;
 extern "C" {
 
 int cnfot_abi_version(void) { return CNFOT_ABI_VERSION; }
+static unsigned long long* g_step_timeline = nullptr;
+void cnfot_debug_step_timeline(void* device_words) { g_step_timeline = (unsigned long long*)device_words; }
+
 void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* tensor_cores) {
   if (grid) *grid = g_last_launch[0];
   if (smem_bytes) *smem_bytes = g_last_launch[1];
@@ -689,6 +696,50 @@ int cnfot_flow_inverse_vjp(void* stream, const cnfot_flow_desc* flow, const floa
                        g_in, g_weights, workspace, workspace_bytes);
 }
 
+// ---- persistent step workspaces -------------------------------------------------------------------------
+// A registered workspace is only ever touched by the step entries (stream-ordered): every step leaves its reduction
+// buffers and counters clean for the next one (the kernel's tail zeroes what it read), so no memset sits between two
+// consecutive step kernels -- which is also what lets the next launch overlap the previous kernel's end (below).
+static std::mutex g_ws_mu;
+static std::vector<std::pair<void*, int64_t>> g_ws_registered;
+static bool ws_registered(const void* ws) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  for (const auto& e : g_ws_registered)
+    if (e.first == ws) return true;
+  return false;
+}
+int cnfot_workspace_release(void* workspace) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  for (size_t i = 0; i < g_ws_registered.size(); ++i)
+    if (g_ws_registered[i].first == workspace) {
+      g_ws_registered.erase(g_ws_registered.begin() + i);
+      return 0;
+    }
+  return 0;
+}
+
+// Launch of the persistent flow kernels with programmatic stream serialisation: the kernel may be scheduled while the
+// previous kernel of the stream is still in its tail; it executes griddepcontrol.wait before its first global access
+// (flow_kernels.cuh), so only the launch latency and the CTA ramp-up overlap, never any data.  CNFOT_PDL=0: plain launch.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CNFOT_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+static cudaError_t launch_step_kernel(const void* kernel, int grid, void** args, size_t smem, cudaStream_t s) {
+  if (!pdl_enabled()) return cudaLaunchKernel(kernel, dim3(grid), dim3(kTile), args, smem, s);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(kTile); lc.dynamicSmemBytes = smem; lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelExC(&lc, kernel, args);
+}
+
 // ---- seam 3 ---------------------------------------------------------------------------
 static int64_t step_ws_bytes(const cnfot_flow_desc* flow, const FlowLayout& lay, int64_t rows_B, int64_t rows_b) {
   return use_wide(flow, lay) ? wide_step_workspace_bytes(lay, rows_B, rows_b) : step_bytes(lay);
@@ -781,6 +832,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   FlowLayout lay;
   if (int rc = check_flow(flow, &lay)) return rc;
   if (use_wide(flow, lay)) {
+    cnfot_workspace_release(workspace);   // the wide engine uses the memory as plain scratch: not clean afterwards
     if (io.rng || io.stateful)
       return fail(CNFOT_ERR_ARG, "the wide-conditioner engine takes explicit row arrays: fill them with cnfot_philox_rows "
                                  "and call cnfot_mfc_step (+ cnfot_adam_update)");
@@ -865,6 +917,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   a.n_tiles = tiles;
   a.key = io.key;
   a.step = io.step;
+  a.timeline = g_step_timeline;
   a.salt_B = philox_salt(kDrawNormal, (uint64_t)global_B);
   a.salt_Bc = philox_salt(kDrawCategorical, (uint64_t)global_B);
   a.salt_b = philox_salt(kDrawNormal, (uint64_t)global_b);
@@ -880,7 +933,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   }
   a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.stash = nullptr;
-  a.stash_cta_floats = (engine == kEngMma || engine == kEngMmaStream) && cfg.grid <= 4 * 148 ? stash_cta_floats(lay) : 0;
+  a.stash_cta_floats = (engine == kEngMma || engine == kEngMmaStream) && cfg.grid <= kStashMaxGrid ? stash_cta_floats(lay) : 0;
   if (a.stash_cta_floats > 0) a.stash = (float*)((char*)workspace + partial_bytes(lay));
   // workspace / train state: [header: sync words, state words, loss row | partial gradient rows]
   TailArgs& t = a.tail;
@@ -888,10 +941,11 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   t.sync = (uint32_t*)wsb;
   t.loss_row = (double*)(wsb) + kLossRowOffset;
   t.grad_rows = (float*)(wsb + kCounterBytes);
+  const bool persistent = io.stateful || ws_registered(workspace);   // the previous step left the buffers clean
   t.n_rows = cfg.grid < kStepRows ? cfg.grid : kStepRows;
   if (const char* e = getenv("CNFOT_STEP_ROWS")) {   // tuning knob: partial gradient rows (<= 1184)
     const int v = atoi(e);
-    if (v >= 1 && v <= (io.stateful ? kStepRows : kMaxGrid)) t.n_rows = v < cfg.grid ? v : cfg.grid;
+    if (v >= 1 && v <= (persistent ? kStepRows : kMaxGrid)) t.n_rows = v < cfg.grid ? v : cfg.grid;
   }
   const int n_slices = (lay.total + kNumSlots + 7) / 8;
   // CTAs that stay for the reduction: at most half of the grid (the rest exits and frees its SM slots, so a grid
@@ -910,12 +964,14 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     t.weights = io.weights_rw; t.adam_m = io.adam_m; t.adam_v = io.adam_v;
     t.lr = io.lr; t.b1 = io.b1; t.b2 = io.b2; t.eps = io.eps;
     t.loss_hist = io.loss_hist; t.loss_hist_len = io.loss_hist_len;
+  } else if (persistent) {
+    t.self_clean = 1;
   } else {
     cudaError_t e = cudaMemsetAsync(wsb, 0, (size_t)kCounterBytes + (size_t)t.n_rows * lay.total * sizeof(float), s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   }
   void* args[] = {&a};
-  cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
+  cudaError_t e = launch_step_kernel(kernel, cfg.grid, args, cfg.smem, s);
   if (e != cudaSuccess) return cuda_fail(e, "mfc_step_kernel launch");
   return 0;
 }
@@ -948,6 +1004,22 @@ int cnfot_mfc_step_dp(void* stream, const cnfot_flow_desc* flow, const cnfot_pro
   io.out = out; io.peers = peers;
   return mfc_step_impl(stream, flow, problem, weights, io, n_t, rows_B, rows_b, global_B, global_b, lambda, workspace,
                        workspace_bytes);
+}
+
+int cnfot_workspace_register(void* stream, const cnfot_flow_desc* flow, void* workspace, int64_t workspace_bytes) {
+  FlowLayout lay;
+  if (int rc = check_flow(flow, &lay)) return rc;
+  if (use_wide(flow, lay)) return fail(CNFOT_ERR_ARG, "persistent workspaces serve the fused per-row step kernel, not the wide-conditioner engine");
+  if (!workspace) return fail(CNFOT_ERR_ARG, "NULL buffer");
+  if (workspace_bytes < step_bytes(lay)) return fail(CNFOT_ERR_WORKSPACE, "workspace too small: %lld < %lld",
+                                                     (long long)workspace_bytes, (long long)step_bytes(lay));
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)kCounterBytes + (size_t)kStepRows * lay.total * sizeof(float),
+                                  (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  cnfot_workspace_release(workspace);
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  g_ws_registered.emplace_back(workspace, workspace_bytes);
+  return 0;
 }
 
 int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cnfot_problem_desc* problem,

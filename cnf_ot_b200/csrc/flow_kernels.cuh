@@ -415,6 +415,7 @@ struct StepArgs {
   unsigned long long key;       // on-chip draws (philox.cuh): key and step, or read from the train state
   unsigned long long salt_B, salt_Bc, salt_b, salt_t;   // key modifiers: normal (B, D), categorical (B,), normal (b, D), uniform (n_t,)
   uint32_t step;
+  unsigned long long* timeline;   // diagnostics (cnfot_debug_step_timeline): globaltimer stamps, or nullptr
   Segment seg[kMaxSegments];
   TailArgs tail;
 };
@@ -621,11 +622,16 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
 template <class Net, class DimsT, int ENG>
 __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
-  __shared__ double scratch[kWarps];
+  __shared__ double scratch4[kWarps][4];
   __shared__ long long s_tile;
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
   using Ctx = typename CtxSelect<Net, ENG>::type;
+  // Programmatic dependent launch (api.cu: launch_step_kernel): this grid may have been scheduled while the previous
+  // kernel of the stream was still in its tail; nothing is read or written before that kernel has completed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  unsigned long long t_start = 0;
+  if (a.timeline && threadIdx.x == 0) { t_start = global_timer_ns(); atomicMin(a.timeline + 0, t_start); atomicMax(a.timeline + 7, t_start); }   // first / last CTA starts
   float* sAcc = Ctx::kAccInGlobal ? nullptr : smem + a.plan.off_acc;
   float* my_row = a.tail.grad_rows + (int64_t)(blockIdx.x % a.tail.n_rows) * a.plan.total;
   Ctx ctx;
@@ -633,7 +639,8 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
   ctx.bind_partials(my_row, false);   // shared, pre-zeroed partial rows: the context must not clear them
   ctx.bind_frags(a.frags);
   ctx.bind_stash(a.stash ? a.stash + (size_t)blockIdx.x * a.stash_cta_floats : nullptr);
-  ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
+  ctx_setup(ctx, DimsT{a.D, a.L}.D(), DimsT{a.D, a.L}.L(), &tc_mbar, &tc_slot);   // compile-time shape where the kernel has one
+  if (a.timeline && threadIdx.x == 0) { const unsigned long long now = global_timer_ns(); atomicMax(a.timeline + 1, now); atomicMax(a.timeline + 6, now - t_start); }   // last CTA is set up; longest setup
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
   const int D = dm.D();
@@ -698,6 +705,14 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
       loss[kSlotPotential] += (double)lp;
     }
   }
+  // Out of tiles: the next kernel of the stream may take the SM slots this grid frees from here on (every CTA of this
+  // grid is resident or done by the time the last one gets here, so the newcomers cannot keep any of them out).
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (a.timeline && threadIdx.x == 0) {   // this CTA ran out of tiles
+    const unsigned long long now = global_timer_ns();
+    atomicMin(a.timeline + 2, now);
+    atomicMax(a.timeline + 3, now);
+  }
   {
     float graw[Net::kPp];
 #pragma unroll
@@ -712,13 +727,26 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
       const float v = sAcc[i];
       if (v != 0.f) atomicAdd(my_row + i, v);
     }
+  {   // the four live slots (fit0, fitT, potential, kinetic): warp sums, then one thread per slot
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {   // the four live slots (fit0, fitT, potential, kinetic)
-    const double v = block_sum(loss[s], scratch);
-    if (threadIdx.x == 0 && v != 0.0) atomicAdd(a.tail.loss_row + s, v);
+    for (int s = 0; s < 4; ++s) {
+      double v = loss[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) scratch4[threadIdx.x >> 5][s] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += scratch4[w][threadIdx.x];
+      if (v != 0.0) atomicAdd(a.tail.loss_row + threadIdx.x, v);
+    }
   }
   ctx_teardown(ctx);
+  if (a.timeline && threadIdx.x == 0) atomicMax(a.timeline + 4, global_timer_ns());   // last CTA enters the tail
   step_tail(a.tail);
+  if (a.timeline && threadIdx.x == 0) atomicMax(a.timeline + 5, global_timer_ns());   // last CTA leaves
 }
 
 }  // namespace cnfot

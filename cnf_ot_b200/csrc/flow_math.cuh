@@ -326,6 +326,9 @@ CNFOT_CALL T flow_pass(const DimsT& dm, const SC& sc, T t, T* states,
           mlp_forward<T, Net, Ctx>(W, layer * (D - 1) + d - 1, d + 1, tl, theta, ctx);
         }
         rqs_locate_raw<DIR == 0, T, K>(v[i], theta, sc, st);
+        if constexpr (Ctx::kWarpMlp) {
+          if (stash) ctx.stash_state(D, layer, d, st);
+        }
       }
       T out, ld;
       if (DIR == 0) rqs_inverse_map<T, K>(v[i], st, sc, out, ld);
@@ -372,11 +375,13 @@ CNFOT_CALL void flow_pass_bwd(const DimsT& dm, const SC& sc, T t, const T* state
       const T* W = nullptr;
       if (d == 0) {
         rqs_locate_first<DIR == 0, T, K>(v[i], ctx.first_knots(), sc, st);
+      } else if (Ctx::kWarpMlp && stash) {
+        // the forward pass of the same rows left the activations and the located spline in the stash
+        if constexpr (Ctx::kWarpMlp) ctx.cond_restore(D, layer, d, st, sc.min_slope);
       } else {
         T theta[Pp];
         if constexpr (Ctx::kWarpMlp) {
-          if (stash) ctx.cond_restore(D, layer, d, theta);
-          else ctx.cond_forward(D, layer, d, t, cvec, theta, true);
+          ctx.cond_forward(D, layer, d, t, cvec, theta, true);
         } else {
           w_off = mlp_offset<Net>(D, layer, d);
           ctx.begin();  // the tiles of the previous conditioner are free again

@@ -63,21 +63,28 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 
 // Shared-memory plan of the warp-MMA kernels (same struct as the CUDA-core plan; the row tiles
 // of the latter are not used).
-// resident: the blob (input layers, biases, `first`) and the hi/lo fragments of the 16x16 matrices
-// live in shared memory (measured on cfg 2: reading the input layers from global/L1 instead costs
+// resident: what the CUDA cores read of the blob (`first`, input layers, biases: compact copy, cw_floats) and the
+// hi/lo fragments of the 16x16 matrices live in shared memory (measured on cfg 2: reading the input layers from global/L1 instead costs
 // ~3 %, and a fifth CTA per SM at <= 102 registers is slower than four at 128).
 // streamed (larger flows, e.g. dim 10): only `first` is resident; input layers / biases are read
 // from the blob and the fragments from a buffer a prep kernel fills (build_frags_kernel), both in
 // global memory through L1.
+// Compact resident copy of the blob (resident plan): [first (Pp) | per conditioner: W0 ((d+1) x 16), b0, b1 .. b_{M-1}, bout].
+// The 16 x 16 matrices themselves are only read as MMA fragments, so they are not copied.
+__host__ __device__ inline int cw_layer_stride(int D, int M) { return 16 * ((D - 1) * (D + 2) / 2) + (D - 1) * (M + 1) * 16; }
+__host__ __device__ inline int cw_offset(int D, int M, int Pp, int layer, int d) {
+  return Pp + layer * cw_layer_stride(D, M) + 16 * ((d - 1) * (d + 2) / 2) + (d - 1) * (M + 1) * 16;
+}
+__host__ __device__ inline int cw_floats(int D, int L, int M, int Pp) { return Pp + L * cw_layer_stride(D, M); }
+
 inline SmemPlan plan_smem_mma(const FlowLayout& f, bool with_grad, bool resident = true) {
   SmemPlan p;
   p.total = f.total;
   p.w_in_smem = resident ? 1 : 0;
-  const int tot4 = (f.total + 3) / 4 * 4;
   p.ld_in = p.ld_h = p.ld_p = 0;
   p.off_w = 0;
   p.w_stage = 0;
-  int o = resident ? tot4 : f.Pp;
+  int o = resident ? cw_floats(f.D, f.L, f.M, f.Pp) : f.Pp;
   p.off_acc = -1;   // weight gradients go straight to the CTA's partial row in global memory
   p.off_in = p.off_hid = p.off_gh = p.off_gth = p.off_lo = p.off_wmma = -1;
   o = align_up(o, 32);
@@ -166,6 +173,8 @@ struct WRef<false> {
 //   dir 0 (y = x W):    b0 = W[8ks+2t][8nt+g]   b1 = W[8ks+2t+1][8nt+g]
 //   dir 1 (y = g W^T):  b0 = W[8nt+g][8ks+2t]   b1 = W[8nt+g][8ks+2t+1]
 //   value = { b0_hi, b1_hi, b0_lo, b1_lo }
+// LDG: the blob is in global memory (read-only path); false: a staged copy in shared memory
+template <bool LDG = true>
 __device__ __forceinline__ float4 frag_element(const float* __restrict__ blob, int D, int M, int e) {
   constexpr int H = 16, Pp = 16;
   const int ln = e & 31, ksnt = (e >> 5) & 3, dir = (e >> 7) & 1, mat = e >> 8;
@@ -177,13 +186,10 @@ __device__ __forceinline__ float4 frag_element(const float* __restrict__ blob, i
                     (d + 1) * H + H + slot * (H * H + H);
   const int ks = ksnt >> 1, nt = ksnt & 1, gg = ln >> 2, tt = ln & 3;
   float b0, b1;
-  if (dir == 0) {
-    b0 = __ldg(Ws + (8 * ks + 2 * tt) * 16 + 8 * nt + gg);
-    b1 = __ldg(Ws + (8 * ks + 2 * tt + 1) * 16 + 8 * nt + gg);
-  } else {
-    b0 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt);
-    b1 = __ldg(Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt + 1);
-  }
+  const float* q0 = dir == 0 ? Ws + (8 * ks + 2 * tt) * 16 + 8 * nt + gg : Ws + (8 * nt + gg) * 16 + 8 * ks + 2 * tt;
+  const float* q1 = q0 + (dir == 0 ? 16 : 1);
+  if constexpr (LDG) { b0 = __ldg(q0); b1 = __ldg(q1); }
+  else { b0 = *q0; b1 = *q1; }
   uint32_t h0, l0, h1, l1;
   split_tf32(b0, h0, l0);
   split_tf32(b1, h1, l1);
@@ -238,10 +244,13 @@ struct DeviceCtxMma {
   uint32_t s_wt;        // shared-window address of this warp's tiles
   // Activation stash (this CTA's slice of a global buffer that stays in L2): the forward pass of a row that is
   // differentiated right away (KL / reverse-KL / potential rows: 97 % of a step) leaves every conditioner's hidden
-  // activations and raw spline parameters here, exactly as the warp holds them (MMA fragments), and the backward
-  // pass reads them back instead of evaluating the conditioner a second time.  nullptr: recompute.
+  // activations (as the warp holds them: MMA fragments) and the located spline (SplineState of the thread's row: softmax
+  // probabilities, the gathered knots, slope logits) here, and the backward pass reads them back instead of evaluating
+  // the conditioner and normalising the knots a second time.  nullptr: recompute.
   float* stash = nullptr;
-  static constexpr int kStashChunks = 4 * (M + 1);            // float4 per thread and conditioner: M hidden layers + theta
+  static constexpr int kStateFloats = 2 * Net::kK + 10;
+  static constexpr int kStateChunks = (kStateFloats + 3) / 4;
+  static constexpr int kStashChunks = 4 * M + kStateChunks;   // float4 per thread and conditioner
   static constexpr int kStashCondFloats = kStashChunks * kTile * 4;
   __device__ __forceinline__ void bind_stash(float* q) { stash = q; }
   __device__ __forceinline__ bool stash_on() const { return stash != nullptr; }
@@ -254,12 +263,22 @@ struct DeviceCtxMma {
       __stcg(reinterpret_cast<float4*>(q + (chunk0 + c) * kTile * 4),
              make_float4(v[c >> 1][c & 1][0], v[c >> 1][c & 1][1], v[c >> 1][c & 1][2], v[c >> 1][c & 1][3]));
   }
-  __device__ __forceinline__ static void stash_get(const float* q, int chunk0, float (&v)[2][2][4]) {
+  // the located spline of the calling thread's row (after rqs_locate_raw in the forward pass)
+  __device__ __forceinline__ void stash_state(int D, int layer, int d, const SplineState<float, Net::kK>& st) const {
+    constexpr int K = Net::kK;
+    float b[kStateChunks * 4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 f = __ldcg(reinterpret_cast<const float4*>(q + (chunk0 + c) * kTile * 4));
-      v[c >> 1][c & 1][0] = f.x; v[c >> 1][c & 1][1] = f.y; v[c >> 1][c & 1][2] = f.z; v[c >> 1][c & 1][3] = f.w;
-    }
+    for (int k = 0; k < K; ++k) { b[k] = st.pw[k]; b[K + k] = st.ph[k]; }
+    b[2 * K] = st.x0; b[2 * K + 1] = st.x1; b[2 * K + 2] = st.y0; b[2 * K + 3] = st.y1;
+    b[2 * K + 4] = st.d0; b[2 * K + 5] = st.d1; b[2 * K + 6] = st.u0; b[2 * K + 7] = st.u1;
+    b[2 * K + 8] = st.u_tail;
+    b[2 * K + 9] = __int_as_float(st.idx | (st.tail << 8));
+#pragma unroll
+    for (int j = kStateFloats; j < kStateChunks * 4; ++j) b[j] = 0.f;
+    float* q = stash_of(D, layer, d) + 4 * M * kTile * 4;
+#pragma unroll
+    for (int c = 0; c < kStateChunks; ++c)
+      __stcg(reinterpret_cast<float4*>(q + c * kTile * 4), make_float4(b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]));
   }
 
   bool clear_acc;       // setup() zeroes the partial row (false: rows shared between CTAs, cleared by the caller)
@@ -275,16 +294,61 @@ struct DeviceCtxMma {
   __device__ __forceinline__ void setup(int D, int L, uint64_t*, uint32_t*) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
-    load_weights(smem + p.off_w, gW, RES ? p.total : Pp);
     if (gacc && clear_acc)
       for (int i = threadIdx.x; i < p.total; i += blockDim.x) gacc[i] = 0.f;
     if constexpr (RES) {
       w_ref = Ref{s0 + (uint32_t)p.off_w * 4u};
       frag_ref = Ref{s0 + (uint32_t)p.off_frag * 4u};
+      // The blob is staged in the warps' tiles (free until the first conditioner) with one coalesced copy; everything
+      // below reads the staged copy.  (Building the fragments straight from global memory was 8 dependent L2 round
+      // trips per thread: 4 of the 6 us a CTA spent here, tools/step_timeline.py.)
+      float* stage = smem + p.off_wt;
+      const bool staged = p.total <= kWarps * p.wt_stride;
+      if (staged) {
+        load_weights(stage, gW, p.total);
+        __syncthreads();
+      }
+      const float* blob = staged ? stage : gW;
+      for (int i = threadIdx.x; i < Pp; i += blockDim.x) smem[p.off_w + i] = blob[i];
+      // compact copy: input layer + first bias are contiguous in the blob, the other biases follow their matrices
+      for (int mlp = 0; mlp < L * (D - 1); ++mlp) {
+        const int layer = mlp / (D - 1), d = mlp - layer * (D - 1) + 1;
+        const float* src = blob + mlp_offset<Net>(D, layer, d);
+        float* dst = smem + p.off_w + cw_offset(D, M, Pp, layer, d);
+        const int n0 = (d + 2) * 16;
+        for (int i = threadIdx.x; i < n0 + M * 16; i += blockDim.x) {
+          int so = i;
+          if (i >= n0) {
+            const int m = (i - n0) >> 4, j = i & 15;   // bias of dense matrix m (hidden m + 1, or the output layer)
+            so = n0 + m * (H * H + H) + H * H + j;
+          }
+          dst[i] = src[so];
+        }
+      }
+      // One thread of the last warp normalises the knots of the shared `first` spline (a serial ~400-instruction
+      // chain) while the other warps build the weight fragments.
       const int n_mat = L * (D - 1) * M;
+      const int nb = (int)blockDim.x - 32;
+      if (staged) {
+        if ((int)threadIdx.x >= nb) {
+          if ((int)threadIdx.x == nb) {
+          float theta[Pp];
+#pragma unroll
+          for (int j = 0; j < Pp; ++j) theta[j] = stage[j];
+          first_knots_build<float, Net::kK>(theta, FixedSplineConsts<float, Net::kK>(),
+                                            *reinterpret_cast<FirstKnots<float, Net::kK>*>(smem + p.off_fk));
+          }
+        } else {
+          for (int e = threadIdx.x; e < n_mat * 256; e += nb)
+            reinterpret_cast<float4*>(smem + p.off_frag)[e] = frag_element<false>(stage, D, M, e);
+        }
+        __syncthreads();
+        return;
+      }
       for (int e = threadIdx.x; e < n_mat * 256; e += blockDim.x)
-        reinterpret_cast<float4*>(smem + p.off_frag)[e] = frag_element(gW, D, M, e);
+        reinterpret_cast<float4*>(smem + p.off_frag)[e] = frag_element<true>(gW, D, M, e);
     } else {
+      load_weights(smem + p.off_w, gW, Pp);
       w_ref = Ref{gW};
       frag_ref = Ref{gfrag};
     }
@@ -401,14 +465,14 @@ struct DeviceCtxMma {
 
   // Conditioner forward for the warp's 32 rows: theta[0..16) of the calling thread's row.
   // keep: store the hidden activations in the warp's tiles for cond_backward.
-  // put: also leave them (and theta) in the activation stash for cond_restore.
+  // put: also leave them in the activation stash for cond_restore (the caller adds the located spline: stash_state).
   __device__ __forceinline__ void cond_forward(int D, int layer, int d, float tval, const float* cvec,
                                                float* theta, bool keep, bool put = false) const {
     float* sq = put ? stash_of(D, layer, d) : nullptr;
     const MmaLane ln;
     const uint32_t wt = s_wt;
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
-    const Ref W = w_ref + mlp_offset<Net>(D, layer, d);
+    const Ref W = w_ref + (RES ? cw_offset(D, M, Pp, layer, d) : mlp_offset<Net>(D, layer, d));
     const Ref b0 = W + n_in * H;
     const Ref frag = frag_ref + mlp * M * kFragFloats;
     float x[2][2][4], a[2][2][4];
@@ -442,17 +506,17 @@ struct DeviceCtxMma {
       store_a(wt, ln, a);
     }
     if (put) stash_put(sq, 0, a);
-    Ref Wm = b0 + H;
+    // bias of dense matrix m: compact copy = right after b0; blob = after its matrix
+    Ref bm = RES ? b0 + H : b0 + (H + H * H);
 #pragma unroll
     for (int m = 1; m < M; ++m) {
-      dense16(a, frag + (m - 1) * kFragFloats, Wm + H * H, ln, x);
+      dense16(a, frag + (m - 1) * kFragFloats, bm, ln, x);
       relu_to_a(x, a);
       if (keep) store_a(wt + m * kWtFloats * 4, ln, a);
       if (put) stash_put(sq, 4 * m, a);
-      Wm = Wm + (H * H + H);
+      bm = bm + (RES ? H : H * H + H);
     }
-    dense16(a, frag + (M - 1) * kFragFloats, Wm + H * Pp, ln, x);
-    if (put) stash_put(sq, 4 * M, x);
+    dense16(a, frag + (M - 1) * kFragFloats, bm, ln, x);
     const uint32_t scratch = wt + (keep ? M : 0) * kWtFloats * 4;
     __syncwarp();
     store_c(scratch, ln, x);
@@ -460,26 +524,44 @@ struct DeviceCtxMma {
     load_row(scratch, ln, theta);
   }
 
-  // What cond_forward(keep = true) leaves behind -- hidden activations in the warp's tiles, theta of the calling
-  // thread's row -- read back from the activation stash the forward pass of the same rows filled (put = true).
-  __device__ __forceinline__ void cond_restore(int D, int layer, int d, float* theta) const {
+  // What cond_forward(keep = true) + rqs_locate_raw leave behind -- hidden activations in the warp's tiles, the located
+  // spline of the calling thread's row -- read back from the activation stash the forward pass of the same rows filled
+  // (cond_forward(put = true), stash_state).  Every load is issued before the first use: ONE L2 round trip.
+  __device__ __forceinline__ void cond_restore(int D, int layer, int d, SplineState<float, Net::kK>& st, float min_slope) const {
+    constexpr int K = Net::kK;
     const MmaLane ln;
     const uint32_t wt = s_wt;
     const float* sq = stash_of(D, layer, d);
-    float a[2][2][4];
-    stash_get(sq, 0, a);
-    __syncwarp();   // the previous conditioner's readers are done with the tiles
-    store_a(wt, ln, a);
+    float4 f[kStashChunks];
 #pragma unroll
-    for (int m = 1; m < M; ++m) {
-      stash_get(sq, 4 * m, a);
+    for (int c = 0; c < kStashChunks; ++c) f[c] = __ldcg(reinterpret_cast<const float4*>(sq + c * kTile * 4));
+    __syncwarp();   // the previous conditioner's readers are done with the tiles
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float a[2][2][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = f[4 * m + c];
+        a[c >> 1][c & 1][0] = v.x; a[c >> 1][c & 1][1] = v.y; a[c >> 1][c & 1][2] = v.z; a[c >> 1][c & 1][3] = v.w;
+      }
       store_a(wt + m * kWtFloats * 4, ln, a);
     }
-    stash_get(sq, 4 * M, a);
-    const uint32_t scratch = wt + M * kWtFloats * 4;
-    store_c(scratch, ln, a);
-    __syncwarp();
-    load_row(scratch, ln, theta);
+    float b[kStateChunks * 4];
+#pragma unroll
+    for (int c = 0; c < kStateChunks; ++c) {
+      const float4 v = f[4 * M + c];
+      b[4 * c] = v.x; b[4 * c + 1] = v.y; b[4 * c + 2] = v.z; b[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { st.pw[k] = b[k]; st.ph[k] = b[K + k]; }
+    st.x0 = b[2 * K]; st.x1 = b[2 * K + 1]; st.y0 = b[2 * K + 2]; st.y1 = b[2 * K + 3];
+    st.d0 = b[2 * K + 4]; st.d1 = b[2 * K + 5]; st.u0 = b[2 * K + 6]; st.u1 = b[2 * K + 7];
+    st.u_tail = b[2 * K + 8];
+    const int it = __float_as_int(b[2 * K + 9]);
+    st.idx = it & 0xff;
+    st.tail = it >> 8;
+    st.s_tail = st.d0;
+    if (st.tail == 2) st.s_tail = softplus(st.u_tail) + min_slope;
   }
 
   // 4 per-thread partial sums (columns 2t, 2t+1, 8+2t, 9+2t of a 16-wide row) -> summed over the
@@ -555,7 +637,7 @@ struct DeviceCtxMma {
     const uint32_t wt = s_wt;
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
     const int w_off = mlp_offset<Net>(D, layer, d);
-    const Ref W = w_ref + w_off;
+    const Ref W = w_ref + (RES ? cw_offset(D, M, Pp, layer, d) : w_off);
     float* A = gacc + w_off;
     const Ref frag = frag_ref + (mlp * M * kFragFloats + 512);
     const uint32_t tg = wt + M * kWtFloats * 4;

@@ -143,6 +143,42 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
   return ws
 
 
+_step_workspaces = {}
+
+
+class _StepWorkspace:
+  """A dedicated, registered workspace of the fused train step (cnfot_workspace_register): consecutive steps need no
+  memset between them and their launches overlap (see include/cnfot.h)."""
+
+  def __init__(self, buf):
+    self.buf = buf
+
+  def __del__(self):
+    try:
+      _lib.load().cnfot_workspace_release(self.buf.data_ptr())
+    except Exception:
+      pass
+
+
+def _step_workspace(shape: FlowShape, desc, nbytes: int, device) -> torch.Tensor:
+  """Scratch memory of the train step for the calling (device, stream, flow shape).  Fused per-row engine: a
+  persistent registered workspace; wide-conditioner engine: the shared scratch buffer."""
+  device = torch.device(device)
+  lib = _lib.load()
+  if not fused_update_supported(shape):
+    return _workspace(nbytes, device)
+  index = device.index if device.index is not None else torch.cuda.current_device()
+  key = (index, torch.cuda.current_stream(index).cuda_stream, shape)
+  ent = _step_workspaces.get(key)
+  if ent is None or ent.buf.numel() < nbytes:
+    with torch.cuda.device(index):
+      buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+      _lib.check(lib.cnfot_workspace_register(_stream(), desc, buf.data_ptr(), buf.numel()))
+    ent = _StepWorkspace(buf)
+    _step_workspaces[key] = ent
+  return ent.buf
+
+
 def flow_vjp(shape: FlowShape, weights, x, cond, g_out, g_logdet, inverse: bool, add_base=False,
              want_g_in=True):
   """(g_in, g_weights) of flow_eval; g_weights is summed over rows (blob layout)."""
@@ -215,7 +251,7 @@ def mfc_step(shape: FlowShape, problem: _lib.ProblemDesc, weights, latent, laten
     out = torch.empty(shape.blob_size + _lib.NUM_LOSS_SLOTS, dtype=torch.float32, device=device)
   desc = _lib.flow_desc(shape)
   nbytes = lib.cnfot_mfc_step_workspace_bytes(desc, rows_B, rows_b, n_t)
-  ws = _workspace(nbytes, device)
+  ws = _step_workspace(shape, desc, nbytes, device)
   with torch.cuda.device(device):
     if peers is None:
       _lib.check(lib.cnfot_mfc_step(_stream(), desc, problem, _ptr(weights), _ptr(latent),
@@ -295,7 +331,7 @@ def mfc_step_rng(shape: FlowShape, problem: _lib.ProblemDesc, weights, key: int,
   if out is None:
     out = torch.empty(shape.blob_size + _lib.NUM_LOSS_SLOTS, dtype=torch.float32, device=device)
   desc = _lib.flow_desc(shape)
-  ws = _workspace(lib.cnfot_mfc_step_workspace_bytes(desc, rB.stop - rB.start, rb.stop - rb.start, n_t), device)
+  ws = _step_workspace(shape, desc, lib.cnfot_mfc_step_workspace_bytes(desc, rB.stop - rB.start, rb.stop - rb.start, n_t), device)
   pd = None if peers is None else peers.next_desc(shape)
   with torch.cuda.device(device):
     _lib.check(lib.cnfot_mfc_step_rng(_stream(), desc, problem, _ptr(weights), int(key) & (2**64 - 1),

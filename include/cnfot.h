@@ -91,6 +91,11 @@ CNFOT_API const char* cnfot_last_error(void);
  * GEMMs, the other three fields are 0). */
 CNFOT_API void cnfot_last_launch_info(int32_t* grid, int32_t* smem_bytes, int32_t* ctas_per_sm,
                                       int32_t* tensor_cores);
+/* Diagnostics (tools/step_timeline.py): while `device_words` is non-NULL (8 uint64 in device memory, initialised by the
+ * caller to {~0, 0, ~0, 0, 0, 0, 0, 0}) every fused train step records %globaltimer stamps there: [0] first CTA starts,
+ * [1] last CTA finished its setup, [2] / [3] first / last CTA ran out of row tiles, [4] last CTA enters the
+ * reduction tail, [5] last CTA leaves the kernel, [6] the longest per-CTA setup (a duration), [7] last CTA starts.  NULL switches it off (the default; process-wide, not thread-safe). */
+CNFOT_API void cnfot_debug_step_timeline(void* device_words);
 
 /* ---- parameter blob ---------------------------------------------------------------
  * The haiku pytree of SURVEY.md A.3 flattened into one fp32 buffer (layout documented in
@@ -193,6 +198,15 @@ CNFOT_API int cnfot_mfc_step(void* stream, const cnfot_flow_desc* flow, const cn
                    const float* src, const float* tgt, const float* t_batch_host, int32_t n_t,
                    int64_t rows_B, int64_t rows_b, int64_t global_B, int64_t global_b,
                    float lambda, float* out, void* workspace, int64_t workspace_bytes);
+/* Persistent step workspace (optional): cnfot_workspace_register zero-initialises `workspace` (stream-ordered) and
+ * records the pointer; from then on cnfot_mfc_step / _dp / _rng calls that are given this workspace skip their
+ * per-call memset, because every step's reduction tail leaves the buffers clean for the next one -- two consecutive
+ * steps are then two back-to-back kernel launches, and the second is scheduled (programmatic dependent launch) while
+ * the first is still in its tail.  Contract: between cnfot_workspace_register and cnfot_workspace_release the memory
+ * is only used by those calls, one stream at a time; a step that reported a peer time-out leaves it dirty (register
+ * it again).  Not for the wide-conditioner engine.  cnfot_train_state (below) has the same property built in. */
+CNFOT_API int cnfot_workspace_register(void* stream, const cnfot_flow_desc* flow, void* workspace, int64_t workspace_bytes);
+CNFOT_API int cnfot_workspace_release(void* workspace);
 /* ---- data-parallel step: the train step fused with its all-reduce -------
  * Same as cnfot_mfc_step on this rank's shard, but the step kernel's tail also exchanges the
  * [gradient | loss slots] buffer with the peer GPUs of the node through peer-mapped memory

@@ -1,6 +1,6 @@
 """A few train steps of a BASELINE config (short: for ncu, and for A/B timing of tuning knobs).
 
-  python tools/prof_step.py [cfg2|cfg1|cfg3|cfg4] [n] [explicit|rng|update] [--time]
+  python tools/prof_step.py [cfg2|cfg1|cfg3|cfg4] [n] [explicit|rng|update] [--time] [--rows=R]
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,7 +22,8 @@ class _D:
 
 
 torch.cuda.set_device(0)
-w = bench.Workload(name, _D(), rows_override=(1 << 19) if name == "cfg4" else None)
+rows = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--rows=")), None)
+w = bench.Workload(name, _D(), rows_override=rows or ((1 << 19) if name == "cfg4" else None))
 state = ops.TrainState(w.shape, w.W, 1234) if mode == "update" else None
 
 
@@ -42,7 +43,7 @@ if timing:
   ts = []
   for r in range(5):
     ts.append(bench.time_region(step, n, torch.cuda.synchronize, first=r * n) / n * 1e3)
-  print(f"{name} {mode} env[{os.environ.get('CNFOT_STEP_UNIT', '-')},{os.environ.get('CNFOT_STEP_ROWS', '-')},{os.environ.get('CNFOT_ENGINE', '-')}]: "
+  print(f"{name} {mode} rows {w.B} env[{os.environ.get('CNFOT_STEP_UNIT', '-')},{os.environ.get('CNFOT_STEP_ROWS', '-')},{os.environ.get('CNFOT_ENGINE', '-')}]: "
         f"{sorted(ts)[2]:.4f} ms/step (min {min(ts):.4f}, max {max(ts):.4f}); {_lib.last_launch_info()}; loss {float(w.out[w.shape.blob_size]):.6e}")
 else:
   for i in range(n):
