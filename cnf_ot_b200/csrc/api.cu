@@ -947,13 +947,11 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     const int v = atoi(e);
     if (v >= 1 && v <= (persistent ? kStepRows : kMaxGrid)) t.n_rows = v < cfg.grid ? v : cfg.grid;
   }
-  const int n_slices = (lay.total + kNumSlots + 7) / 8;
-  // CTAs that stay for the reduction: at most half of the grid (the rest exits and frees its SM slots, so a grid
-  // that is not fully resident -- another kernel on the GPU -- still makes progress), at most one per pass of slices
-  const int per_pass = t.n_rows > 64 ? 1 : 4;
-  int n_tail = cfg.grid / (cfg.grid >= 2 * kStepRows ? 4 : 2);
+  // CTAs that stay for the reduction (the first to finish their tiles): four threads per output column
+  int n_tail = (lay.total + kNumSlots + kTile / 4 - 1) / (kTile / 4);
+  if (n_tail > cfg.grid) n_tail = cfg.grid;
+  if (n_tail > 2 * 148) n_tail = 2 * 148;   // waiting CTAs hold SM slots: keep them a fraction of the resident grid
   if (n_tail < 1) n_tail = 1;
-  if (n_tail > (n_slices + per_pass - 1) / per_pass) n_tail = (n_slices + per_pass - 1) / per_pass;
   t.n_tail = n_tail;
   t.total = lay.total;
   t.accumulate = io.accumulate ? 1 : 0;

@@ -459,15 +459,18 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 
 // The kernel's tail (see above).  Called by every thread of every CTA after its partial results are written.
 //
-// Reduction: an 8-column slice of the partial rows is summed by a group of 8 x G threads (G row groups; G = 16: the
-// whole CTA works on one slice, G = 4: every warp on its own slice -- small grids have few rows and few CTAs).
-// Exchange (world > 1): the slice's 8 sums are written into every peer's buffer as 64-bit {value, epoch} words
-// (one store each; an aligned 8-byte store arrives whole, so the data carries its own arrival flag: no fence, no
-// flag round trip -- the latency of ONE NVLink write), and the receiver spins on the epoch of each word it needs.
+// Reduction: one THREAD per output column sums the (<= 32) partial rows of its column -- up to 16 coalesced loads in
+// flight, no shared memory, no barrier -- so the whole buffer is one pass of ceil(columns / 128) CTAs.  The CTAs that
+// stay are the FIRST n_tail to finish their tiles: everything that does not depend on the other CTAs (the state words,
+// Adam's bias corrections -- two double-precision pow()) is done while they wait, and what remains after the last CTA
+// has arrived is one L2 round trip, the update and the stores.  (The round-2 start had the last n_tail arrivals run a
+// slice-per-CTA reduction over shared memory: 8 us at 592 CTAs, 20 us of a 50 us step at 32 CTAs.)
+// Exchange (world > 1): the column's sum is written into every peer's buffer as ONE 64-bit {value, epoch} word (an
+// aligned 8-byte store arrives whole, so the data carries its own arrival flag: no fence, no flag round trip -- the
+// latency of one NVLink write), and the same thread spins on the epoch of each peer's word for that column.
 // Buffers are double-buffered by the epoch's parity: a rank can be at most one step ahead of a peer, because
 // finishing a step needs every peer's words of that step.
 static __device__ __noinline__ void step_tail(const TailArgs& t) {
-  __shared__ double sh[16][8];
   __shared__ unsigned s_ticket;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
@@ -476,130 +479,108 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   if (tid == 0) s_ticket = atomicAdd(t.sync + kSyncDone, 1u);
   __syncthreads();
   const unsigned grid = gridDim.x, S = (unsigned)t.n_tail, ticket = s_ticket;
-  if (ticket + S < grid) return;
-  const int k = (int)(ticket - (grid - S));
-  if (tid == 0) {
-    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(20);
-    s_bad = 0;
-  }
-  __syncthreads();
-  const int total = t.total, n_out = total + kNumSlots, n_slices = (n_out + 7) >> 3;
-  const int G = t.n_rows > 64 ? 16 : 4;        // row groups per slice
-  const int per_pass = 16 / G;                 // slices the CTA works on at once
-  const int grp = tid >> 3, j = tid & 7;
-  const int sub = grp / G, g = grp - sub * G;  // which of the pass's slices, which row group
-  const bool owner = g == 0;                   // the 8 threads that finish a slice (the first 8 lanes of a warp)
-  const int lane = tid & 31;
+  if (ticket >= S) return;
+  const int k = (int)ticket;
+  const int total = t.total, n_out = total + kNumSlots;
   const bool dp = t.pa.world > 1;
   uint32_t epoch = t.pa.epoch, stepno = 0;
-  if (t.state) {
+  if (t.state) {   // written by the previous launch only
     stepno = (uint32_t)__ldcg(t.state + 1);
     if (dp) epoch = (uint32_t)__ldcg(t.state + 2);
   }
   float c1 = 1.f, c2 = 1.f;
-  if (t.weights && owner) {
+  if (t.weights) {
     c1 = (float)(1.0 - pow((double)t.b1, (double)stepno + 1.0));
     c2 = (float)(1.0 - pow((double)t.b2, (double)stepno + 1.0));
   }
   const size_t par_off = (size_t)(epoch & 1u) * t.pa.world * t.pa.stride;
-  if (dp && tid == 0 && ld_acquire_sys(t.pa.flags[t.pa.rank]) != 0u) s_bad = 1;   // a peer gave up earlier: stay poisoned
+  if (tid == 0) {
+    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(20);
+    s_bad = (dp && ld_acquire_sys(t.pa.flags[t.pa.rank]) != 0u) ? 1 : 0;   // a peer gave up earlier: stay poisoned
+  }
   __syncthreads();
 
   auto finish = [&](int col, float v) {   // the owner of an output column
     if (col < total) {
       if (t.out) t.out[col] = t.accumulate ? t.out[col] + v : v;
       if (t.weights && v == v) adam_one(t, col, v, c1, c2);   // a poisoned (NaN) gradient leaves the parameters alone
-    } else if (col < n_out) {
+    } else {
       const int sl = col - total;
       if (t.out) t.out[col] = sl <= 4 ? (t.accumulate ? t.out[col] + v : v) : 0.f;
       if (sl == 0 && t.loss_hist && (long long)stepno < t.loss_hist_len) t.loss_hist[stepno] = v;
     }
   };
 
-  // phase A: this CTA's slices of the partial rows -> one float per column (sent to the peers, or final)
-  const int n_pass = (n_slices + per_pass - 1) / per_pass;
-  for (int ps = k; ps < n_pass; ps += (int)S) {
-    const int s = ps * per_pass + sub;
-    const int col = 8 * s + j;
+  // four adjacent lanes share a column: lane j of the quad sums rows j, j + 4, ... (8 loads in flight for the 32 rows
+  // of a persistent workspace), two shuffles fold the quad, its first lane owns the column from there on
+  const int stride_cols = (int)S * (int)(blockDim.x >> 2);
+  const int rg = tid & 3;
+  const bool owner = rg == 0;
+  const unsigned long long* mybuf = dp ? t.pa.xbuf[t.pa.rank] + par_off : nullptr;
+  const uint32_t* abort_word = dp ? t.pa.flags[t.pa.rank] : nullptr;
+  const int n_cols = (n_out + 7) & ~7;   // whole warps take part in the shuffles
+  for (int col = k * (int)(blockDim.x >> 2) + (tid >> 2); col < n_cols; col += stride_cols) {
+    // phase A: this quad's column of the partial rows -> one float (sent to the peers, or final)
     double acc = 0.0;
-    if (s < n_slices && col < total) {
-      // up to 16 loads in flight per thread (the reduction is latency-bound: every load is an L2 round trip)
+    if (col < total) {
       float* p = t.grad_rows + col;
-      for (int r0 = g; r0 < t.n_rows; r0 += G * 16) {
-        float v[16];
+      for (int r0 = rg; r0 < t.n_rows; r0 += 32) {
+        float v[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int r = r0 + G * q;
-          v[q] = r < t.n_rows ? __ldcg(p + (size_t)r * total) : 0.f;
-        }
+        for (int q = 0; q < 8; ++q) v[q] = r0 + 4 * q < t.n_rows ? __ldcg(p + (size_t)(r0 + 4 * q) * total) : 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) acc += (double)v[q];
+        for (int q = 0; q < 8; ++q) acc += (double)v[q];
         if (t.self_clean) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const int r = r0 + G * q;
-            if (r < t.n_rows) __stcg(p + (size_t)r * total, 0.f);
-          }
+          for (int q = 0; q < 8; ++q)
+            if (r0 + 4 * q < t.n_rows) __stcg(p + (size_t)(r0 + 4 * q) * total, 0.f);
         }
       }
-    } else if (s < n_slices && col < n_out && owner) {
+    } else if (col < n_out && owner) {
       // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
       const int sl = col - total;
       if (sl == 0) acc = __ldcg(t.loss_row) + __ldcg(t.loss_row + 1) + __ldcg(t.loss_row + 2) + __ldcg(t.loss_row + 3);
       else if (sl <= 4) acc = __ldcg(t.loss_row + sl - 1);
     }
-    sh[grp][j] = acc;
-    __syncthreads();
-    if (owner && s < n_slices) {
-      double tot = 0.0;
-      for (int q = 0; q < G; ++q) tot += sh[grp + q][j];
-      const float mine = (float)tot;
-      if (!dp) {
-        finish(col, mine);
-      } else if (col < n_out) {
-        const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
-        for (int p = 0; p < t.pa.world; ++p)
-          st_relaxed_sys_u64(t.pa.xbuf[p] + par_off + (size_t)t.pa.rank * t.pa.stride + col, word);
-      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (!owner || col >= n_out) continue;
+    const float mine = (float)acc;
+    if (!dp) {
+      finish(col, mine);
+      continue;
     }
-    __syncthreads();
-  }
-  // phase B: every peer's words of this CTA's slices, summed in rank order
-  if (dp && owner) {
-    const unsigned long long* mybuf = t.pa.xbuf[t.pa.rank] + par_off;
-    const uint32_t* abort_word = t.pa.flags[t.pa.rank];
-    for (int ps = k; ps < n_pass; ps += (int)S) {
-      const int s = ps * per_pass + sub;
-      const int col = 8 * s + j;
-      if (s >= n_slices || col >= n_out) continue;
-      bool bad = *(volatile int*)&s_bad != 0;
-      float sum = 0.f;
-      for (int q = 0; q < t.pa.world && !bad; ++q) {
-        const unsigned long long* w = mybuf + (size_t)q * t.pa.stride + col;
-        unsigned long long v = ld_relaxed_sys_u64(w);
-        if ((uint32_t)(v >> 32) != epoch) {
-          const unsigned long long t0 = global_timer_ns();
-          unsigned spins = 0;
-          while ((uint32_t)((v = ld_relaxed_sys_u64(w)) >> 32) != epoch) {
-            if ((++spins & 255u) == 0u &&
-                (ld_acquire_sys(abort_word) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns)) {
-              bad = true;
-              break;
-            }
+    const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
+    for (int p = 0; p < t.pa.world; ++p)
+      st_relaxed_sys_u64(t.pa.xbuf[p] + par_off + (size_t)t.pa.rank * t.pa.stride + col, word);
+    // phase B: every peer's word of this column, summed in rank order
+    bool bad = *(volatile int*)&s_bad != 0;
+    float sum = 0.f;
+    for (int q = 0; q < t.pa.world && !bad; ++q) {
+      const unsigned long long* w = mybuf + (size_t)q * t.pa.stride + col;
+      unsigned long long v = ld_relaxed_sys_u64(w);
+      if ((uint32_t)(v >> 32) != epoch) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while ((uint32_t)((v = ld_relaxed_sys_u64(w)) >> 32) != epoch) {
+          if ((++spins & 255u) == 0u &&
+              (ld_acquire_sys(abort_word) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns)) {
+            bad = true;
+            break;
           }
         }
-        sum += __uint_as_float((uint32_t)v);
       }
-      if (bad) {
-        // a peer never arrived (or gave up): poison this rank's result AND tell every peer, so no rank
-        // continues with a sum the others do not have; the status word is read by the host
-        for (int p = 0; p < t.pa.world; ++p) st_release_sys(t.pa.flags[p], 1u);
-        s_bad = 1;
-        t.sync[kSyncStatus] = 1u;
-        sum = __int_as_float(0x7fc00000);
-      }
-      finish(col, sum);
+      sum += __uint_as_float((uint32_t)v);
     }
+    if (bad) {
+      // a peer never arrived (or gave up): poison this rank's result AND tell every peer, so no rank
+      // continues with a sum the others do not have; the status word is read by the host
+      for (int p = 0; p < t.pa.world; ++p) st_release_sys(t.pa.flags[p], 1u);
+      s_bad = 1;
+      t.sync[kSyncStatus] = 1u;
+      sum = __int_as_float(0x7fc00000);
+    }
+    finish(col, sum);
   }
   __syncthreads();
   if (tid == 0) {
@@ -616,7 +597,6 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
       __threadfence();
     }
   }
-  (void)lane;
 }
 
 template <class Net, class DimsT, int ENG>

@@ -20,4 +20,5 @@ def test_fused_step_allreduce_matches_nccl():
          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "check_dp.py")]
   r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
   assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-  assert "CHECK_DP PASS" in r.stdout, r.stdout[-2000:]
+  out = r.stdout + r.stderr   # importing bench.py routes fd 1 to stderr (its stdout carries only the JSON line)
+  assert "CHECK_DP PASS" in out, out[-2000:]
