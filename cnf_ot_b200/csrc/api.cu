@@ -896,22 +896,38 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   int ns = 0;
   int64_t tiles = 0;
   auto add = [&](int kind, int slot, int do_fit, int do_pot, float t, int t_index, const float* rows, int source,
-                 int64_t row0, int64_t n) {
+                 int64_t row0, int64_t n, int group) {
     if (n <= 0) return;
     Segment& sg = a.seg[ns++];
     sg.kind = kind; sg.slot = slot; sg.do_fit = do_fit; sg.do_pot = do_pot; sg.t = t; sg.t_index = t_index;
     sg.rows = rows; sg.source = io.rng ? source : (int)kRowsMemory; sg.row0 = row0;
-    sg.n = n; sg.first_tile = tiles;
-    tiles += (n + unit - 1) / unit;
+    sg.n = n; sg.first_tile = tiles; sg.group = group;
+    tiles += (n * group + unit - 1) / unit;
   };
+  // Small steps (the reference's default batch sizes): one thread per kinetic row is the latency of the whole step, so
+  // the passes of a row are spread over a group of lanes (row_kinetic_split) when the step would not fill the GPU twice.
+  // CNFOT_KINETIC_SPLIT=0 / 1 forces the choice.
+  int group = 1;
+  {
+    const bool with_score = problem->type != CNFOT_OT;
+    const bool need_r3 = with_score || a.pc.potential == kPotObstacle;
+    int g = with_score ? 4 : (need_r3 ? 4 : 2);
+    while (with_score && g < 2 * lay.D) g <<= 1;
+    const int64_t fit_tiles = (problem->type == CNFOT_FP ? 1 : 2) * ((rows_B + unit - 1) / unit);
+    const int64_t serial_tiles = fit_tiles + (int64_t)n_t * ((rows_b + unit - 1) / unit);
+    bool split = g <= 32 && serial_tiles <= kMaxGrid;
+    if (const char* e = getenv("CNFOT_KINETIC_SPLIT")) split = g <= 32 && e[0] != '0';
+    if (split) group = g;
+  }
   for (int i = 0; i < n_t; ++i)
-    add(kSegKinetic, kSlotKinetic, 0, 0, io.rng ? 0.f : io.t_batch_host[i], io.rng ? i : -1, io.latent_sub, kRowsNormal, io.row0_b, rows_b);
+    add(group > 1 ? kSegKineticSplit : kSegKinetic, kSlotKinetic, 0, 0, io.rng ? 0.f : io.t_batch_host[i], io.rng ? i : -1,
+        io.latent_sub, kRowsNormal, io.row0_b, rows_b, group);
   if (problem->type == CNFOT_OT) {
-    add(kSegNll, kSlotFit0, 1, 0, 0.f, -1, io.src, kRowsOtSource, io.row0_B, rows_B);
-    add(kSegNll, kSlotFitT, 1, 0, (float)a.pc.horizon, -1, io.tgt, kRowsNormal, io.row0_B, rows_B);
+    add(kSegNll, kSlotFit0, 1, 0, 0.f, -1, io.src, kRowsOtSource, io.row0_B, rows_B, 1);
+    add(kSegNll, kSlotFitT, 1, 0, (float)a.pc.horizon, -1, io.tgt, kRowsNormal, io.row0_B, rows_B, 1);
   } else {
-    add(kSegSample, kSlotFit0, 1, 0, 0.f, -1, io.latent, kRowsNormal, io.row0_B, rows_B);
-    if (problem->type == CNFOT_RWPO) add(kSegSample, kSlotFit0, 0, 1, (float)a.pc.horizon, -1, io.latent, kRowsNormal, io.row0_B, rows_B);
+    add(kSegSample, kSlotFit0, 1, 0, 0.f, -1, io.latent, kRowsNormal, io.row0_B, rows_B, 1);
+    if (problem->type == CNFOT_RWPO) add(kSegSample, kSlotFit0, 0, 1, (float)a.pc.horizon, -1, io.latent, kRowsNormal, io.row0_B, rows_B, 1);
   }
   a.n_seg = ns;
   a.n_tiles = tiles;

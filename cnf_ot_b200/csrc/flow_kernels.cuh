@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) densi
 //     exchange buffer (NVLink / NVSwitch stores), flagged, and summed in rank order once every peer's
 //     slice has arrived (bit-identical on all ranks); the owner of a column then writes the output and
 //     applies the Adam update of that parameter.
-enum SegmentKind { kSegNll = 0, kSegSample = 1, kSegKinetic = 2 };
+enum SegmentKind { kSegNll = 0, kSegSample = 1, kSegKinetic = 2, kSegKineticSplit = 3 /* step_math.cuh: row_kinetic_split */ };
 
 struct Segment {
   int kind;
@@ -363,6 +363,7 @@ struct Segment {
   int64_t row0;      // global index of this shard's first row (on-chip draws)
   int64_t n;
   int64_t first_tile;  // in 128-row tiles
+  int group;         // kSegKineticSplit: lanes per row (a tile holds 128 / group rows); 1 otherwise
 };
 
 constexpr int kMaxSegments = 36;
@@ -651,7 +652,9 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
     int si = 0;
     while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
     const Segment& sg = a.seg[si];
-    const int64_t r = (tile - sg.first_tile) * kTile + ctx.row_in_tile();
+    const bool split = sg.kind == kSegKineticSplit;   // the lanes of a group share a row
+    const int64_t r = split ? (tile - sg.first_tile) * (kTile / sg.group) + (int)threadIdx.x / sg.group
+                            : (tile - sg.first_tile) * kTile + ctx.row_in_tile();
     const bool live = r < sg.n;
     float row[kMaxDim];
     if (sg.source == kRowsMemory) {
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
     } else {
       for (int i = 0; i < D; ++i) row[i] = 0.f;
       if (live)
-        philox_row(key ^ (sg.kind == kSegKinetic ? a.salt_b : a.salt_B), key ^ a.salt_Bc, step, sg.source,
+        philox_row(key ^ (sg.kind >= kSegKinetic ? a.salt_b : a.salt_B), key ^ a.salt_Bc, step, sg.source,
                    (uint64_t)(sg.row0 + r), D, row);
     }
     const float tval = sg.t_index >= 0 ? philox_time(key ^ a.salt_t, step, sg.t_index, a.pc.horizon) : sg.t;
@@ -674,6 +677,14 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
       row_sample_terms<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, sg.do_fit != 0,
                                                           sg.do_pot != 0, pc, &lf, &lp, gfirst, tl, ctx);
       loss[sg.slot] += (double)lf;
+      loss[kSlotPotential] += (double)lp;
+    } else if (split) {
+      StepConsts<float> pc = a.pc;
+      if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
+      float lk = 0.f, lp = 0.f;
+      row_kinetic_split<Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, sg.group, &lk, &lp, gfirst,
+                                         tl, ctx);
+      loss[kSlotKinetic] += (double)lk;
       loss[kSlotPotential] += (double)lp;
     } else {
       StepConsts<float> pc = a.pc;

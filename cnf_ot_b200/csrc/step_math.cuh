@@ -261,6 +261,95 @@ CNFOT_HD void row_kinetic(const DimsT& dm, const SC& sc, T t, const T* latent,
   if (need_r3) flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, t, s3, g3, (T)0, gfirst, tl, ctx);
 }
 
+#if defined(__CUDACC__)
+// ---- kinetic rows, the passes of ONE row spread over a group of G consecutive lanes ------------------------------
+// A kinetic row is 2-3 sample passes, (rwpo / fp) 2D shifted log-prob passes forward and backward, and 2-3 backward
+// sample passes: one thread walking through all of them is the latency of a whole train step when the sub-batch
+// (B // 32 rows) does not fill the GPU -- the reference's own default sizes.  Here lane `sub` of a group does
+//   phase 1  the sample pass at t - dt/2 (sub 0), t + dt/2 (sub 1), t (sub >= 2: every further lane gets its own r3)
+//   phase 2  (score) the log-prob pass at r3 +- dx/2 e_i, i = sub / 2, side = sub % 2, forward and -- straight away, so
+//            the activation stash applies -- backward; the score, the residual and the adjoints are exchanged with
+//            shuffles inside the group
+//   phase 3  the backward sample pass of phase 1's pass (sub 0: -g2, sub 1: +g2, sub 2: g3, others: zero adjoint)
+// G = 2 (ot without r3), 4 (ot / obstacle; score terms at D = 2) or the power of two >= 2D (<= 32).  The same sums as
+// row_kinetic in another order of additions; the host picks this form when the step is too small to fill the GPU.
+template <class Net, class DimsT, class Ctx, class SC, class FG>
+__device__ __forceinline__ void row_kinetic_split(const DimsT& dm, const SC& sc, float t, const float* latent,
+                                                  const StepConsts<float>& pc, int G, float* loss_kin, float* loss_pot,
+                                                  FG& gfirst, const RowTiles<float, Net>& tl, Ctx& ctx) {
+  using T = float;
+  constexpr unsigned kAll = 0xffffffffu;
+  const int D = dm.D(), L = dm.L();
+  const unsigned lane = threadIdx.x & 31u, sub = lane & (unsigned)(G - 1), base = lane & ~(unsigned)(G - 1);
+  const bool with_score = pc.type != kOT;
+  const bool need_r3 = with_score || pc.potential == kPotObstacle;
+  const T tq = sub == 0 ? t - pc.dt / (T)2 : (sub == 1 ? t + pc.dt / (T)2 : t);
+  T s[kMaxStateFloats];
+  for (int i = 0; i < D; ++i) s[i] = latent[i];
+  flow_pass<0, T, Net, DimsT, Ctx>(dm, sc, tq, s, tl, ctx);
+  T r1[kMaxDim], r2[kMaxDim], r3[kMaxDim], gq[kMaxDim];
+  for (int i = 0; i < D; ++i) {
+    const T mine = s[L * D + i];
+    r1[i] = __shfl_sync(kAll, mine, base);
+    r2[i] = __shfl_sync(kAll, mine, base | 1u);
+    r3[i] = need_r3 ? __shfl_sync(kAll, mine, base | 2u) : (T)0;
+    gq[i] = (T)0;
+  }
+  if (!with_score) {
+    T acc = (T)0;
+    for (int i = 0; i < D; ++i) {
+      const T v = (r2[i] - r1[i]) / pc.dt;
+      acc += v * v;
+      const T g2 = (T)2 * pc.w_kin * v / pc.dt;
+      gq[i] = sub == 0 ? -g2 : (sub == 1 ? g2 : (T)0);
+    }
+    if (sub == 0) *loss_kin += pc.w_kin * acc;
+    if (pc.potential == kPotObstacle) {
+      T gp[kMaxDim];
+      const T v = potential_value_grad<T>(kPotObstacle, (T)0, r3, D, gp);
+      if (sub == 2) {
+        *loss_pot += pc.w_pot * v;
+        for (int i = 0; i < D; ++i) gq[i] = pc.w_pot * gp[i];
+      }
+    }
+  } else {
+    T truth[kMaxDim];
+    for (int i = 0; i < D; ++i) truth[i] = (T)0;
+    if (pc.type == kFP) drift_value<T>(pc.drift, pc.a, r3, D, truth);
+    const bool active = (int)sub < 2 * D;
+    const int ci = active ? (int)(sub >> 1) : 0;
+    const bool minus = (sub & 1u) != 0u;
+    T sp[kMaxStateFloats];
+    for (int j = 0; j < D; ++j) sp[j] = r3[j];
+    sp[ci] = r3[ci] + (minus ? -pc.dx : pc.dx) / (T)2;
+    const bool stash = ctx.stash_on();   // forward and backward of the same pass, back to back
+    const T ld = flow_pass<1, T, Net, DimsT, Ctx>(dm, sc, t, sp, tl, ctx, stash);
+    const T lp = base_log_prob<T>(sp + L * D, D) + ld;
+    const T lpo = __shfl_xor_sync(kAll, lp, 1);
+    const T score = (minus ? lpo - lp : lp - lpo) / pc.dx;
+    const T resid = (r2[ci] - r1[ci]) / pc.dt + pc.kappa * score - truth[ci];
+    const T gres_mine = active ? (T)2 * pc.w_kin * resid : (T)0;
+    if (active && !minus) *loss_kin += pc.w_kin * resid * resid;
+    const T glp = (minus ? -gres_mine : gres_mine) * pc.kappa / pc.dx;
+    T g[kMaxDim], g3[kMaxDim], gres[kMaxDim];
+    for (int j = 0; j < D; ++j) g[j] = -glp * sp[L * D + j];   // d lp / d latent = -x
+    flow_pass_bwd<1, T, Net, DimsT, Ctx>(dm, sc, t, sp, g, glp, gfirst, tl, ctx, stash);
+    for (int j = 0; j < D; ++j) {
+      T v = g[j];
+      for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(kAll, v, o);
+      g3[j] = v;
+      gres[j] = __shfl_sync(kAll, gres_mine, base | (unsigned)(2 * j));
+    }
+    if (pc.type == kFP) drift_pullback<T>(pc.drift, pc.a, r3, D, gres, g3);
+    for (int i = 0; i < D; ++i) {
+      const T g2 = gres[i] / pc.dt;
+      gq[i] = sub == 0 ? -g2 : (sub == 1 ? g2 : (sub == 2 ? g3[i] : (T)0));
+    }
+  }
+  flow_pass_bwd<0, T, Net, DimsT, Ctx>(dm, sc, tq, s, gq, (T)0, gfirst, tl, ctx);
+}
+#endif
+
 // ---- evaluation energies (forward only) --------------------------------------------------
 // One row's  sum_i v_i^2  of utils.calc_kinetic_energy (with_score = false,
 // /root/reference/cnf_ot/utils.py:311-340: v = (r(t+dt/2) - r(t-dt/2)) / dt) or of
