@@ -716,6 +716,34 @@ def per_config_entry(name, dist, args, pk, pk_src):
   return entry
 
 
+def timeline_block(w, n=24):
+  """Where one step's time goes: %globaltimer stamps written by the kernel itself (cnfot_debug_step_timeline)."""
+  from cnf_ot_b200 import _lib
+  lib = _lib.load()
+  dev = w.out.device
+  init = torch.tensor([-1, 0, -1, 0, 0, 0, 0, 0], dtype=torch.int64)
+  words = torch.empty(n, 8, dtype=torch.int64, device=dev)
+  for i in range(n):
+    words[i].copy_(init)
+  torch.cuda.synchronize()
+  try:
+    for i in range(n):
+      lib.cnfot_debug_step_timeline(words[i].data_ptr())
+      w.step(i)
+  finally:
+    lib.cnfot_debug_step_timeline(None)
+  torch.cuda.synchronize()
+  t = words.cpu().double()[4:]
+  med = lambda x: float(x.median()) / 1e3
+  return {"unit": "us", "kernel_span": med(t[:, 5] - t[:, 0]), "cta_setup": med(t[:, 1] - t[:, 0]),
+          "tiles_until_first_cta_idle": med(t[:, 2] - t[:, 1]), "tiles_until_last_cta_idle": med(t[:, 3] - t[:, 1]),
+          "flush": med(t[:, 4] - t[:, 3]), "reduction_tail": med(t[:, 5] - t[:, 4]),
+          "gap_to_next_kernel": med(t[1:, 0] - t[:-1, 5]),
+          "note": "medians over 20 consecutive steps of the timed workload, stamped by the kernel (tools/step_timeline.py); the "
+                  "tail is reduction (+ all-reduce at N > 1), measured from the last CTA's arrival to the last CTA's exit"}
+
+
+
 def run_ours(args):
   from cnf_ot_b200 import _lib, ops
   dist = Dist()
@@ -824,6 +852,7 @@ def run_ours(args):
   for i in range(3):
     step_rng(i)
   t_rng = statistics.median(timed_reps(dist, step_rng, args.steps, args.reps))
+  timeline = timeline_block(w)
 
   line = None
   if rank == 0:
@@ -831,9 +860,10 @@ def run_ours(args):
     traffic, insts, tsrc = profile_constants()
     rf["roofline"]["traffic"] = traffic
     rf["roofline"]["traffic_source"] = tsrc
-    rf["roofline"]["note"] = ("the fused step kernel is bound by instruction issue, not by HBM or the tensor pipe "
-                              "(SURVEY.md §8d; ncu: profiles/): see roofline_issue / roofline_fp32; the HBM-bound kernels "
-                              "of the path are the stand-alone spline kernels in roofline_spline")
+    rf["roofline"]["note"] = ("the fused step kernel is bound neither by HBM nor by the tensor pipe: it is latency-bound at 16 "
+                              "warps per SM, half of the issue slots used (SURVEY.md §8d; DESIGN.md §4.2; ncu: profiles/): see "
+                              "roofline_issue / roofline_fp32 / step_timeline; the HBM-bound kernels of the path are the "
+                              "stand-alone spline kernels in roofline_spline")
     issue_peak = 148 * 4 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6  # warp instructions / s
     line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -856,6 +886,7 @@ def run_ours(args):
       "gpu_launches": args.steps * args.reps,  # ONE kernel per step: mfc_step_kernel (reduction, all-reduce in its tail)
       "clocks": clk.summary(),
       "parity": parity, "dp_check": dp_check,
+      "step_timeline": timeline,
       "roofline": rf["roofline"],
       "roofline_issue": {"bound": "issue", "kernel": "mfc_step_kernel",
                          "achieved": (insts / t_step / 1e9) if insts else None, "peak": issue_peak / 1e9,

@@ -889,7 +889,6 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   SmemPlan sp;
   int engine;
   if (int rc = make_plan(lay, true, &sp, &engine)) return rc;
-  const void* kernel = find_mfc_step_kernel(lay, engine);
   const int unit = kTile;
 
   // segments, most expensive first (kinetic rows run 3..3+4D passes each)
@@ -919,6 +918,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     if (const char* e = getenv("CNFOT_KINETIC_SPLIT")) split = g <= 32 && e[0] != '0';
     if (split) group = g;
   }
+  const void* kernel = find_mfc_step_kernel(lay, engine, group > 1);
   for (int i = 0; i < n_t; ++i)
     add(group > 1 ? kSegKineticSplit : kSegKinetic, kSlotKinetic, 0, 0, io.rng ? 0.f : io.t_batch_host[i], io.rng ? i : -1,
         io.latent_sub, kRowsNormal, io.row0_b, rows_b, group);

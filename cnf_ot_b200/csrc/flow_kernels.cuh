@@ -600,7 +600,10 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   }
 }
 
-template <class Net, class DimsT, int ENG>
+// SPLIT: the kinetic segments are of kind kSegKineticSplit (row_kinetic_split: the passes of a row spread over a lane
+// group; the host picks this instantiation for steps too small to fill the GPU), else kSegKinetic (row_kinetic).  Two
+// kernels rather than one branch: either routine inlined next to the other costs the common path registers.
+template <class Net, class DimsT, int ENG, bool SPLIT = false>
 __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch4[kWarps][4];
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
     int si = 0;
     while (si + 1 < a.n_seg && tile >= a.seg[si + 1].first_tile) ++si;
     const Segment& sg = a.seg[si];
-    const bool split = sg.kind == kSegKineticSplit;   // the lanes of a group share a row
+    const bool split = SPLIT && sg.kind == kSegKineticSplit;   // the lanes of a group share a row
     const int64_t r = split ? (tile - sg.first_tile) * (kTile / sg.group) + (int)threadIdx.x / sg.group
                             : (tile - sg.first_tile) * kTile + ctx.row_in_tile();
     const bool live = r < sg.n;
@@ -678,20 +681,16 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_s
                                                           sg.do_pot != 0, pc, &lf, &lp, gfirst, tl, ctx);
       loss[sg.slot] += (double)lf;
       loss[kSlotPotential] += (double)lp;
-    } else if (split) {
-      StepConsts<float> pc = a.pc;
-      if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
-      float lk = 0.f, lp = 0.f;
-      row_kinetic_split<Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, sg.group, &lk, &lp, gfirst,
-                                         tl, ctx);
-      loss[kSlotKinetic] += (double)lk;
-      loss[kSlotPotential] += (double)lp;
     } else {
       StepConsts<float> pc = a.pc;
       if (!live) { pc.w_kin = 0.f; pc.w_pot = 0.f; }
       float lk = 0.f, lp = 0.f;
-      row_kinetic<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, &lk, &lp, gfirst,
-                                                     tl, ctx);
+      if constexpr (SPLIT)
+        row_kinetic_split<Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, sg.group, &lk, &lp,
+                                           gfirst, tl, ctx);
+      else
+        row_kinetic<float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), tval, row, pc, &lk, &lp, gfirst,
+                                            tl, ctx);
       loss[kSlotKinetic] += (double)lk;
       loss[kSlotPotential] += (double)lp;
     }

@@ -1,0 +1,3 @@
+// The fused train-step kernel with split kinetic rows (flow_kernels.cuh: SPLIT), engine "mma".
+#define CNFOT_STEP_SPLIT 1
+#include "step_mma.cu"

@@ -63,6 +63,33 @@ def test_loss_and_gradient(typ, sub, kw, engine):
   assert float((G - Gor).abs().max() / Gor.abs().max()) <= TOL_GRAD
 
 
+@pytest.mark.parametrize("typ,sub,kw", [("ot", "free", {}), ("ot", "obstacle", {}), ("rwpo", "double_well", {}),
+                                        ("fp", "nongradient", {}), ("fp", "lorenz", dict(dim=3, L=3, sigma=0.1)),
+                                        ("fp", "nongradient", dict(dim=10, sigma=0.05, B=320)),
+                                        ("rwpo", "quadratic", dict(dim=4, H=32, K=8, sigma=0.1, B=320))])
+def test_kinetic_row_forms_agree(typ, sub, kw, monkeypatch):
+  """The two forms of the kinetic rows -- one thread per row (row_kinetic: what large batches run) and the passes of a
+  row spread over a lane group (row_kinetic_split: what small steps run) -- against the oracle and against each other."""
+  kw = dict(kw)
+  sigma = kw.pop("sigma", 0.3)
+  cfg = make_cfg(typ, sub, Tn=2, lam=500.0, **({"B": 1024 + 64} | kw))
+  shape = shape_of(cfg)
+  spec, params = make_params(cfg, sigma)
+  inputs = make_inputs(cfg)
+  loss, grads = olosses.value_and_grad(cfg, spec, params, inputs)
+  Gor = pack(shape, grads, torch.float64)
+  outs = {}
+  for form in ("0", "1"):
+    monkeypatch.setenv("CNFOT_KINETIC_SPLIT", form)
+    out = run_gpu(cfg, shape, params, inputs, 500.0)
+    G, slots = out[:shape.blob_size], out[shape.blob_size:]
+    assert abs(float(slots[0]) - float(loss)) <= TOL_LOSS * abs(float(loss)), (form, float(slots[0]), float(loss))
+    assert float((G - Gor).abs().max() / Gor.abs().max()) <= TOL_GRAD, form
+    outs[form] = out
+  d = (outs["0"] - outs["1"])[:shape.blob_size].abs().max() / Gor.abs().max()
+  assert float(d) <= TOL_GRAD
+
+
 def test_shards_sum_to_whole_batch():
   """Data-parallel contract: out buffers of row shards add up to the
   whole-batch loss and gradient."""
