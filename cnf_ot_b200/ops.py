@@ -341,23 +341,42 @@ def mfc_step_rng(shape: FlowShape, problem: _lib.ProblemDesc, weights, key: int,
   return out
 
 
+_rng_host_cache = {}
+
+
 def mfc_step_rng_host(shape: FlowShape, problem: _lib.ProblemDesc, weights_host, key: int, step: int, n_t: int, lam: float,
                       global_B: int, global_b: int, out_host: torch.Tensor, device=None) -> torch.Tensor:
-  """The same with HOST weights in and HOST [gradient | loss] out (transfers and a stream synchronisation inside)."""
-  lib = _lib.load()
-  device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+  """The same with HOST weights in and HOST [gradient | loss] out (transfers and a stream synchronisation inside).
+  The per-(flow shape, device, stream) set-up (descriptor, persistent workspace) is cached: a call is one ctypes call."""
   for name, t in (("weights", weights_host), ("out", out_host)):
     if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
       raise _lib.CnfotError(f"{name}: expected a contiguous float32 host tensor")
-  desc = _lib.flow_desc(shape)
-  nbytes = lib.cnfot_mfc_step_rng_host_workspace_bytes(desc)
-  if nbytes < 0:
-    _lib.check(1)
-  ws = _workspace(nbytes, device)
-  with torch.cuda.device(device):
-    _lib.check(lib.cnfot_mfc_step_rng_host(_stream(), desc, problem, _ptr(weights_host), int(key) & (2**64 - 1),
-                                           int(step) & 0xFFFFFFFF, int(n_t), 0, global_B, 0, global_b, global_B,
-                                           global_b, float(lam), _ptr(out_host), ws.data_ptr(), ws.numel()))
+  index = torch.cuda.current_device() if device is None else torch.device(device).index
+  if index is None:
+    index = torch.cuda.current_device()
+  stream = torch.cuda.current_stream(index).cuda_stream
+  ck = (shape, index, stream)
+  ent = _rng_host_cache.get(ck)
+  if ent is None:
+    lib = _lib.load()
+    desc = _lib.flow_desc(shape)
+    nbytes = lib.cnfot_mfc_step_rng_host_workspace_bytes(desc)
+    if nbytes < 0:
+      _lib.check(1)
+    dev = torch.device("cuda", index)
+    with torch.cuda.device(index):
+      ws = _step_workspace(shape, desc, nbytes, dev)   # persistent: no memset between two calls
+    ent = (lib, desc, ws, ws.data_ptr(), ws.numel())
+    _rng_host_cache[ck] = ent
+  lib, desc, ws, ws_ptr, ws_bytes = ent
+  args = (stream, desc, problem, weights_host.data_ptr(), int(key) & (2**64 - 1), int(step) & 0xFFFFFFFF, int(n_t), 0,
+          global_B, 0, global_b, global_B, global_b, float(lam), out_host.data_ptr(), ws_ptr, ws_bytes)
+  if torch.cuda.current_device() == index:
+    rc = lib.cnfot_mfc_step_rng_host(*args)
+  else:
+    with torch.cuda.device(index):
+      rc = lib.cnfot_mfc_step_rng_host(*args)
+  _lib.check(rc)
   return out_host
 
 
