@@ -441,12 +441,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // optax.adam (scale_by_adam + scale(-lr); cnf_ot/mfc/solvers.py:55,95-96) of one parameter
-__device__ __forceinline__ void adam_one(const TailArgs& t, int i, float g, float c1, float c2) {
-  const float mi = t.b1 * t.adam_m[i] + (1.f - t.b1) * g;
-  const float vi = t.b2 * t.adam_v[i] + (1.f - t.b2) * g * g;
+// (m0, v0, w0: the old moments and parameter, loaded by the caller together with the partial rows: one L2 round trip)
+__device__ __forceinline__ void adam_one(const TailArgs& t, int i, float g, float c1, float c2, float m0, float v0, float w0) {
+  const float mi = t.b1 * m0 + (1.f - t.b1) * g;
+  const float vi = t.b2 * v0 + (1.f - t.b2) * g * g;
   t.adam_m[i] = mi;
   t.adam_v[i] = vi;
-  t.weights[i] -= t.lr * (mi / c1) / (sqrtf(vi / c2) + t.eps);
+  t.weights[i] = w0 - t.lr * (mi / c1) / (sqrtf(vi / c2) + t.eps);
 }
 
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -463,7 +464,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 // Reduction: one THREAD per output column sums the (<= 32) partial rows of its column -- up to 16 coalesced loads in
 // flight, no shared memory, no barrier -- so the whole buffer is one pass of ceil(columns / 128) CTAs.  The CTAs that
 // stay are the FIRST n_tail to finish their tiles: everything that does not depend on the other CTAs (the state words,
-// Adam's bias corrections -- two double-precision pow()) is done while they wait, and what remains after the last CTA
+// Adam's bias corrections) is done while they wait, and what remains after the last CTA
 // has arrived is one L2 round trip, the update and the stores.  (The round-2 start had the last n_tail arrivals run a
 // slice-per-CTA reduction over shared memory: 8 us at 592 CTAs, 20 us of a 50 us step at 32 CTAs.)
 // Exchange (world > 1): the column's sum is written into every peer's buffer as ONE 64-bit {value, epoch} word (an
@@ -491,8 +492,11 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   }
   float c1 = 1.f, c2 = 1.f;
   if (t.weights) {
-    c1 = (float)(1.0 - pow((double)t.b1, (double)stepno + 1.0));
-    c2 = (float)(1.0 - pow((double)t.b2, (double)stepno + 1.0));
+    // 1 - b^(step + 1) without the cancellation: -expm1((step + 1) log b); float32 is accurate to ~2e-7 relative here
+    // (optax itself evaluates 1 - b ** count in float32), and two double-precision pow() were 2 us of a small step's tail
+    const float n1 = (float)stepno + 1.f;
+    c1 = -expm1f(n1 * logf(t.b1));
+    c2 = -expm1f(n1 * logf(t.b2));
   }
   const size_t par_off = (size_t)(epoch & 1u) * t.pa.world * t.pa.stride;
   if (tid == 0) {
@@ -501,10 +505,10 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   }
   __syncthreads();
 
-  auto finish = [&](int col, float v) {   // the owner of an output column
+  auto finish = [&](int col, float v, float m0, float v0, float w0) {   // the owner of an output column
     if (col < total) {
       if (t.out) t.out[col] = t.accumulate ? t.out[col] + v : v;
-      if (t.weights && v == v) adam_one(t, col, v, c1, c2);   // a poisoned (NaN) gradient leaves the parameters alone
+      if (t.weights && v == v) adam_one(t, col, v, c1, c2, m0, v0, w0);   // a poisoned (NaN) gradient leaves the parameters alone
     } else {
       const int sl = col - total;
       if (t.out) t.out[col] = sl <= 4 ? (t.accumulate ? t.out[col] + v : v) : 0.f;
@@ -523,6 +527,10 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   for (int col = k * (int)(blockDim.x >> 2) + (tid >> 2); col < n_cols; col += stride_cols) {
     // phase A: this quad's column of the partial rows -> one float (sent to the peers, or final)
     double acc = 0.0;
+    float m0 = 0.f, v0 = 0.f, w0 = 0.f;
+    if (t.weights && owner && col < total) {   // in flight together with the partial rows
+      m0 = __ldcg(t.adam_m + col); v0 = __ldcg(t.adam_v + col); w0 = __ldcg(t.weights + col);
+    }
     if (col < total) {
       float* p = t.grad_rows + col;
       for (int r0 = rg; r0 < t.n_rows; r0 += 32) {
@@ -548,7 +556,7 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
     if (!owner || col >= n_out) continue;
     const float mine = (float)acc;
     if (!dp) {
-      finish(col, mine);
+      finish(col, mine, m0, v0, w0);
       continue;
     }
     const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
@@ -581,7 +589,7 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
       t.sync[kSyncStatus] = 1u;
       sum = __int_as_float(0x7fc00000);
     }
-    finish(col, sum);
+    finish(col, sum, m0, v0, w0);
   }
   __syncthreads();
   if (tid == 0) {
