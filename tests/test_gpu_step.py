@@ -105,6 +105,54 @@ def test_shards_sum_to_whole_batch():
   assert float((tot - whole).abs().max() / whole.abs().max()) < 2e-6
 
 
+def test_persistent_workspace_and_plain_workspace_agree(monkeypatch):
+  """C ABI: a workspace registered with cnfot_workspace_register is left clean by every step (no memset between two
+  calls, back-to-back launches with programmatic stream serialisation); an unregistered one is zeroed per call.  Same
+  results either way, with and without CNFOT_PDL, for consecutive calls of different batch sizes on the same buffer."""
+  import ctypes
+  from cnf_ot_b200 import _lib
+  lib = _lib.load()
+  cfg = make_cfg("ot", "obstacle", B=4096)
+  shape = shape_of(cfg)
+  _, params = make_params(cfg, 0.3)
+  inputs = make_inputs(cfg)
+  desc, prob = _lib.flow_desc(shape), ops.problem_desc(cfg)
+  W = pack(shape, params).cuda()
+  f = lambda t: t.float().cuda().contiguous()
+  sub, src, tgt = f(inputs["latent"][:128]), f(inputs["src"]), f(inputs["tgt"])
+  tb = torch.tensor([0.3], dtype=torch.float32)
+  nbytes = lib.cnfot_mfc_step_workspace_bytes(desc, 4096, 128, 1)
+  stream = torch.cuda.current_stream().cuda_stream
+
+  def call(ws, rows, out):
+    _lib.check(lib.cnfot_mfc_step(stream, desc, prob, W.data_ptr(), None, sub[:rows // 32].data_ptr(), src[:rows].data_ptr(),
+                                  tgt[:rows].data_ptr(), tb.data_ptr(), 1, rows, rows // 32, rows, rows // 32, 5000.0,
+                                  out.data_ptr(), ws.data_ptr(), ws.numel()))
+
+  plain = torch.full((nbytes,), 0x5A, dtype=torch.uint8, device="cuda")   # garbage: the call must clear what it uses
+  ref = {}
+  for rows in (4096, 1024):
+    ref[rows] = torch.empty(shape.blob_size + 8, device="cuda")
+    call(plain, rows, ref[rows])
+  torch.cuda.synchronize()
+  ws = torch.full((nbytes,), 0x5A, dtype=torch.uint8, device="cuda")
+  _lib.check(lib.cnfot_workspace_register(stream, desc, ws.data_ptr(), ws.numel()))
+  try:
+    for pdl in ("1", "0"):
+      monkeypatch.setenv("CNFOT_PDL", pdl)   # read once per process: this only documents that both paths are legal
+      for rows in (4096, 1024, 4096, 4096, 1024):
+        out = torch.empty(shape.blob_size + 8, device="cuda")
+        call(ws, rows, out)
+        torch.cuda.synchronize()
+        assert float((out - ref[rows]).abs().max() / ref[rows].abs().max()) < 2e-6, (pdl, rows)
+  finally:
+    lib.cnfot_workspace_release(ws.data_ptr())
+  out = torch.empty(shape.blob_size + 8, device="cuda")
+  call(ws, 4096, out)   # released: zeroed per call again
+  torch.cuda.synchronize()
+  assert float((out - ref[4096]).abs().max() / ref[4096].abs().max()) < 2e-6
+
+
 def test_host_entry_matches_device_entry():
   cfg = make_cfg("ot", "obstacle", B=2048)
   shape = shape_of(cfg)
