@@ -584,8 +584,20 @@ def dense_roofline(dev, pk, pk_src):
   tk = time_region(fn, 20, torch.cuda.synchronize) / 20
   tf32_peak = float(pk.get("bf16_tflops_sustained", 1392.5)) / 2.0
   pipe = 3 * 2.0 * rows * H * H / tk / 1e12   # tf32 MMA flops issued (3 per fp32-fidelity product)
+  traffic, tsrc = None, "no profiles/traffic.json entry"
+  tpath = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tpath):
+    with open(tpath) as f:
+      tj = json.load(f)
+    if tj.get("csrc_sha16") == kernel_fingerprint() and tj.get("dense_tc_kernel_256_1_dram_bytes_per_launch"):
+      # captured on 2^18 rows: the kernel streams X once and writes Y once, so the bytes scale with the rows
+      traffic = int(tj["dense_tc_kernel_256_1_dram_bytes_per_launch"] * rows / float(1 << 18))
+      tsrc = tj.get("dense_tc_kernel_source", "") + f", 2^18 rows, scaled to {rows} rows"
+    else:
+      tsrc = "profiles/traffic.json was captured from other kernel sources: not used"
   return {"bound": "tensor", "kernel": "dense_tc_kernel<256,1> (hidden layer, rows x 512 x 512, timed alone)",
-          "achieved": pipe, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pipe / tf32_peak, "traffic": None,
+          "achieved": pipe, "peak": tf32_peak, "unit": "TFLOP/s", "frac": pipe / tf32_peak, "traffic": traffic,
+          "traffic_source": tsrc, "algorithmic_bytes_per_launch": 2 * rows * H * 4 + 2 * H * H * 4,
           "peak_source": pk_src + ": bf16_tflops_sustained / 2 (tf32)", "fp32_fidelity_tflops": pipe / 3,
           "us_per_launch": tk * 1e6}
 
