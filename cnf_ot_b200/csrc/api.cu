@@ -964,9 +964,13 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     if (v >= 1 && v <= (persistent ? kStepRows : kMaxGrid)) t.n_rows = v < cfg.grid ? v : cfg.grid;
   }
   // CTAs that stay for the reduction (the first to finish their tiles): four threads per output column
+  // The waiting CTAs hold their SM slots until every CTA of the grid has arrived, so they must stay a fraction of
+  // what is resident: at most half of a grid that spans more than one CTA per SM (a GPU shared with another kernel may
+  // not hold all of it at once; the CTAs that exit make room for the rest), all of a smaller one.
   int n_tail = (lay.total + kNumSlots + kTile / 4 - 1) / (kTile / 4);
   if (n_tail > cfg.grid) n_tail = cfg.grid;
-  if (n_tail > 2 * 148) n_tail = 2 * 148;   // waiting CTAs hold SM slots: keep them a fraction of the resident grid
+  if (cfg.grid > 148 && n_tail > cfg.grid / 2) n_tail = cfg.grid / 2;
+  if (n_tail > 2 * 148) n_tail = 2 * 148;
   if (n_tail < 1) n_tail = 1;
   t.n_tail = n_tail;
   t.total = lay.total;
