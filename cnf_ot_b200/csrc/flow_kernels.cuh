@@ -20,14 +20,29 @@ enum Engine { kEngCuda = 0, kEngTc = 1, kEngMma = 2, kEngMmaStream = 3, kEngWide
 #define CNFOT_MMA_MIN_CTAS 4
 #endif
 constexpr int kMmaMinCtas = CNFOT_MMA_MIN_CTAS;   // register budget of the warp-MMA kernels: 65536 / (128 * n)
-template <class Net, int ENG>
+// The train-step kernel runs THREE CTAs (12 warps) per SM at up to 168 registers: measured on B200 against four at 128
+// (round 1 and most of round 2) -- cfg 2 0.1467 vs 0.1501 ms, cfg 3 0.602 vs 0.655, cfg 4 (2^19 rows) 4.26 vs 4.70: the
+// kernel is latency-bound and register-starved (spills, context members re-loaded from local memory after every asm
+// memory clobber), and a warp with 168 registers is a third faster than one with 128.  Five CTAs at 102: 0.178 ms.
+#ifndef CNFOT_STEP_MIN_CTAS
+#define CNFOT_STEP_MIN_CTAS 3
+#endif
+constexpr int kStepMinCtas = CNFOT_STEP_MIN_CTAS;
+// ... and TWO (8 warps, up to 255 registers) on the streamed plan (flows too large for resident fragments, e.g. dim 10):
+// cfg 4 at 2^19 rows 3.93 ms vs 4.25 at three and 4.70 at four (the resident plan is slower at two: cfg 2 0.174 ms).
+#ifndef CNFOT_STEP_MIN_CTAS_STREAM
+#define CNFOT_STEP_MIN_CTAS_STREAM 2
+#endif
+constexpr int kStepMinCtasStream = CNFOT_STEP_MIN_CTAS_STREAM;
+// DC, LC: compile-time flow shape (0 = runtime), passed by the train-step kernel only (warp_mlp.cuh: kConstPlan)
+template <class Net, int ENG, int DC = 0, int LC = 0>
 struct CtxSelect { using type = DeviceCtx<Net>; };
-template <class Net>
-struct CtxSelect<Net, kEngTc> { using type = DeviceCtxTC<Net>; };
-template <class Net>
-struct CtxSelect<Net, kEngMma> { using type = DeviceCtxMma<Net, true>; };
-template <class Net>
-struct CtxSelect<Net, kEngMmaStream> { using type = DeviceCtxMma<Net, false>; };
+template <class Net, int DC, int LC>
+struct CtxSelect<Net, kEngTc, DC, LC> { using type = DeviceCtxTC<Net>; };
+template <class Net, int DC, int LC>
+struct CtxSelect<Net, kEngMma, DC, LC> { using type = DeviceCtxMma<Net, true, DC, LC>; };
+template <class Net, int DC, int LC>
+struct CtxSelect<Net, kEngMmaStream, DC, LC> { using type = DeviceCtxMma<Net, false>; };
 
 template <class Ctx>
 __device__ __forceinline__ void ctx_setup(Ctx& ctx, int D, int L, uint64_t* mbar, uint32_t* slot) {
@@ -612,13 +627,14 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
 // group; the host picks this instantiation for steps too small to fill the GPU), else kSegKinetic (row_kinetic).  Two
 // kernels rather than one branch: either routine inlined next to the other costs the common path registers.
 template <class Net, class DimsT, int ENG, bool SPLIT = false>
-__global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) mfc_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kTile, ENG == kEngMmaStream ? kStepMinCtasStream : (ENG >= kEngMma ? kStepMinCtas : 1))
+mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch4[kWarps][4];
   __shared__ long long s_tile;
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
-  using Ctx = typename CtxSelect<Net, ENG>::type;
+  using Ctx = typename CtxSelect<Net, ENG, DimsT::kD, DimsT::kL>::type;
   // Programmatic dependent launch (api.cu: launch_step_kernel): this grid may have been scheduled while the previous
   // kernel of the stream was still in its tail; nothing is read or written before that kernel has completed.
   asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -70,6 +70,7 @@ struct NetCfg {
 // Runtime (DC == 0) or compile-time (DC > 0) flow shape.
 template <int DC, int LC>
 struct Dims {
+  static constexpr int kD = DC, kL = LC;   // > 0: compile-time
   int D_, L_;
   CNFOT_HD int D() const { return DC > 0 ? DC : D_; }
   CNFOT_HD int L() const { return LC > 0 ? LC : L_; }

@@ -227,10 +227,45 @@ struct MmaLane {
   }
 };
 
-template <class Net, bool RES>
+// Shared-window address of the CTA's dynamic shared memory: every `extern __shared__` array starts there, and the
+// address is a link-time constant.
+__device__ __forceinline__ uint32_t dyn_smem_base() {
+  extern __shared__ __align__(1024) float cnfot_dyn_smem[];
+  return (uint32_t)__cvta_generic_to_shared(cnfot_dyn_smem);
+}
+__device__ __forceinline__ float* dyn_smem_ptr() {
+  extern __shared__ __align__(1024) float cnfot_dyn_smem[];
+  return cnfot_dyn_smem;
+}
+
+// DC, LC > 0 (the train-step kernel specialised for the mfc.yaml flow, resident plan, with gradients): the shared-memory
+// plan is a compile-time constant, so the tile / weight / fragment / knot addresses the engine needs all the time are
+// immediates (+ the warp index) instead of members of a context that lives in the caller's local memory and has to be
+// re-loaded after every asm memory clobber (a quarter of the kernel's long-scoreboard stalls, tools/ncu_stall_lines.py).
+template <class Net, bool RES, int DC = 0, int LC = 0>
 struct DeviceCtxMma {
   using NetT = Net;
   using Ref = WRef<RES>;
+  static constexpr bool kConstPlan = RES && DC > 0 && LC > 0;
+  // mirror of plan_smem_mma(f, with_grad = true, resident = true), in floats
+  static constexpr int kcW = 0;
+  static constexpr int kcCw = Net::kPp + LC * (16 * ((DC - 1) * (DC + 2) / 2) + (DC - 1) * (Net::kM + 1) * 16);
+  static constexpr int kcFrag = (kcCw + 31) / 32 * 32;
+  static constexpr int kcWt = kcFrag + LC * (DC - 1) * Net::kM * kFragFloats;
+  static constexpr int kcWtStride = (Net::kM + 1) * kWtFloats;
+  static constexpr int kcFk = kcWt + kWarps * kcWtStride;
+  __device__ __forceinline__ Ref wref() const {
+    if constexpr (kConstPlan) return Ref{dyn_smem_base() + (uint32_t)kcW * 4u};
+    else return w_ref;
+  }
+  __device__ __forceinline__ Ref fref() const {
+    if constexpr (kConstPlan) return Ref{dyn_smem_base() + (uint32_t)kcFrag * 4u};
+    else return frag_ref;
+  }
+  __device__ __forceinline__ uint32_t swt() const {
+    if constexpr (kConstPlan) return dyn_smem_base() + ((uint32_t)kcWt + (threadIdx.x >> 5) * (uint32_t)kcWtStride) * 4u;
+    else return s_wt;
+  }
   static constexpr bool kWarpMlp = true;
   static constexpr bool kAccInGlobal = true;
   static constexpr int H = Net::kH, M = Net::kM, Pp = Net::kPp;
@@ -294,6 +329,11 @@ struct DeviceCtxMma {
   __device__ __forceinline__ void setup(int D, int L, uint64_t*, uint32_t*) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     s_wt = s0 + (p.off_wt + (threadIdx.x >> 5) * p.wt_stride) * 4;
+    if constexpr (kConstPlan) {   // the host's plan must be the one compiled in
+      if (D != DC || L != LC || p.off_w != kcW || p.off_frag != kcFrag || p.off_wt != kcWt || p.wt_stride != kcWtStride ||
+          p.off_fk != kcFk || smem != dyn_smem_ptr())
+        __trap();
+    }
     if (gacc && clear_acc)
       for (int i = threadIdx.x; i < p.total; i += blockDim.x) gacc[i] = 0.f;
     if constexpr (RES) {
@@ -360,7 +400,8 @@ struct DeviceCtxMma {
 
   __device__ __forceinline__ const float* first_params() const { return smem + p.off_w; }
   __device__ __forceinline__ const FirstKnots<float, Net::kK>& first_knots() const {
-    return *reinterpret_cast<const FirstKnots<float, Net::kK>*>(smem + p.off_fk);
+    if constexpr (kConstPlan) return *reinterpret_cast<const FirstKnots<float, Net::kK>*>(dyn_smem_ptr() + kcFk);
+    else return *reinterpret_cast<const FirstKnots<float, Net::kK>*>(smem + p.off_fk);
   }
 
   // ---- register layouts of a [32 x 16] matrix (thread (g, t); mt = m-tile, nt / ks = 8-column block)
@@ -470,11 +511,11 @@ struct DeviceCtxMma {
                                                float* theta, bool keep, bool put = false) const {
     float* sq = put ? stash_of(D, layer, d) : nullptr;
     const MmaLane ln;
-    const uint32_t wt = s_wt;
+    const uint32_t wt = swt();
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
-    const Ref W = w_ref + (RES ? cw_offset(D, M, Pp, layer, d) : mlp_offset<Net>(D, layer, d));
+    const Ref W = wref() + (RES ? cw_offset(D, M, Pp, layer, d) : mlp_offset<Net>(D, layer, d));
     const Ref b0 = W + n_in * H;
-    const Ref frag = frag_ref + mlp * M * kFragFloats;
+    const Ref frag = fref() + mlp * M * kFragFloats;
     float x[2][2][4], a[2][2][4];
     {
       const float2 c0 = (b0 + 2 * ln.t).ld2();
@@ -530,7 +571,7 @@ struct DeviceCtxMma {
   __device__ __forceinline__ void cond_restore(int D, int layer, int d, SplineState<float, Net::kK>& st, float min_slope) const {
     constexpr int K = Net::kK;
     const MmaLane ln;
-    const uint32_t wt = s_wt;
+    const uint32_t wt = swt();
     const float* sq = stash_of(D, layer, d);
     float4 f[kStashChunks];
 #pragma unroll
@@ -634,12 +675,12 @@ struct DeviceCtxMma {
   __device__ __forceinline__ void cond_backward(int D, int layer, int d, float tval, const float* cvec,
                                                 const float* gtheta, float* gvec) const {
     const MmaLane ln;
-    const uint32_t wt = s_wt;
+    const uint32_t wt = swt();
     const int n_in = d + 1, mlp = layer * (D - 1) + d - 1;
     const int w_off = mlp_offset<Net>(D, layer, d);
-    const Ref W = w_ref + (RES ? cw_offset(D, M, Pp, layer, d) : w_off);
+    const Ref W = wref() + (RES ? cw_offset(D, M, Pp, layer, d) : w_off);
     float* A = gacc + w_off;
-    const Ref frag = frag_ref + (mlp * M * kFragFloats + 512);
+    const Ref frag = fref() + (mlp * M * kFragFloats + 512);
     const uint32_t tg = wt + M * kWtFloats * 4;
     __syncwarp();
     store_row(tg, ln, gtheta);
