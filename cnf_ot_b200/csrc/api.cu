@@ -918,7 +918,14 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
     if (const char* e = getenv("CNFOT_KINETIC_SPLIT")) split = g <= 32 && e[0] != '0';
     if (split) group = g;
   }
-  const void* kernel = find_mfc_step_kernel(lay, engine, group > 1);
+  // streamed plan: few rounds of tiles -> the long kinetic tiles set the time: the two-CTAs-per-SM instantiation
+  bool latency = false;
+  {
+    const int64_t fit_tiles = (problem->type == CNFOT_FP ? 1 : 2) * ((rows_B + unit - 1) / unit);
+    latency = fit_tiles + (int64_t)n_t * ((rows_b + unit - 1) / unit) < 8 * 4 * 148;
+    if (const char* e = getenv("CNFOT_STEP_LATENCY")) latency = e[0] != '0';
+  }
+  const void* kernel = find_mfc_step_kernel(lay, engine, group > 1, latency);
   for (int i = 0; i < n_t; ++i)
     add(group > 1 ? kSegKineticSplit : kSegKinetic, kSlotKinetic, 0, 0, io.rng ? 0.f : io.t_batch_host[i], io.rng ? i : -1,
         io.latent_sub, kRowsNormal, io.row0_b, rows_b, group);

@@ -14,7 +14,8 @@ namespace cnfot {
 // for hidden == 16 and num_bins == 5 only (tc_available()).
 const void* find_flow_eval_kernel(const FlowLayout& f, int engine = 0);
 const void* find_flow_vjp_kernel(const FlowLayout& f, int engine = 0);
-const void* find_mfc_step_kernel(const FlowLayout& f, int engine = 0, bool split = false);   // split: flow_kernels.cuh SPLIT
+// split: flow_kernels.cuh SPLIT; latency: the two-CTAs-per-SM instantiation of the streamed plan (LAT)
+const void* find_mfc_step_kernel(const FlowLayout& f, int engine = 0, bool split = false, bool latency = false);
 const void* find_energy_kernel(const FlowLayout& f, int engine = 0);
 const void* find_density_kernel(const FlowLayout& f, int engine = 0);
 inline bool tc_available(const FlowLayout& f) { return f.H == 16 && f.K == 5 && f.D >= 2 && f.M <= 3; }

@@ -28,12 +28,12 @@ constexpr int kMmaMinCtas = CNFOT_MMA_MIN_CTAS;   // register budget of the warp
 #define CNFOT_STEP_MIN_CTAS 3
 #endif
 constexpr int kStepMinCtas = CNFOT_STEP_MIN_CTAS;
-// ... and TWO (8 warps, up to 255 registers) on the streamed plan (flows too large for resident fragments, e.g. dim 10):
-// cfg 4 at 2^19 rows 3.93 ms vs 4.25 at three and 4.70 at four (the resident plan is slower at two: cfg 2 0.174 ms).
-#ifndef CNFOT_STEP_MIN_CTAS_STREAM
-#define CNFOT_STEP_MIN_CTAS_STREAM 2
-#endif
-constexpr int kStepMinCtasStream = CNFOT_STEP_MIN_CTAS_STREAM;
+// The streamed plan (flows too large for resident fragments, e.g. dim 10) has two instantiations: FOUR CTAs per SM for
+// throughput and TWO (8 warps, up to 255 registers: the fastest single warp) for steps of few tile rounds, where the
+// long kinetic tiles set the time -- cfg 4 (ms per step at 2^19 / 2^20 / 2^22 rows): two CTAs 3.93 / 7.76 / 30.8, three
+// 4.28 / 5.98 / 23.7, four 4.75 / 5.55 / 21.5.  The host picks (api.cu: mfc_step_impl).
+constexpr int kStepMinCtasStream = 4;
+constexpr int kStepMinCtasStreamLatency = 2;
 // DC, LC: compile-time flow shape (0 = runtime), passed by the train-step kernel only (warp_mlp.cuh: kConstPlan)
 template <class Net, int ENG, int DC = 0, int LC = 0>
 struct CtxSelect { using type = DeviceCtx<Net>; };
@@ -626,8 +626,9 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
 // SPLIT: the kinetic segments are of kind kSegKineticSplit (row_kinetic_split: the passes of a row spread over a lane
 // group; the host picks this instantiation for steps too small to fill the GPU), else kSegKinetic (row_kinetic).  Two
 // kernels rather than one branch: either routine inlined next to the other costs the common path registers.
-template <class Net, class DimsT, int ENG, bool SPLIT = false>
-__global__ void __launch_bounds__(kTile, ENG == kEngMmaStream ? kStepMinCtasStream : (ENG >= kEngMma ? kStepMinCtas : 1))
+template <class Net, class DimsT, int ENG, bool SPLIT = false, bool LAT = false>
+__global__ void __launch_bounds__(kTile, ENG == kEngMmaStream ? (LAT || SPLIT ? kStepMinCtasStreamLatency : kStepMinCtasStream)
+                                                              : (ENG >= kEngMma ? kStepMinCtas : 1))
 mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch4[kWarps][4];
