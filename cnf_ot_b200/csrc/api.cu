@@ -981,6 +981,7 @@ static int mfc_step_impl(void* stream, const cnfot_flow_desc* flow, const cnfot_
   if (n_tail < 1) n_tail = 1;
   t.n_tail = n_tail;
   t.total = lay.total;
+  t.n_tiles = tiles;
   t.accumulate = io.accumulate ? 1 : 0;
   t.out = io.out;
   if (io.stateful) {

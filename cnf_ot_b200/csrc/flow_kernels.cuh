@@ -384,7 +384,13 @@ struct Segment {
 constexpr int kMaxSegments = 36;
 
 // header words (uint32) of the step workspace / train state
-enum SyncWord { kSyncTile = 0 /* 64-bit: words 0, 1 */, kSyncDone = 2, kSyncTailDone = 3, kSyncStatus = 4 };
+// Counters are MONOTONIC across launches: kSyncTile (tile claims) and kSyncDone (arrived CTAs) are never reset; their
+// values at the start of a launch are kept in kSyncTileBase / kSyncDoneBase, and kSyncSeq counts launches (its parity
+// selects which half of the loss row a launch adds into).  All three are advanced by ONE thread of the tail (the first
+// tail CTA) once every CTA has arrived -- every CTA read them when it started -- so a launch ends when its last column
+// is written, with no "who is last" election.  A zeroed header (memset, cnfot_workspace_register) is a valid state.
+enum SyncWord { kSyncTile = 0 /* 64-bit: words 0, 1 */, kSyncDone = 2, kSyncStatus = 4, kSyncDoneBase = 5, kSyncSeq = 6,
+                kSyncTileBase = 8 /* 64-bit: words 8, 9 */ };
 constexpr int kStateWordOffset = 16;   // 64-bit words [key, step, epoch] start at byte 128 of the header
 constexpr int kLossRowOffset = 24;     // 8 doubles at byte 192 of the header
 constexpr int kStepRows = 32;          // partial gradient rows of the step kernel (CTA b adds into row b mod 32)
@@ -404,6 +410,7 @@ struct TailArgs {
   int total;           // gradient floats
   int accumulate;      // out += result (chunked host entry)
   int self_clean;      // zero what was read (device-resident update: the next launch needs no memset)
+  long long n_tiles;   // tiles of this launch (the tile counter advances by n_tiles + gridDim.x)
   uint32_t* sync;      // header words
   double* loss_row;    // [kNumSlots], atomically accumulated
   float* grad_rows;    // [n_rows][total]
@@ -487,24 +494,26 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 // latency of one NVLink write), and the same thread spins on the epoch of each peer's word for that column.
 // Buffers are double-buffered by the epoch's parity: a rank can be at most one step ahead of a peer, because
 // finishing a step needs every peer's words of that step.
-static __device__ __noinline__ void step_tail(const TailArgs& t) {
+struct LaunchHeader {   // the header words of the previous launch's end, read once per CTA (thread 0 -> shared memory)
+  uint32_t done_base, seq, stepno, epoch;
+  unsigned long long tile_base;
+};
+
+static __device__ __noinline__ void step_tail(const TailArgs& t, const LaunchHeader& h) {
   __shared__ unsigned s_ticket;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(t.sync + kSyncDone, 1u);
+  if (tid == 0) s_ticket = atomicAdd(t.sync + kSyncDone, 1u) - h.done_base;
   __syncthreads();
   const unsigned grid = gridDim.x, S = (unsigned)t.n_tail, ticket = s_ticket;
   if (ticket >= S) return;
   const int k = (int)ticket;
   const int total = t.total, n_out = total + kNumSlots;
   const bool dp = t.pa.world > 1;
-  uint32_t epoch = t.pa.epoch, stepno = 0;
-  if (t.state) {   // written by the previous launch only
-    stepno = (uint32_t)__ldcg(t.state + 1);
-    if (dp) epoch = (uint32_t)__ldcg(t.state + 2);
-  }
+  const uint32_t stepno = h.stepno, epoch = h.epoch;   // the state words as every CTA saw them when it started
+  double* const loss_row = t.loss_row + 4 * (h.seq & 1u);   // this launch's half of the loss row
   float c1 = 1.f, c2 = 1.f;
   if (t.weights) {
     // 1 - b^(step + 1) without the cancellation: -expm1((step + 1) log b); float32 is accurate to ~2e-7 relative here
@@ -515,8 +524,20 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
   }
   const size_t par_off = (size_t)(epoch & 1u) * t.pa.world * t.pa.stride;
   if (tid == 0) {
-    while (ld_acquire_gpu(t.sync + kSyncDone) < grid) __nanosleep(20);
+    while (ld_acquire_gpu(t.sync + kSyncDone) - h.done_base < grid) __nanosleep(20);
     s_bad = (dp && ld_acquire_sys(t.pa.flags[t.pa.rank]) != 0u) ? 1 : 0;   // a peer gave up earlier: stay poisoned
+    if (k == 0) {
+      // every CTA has arrived, i.e. has read the header: advance it for the next launch (nothing below reads it)
+      t.sync[kSyncDoneBase] = h.done_base + grid;
+      t.sync[kSyncSeq] = h.seq + 1u;
+      *reinterpret_cast<unsigned long long*>(t.sync + kSyncTileBase) = h.tile_base + (unsigned long long)t.n_tiles + grid;
+      double* other = t.loss_row + 4 * ((h.seq & 1u) ^ 1u);   // the next launch's half: last read one launch ago
+      other[0] = 0.0; other[1] = 0.0; other[2] = 0.0; other[3] = 0.0;
+      if (t.state) {
+        t.state[1] = (unsigned long long)h.stepno + 1ULL;
+        t.state[2] = (unsigned long long)h.epoch + 1ULL;
+      }
+    }
   }
   __syncthreads();
 
@@ -563,8 +584,8 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
     } else if (col < n_out && owner) {
       // loss slots: out slot 0 = total of the 4 internal slots, 1..4 = internal 0..3, 5..7 = 0
       const int sl = col - total;
-      if (sl == 0) acc = __ldcg(t.loss_row) + __ldcg(t.loss_row + 1) + __ldcg(t.loss_row + 2) + __ldcg(t.loss_row + 3);
-      else if (sl <= 4) acc = __ldcg(t.loss_row + sl - 1);
+      if (sl == 0) acc = __ldcg(loss_row) + __ldcg(loss_row + 1) + __ldcg(loss_row + 2) + __ldcg(loss_row + 3);
+      else if (sl <= 4) acc = __ldcg(loss_row + sl - 1);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -606,21 +627,6 @@ static __device__ __noinline__ void step_tail(const TailArgs& t) {
     }
     finish(col, sum, m0, v0, w0);
   }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(t.sync + kSyncTailDone, 1u) == S - 1) {
-      // the last CTA of the launch: leave the header ready for the next one
-      t.sync[kSyncTile] = 0u; t.sync[kSyncTile + 1] = 0u; t.sync[kSyncDone] = 0u; t.sync[kSyncTailDone] = 0u;
-      if (t.self_clean)
-        for (int q = 0; q < kNumSlots; ++q) t.loss_row[q] = 0.0;
-      if (t.state) {
-        t.state[1] += 1ULL;
-        t.state[2] += 1ULL;
-      }
-      __threadfence();
-    }
-  }
 }
 
 // SPLIT: the kinetic segments are of kind kSegKineticSplit (row_kinetic_split: the passes of a row spread over a lane
@@ -633,12 +639,20 @@ mfc_step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double scratch4[kWarps][4];
   __shared__ long long s_tile;
+  __shared__ LaunchHeader s_hdr;
   __shared__ __align__(8) uint64_t tc_mbar;
   __shared__ uint32_t tc_slot;
   using Ctx = typename CtxSelect<Net, ENG, DimsT::kD, DimsT::kL>::type;
   // Programmatic dependent launch (api.cu: launch_step_kernel): this grid may have been scheduled while the previous
   // kernel of the stream was still in its tail; nothing is read or written before that kernel has completed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) {   // the header as the previous launch left it (visible to the CTA after the set-up's barriers)
+    s_hdr.done_base = __ldcg(a.tail.sync + kSyncDoneBase);
+    s_hdr.seq = __ldcg(a.tail.sync + kSyncSeq);
+    s_hdr.tile_base = __ldcg(reinterpret_cast<const unsigned long long*>(a.tail.sync + kSyncTileBase));
+    s_hdr.stepno = a.tail.state ? (uint32_t)__ldcg(a.tail.state + 1) : 0u;
+    s_hdr.epoch = a.tail.state && a.tail.pa.world > 1 ? (uint32_t)__ldcg(a.tail.state + 2) : a.tail.pa.epoch;
+  }
   unsigned long long t_start = 0;
   if (a.timeline && threadIdx.x == 0) { t_start = global_timer_ns(); atomicMin(a.timeline + 0, t_start); atomicMax(a.timeline + 7, t_start); }   // first / last CTA starts
   float* sAcc = Ctx::kAccInGlobal ? nullptr : smem + a.plan.off_acc;
@@ -673,7 +687,7 @@ mfc_step_kernel(const __grid_constant__ StepArgs a) {
   // an SM run at different speeds, and only the counter evens that out.)
   while (true) {
     __syncthreads();
-    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1ULL);
+    if (threadIdx.x == 0) s_tile = (long long)(atomicAdd(tile_counter, 1ULL) - s_hdr.tile_base);
     __syncthreads();
     const long long tile = s_tile;
     if (tile >= a.n_tiles) break;
@@ -755,12 +769,12 @@ mfc_step_kernel(const __grid_constant__ StepArgs a) {
       double v = 0.0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) v += scratch4[w][threadIdx.x];
-      if (v != 0.0) atomicAdd(a.tail.loss_row + threadIdx.x, v);
+      if (v != 0.0) atomicAdd(a.tail.loss_row + 4 * (s_hdr.seq & 1u) + threadIdx.x, v);
     }
   }
   ctx_teardown(ctx);
   if (a.timeline && threadIdx.x == 0) atomicMax(a.timeline + 4, global_timer_ns());   // last CTA enters the tail
-  step_tail(a.tail);
+  step_tail(a.tail, s_hdr);
   if (a.timeline && threadIdx.x == 0) atomicMax(a.timeline + 5, global_timer_ns());   // last CTA leaves
 }
 
