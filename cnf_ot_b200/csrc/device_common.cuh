@@ -107,16 +107,57 @@ __device__ inline void load_weights(float* sW, const float* __restrict__ gW, int
   for (int i = (n4 << 2) + threadIdx.x; i < total; i += blockDim.x) sW[i] = __ldg(gW + i);
 }
 
-// once per CTA: the normalised knots of the shared `first` spline (one thread; ~300 instructions)
+// The normalised knots of the shared `first` spline (rqs_math.cuh: first_knots_build) by ONE WARP: lane k owns bin k and
+// knot k; maxima, sums and the cumulative sums of the bin sizes travel with shuffles.  (One thread doing it serially was
+// a ~400-instruction dependent chain, 1.7 us, on the critical path of every CTA's set-up.)  All 32 lanes must call.
+template <int K, class SC>
+__device__ __forceinline__ void first_knots_build_warp(const float* theta, const SC& c, FirstKnots<float, K>& fk) {
+  static_assert(K + 1 <= 32, "one lane per knot");
+  constexpr unsigned kAll = 0xffffffffu;
+  const int k = threadIdx.x & 31;
+  const bool bin = k < K;
+  float pos[2], prob[2];
+#pragma unroll
+  for (int axis = 0; axis < 2; ++axis) {
+    const float u = bin ? theta[axis * K + k] : -INFINITY;
+    float m = u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kAll, m, o));
+    const float e = bin ? m_exp_shifted(u, m_exp_shift_prep(m)) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kAll, sum, o);
+    const float inv = m_rcp(sum);
+    const float size = bin ? e * (inv * c.bin_scale) + c.min_bin : 0.f;
+    prob[axis] = e * inv;
+    float acc = size;   // inclusive scan: lane k ends with size[0] + ... + size[k]
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_up_sync(kAll, acc, o);
+      if (k >= o) acc += v;
+    }
+    pos[axis] = c.lo + acc;   // position of knot k + 1
+  }
+  if (bin) {
+    fk.pw[k] = prob[0];
+    fk.ph[k] = prob[1];
+    if (k + 1 <= K - 1) { fk.xp[k + 1] = pos[0]; fk.yp[k + 1] = pos[1]; }
+  }
+  if (k == 0) { fk.xp[0] = c.lo; fk.yp[0] = c.lo; fk.xp[K] = c.hi; fk.yp[K] = c.hi; }
+  if (k <= K) {
+    const float u = theta[2 * K + k] + c.slope_offset;
+    fk.dk[k] = softplus(u) + c.min_slope;
+    fk.sg[k] = sigmoid(u);
+  }
+}
+
+// once per CTA: the normalised knots of the shared `first` spline, by warp 0
 template <class Net>
 __device__ inline void build_first_knots(const float* first_smem, float* fk_smem) {
   static_assert(sizeof(FirstKnots<float, Net::kK>) <= kFirstKnotFloats * sizeof(float), "FirstKnots does not fit its slot");
-  if (threadIdx.x == 0) {
-    float theta[Net::kPp];
-    for (int j = 0; j < Net::kPp; ++j) theta[j] = first_smem[j];
-    first_knots_build<float, Net::kK>(theta, FixedSplineConsts<float, Net::kK>(),
-                                      *reinterpret_cast<FirstKnots<float, Net::kK>*>(fk_smem));
-  }
+  if (threadIdx.x < 32)
+    first_knots_build_warp<Net::kK>(first_smem, FixedSplineConsts<float, Net::kK>(),
+                                    *reinterpret_cast<FirstKnots<float, Net::kK>*>(fk_smem));
 }
 
 template <class Net>

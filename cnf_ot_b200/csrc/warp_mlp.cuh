@@ -365,19 +365,14 @@ struct DeviceCtxMma {
           dst[i] = src[so];
         }
       }
-      // One thread of the last warp normalises the knots of the shared `first` spline (a serial ~400-instruction
-      // chain) while the other warps build the weight fragments.
+      // The last warp normalises the knots of the shared `first` spline (device_common.cuh: first_knots_build_warp) while
+      // the other warps build the weight fragments.
       const int n_mat = L * (D - 1) * M;
       const int nb = (int)blockDim.x - 32;
       if (staged) {
         if ((int)threadIdx.x >= nb) {
-          if ((int)threadIdx.x == nb) {
-          float theta[Pp];
-#pragma unroll
-          for (int j = 0; j < Pp; ++j) theta[j] = stage[j];
-          first_knots_build<float, Net::kK>(theta, FixedSplineConsts<float, Net::kK>(),
-                                            *reinterpret_cast<FirstKnots<float, Net::kK>*>(smem + p.off_fk));
-          }
+          first_knots_build_warp<Net::kK>(stage, FixedSplineConsts<float, Net::kK>(),
+                                          *reinterpret_cast<FirstKnots<float, Net::kK>*>(smem + p.off_fk));
         } else {
           for (int e = threadIdx.x; e < n_mat * 256; e += nb)
             reinterpret_cast<float4*>(smem + p.off_frag)[e] = frag_element<false>(stage, D, M, e);
