@@ -43,6 +43,17 @@ for it in range(6):
   same = all(torch.equal(gathered[0], x) for x in gathered)
   if rank == 0: print(f"step {it}: fused vs NCCL rel err {err:.2e}; identical on all ranks: {same}", flush=True)
   ok = ok and err < 2e-6 and same
+# a small step (the reference's default batch): the kernel instantiation whose kinetic rows are spread over lane groups
+Bs = 2048 // world; bs = Bs // 32
+cfg_s = bench.mfc_cfg("rwpo", "double_well", 2, Bs * world)
+pd_s = ops.problem_desc(cfg_s)
+lat_s = torch.randn(Bs, 2, device=dev, generator=g); sub_s = torch.randn(max(bs, 1), 2, device=dev, generator=g)[:bs]
+ref = ops.mfc_step(shape, pd_s, W, lat_s, sub_s, None, None, [0.4], 500.0, Bs * world, bs * world).clone()
+td.all_reduce(ref)
+got = ops.mfc_step(shape, pd_s, W, lat_s, sub_s, None, None, [0.4], 500.0, Bs * world, bs * world, peers=px).clone()
+err = float((got - ref).abs().max() / ref.abs().max())
+if rank == 0: print(f"small step (B = {Bs * world}, rwpo): fused vs NCCL rel err {err:.2e}", flush=True)
+ok = ok and err < 2e-6
 # on-chip draws: the sharded fused step (global row indices) == the whole batch on one GPU
 gB, gb = B * world, b * world
 rs, ss = dist.shard(gB, rank, world), dist.shard(gb, rank, world)
