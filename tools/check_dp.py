@@ -97,6 +97,21 @@ torch.cuda.synchronize()
 werr = float((Wd - Ws).abs().max())
 if rank == 0: print(f"graph of 4 sharded updates x3 replays vs 12 whole-batch updates: weights max abs diff {werr:.2e}; steps {st_d.step_count()}", flush=True)
 ok = ok and werr < 2e-3 and st_d.step_count() == K + 12 and st_d.status() == 0
+# solvers.main under torchrun: the reference's training loop, device-resident, row shards + the fused exchange, CUDA graphs
+import copy, yaml
+from cnf_ot_b200 import solvers
+mcfg = yaml.safe_load(open(os.path.join(ROOT, "cnf_ot_b200", "config", "mfc.yaml")))
+mcfg = copy.deepcopy(mcfg); mcfg["train"]["epochs"] = 60; mcfg["train"]["batch_size"] = 2048; mcfg["train"]["eval_frequency"] = 20
+params, hist = solvers.main(mcfg)
+torch.cuda.synchronize()
+gp = [torch.empty_like(params.blob) for _ in range(world)]
+td.all_gather(gp, params.blob)
+same_p = all(torch.equal(gp[0], x) for x in gp)
+hist = torch.as_tensor(hist).float()
+if rank == 0:
+  print(f"solvers.main x60 under torchrun (mfc.yaml, B = 2048): loss {float(hist[0]):.3e} -> {float(hist[-1]):.3e}; "
+        f"parameters identical on all ranks: {same_p}", flush=True)
+ok = ok and same_p and bool(torch.isfinite(hist).all()) and float(hist[-1]) < float(hist[0])
 out = torch.empty(shape.blob_size + 8, device=dev)
 def timed(fn, n=100):
   for _ in range(5): fn()
