@@ -621,7 +621,7 @@ int64_t cnfot_flow_vjp_workspace_bytes(const cnfot_flow_desc* flow, int64_t rows
   FlowLayout lay;
   if (check_flow(flow, &lay)) return -1;
   if (use_wide(flow, lay)) return wide_flow_workspace_bytes(lay, rows, true);
-  return partial_bytes(lay);
+  return step_bytes(lay);   // partial results + the activation stash (seam 1 differentiates the rows it just evaluated)
 }
 
 static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, const float* weights,
@@ -675,6 +675,11 @@ static int flow_vjp_call(int dir, void* stream, const cnfot_flow_desc* flow, con
   a.g_out = g_out; a.g_logdet = g_logdet; a.g_in = g_in; a.dir = dir; a.add_base = add_base;
   a.D = lay.D; a.L = lay.L; a.plan = sp;
   a.pb = carve_partials(workspace, &counter);
+  a.stash = nullptr;
+  a.stash_cta_floats = (engine == kEngMma || engine == kEngMmaStream) && cfg.grid <= kStashMaxGrid &&
+                               workspace_bytes >= step_bytes(lay)
+                           ? stash_cta_floats(lay) : 0;
+  if (a.stash_cta_floats > 0) a.stash = (float*)((char*)workspace + partial_bytes(lay));
   void* args[] = {&a};
   cudaError_t e = cudaLaunchKernel(kernel, dim3(cfg.grid), dim3(kTile), args, cfg.smem, s);
   if (e != cudaSuccess) return cuda_fail(e, "flow_vjp_kernel launch");

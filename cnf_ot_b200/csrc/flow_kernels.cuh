@@ -138,6 +138,8 @@ struct VjpArgs {
   int D, L;
   SmemPlan plan;
   PartialBuf pb;
+  float* stash;                 // activation stash (warp-level engines; stash_cta_floats per CTA), or nullptr
+  long long stash_cta_floats;
 };
 
 template <class Net, class DimsT, int ENG>
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
   ctx.smem = smem; ctx.gW = a.W; ctx.p = a.plan;
   ctx.bind_partials(a.pb.grad + (int64_t)blockIdx.x * a.plan.total);
   ctx.bind_frags(a.frags);
+  ctx.bind_stash(a.stash ? a.stash + (size_t)blockIdx.x * a.stash_cta_floats : nullptr);
   ctx_setup(ctx, a.D, a.L, &tc_mbar, &tc_slot);
   const RowTiles<float, Net> tl = make_row_tiles<Net>(smem, a.plan);
   const DimsT dm{a.D, a.L};
@@ -165,8 +168,9 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
     float st[kMaxStateFloats], g[kMaxDim];
     for (int i = 0; i < D; ++i) st[i] = live ? a.in[r * D + i] : 0.f;
     const float t = live ? a.cond[r * a.cond_stride] : 0.f;
-    if (a.dir == 0) flow_pass<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx);
-    else flow_pass<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx);
+    const bool stash = ctx.stash_on();   // forward and backward of the same rows, back to back: keep the activations
+    if (a.dir == 0) flow_pass<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx, stash);
+    else flow_pass<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, tl, ctx, stash);
     const float gl = (live && a.g_logdet) ? a.g_logdet[r] : 0.f;
     for (int i = 0; i < D; ++i) g[i] = live ? a.g_out[r * D + i] : 0.f;
     float gl_pass = gl;
@@ -176,9 +180,9 @@ __global__ void __launch_bounds__(kTile, ENG >= kEngMma ? kMmaMinCtas : 1) flow_
         for (int i = 0; i < D; ++i) g[i] -= gl * st[L * D + i];
     }
     if (a.dir == 0)
-      flow_pass_bwd<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<0, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx, stash);
     else
-      flow_pass_bwd<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx);
+      flow_pass_bwd<1, float, Net, DimsT, Ctx>(dm, FixedSplineConsts<float, Net::kK>(), t, st, g, gl_pass, gfirst, tl, ctx, stash);
     if (a.add_base && a.dir == 0)
       for (int i = 0; i < D; ++i) g[i] -= gl * st[i];
     if (live && a.g_in)
