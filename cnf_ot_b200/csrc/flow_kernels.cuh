@@ -602,24 +602,33 @@ static __device__ __noinline__ void step_tail(const TailArgs& t, const LaunchHea
     const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(mine);
     for (int p = 0; p < t.pa.world; ++p)
       st_relaxed_sys_u64(t.pa.xbuf[p] + par_off + (size_t)t.pa.rank * t.pa.stride + col, word);
-    // phase B: every peer's word of this column, summed in rank order
+    // phase B: every peer's word of this column, summed in rank order.  All (<= 8) words are requested before the first
+    // one is looked at: a sys-scope load is an L2 round trip, and eight of them one after the other were 5 us of the
+    // 8-GPU step even when every word had long arrived.
     bool bad = *(volatile int*)&s_bad != 0;
     float sum = 0.f;
-    for (int q = 0; q < t.pa.world && !bad; ++q) {
-      const unsigned long long* w = mybuf + (size_t)q * t.pa.stride + col;
-      unsigned long long v = ld_relaxed_sys_u64(w);
-      if ((uint32_t)(v >> 32) != epoch) {
-        const unsigned long long t0 = global_timer_ns();
-        unsigned spins = 0;
-        while ((uint32_t)((v = ld_relaxed_sys_u64(w)) >> 32) != epoch) {
-          if ((++spins & 255u) == 0u &&
-              (ld_acquire_sys(abort_word) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns)) {
-            bad = true;
-            break;
+    if (!bad) {
+      const unsigned long long* w0 = mybuf + col;
+      unsigned long long v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = q < t.pa.world ? ld_relaxed_sys_u64(w0 + (size_t)q * t.pa.stride) : 0ULL;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q >= t.pa.world || bad) continue;
+        if ((uint32_t)(v[q] >> 32) != epoch) {
+          const unsigned long long* w = w0 + (size_t)q * t.pa.stride;
+          const unsigned long long t0 = global_timer_ns();
+          unsigned spins = 0;
+          while ((uint32_t)((v[q] = ld_relaxed_sys_u64(w)) >> 32) != epoch) {
+            if ((++spins & 255u) == 0u &&
+                (ld_acquire_sys(abort_word) != 0u || global_timer_ns() - t0 > t.pa.timeout_ns)) {
+              bad = true;
+              break;
+            }
           }
         }
+        sum += __uint_as_float((uint32_t)v[q]);
       }
-      sum += __uint_as_float((uint32_t)v);
     }
     if (bad) {
       // a peer never arrived (or gave up): poison this rank's result AND tell every peer, so no rank
